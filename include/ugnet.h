@@ -1,0 +1,243 @@
+/* ugnet.h — C ABI of libugnet.so: the B200 (sm_100a) engine for the two-stage hot path of
+ * BY-Elysia/UNet-GooLeNet (UNet forward -> mask -> bbox -> ROI crop/resize -> GoogLeNet forward).
+ *
+ * The reference is pure Python and has no FFI of its own; its "interface" for this path is
+ *   nets.basicUnet.UNetTaskAligWeight.forward          (分割/nets/basicUnet.py:406-437)
+ *   nets.tasks.TransformerDecoder.forward              (分割/nets/tasks.py:218-231)
+ *   util.roi.process_and_augment_roi                   (分类/util/roi.py:12-51)
+ *   GoogLeNetClassifier.forward / torchvision GoogLeNet (分类/test.py:64-73)
+ *   inference_all                                      (分类/test.py:74-96, 分割/predict.py:11-51)
+ * The Python shells in unet-goolenet_b200/ keep those names and lower each forward into a list of the ops
+ * declared here (a "program"), which the engine executes on one CUDA stream.  Every entry point:
+ *   - takes raw device pointers and explicit shapes, never owns caller memory, never throws;
+ *   - returns UG_OK (0) or a negative UG_E* code; the message is available via ug_last_error();
+ *   - is asynchronous on the given stream (cudaStream_t passed as void*), except *_host helpers;
+ *   - is not thread-safe per handle (one handle per device/thread).
+ * All activations are NHWC bf16 unless stated; all folded scale/bias vectors are fp32.
+ */
+#ifndef UGNET_H_
+#define UGNET_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UG_VERSION 100
+
+enum { UG_OK = 0, UG_EINVAL = -1, UG_ECUDA = -2, UG_ENOMEM = -3, UG_EUNSUPPORTED = -4 };
+enum { UG_ACT_NONE = 0, UG_ACT_RELU = 1, UG_ACT_GELU = 2 };
+enum { UG_EPI_STORE = 0, UG_EPI_ADD = 1, UG_EPI_GATE = 2, UG_EPI_OUTC = 3 };
+
+typedef struct ug_engine* ug_handle;
+typedef struct ug_program_s* ug_program;
+
+/* ---- implicit-GEMM convolution / linear layer on tcgen05 tensor cores --------------------------------
+ * Replaces nn.Conv2d(3x3,p=1)+BatchNorm2d+ReLU (basicUnet.py:25-40), Conv2dReLU (tasks.py:98-120),
+ * nn.ConvTranspose2d(2,2,s=2) (basicUnet.py:121), nn.Linear (tasks.py:50-53,66-72,127-131),
+ * outc 1x1 (basicUnet.py:391,435) and torchvision BasicConv2d.  Stride is always 1 and 2*pad == R-1.
+ * in : pixel (n,y,x) at in + ((n*H+y)*W+x)*in_cstride, channels [0,Cin)   (channel-slice views allowed)
+ * w  : bf16 [Npad][R*S*Cin_pad], K index = (r*S+s)*Cin_pad + c, Cin_pad = round_up(Cin,64), zero padded
+ * out: value(n,y,x,j) = act(acc*scale[j] + bias[j]) then the epilogue `mode`:
+ *   UG_EPI_STORE: out[((n*OH+oy)*OW+ox)*out_cstride + c] (bf16)
+ *   UG_EPI_ADD  : ... + add[n*add_bstride + (oy*OW+ox)*add_cstride + c]           (residual / pos-embedding)
+ *   UG_EPI_GATE : add[...] + value*(1+gate[n*N+c])        (CoordAtt3: e_1 + g*def_d + def_d, basicUnet.py:229)
+ *   UG_EPI_OUTC : logits[(n*H+y)*W+x] = sum_j value_j*outc_w[j] + outc_b; mask = sigmoid(logit) > 0.5
+ *                 (outc + roi.py:22-23); nothing is written to `out`.  Requires N <= BN.
+ * up == 1: (oy,ox,c) = (y,x,j).  up == 2 (ConvTranspose 2x2 s2): N = 4*convt_cout, q = j/convt_cout,
+ *   (oy,ox,c) = (2y + (q>>1), 2x + (q&1), j % convt_cout).
+ */
+typedef struct ug_conv_desc {
+  const void* in;
+  int in_cstride, Cin;
+  int B, H, W;
+  int R, S, pad;
+  const void* w;
+  int N;
+  const float* scale; /* may be NULL (= 1) */
+  const float* bias;  /* may be NULL (= 0) */
+  int act, mode;
+  void* out;
+  int out_cstride;
+  int up, convt_cout;
+  const void* add;
+  long long add_bstride;
+  int add_cstride;
+  const float* gate;
+  const float* outc_w;
+  float outc_b;
+  float* logits;
+  unsigned char* mask;
+  int TW, TH, TN, BN, stages; /* tiling; 0 = engine chooses */
+} ug_conv_desc;
+
+/* x: fp32 NCHW [B,3,H,W] -> out: bf16 [B*H*W][64], column (r*3+s)*3+c = x[n,c,y+r-1,x+s-1] (0 outside),
+ * columns 27..63 zero.  Feeds `inc` (basicUnet.py:409) as a K=64 GEMM; also performs x.float() (:408). */
+typedef struct ug_inc_im2col_desc {
+  const float* x;
+  void* out;
+  int B, H, W;
+} ug_inc_im2col_desc;
+
+/* Max pooling on NHWC bf16 with -inf padding (nn.MaxPool2d(2), basicUnet.py:47; torchvision GoogLeNet
+ * maxpool1-4 and Inception branch4 with ceil_mode=True: caller passes the ceil-mode OH/OW). */
+typedef struct ug_pool_desc {
+  const void* in;
+  int in_cstride;
+  void* out;
+  int out_cstride;
+  int C, B, H, W, OH, OW, k, stride, pad;
+} ug_pool_desc;
+
+/* nn.LayerNorm(C) over the last dim of [M][C] bf16 tokens (tasks.py:161-164), fp32 statistics. */
+typedef struct ug_layernorm_desc {
+  const void* in;
+  void* out;
+  const float* gamma;
+  const float* beta;
+  int M, C;
+  float eps;
+} ug_layernorm_desc;
+
+/* softmax(q k^T * scale) v per (image, head), dim_head = 64 (tasks.py:132-147 and :73-96).
+ * q/k/v rows are tokens (b*S + i) with the given row strides (elements); head h uses columns [64h,64h+64). */
+typedef struct ug_attn_desc {
+  const void* q;
+  const void* k;
+  const void* v;
+  int q_stride, k_stride, v_stride;
+  void* out;
+  int out_stride;
+  int B, S, heads;
+  float scale;
+} ug_attn_desc;
+
+/* AdaptiveAvgPool2d(1)/AdaptiveMaxPool2d(1) of an NHWC bf16 map (basicUnet.py:217-218), stage 1: each of
+ * `splits` blocks per image reduces a contiguous pixel range to fp32 partial sums / maxima
+ * psum,pmax: [B][splits][C].  Deterministic (no atomics); stage 2 lives in the gate op. */
+typedef struct ug_chanstats_desc {
+  const void* in;
+  int in_cstride, C, B, HW, splits;
+  float* psum;
+  float* pmax;
+} ug_chanstats_desc;
+
+/* avg = sum(psum)/HW, max = max(pmax);  g = sigmoid(W3 (relu(W1 avg + b1) + relu(W2 max + b2)) + b3)
+ * (basicUnet.py:220-225); fp32.  w1,w2: [C/2][C]; w3: [C][C/2]; g: [B][C]. */
+typedef struct ug_gate_desc {
+  const float* psum;
+  const float* pmax;
+  const float *w1, *b1, *w2, *b2, *w3, *b3;
+  float* g;
+  int B, C, HW, splits;
+} ug_gate_desc;
+
+/* mask u8 [B,H,W] -> boxes int32 [B][4] = {x_min, y_min, x_max, y_max} with roi.py:25-36 semantics
+ * (padding, clamp, end-exclusive max, centred fallback for an empty mask). */
+typedef struct ug_bbox_desc {
+  const unsigned char* mask;
+  int* boxes;
+  int B, H, W, padding;
+} ug_bbox_desc;
+
+/* roi.py:39-44 + data_utils.py:102,146-147: crop img[:, y0:y1, x0:x1] (fp32 NCHW in [0,1]) -> trunc(x*255)
+ * uint8 -> channel flip (c -> 2-c) -> PIL-exact bilinear resize (horizontal pass then vertical pass,
+ * 22-bit fixed point, uint8 intermediate) to SxS.  out_u8: [B][S][S][3] (HWC). */
+typedef struct ug_cropresize_desc {
+  const float* img;
+  const int* boxes;
+  unsigned char* out_u8;
+  int B, H, W, S;
+} ug_cropresize_desc;
+
+/* u8 [B][224][224][3] -> bf16 [B*112*112][192] im2col of GoogLeNet conv1 (7x7, stride 2, pad 3) with
+ * to_tensor (/255) and torchvision _transform_input applied per channel before zero padding;
+ * column (r*7+s)*3+c, columns 147..191 zero. */
+typedef struct ug_g1_im2col_desc {
+  const unsigned char* u8;
+  void* out;
+  int B, S;
+} ug_g1_im2col_desc;
+
+/* AdaptiveAvgPool2d(1) + Linear(C, ncls): in NHWC bf16 [B][HW][C], w fp32 [ncls][C], logits fp32 [B][ncls]. */
+typedef struct ug_head_desc {
+  const void* in;
+  const float* w;
+  const float* b;
+  float* logits;
+  int B, HW, C, ncls;
+} ug_head_desc;
+
+enum {
+  UG_OP_CONV = 1,
+  UG_OP_INC_IM2COL = 2,
+  UG_OP_POOL = 3,
+  UG_OP_LAYERNORM = 4,
+  UG_OP_ATTN = 5,
+  UG_OP_CHANSTATS = 6,
+  UG_OP_GATE = 7,
+  UG_OP_BBOX = 8,
+  UG_OP_CROPRESIZE = 9,
+  UG_OP_G1_IM2COL = 10,
+  UG_OP_HEAD = 11
+};
+
+typedef struct ug_op {
+  int kind;
+  int reserved;
+  union {
+    ug_conv_desc conv;
+    ug_inc_im2col_desc inc;
+    ug_pool_desc pool;
+    ug_layernorm_desc ln;
+    ug_attn_desc attn;
+    ug_chanstats_desc stats;
+    ug_gate_desc gate;
+    ug_bbox_desc bbox;
+    ug_cropresize_desc crop;
+    ug_g1_im2col_desc g1;
+    ug_head_desc head;
+  } u;
+} ug_op;
+
+int ug_version(void);
+int ug_create(int device, ug_handle* out);
+int ug_destroy(ug_handle h);
+const char* ug_last_error(ug_handle h);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+long long ug_launch_count(ug_handle h);
+
+/* Single ops (validated, tensor maps built per call) — used by the unit parity tests. */
+int ug_conv(ug_handle h, const ug_conv_desc* d, void* stream);
+int ug_inc_im2col(ug_handle h, const ug_inc_im2col_desc* d, void* stream);
+int ug_pool(ug_handle h, const ug_pool_desc* d, void* stream);
+int ug_layernorm(ug_handle h, const ug_layernorm_desc* d, void* stream);
+int ug_attention(ug_handle h, const ug_attn_desc* d, void* stream);
+int ug_chanstats(ug_handle h, const ug_chanstats_desc* d, void* stream);
+int ug_gate(ug_handle h, const ug_gate_desc* d, void* stream);
+int ug_bbox(ug_handle h, const ug_bbox_desc* d, void* stream);
+int ug_cropresize(ug_handle h, const ug_cropresize_desc* d, void* stream);
+int ug_g1_im2col(ug_handle h, const ug_g1_im2col_desc* d, void* stream);
+int ug_head(ug_handle h, const ug_head_desc* d, void* stream);
+
+/* Programs: a validated op list with tensor maps and launch geometry prepared once; run = launches only. */
+int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out);
+int ug_program_run(ug_handle h, ug_program p, void* stream);
+int ug_program_num_launches(ug_program p);
+int ug_program_destroy(ug_handle h, ug_program p);
+
+/* Host-buffer convenience used for end-to-end timing: H2D copies, run, D2H copies, all on `stream`,
+ * then a stream synchronize.  Host pointers should be pinned. */
+typedef struct ug_copy {
+  void* dst;
+  const void* src;
+  size_t bytes;
+} ug_copy;
+int ug_program_run_host(ug_handle h, ug_program p, const ug_copy* h2d, int n_h2d, const ug_copy* d2h, int n_d2h,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGNET_H_ */

@@ -1,0 +1,139 @@
+"""GPU parity of the tcgen05 implicit-GEMM kernel (ug_conv) against torch fp32 on the same bf16-rounded
+operands.  Tolerance: the kernel accumulates in fp32 and rounds once to bf16, so |err| <= 2^-8 * |ref| plus a
+small absolute term for fp32 summation-order differences."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cuda") * scale)
+
+
+def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_extra=0, in_off=0, out_off=0,
+             seed=0, tile=None, bn=None, stages=0, add_broadcast=False):
+    from ugnet_b200 import engine as E
+    from ugnet_b200 import pack
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pad = (R - 1) // 2
+    in_cs = Cin + in_extra
+    xbuf = _mk((B, H, W, in_cs), g).to(torch.bfloat16)
+    x = xbuf[..., in_off:in_off + Cin]
+    cout = N // 4 if up == 2 else N
+    if up == 2:
+        wt = _mk((Cin, cout, 2, 2), g, (1.0 / Cin) ** 0.5)
+        BN = bn or pack.choose_bn(N, cout)
+        wp, bias = pack.pack_convt_weight(wt, _mk((cout,), g), BN)
+        wq = wp[:N, :Cin].float()  # bf16-rounded GEMM weight [4*cout][Cin]
+        scale = None
+    else:
+        wt = _mk((N, Cin, R, R), g, (1.0 / (Cin * R * R)) ** 0.5)
+        BN = bn or pack.choose_bn(N)
+        wp = pack.pack_conv_weight(wt, BN)
+        wq = wt.to(torch.bfloat16).float()
+        scale = (torch.rand((N,), generator=g, device="cuda") + 0.5)
+        bias = _mk((N,), g)
+    OH, OW = H * up, W * up
+    out_cs = cout + out_extra
+    obuf = torch.full((B, OH, OW, out_cs), 7.0, device="cuda", dtype=torch.bfloat16)
+    d = E.ConvDesc()
+    d.inp = x.data_ptr(); d.in_cstride = in_cs; d.Cin = Cin
+    d.B, d.H, d.W = B, H, W
+    d.R = d.S = R; d.pad = pad
+    d.w = wp.data_ptr(); d.N = N
+    d.scale = E.ptr(scale); d.bias = bias.data_ptr()
+    d.act = act; d.mode = mode
+    d.out = obuf.data_ptr() + 2 * out_off; d.out_cstride = out_cs
+    d.up = up; d.convt_cout = cout if up == 2 else 0
+    d.BN = BN; d.stages = stages
+    if tile:
+        d.TW, d.TH, d.TN = tile
+    addt = gate = outw = logits = mask = None
+    if mode in (E.EPI_ADD, E.EPI_GATE):
+        ab = 1 if add_broadcast else B
+        addt = _mk((ab, OH, OW, cout), g).to(torch.bfloat16)
+        d.add = addt.data_ptr(); d.add_cstride = cout
+        d.add_bstride = 0 if add_broadcast else OH * OW * cout
+        if mode == E.EPI_GATE:
+            gate = torch.rand((B, N), generator=g, device="cuda")
+            d.gate = gate.data_ptr()
+    if mode == E.EPI_OUTC:
+        outw = _mk((N,), g, 0.2)
+        logits = torch.zeros((B, H, W), device="cuda")
+        mask = torch.full((B, H, W), 9, device="cuda", dtype=torch.uint8)
+        d.outc_w = outw.data_ptr(); d.outc_b = 0.05
+        d.logits = logits.data_ptr(); d.mask = mask.data_ptr()
+    engine.run_op(d)
+    torch.cuda.synchronize()
+
+    # ---- reference in fp32 on the same bf16-rounded operands
+    xf = x.float().permute(0, 3, 1, 2)
+    if up == 2:
+        y = torch.einsum("bchw,nc->bnhw", xf, wq) + bias[None, :, None, None]   # [B, 4*cout, H, W]
+        y = y.reshape(B, 2, 2, cout, H, W).permute(0, 3, 4, 1, 5, 2).reshape(B, cout, OH, OW)
+    else:
+        y = F.conv2d(xf, wq, padding=pad) * scale[None, :, None, None] + bias[None, :, None, None]
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = F.gelu(y)
+    y = y.permute(0, 2, 3, 1)  # NHWC
+    if mode == E.EPI_ADD:
+        y = y + addt.float()
+    elif mode == E.EPI_GATE:
+        y = addt.float() + y * (1.0 + gate[:, None, None, :])
+    if mode == E.EPI_OUTC:
+        ref_logit = (y * outw).sum(-1) + 0.05
+        err = (logits - ref_logit).abs().max().item()
+        assert err < 2e-3 * max(1.0, ref_logit.abs().max().item()), f"outc logits err {err}"
+        sure = ref_logit.abs() > 1e-3
+        assert torch.equal(mask[sure], (ref_logit[sure] > 0).to(torch.uint8))
+        return
+    got = obuf[..., out_off:out_off + cout].float()
+    tol = 2.0 ** -7 * y.abs() + 2e-2
+    bad = (got - y).abs() > tol
+    assert not bad.any(), (f"{bad.sum().item()} / {bad.numel()} mismatches, max err "
+                           f"{(got - y).abs().max().item():.4f}, first at {bad.nonzero()[0].tolist()}")
+    # channels outside the written slice must be untouched
+    if out_extra:
+        keep = torch.ones(out_cs, dtype=torch.bool, device="cuda")
+        keep[out_off:out_off + cout] = False
+        assert (obuf[..., keep] == 7.0).all()
+
+
+CASES = [
+    # B, H, W, Cin, N, R
+    dict(B=1, H=1, W=256, Cin=64, N=64, R=1),                      # plain GEMM, one k-step per tap
+    dict(B=1, H=1, W=1000, Cin=512, N=1536, R=1, act=0),           # qkv-shaped GEMM, ragged M
+    dict(B=1, H=1, W=392, Cin=512, N=2048, R=1, act=2),            # FFN up-projection with GELU
+    dict(B=2, H=16, W=16, Cin=64, N=64, R=3),                      # 3x3, exact tiles
+    dict(B=2, H=28, W=28, Cin=128, N=256, R=3),                    # 28-wide rows (112-row tiles)
+    dict(B=3, H=14, W=14, Cin=512, N=512, R=3),                    # bottleneck shape
+    dict(B=2, H=56, W=56, Cin=256, N=128, R=3),
+    dict(B=1, H=224, W=224, Cin=64, N=64, R=3),                    # last decoder stage shape
+    dict(B=5, H=7, W=7, Cin=832, N=48, R=1),                       # GoogLeNet 5a reduce: TN>1, BN=48
+    dict(B=2, H=14, W=14, Cin=24, N=64, R=3, in_extra=40, in_off=16),   # Cin < 64 inside a channel slice
+    dict(B=2, H=28, W=28, Cin=192, N=96, R=1, out_extra=160, out_off=64),  # concat-offset store, N=96
+    dict(B=2, H=14, W=14, Cin=512, N=2048, R=1, up=2, act=0),      # ConvTranspose 2x2 s2 (512 -> 512)
+    dict(B=1, H=112, W=112, Cin=64, N=256, R=1, up=2, act=0, out_extra=64),  # ConvT into a concat buffer
+    dict(B=2, H=14, W=14, Cin=512, N=512, R=3, mode=1, add_broadcast=True),  # conv + pos-embedding
+    dict(B=1, H=1, W=392, Cin=512, N=512, R=1, mode=1, act=0),     # linear + residual
+    dict(B=2, H=28, W=28, Cin=512, N=512, R=3, mode=2),            # CoordAtt3 gate combine
+    dict(B=2, H=32, W=48, Cin=64, N=64, R=3, mode=3),              # fused outc + threshold
+    dict(B=1, H=16, W=16, Cin=64, N=64, R=3, tile=(16, 8, 1), stages=2),
+    dict(B=1, H=16, W=16, Cin=128, N=256, R=3, bn=256, stages=3),  # BN=256
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_parity(engine, case):
+    run_conv(engine, **case)
+
+
+def test_conv_rejects_bad_args(engine):
+    from ugnet_b200 import engine as E
+    d = E.ConvDesc()
+    with pytest.raises(RuntimeError):
+        engine.run_op(d)

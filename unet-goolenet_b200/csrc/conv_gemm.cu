@@ -1,0 +1,387 @@
+// Implicit-GEMM convolution / linear kernel for sm_100a.
+//
+//   D[pixels, Cout] = sum over taps (r,s) and 64-channel chunks of  A_tap[pixels, 64] * W[Cout, 64]^T
+//
+// * A tiles are rectangles of TW x TH x TN output pixels of the NHWC bf16 input, fetched by TMA as 4-D boxes
+//   {64 channels, TW, TH, TN} whose (x,y) origin is shifted by the filter tap; out-of-bounds coordinates
+//   (including negative ones) are zero-filled by TMA, which is exactly the conv zero padding.
+// * B tiles are {64, BN} boxes of the packed weight matrix [Npad][R*S*Cin_pad] (K-major).
+// * Both land in shared memory in the 128B-swizzled K-major layout that tcgen05.mma consumes directly.
+// * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator; four epilogue warps
+//   read it back with tcgen05.ld (one output pixel per thread) and apply folded BN / bias, activation and the
+//   fused epilogue (residual add, CoordAtt3 gate combine, ConvTranspose pixel shuffle, outc+sigmoid+threshold).
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//
+// Reference ops this kernel replaces are listed on ug_conv_desc in include/ugnet.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+#include "engine.h"
+
+namespace ug {
+
+static constexpr int kThreads = 192;
+static constexpr int kABytesPerStage = 128 * 128;  // 128 rows x 64 bf16
+
+__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_stage_bytes = p.BN * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + p.stages * kABytesPerStage;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + p.stages * b_stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);
+  float* sBias = sScale + p.BN;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int mt = blockIdx.x;
+  const int x0 = (mt % p.tiles_x) * p.TW;
+  const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.TH;
+  const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.TN;
+  const int ncol0 = blockIdx.y * p.BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.BN; i += 128) {
+      const int n = ncol0 + i;
+      sScale[i] = (n < p.N) ? (p.scale ? p.scale[n] : 1.0f) : 0.0f;
+      sBias[i] = (n < p.N && p.bias) ? p.bias[n] : 0.0f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
+      int it = 0;
+      for (int tap = 0; tap < p.R * p.S; ++tap) {
+        const int r = tap / p.S, s = tap % p.S;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], tx_bytes);
+          tma_load_4d(sA + stage * kABytesPerStage, &tmA, &full[stage], kc * 64, x0 + s - p.pad, y0 + r - p.pad, n0);
+          tma_load_2d(sB + stage * b_stage_bytes, &tmB, &full[stage], it * 64, ncol0);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < p.num_k; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytesPerStage));
+        const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * b_stage_bytes));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // +32 bytes (= 16 bf16) along K inside the 128B swizzle atom: +2 in the encoded start address
+          umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full);  // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps, 1 pixel / thread)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int tx = row % p.TW;
+    const int trest = row / p.TW;
+    const int ty = trest % p.TH;
+    const int tn = trest / p.TH;
+    const int x = x0 + tx, y = y0 + ty, n = n0 + tn;
+    const bool valid = (row < p.TW * p.TH * p.TN) && (x < p.W) && (y < p.H) && (n < p.B);
+
+    int dy = 0, dx = 0, cbase = ncol0;
+    if (p.up == 2) {
+      const int qd = ncol0 / p.convt_cout;
+      dy = qd >> 1;
+      dx = qd & 1;
+      cbase = ncol0 % p.convt_cout;
+    }
+    const int oy = y * p.up + dy, ox = x * p.up + dx;
+    const long long pix = (long long)oy * p.OW + ox;
+    __nv_bfloat16* out_row =
+        reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)n * p.OH * p.OW + pix) * p.out_cstride + cbase;
+    const __nv_bfloat16* add_row =
+        reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)n * p.add_bstride + pix * p.add_cstride + cbase;
+    const float* gate_row = p.gate + (long long)n * p.N + ncol0;
+
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float dot = 0.0f;
+
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      if (ncol0 + c0 >= p.N) break;  // warp-uniform
+      __syncwarp();                  // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
+      uint32_t v[16];
+      tmem_ld16(taddr + c0, v);
+      tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float t = __uint_as_float(v[j]) * sScale[c0 + j] + sBias[c0 + j];
+        if (p.act == UG_ACT_RELU) t = fmaxf(t, 0.0f);
+        else if (p.act == UG_ACT_GELU) t = gelu_erf(t);
+        f[j] = t;
+      }
+      if (p.mode == UG_EPI_OUTC) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dot += f[j] * __ldg(p.outc_w + ncol0 + c0 + j);
+        continue;
+      }
+      const int groups = !valid ? 0 : ((ncol0 + c0 + 16 <= p.N) ? 2 : 1);  // N is a multiple of 8
+      if (p.mode == UG_EPI_ADD || p.mode == UG_EPI_GATE) {
+        for (int g = 0; g < groups; ++g) {
+          const uint4 a = *reinterpret_cast<const uint4*>(add_row + c0 + g * 8);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float e0 = bf16_lo(aw[j]), e1 = bf16_hi(aw[j]);
+            float& f0 = f[g * 8 + 2 * j];
+            float& f1 = f[g * 8 + 2 * j + 1];
+            if (p.mode == UG_EPI_ADD) {
+              f0 += e0;
+              f1 += e1;
+            } else {
+              const float g0 = __ldg(gate_row + c0 + g * 8 + 2 * j);
+              const float g1 = __ldg(gate_row + c0 + g * 8 + 2 * j + 1);
+              f0 = e0 + f0 * (1.0f + g0);
+              f1 = e1 + f1 * (1.0f + g1);
+            }
+          }
+        }
+      }
+      for (int g = 0; g < groups; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+        o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+        o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+        o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(out_row + c0 + g * 8) = o;
+      }
+    }
+    if (p.mode == UG_EPI_OUTC && valid) {
+      const float logit = dot + p.outc_b;
+      const long long o = ((long long)n * p.H + y) * p.W + x;
+      p.logits[o] = logit;
+      // torch.sigmoid(seg_out) > 0.5 evaluated in fp32 (roi.py:22-23, predict.py:26-27)
+      const float sg = 1.0f / (1.0f + expf(-logit));
+      p.mask[o] = sg > 0.5f ? 1 : 0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Pick the pixel-tile rectangle with the best fill of the 128 MMA rows.
+static void choose_tile(int B, int H, int W, int* TW, int* TH, int* TN) {
+  double best = -1.0;
+  int bw = 1, bh = 1, bn = 1;
+  for (int tw = 1; tw <= W && tw <= 128; ++tw) {
+    for (int th = 1; th <= H && tw * th <= 128; ++th) {
+      int tn = 1;
+      if (tw == W && th == H) tn = std::max(1, std::min(B, 128 / (tw * th)));
+      const double tiles = (double)ceil_div(W, tw) * ceil_div(H, th) * ceil_div(B, tn);
+      const double eff = (double)W * H * B / (tiles * 128.0);
+      // prefer higher efficiency; on ties prefer wider rows (longer contiguous TMA runs)
+      if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > bw)) {
+        best = eff;
+        bw = tw;
+        bh = th;
+        bn = tn;
+      }
+    }
+  }
+  *TW = bw;
+  *TH = bh;
+  *TN = bn;
+}
+
+int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return set_error(h, UG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (!d->in || !d->w) return set_error(h, UG_EINVAL, "conv: null in/w pointer");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->N <= 0)
+    return set_error(h, UG_EINVAL, "conv: non-positive shape");
+  if (d->R <= 0 || d->S <= 0 || 2 * d->pad != d->R - 1 || d->R != d->S)
+    return set_error(h, UG_EINVAL, "conv: only square stride-1 'same' filters (2*pad == R-1) are supported");
+  if (d->in_cstride % 8 || (reinterpret_cast<uintptr_t>(d->in) & 15))
+    return set_error(h, UG_EINVAL, "conv: input channel stride must be a multiple of 8 and base 16B aligned");
+  if (d->N % 8) return set_error(h, UG_EINVAL, "conv: N must be a multiple of 8");
+  if (reinterpret_cast<uintptr_t>(d->w) & 15) return set_error(h, UG_EINVAL, "conv: weights must be 16B aligned");
+  const int up = d->up == 2 ? 2 : 1;
+
+  int BN = d->BN;
+  if (BN <= 0) {
+    if (d->N >= 128) BN = 128;
+    else BN = ceil_div(d->N, 16) * 16;
+    if (up == 2) BN = std::min(128, d->convt_cout);
+  }
+  if (BN % 16 || BN < 16 || BN > 256) return set_error(h, UG_EINVAL, "conv: BN must be a multiple of 16 in [16,256]");
+  if (up == 2) {
+    if (d->convt_cout <= 0 || d->N != 4 * d->convt_cout || d->convt_cout % BN)
+      return set_error(h, UG_EINVAL, "conv: ConvTranspose mode needs N == 4*cout and BN | cout");
+    if (d->R != 1) return set_error(h, UG_EINVAL, "conv: ConvTranspose mode is a 1x1 GEMM");
+  }
+  if (d->mode == UG_EPI_OUTC) {
+    if (d->N > BN || !d->outc_w || !d->logits || !d->mask)
+      return set_error(h, UG_EINVAL, "conv: OUTC epilogue needs N <= BN and outc_w/logits/mask");
+  } else {
+    if (!d->out || d->out_cstride % 8 || (reinterpret_cast<uintptr_t>(d->out) & 15))
+      return set_error(h, UG_EINVAL, "conv: output must be 16B aligned with channel stride multiple of 8");
+  }
+  if (d->mode == UG_EPI_ADD || d->mode == UG_EPI_GATE) {
+    if (!d->add || d->add_cstride % 8 || d->add_bstride % 8 || (reinterpret_cast<uintptr_t>(d->add) & 15))
+      return set_error(h, UG_EINVAL, "conv: add tensor must be 16B aligned with strides multiple of 8");
+    if (d->mode == UG_EPI_GATE && !d->gate) return set_error(h, UG_EINVAL, "conv: GATE epilogue needs gate");
+  }
+
+  int TW = d->TW, TH = d->TH, TN = d->TN;
+  if (TW <= 0 || TH <= 0 || TN <= 0) choose_tile(d->B, d->H, d->W, &TW, &TH, &TN);
+  if (TW * TH * TN > 128 || TW > 256 || TH > 256 || TN > 256)
+    return set_error(h, UG_EINVAL, "conv: tile %dx%dx%d exceeds 128 rows", TW, TH, TN);
+
+  const int cin_pad = ceil_div(d->Cin, 64) * 64;
+  const int kchunks = cin_pad / 64;
+  const int num_k = d->R * d->S * kchunks;
+  const int n_tiles = ceil_div(d->N, BN);
+  const long long ktot = (long long)d->R * d->S * cin_pad;
+
+  int stages = d->stages;
+  if (stages <= 0) {
+    const int per_stage = kABytesPerStage + BN * 128;
+    stages = (108 * 1024) / per_stage;  // two CTAs per SM
+    stages = std::max(2, std::min(stages, 8));
+  }
+  stages = std::min(stages, std::max(2, num_k));
+
+  ConvKParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  p.H = d->H; p.W = d->W; p.B = d->B;
+  p.TW = TW; p.TH = TH; p.TN = TN;
+  p.tiles_x = ceil_div(d->W, TW);
+  p.tiles_y = ceil_div(d->H, TH);
+  const int tiles_n = ceil_div(d->B, TN);
+  p.R = d->R; p.S = d->S; p.pad = d->pad;
+  p.kchunks = kchunks; p.num_k = num_k;
+  p.N = d->N; p.BN = BN; p.stages = stages;
+  int tc = 32;
+  while (tc < BN) tc <<= 1;
+  p.tmem_cols = tc;
+  p.a_bytes = (unsigned)(TW * TH * TN) * 128u;
+  p.b_bytes = (unsigned)BN * 128u;
+  p.scale = d->scale; p.bias = d->bias;
+  p.act = d->act; p.mode = d->mode;
+  p.out = d->out; p.out_cstride = d->out_cstride;
+  p.up = up; p.convt_cout = d->convt_cout;
+  p.OH = d->H * up; p.OW = d->W * up;
+  p.add = d->add; p.add_bstride = d->add_bstride; p.add_cstride = d->add_cstride;
+  p.gate = d->gate; p.outc_w = d->outc_w; p.outc_b = d->outc_b;
+  p.logits = d->logits; p.mask = d->mask;
+
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)d->W * d->in_cstride * 2,
+                             (cuuint64_t)d->H * d->W * d->in_cstride * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&L->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->in), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv: activation tensor map encode failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)n_tiles * BN};
+    cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv: weight tensor map encode failed (%d)", (int)r);
+  }
+  L->grid = dim3((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)n_tiles, 1);
+  L->smem = 1024 + (size_t)stages * (kABytesPerStage + BN * 128) + 8 * (2 * stages + 1) + 8 + 2 * BN * sizeof(float);
+  if (L->smem > 227 * 1024) return set_error(h, UG_EINVAL, "conv: shared memory request %zu too large", L->smem);
+  return UG_OK;
+}
+
+int conv_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_gemm_kernel)");
+    attr_set = true;
+  }
+  conv_gemm_kernel<<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->p);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "conv_gemm_kernel launch");
+}
+
+}  // namespace ug

@@ -1,0 +1,176 @@
+// C ABI of libugnet.so: handle management, single-op entry points and the program executor.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "engine.h"
+
+namespace ug {
+
+int set_error(ug_engine* h, int code, const char* fmt, ...) {
+  if (h) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    h->last_error = buf;
+  }
+  return code;
+}
+
+int check_cuda(ug_engine* h, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return UG_OK;
+  return set_error(h, UG_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+}  // namespace ug
+
+using namespace ug;
+
+struct PreparedOp {
+  int kind;
+  ConvLaunch conv;  // valid when kind == UG_OP_CONV
+  ug_op op;         // descriptor copy for the other kinds
+};
+
+struct ug_program_s {
+  std::vector<PreparedOp> ops;
+};
+
+static int run_simple(ug_engine* h, const ug_op* op, cudaStream_t s) {
+  switch (op->kind) {
+    case UG_OP_INC_IM2COL: return launch_inc_im2col(h, &op->u.inc, s);
+    case UG_OP_POOL: return launch_pool(h, &op->u.pool, s);
+    case UG_OP_LAYERNORM: return launch_layernorm(h, &op->u.ln, s);
+    case UG_OP_ATTN: return launch_attention(h, &op->u.attn, s);
+    case UG_OP_CHANSTATS: return launch_chanstats(h, &op->u.stats, s);
+    case UG_OP_GATE: return launch_gate(h, &op->u.gate, s);
+    case UG_OP_BBOX: return launch_bbox(h, &op->u.bbox, s);
+    case UG_OP_CROPRESIZE: return launch_cropresize(h, &op->u.crop, s);
+    case UG_OP_G1_IM2COL: return launch_g1_im2col(h, &op->u.g1, s);
+    case UG_OP_HEAD: return launch_head(h, &op->u.head, s);
+    default: return set_error(h, UG_EINVAL, "unknown op kind %d", op->kind);
+  }
+}
+
+extern "C" {
+
+int ug_version(void) { return UG_VERSION; }
+
+int ug_create(int device, ug_handle* out) {
+  if (!out) return UG_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return UG_ECUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return UG_ECUDA;
+  if (prop.major != 10) return UG_EUNSUPPORTED;  // sm_100a only: there is no fallback path
+  if (cudaSetDevice(device) != cudaSuccess) return UG_ECUDA;
+  ug_engine* h = new (std::nothrow) ug_engine();
+  if (!h) return UG_ENOMEM;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return UG_OK;
+}
+
+int ug_destroy(ug_handle h) {
+  delete h;
+  return UG_OK;
+}
+
+const char* ug_last_error(ug_handle h) { return h ? h->last_error.c_str() : "null handle"; }
+long long ug_launch_count(ug_handle h) { return h ? h->launches : 0; }
+
+int ug_conv(ug_handle h, const ug_conv_desc* d, void* stream) {
+  if (!h || !d) return UG_EINVAL;
+  ConvLaunch L;
+  int rc = conv_prepare(h, d, &L);
+  if (rc != UG_OK) return rc;
+  return conv_launch(h, &L, static_cast<cudaStream_t>(stream));
+}
+
+#define UG_SIMPLE_ENTRY(name, type, fn)                         \
+  int name(ug_handle h, const type* d, void* stream) {          \
+    if (!h || !d) return UG_EINVAL;                             \
+    return fn(h, d, static_cast<cudaStream_t>(stream));         \
+  }
+UG_SIMPLE_ENTRY(ug_inc_im2col, ug_inc_im2col_desc, launch_inc_im2col)
+UG_SIMPLE_ENTRY(ug_pool, ug_pool_desc, launch_pool)
+UG_SIMPLE_ENTRY(ug_layernorm, ug_layernorm_desc, launch_layernorm)
+UG_SIMPLE_ENTRY(ug_attention, ug_attn_desc, launch_attention)
+UG_SIMPLE_ENTRY(ug_chanstats, ug_chanstats_desc, launch_chanstats)
+UG_SIMPLE_ENTRY(ug_gate, ug_gate_desc, launch_gate)
+UG_SIMPLE_ENTRY(ug_bbox, ug_bbox_desc, launch_bbox)
+UG_SIMPLE_ENTRY(ug_cropresize, ug_cropresize_desc, launch_cropresize)
+UG_SIMPLE_ENTRY(ug_g1_im2col, ug_g1_im2col_desc, launch_g1_im2col)
+UG_SIMPLE_ENTRY(ug_head, ug_head_desc, launch_head)
+
+int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out) {
+  if (!h || !ops || n_ops <= 0 || !out) return UG_EINVAL;
+  *out = nullptr;
+  ug_program_s* p = new (std::nothrow) ug_program_s();
+  if (!p) return UG_ENOMEM;
+  p->ops.resize(n_ops);
+  for (int i = 0; i < n_ops; ++i) {
+    PreparedOp& po = p->ops[i];
+    po.kind = ops[i].kind;
+    po.op = ops[i];
+    if (po.kind == UG_OP_CONV) {
+      int rc = conv_prepare(h, &ops[i].u.conv, &po.conv);
+      if (rc != UG_OK) {
+        std::string msg = h->last_error;
+        set_error(h, rc, "op %d: %s", i, msg.c_str());
+        delete p;
+        return rc;
+      }
+    } else if (po.kind < UG_OP_CONV || po.kind > UG_OP_HEAD) {
+      delete p;
+      return set_error(h, UG_EINVAL, "op %d: unknown kind %d", i, po.kind);
+    }
+  }
+  *out = p;
+  return UG_OK;
+}
+
+int ug_program_run(ug_handle h, ug_program p, void* stream) {
+  if (!h || !p) return UG_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const PreparedOp& po = p->ops[i];
+    int rc = (po.kind == UG_OP_CONV) ? conv_launch(h, &po.conv, s) : run_simple(h, &po.op, s);
+    if (rc != UG_OK) {
+      std::string msg = h->last_error;
+      return set_error(h, rc, "op %zu: %s", i, msg.c_str());
+    }
+  }
+  return UG_OK;
+}
+
+int ug_program_num_launches(ug_program p) { return p ? (int)p->ops.size() : 0; }
+
+int ug_program_destroy(ug_handle h, ug_program p) {
+  (void)h;
+  delete p;
+  return UG_OK;
+}
+
+int ug_program_run_host(ug_handle h, ug_program p, const ug_copy* h2d, int n_h2d, const ug_copy* d2h, int n_d2h,
+                        void* stream) {
+  if (!h || !p) return UG_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n_h2d; ++i) {
+    int rc = check_cuda(h, cudaMemcpyAsync(h2d[i].dst, h2d[i].src, h2d[i].bytes, cudaMemcpyHostToDevice, s), "H2D copy");
+    if (rc != UG_OK) return rc;
+  }
+  int rc = ug_program_run(h, p, stream);
+  if (rc != UG_OK) return rc;
+  for (int i = 0; i < n_d2h; ++i) {
+    rc = check_cuda(h, cudaMemcpyAsync(d2h[i].dst, d2h[i].src, d2h[i].bytes, cudaMemcpyDeviceToHost, s), "D2H copy");
+    if (rc != UG_OK) return rc;
+  }
+  return check_cuda(h, cudaStreamSynchronize(s), "stream synchronize");
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// Internal engine declarations shared by the .cu translation units of libugnet.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/ugnet.h"
+
+struct ug_engine {
+  int device = 0;
+  int num_sms = 148;
+  std::string last_error;
+  long long launches = 0;
+};
+
+namespace ug {
+
+// Kernel-side parameter block of the implicit-GEMM kernel (kept POD; passed by value).
+struct ConvKParams {
+  int H, W, B;
+  int TW, TH, TN, tiles_x, tiles_y;
+  int R, S, pad, kchunks, num_k;
+  int N, BN, stages, tmem_cols;
+  unsigned a_bytes, b_bytes;
+  const float* scale;
+  const float* bias;
+  int act, mode;
+  void* out;
+  int out_cstride, OH, OW, up, convt_cout;
+  const void* add;
+  long long add_bstride;
+  int add_cstride;
+  const float* gate;
+  const float* outc_w;
+  float outc_b;
+  float* logits;
+  unsigned char* mask;
+};
+
+// A fully prepared launch of the implicit-GEMM kernel.
+struct ConvLaunch {
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmB;
+  ConvKParams p;
+  dim3 grid;
+  size_t smem;
+};
+
+int set_error(ug_engine* h, int code, const char* fmt, ...);
+int check_cuda(ug_engine* h, cudaError_t e, const char* what);
+
+int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
+int conv_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
+
+int launch_inc_im2col(ug_engine* h, const ug_inc_im2col_desc* d, cudaStream_t s);
+int launch_pool(ug_engine* h, const ug_pool_desc* d, cudaStream_t s);
+int launch_layernorm(ug_engine* h, const ug_layernorm_desc* d, cudaStream_t s);
+int launch_attention(ug_engine* h, const ug_attn_desc* d, cudaStream_t s);
+int launch_chanstats(ug_engine* h, const ug_chanstats_desc* d, cudaStream_t s);
+int launch_gate(ug_engine* h, const ug_gate_desc* d, cudaStream_t s);
+int launch_bbox(ug_engine* h, const ug_bbox_desc* d, cudaStream_t s);
+int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s);
+int launch_g1_im2col(ug_engine* h, const ug_g1_im2col_desc* d, cudaStream_t s);
+int launch_head(ug_engine* h, const ug_head_desc* d, cudaStream_t s);
+
+}  // namespace ug

@@ -1,0 +1,655 @@
+// Memory-bound kernels of the hot path (NHWC bf16 activations, 16-byte vector accesses, coalesced along C):
+// input im2col packs, max pooling, LayerNorm, attention, CoordAtt3 statistics + gate, mask -> bbox,
+// PIL-exact crop/resize and the GoogLeNet head.  Reference lines are cited on the descriptors in ugnet.h.
+#include <cfloat>
+#include "common.cuh"
+#include "engine.h"
+
+namespace ug {
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// inc im2col: fp32 NCHW [B,3,H,W] -> bf16 [B*H*W][64]; one thread per pixel writes one 128-byte row.
+__global__ void __launch_bounds__(256) inc_im2col_kernel(const float* __restrict__ x, uint4* __restrict__ out, int B,
+                                                         int H, int W) {
+  const long long total = (long long)B * H * W;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int px = (int)(p % W);
+  const int py = (int)((p / W) % H);
+  const int n = (int)(p / ((long long)W * H));
+  const float* xn = x + (long long)n * 3 * H * W;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = py + r - 1;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int ix = px + s - 1;
+      const bool in = (iy >= 0) && (iy < H) && (ix >= 0) && (ix < W);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = in ? __ldg(xn + ((long long)c * H + iy) * W + ix) : 0.0f;
+    }
+  }
+  uint4* row = out + p * 8;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 o;
+    o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+    o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+    o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+    o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+    row[g] = o;
+  }
+  const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int g = 4; g < 8; ++g) row[g] = z;
+}
+
+int launch_inc_im2col(ug_engine* h, const ug_inc_im2col_desc* d, cudaStream_t s) {
+  if (!d->x || !d->out || d->B <= 0 || d->H <= 0 || d->W <= 0) return set_error(h, UG_EINVAL, "inc_im2col: bad args");
+  const long long total = (long long)d->B * d->H * d->W;
+  inc_im2col_kernel<<<cdiv(total, 256), 256, 0, s>>>(d->x, reinterpret_cast<uint4*>(d->out), d->B, d->H, d->W);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "inc_im2col launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// max pooling: one thread per (output pixel, 8-channel group); channel groups vary fastest.
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+__global__ void __launch_bounds__(256) pool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                   ug_pool_desc d) {
+  const int cg = d.C / 8;
+  const long long total = (long long)d.B * d.OH * d.OW * cg;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int g = (int)(t % cg);
+  long long pp = t / cg;
+  const int ox = (int)(pp % d.OW);
+  pp /= d.OW;
+  const int oy = (int)(pp % d.OH);
+  const int n = (int)(pp / d.OH);
+  const uint32_t ninf = 0xFF80FF80u;  // (-inf, -inf) in bf16
+  uint4 m = make_uint4(ninf, ninf, ninf, ninf);
+  for (int r = 0; r < d.k; ++r) {
+    const int iy = oy * d.stride + r - d.pad;
+    if (iy < 0 || iy >= d.H) continue;
+    for (int s = 0; s < d.k; ++s) {
+      const int ix = ox * d.stride + s - d.pad;
+      if (ix < 0 || ix >= d.W) continue;
+      const uint4 v =
+          *reinterpret_cast<const uint4*>(in + (((long long)n * d.H + iy) * d.W + ix) * d.in_cstride + g * 8);
+      m.x = bf16x2_max(m.x, v.x);
+      m.y = bf16x2_max(m.y, v.y);
+      m.z = bf16x2_max(m.z, v.z);
+      m.w = bf16x2_max(m.w, v.w);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (((long long)n * d.OH + oy) * d.OW + ox) * d.out_cstride + g * 8) = m;
+}
+
+int launch_pool(ug_engine* h, const ug_pool_desc* d, cudaStream_t s) {
+  if (!d->in || !d->out || d->C % 8 || d->in_cstride % 8 || d->out_cstride % 8 || d->k <= 0 || d->stride <= 0)
+    return set_error(h, UG_EINVAL, "pool: bad args (C and strides must be multiples of 8)");
+  if ((d->OH - 1) * d->stride - d->pad >= d->H || (d->OW - 1) * d->stride - d->pad >= d->W)
+    return set_error(h, UG_EINVAL, "pool: last window starts outside the input");
+  const long long total = (long long)d->B * d->OH * d->OW * (d->C / 8);
+  pool_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d->in),
+                                               reinterpret_cast<__nv_bfloat16*>(d->out), *d);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "pool launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per token, C in {256, 512, 768, 1024}; two-pass statistics in registers.
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ in,
+                                                        __nv_bfloat16* __restrict__ out,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int M, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nv = C / 256;  // 16-byte vectors per lane
+  const __nv_bfloat16* row = in + (long long)warp * C;
+  float v[32];
+  float sum = 0.0f;
+  for (int i = 0; i < nv; ++i) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + (i * 32 + lane) * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[i * 8 + 2 * j] = bf16_lo(w[j]);
+      v[i * 8 + 2 * j + 1] = bf16_hi(w[j]);
+      sum += v[i * 8 + 2 * j] + v[i * 8 + 2 * j + 1];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.0f;
+  for (int i = 0; i < nv * 8; ++i) {
+    const float dlt = v[i] - mean;
+    sq += dlt * dlt;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+  __nv_bfloat16* orow = out + (long long)warp * C;
+  for (int i = 0; i < nv; ++i) {
+    const int c0 = (i * 32 + lane) * 8;
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = (v[i * 8 + j] - mean) * rstd * __ldg(gamma + c0 + j) + __ldg(beta + c0 + j);
+    uint4 o;
+    o.x = pack_bf16x2(r[0], r[1]);
+    o.y = pack_bf16x2(r[2], r[3]);
+    o.z = pack_bf16x2(r[4], r[5]);
+    o.w = pack_bf16x2(r[6], r[7]);
+    *reinterpret_cast<uint4*>(orow + c0) = o;
+  }
+}
+
+int launch_layernorm(ug_engine* h, const ug_layernorm_desc* d, cudaStream_t s) {
+  if (!d->in || !d->out || !d->gamma || !d->beta || d->M <= 0 || d->C % 256 || d->C > 1024 || d->C <= 0)
+    return set_error(h, UG_EINVAL, "layernorm: C must be a multiple of 256 up to 1024");
+  layernorm_kernel<<<cdiv((long long)d->M * 32, 256), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d->in), reinterpret_cast<__nv_bfloat16*>(d->out), d->gamma, d->beta, d->M,
+      d->C, d->eps);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "layernorm launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention: one block per (image, head); K and V of the head staged in shared memory as bf16, one query row
+// per thread, fp32 online softmax over key blocks of 4.  S <= 256, dim_head = 64.
+static constexpr int kAttnThreads = 256;
+
+__global__ void __launch_bounds__(kAttnThreads) attention_kernel(ug_attn_desc d) {
+  extern __shared__ uint4 attn_smem[];
+  uint4* sK = attn_smem;          // [S][8] uint4 (64 bf16 per row)
+  uint4* sV = attn_smem + d.S * 8;
+  const int b = blockIdx.x / d.heads;
+  const int hd = blockIdx.x % d.heads;
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(d.q);
+  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(d.k);
+  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(d.v);
+  for (int i = threadIdx.x; i < d.S * 8; i += blockDim.x) {
+    const int row = i >> 3, part = i & 7;
+    const long long tok = (long long)b * d.S + row;
+    sK[i] = *reinterpret_cast<const uint4*>(k + tok * d.k_stride + hd * 64 + part * 8);
+    sV[i] = *reinterpret_cast<const uint4*>(v + tok * d.v_stride + hd * 64 + part * 8);
+  }
+  __syncthreads();
+  const int i = threadIdx.x;
+  if (i >= d.S) return;
+  const long long tok = (long long)b * d.S + i;
+  float qr[64], o[64];
+  const float qs = d.scale * 1.4426950408889634f;  // fold log2(e) so that exp2f can be used
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const uint4 u = *reinterpret_cast<const uint4*>(q + tok * d.q_stride + hd * 64 + p * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      qr[p * 8 + 2 * j] = bf16_lo(w[j]) * qs;
+      qr[p * 8 + 2 * j + 1] = bf16_hi(w[j]) * qs;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 64; ++c) o[c] = 0.0f;
+  float m = -FLT_MAX, l = 0.0f;
+  for (int j0 = 0; j0 < d.S; j0 += 4) {
+    float sc[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + jj;
+      float acc = 0.0f;
+      if (j < d.S) {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const uint4 u = sK[j * 8 + p];
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            acc += qr[p * 8 + 2 * t] * bf16_lo(w[t]);
+            acc += qr[p * 8 + 2 * t + 1] * bf16_hi(w[t]);
+          }
+        }
+      } else {
+        acc = -FLT_MAX;
+      }
+      sc[jj] = acc;
+    }
+    const float bm = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+    if (bm > m) {
+      const float corr = exp2f(m - bm);
+      l *= corr;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) o[c] *= corr;
+      m = bm;
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + jj;
+      if (j >= d.S) break;
+      const float pj = exp2f(sc[jj] - m);
+      l += pj;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const uint4 u = sV[j * 8 + p];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          o[p * 8 + 2 * t] += pj * bf16_lo(w[t]);
+          o[p * 8 + 2 * t + 1] += pj * bf16_hi(w[t]);
+        }
+      }
+    }
+  }
+  const float inv = 1.0f / l;
+  __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(d.out) + tok * d.out_stride + hd * 64;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    uint4 u;
+    u.x = pack_bf16x2(o[p * 8 + 0] * inv, o[p * 8 + 1] * inv);
+    u.y = pack_bf16x2(o[p * 8 + 2] * inv, o[p * 8 + 3] * inv);
+    u.z = pack_bf16x2(o[p * 8 + 4] * inv, o[p * 8 + 5] * inv);
+    u.w = pack_bf16x2(o[p * 8 + 6] * inv, o[p * 8 + 7] * inv);
+    *reinterpret_cast<uint4*>(orow + p * 8) = u;
+  }
+}
+
+int launch_attention(ug_engine* h, const ug_attn_desc* d, cudaStream_t s) {
+  if (!d->q || !d->k || !d->v || !d->out || d->S <= 0 || d->S > kAttnThreads || d->heads <= 0 || d->B <= 0)
+    return set_error(h, UG_EINVAL, "attention: bad args (S <= 256)");
+  if (d->q_stride % 8 || d->k_stride % 8 || d->v_stride % 8 || d->out_stride % 8)
+    return set_error(h, UG_EINVAL, "attention: row strides must be multiples of 8");
+  const size_t smem = (size_t)d->S * 8 * sizeof(uint4) * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(attention_kernel)");
+    attr_set = true;
+  }
+  attention_kernel<<<d->B * d->heads, kAttnThreads, smem, s>>>(*d);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "attention launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// CoordAtt3 statistics, stage 1: block (split, image) reduces its pixel range; threads are laid out as
+// (C/8 channel groups) x (256/(C/8) pixel lanes), partial results combined through shared memory.
+__global__ void __launch_bounds__(256) chanstats_kernel(ug_chanstats_desc d) {
+  __shared__ float s_sum[256 * 8];
+  __shared__ float s_max[256 * 8];
+  const int cg = d.C / 8;       // channel groups (<= 64)
+  const int lanes = 256 / cg;   // pixel lanes per group
+  const int g = threadIdx.x % cg;
+  const int pl = threadIdx.x / cg;
+  const int split = blockIdx.x, n = blockIdx.y;
+  const int per = (d.HW + d.splits - 1) / d.splits;
+  const int p0 = split * per;
+  const int p1 = min(d.HW, p0 + per);
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(d.in) + (long long)n * d.HW * d.in_cstride + g * 8;
+  float sum[8], mx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sum[j] = 0.0f;
+    mx[j] = -FLT_MAX;
+  }
+  for (int p = p0 + pl; p < p1; p += lanes) {
+    const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)p * d.in_cstride);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_lo(w[j]), b = bf16_hi(w[j]);
+      sum[2 * j] += a;
+      sum[2 * j + 1] += b;
+      mx[2 * j] = fmaxf(mx[2 * j], a);
+      mx[2 * j + 1] = fmaxf(mx[2 * j + 1], b);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_sum[threadIdx.x * 8 + j] = sum[j];
+    s_max[threadIdx.x * 8 + j] = mx[j];
+  }
+  __syncthreads();
+  // thread c (< C) folds the pixel lanes of channel c in a fixed order
+  for (int c = threadIdx.x; c < d.C; c += 256) {
+    const int gg = c / 8, j = c % 8;
+    float a = 0.0f, b = -FLT_MAX;
+    for (int l = 0; l < lanes; ++l) {
+      a += s_sum[(l * cg + gg) * 8 + j];
+      b = fmaxf(b, s_max[(l * cg + gg) * 8 + j]);
+    }
+    const long long o = ((long long)n * d.splits + split) * d.C + c;
+    d.psum[o] = a;
+    d.pmax[o] = b;
+  }
+}
+
+int launch_chanstats(ug_engine* h, const ug_chanstats_desc* d, cudaStream_t s) {
+  if (!d->in || !d->psum || !d->pmax || d->C % 8 || d->C > 512 || d->C < 8 || (256 % (d->C / 8)) || d->splits <= 0 ||
+      d->in_cstride % 8)
+    return set_error(h, UG_EINVAL, "chanstats: C must be 8*2^k <= 512");
+  chanstats_kernel<<<dim3(d->splits, d->B), 256, 0, s>>>(*d);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "chanstats launch");
+}
+
+// stage 2 + gate MLP: one block per image.
+__global__ void __launch_bounds__(256) gate_kernel(ug_gate_desc d) {
+  __shared__ float s_avg[512], s_max[512], s_hid[256];
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+    float a = 0.0f, b = -FLT_MAX;
+    for (int sp = 0; sp < d.splits; ++sp) {
+      const long long o = ((long long)n * d.splits + sp) * d.C + c;
+      a += d.psum[o];
+      b = fmaxf(b, d.pmax[o]);
+    }
+    s_avg[c] = a / (float)d.HW;
+    s_max[c] = b;
+  }
+  __syncthreads();
+  const int hid = d.C / 2;
+  for (int j = warp; j < hid; j += 8) {
+    float a = 0.0f, b = 0.0f;
+    for (int c = lane; c < d.C; c += 32) {
+      a += d.w1[(long long)j * d.C + c] * s_avg[c];
+      b += d.w2[(long long)j * d.C + c] * s_max[c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) s_hid[j] = fmaxf(a + d.b1[j], 0.0f) + fmaxf(b + d.b2[j], 0.0f);
+  }
+  __syncthreads();
+  for (int c = warp; c < d.C; c += 8) {
+    float a = 0.0f;
+    for (int j = lane; j < hid; j += 32) a += d.w3[(long long)c * hid + j] * s_hid[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) d.g[(long long)n * d.C + c] = 1.0f / (1.0f + expf(-(a + d.b3[c])));
+  }
+}
+
+int launch_gate(ug_engine* h, const ug_gate_desc* d, cudaStream_t s) {
+  if (!d->psum || !d->pmax || !d->w1 || !d->w2 || !d->w3 || !d->b1 || !d->b2 || !d->b3 || !d->g || d->C > 512 ||
+      d->C % 2 || d->HW <= 0 || d->splits <= 0)
+    return set_error(h, UG_EINVAL, "gate: bad args (C <= 512)");
+  gate_kernel<<<d->B, 256, 0, s>>>(*d);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "gate launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask -> bbox: one block per image; warp-shuffle min/max, then one thread applies roi.py:25-36.
+__global__ void __launch_bounds__(1024) bbox_kernel(const unsigned char* __restrict__ mask, int* __restrict__ boxes, int H,
+                                                    int W, int padding) {
+  __shared__ int s_red[4][32];
+  const int n = blockIdx.x;
+  const unsigned char* m = mask + (long long)n * H * W;
+  int xmin = INT_MAX, ymin = INT_MAX, xmax = -1, ymax = -1;
+  const int total = H * W;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    if (m[i] == 1) {
+      const int y = i / W, x = i - y * W;
+      xmin = min(xmin, x);
+      xmax = max(xmax, x);
+      ymin = min(ymin, y);
+      ymax = max(ymax, y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+    xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_red[0][warp] = xmin;
+    s_red[1][warp] = ymin;
+    s_red[2][warp] = xmax;
+    s_red[3][warp] = ymax;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    xmin = lane < nw ? s_red[0][lane] : INT_MAX;
+    ymin = lane < nw ? s_red[1][lane] : INT_MAX;
+    xmax = lane < nw ? s_red[2][lane] : -1;
+    ymax = lane < nw ? s_red[3][lane] : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+      ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+      xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+      ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if (lane == 0) {
+      int x0, y0, x1, y1;
+      if (xmax < 0) {  // empty mask: centred square of side min(h,w)//2 (roi.py:26-31)
+        const int cx = W / 2, cy = H / 2, size = min(H, W) / 2;
+        x0 = cx - size / 2;
+        x1 = cx + size / 2;
+        y0 = cy - size / 2;
+        y1 = cy + size / 2;
+      } else {  // roi.py:33-36 (max is an exclusive slice end)
+        x0 = max(xmin - padding, 0);
+        x1 = min(xmax + padding, W);
+        y0 = max(ymin - padding, 0);
+        y1 = min(ymax + padding, H);
+      }
+      boxes[n * 4 + 0] = x0;
+      boxes[n * 4 + 1] = y0;
+      boxes[n * 4 + 2] = x1;
+      boxes[n * 4 + 3] = y1;
+    }
+  }
+}
+
+int launch_bbox(ug_engine* h, const ug_bbox_desc* d, cudaStream_t s) {
+  if (!d->mask || !d->boxes || d->B <= 0 || d->H <= 0 || d->W <= 0) return set_error(h, UG_EINVAL, "bbox: bad args");
+  bbox_kernel<<<d->B, 1024, 0, s>>>(d->mask, d->boxes, d->H, d->W, d->padding);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "bbox launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// PIL-exact crop + bilinear resize (Pillow ImagingResample, 8 bits per channel):
+//   coefficient tables per axis are computed in fp64 exactly as precompute_coeffs() does, then quantised to
+//   22-bit fixed point; horizontal pass first (uint8 result), vertical pass second.
+static constexpr int kPrecBits = 22;  // 32 - 8 - 2
+
+struct AxisCoef {
+  int xmin;
+  int n;
+  int kk[3];
+};
+
+__device__ void pil_coef(int in_size, int out_size, int xx, AxisCoef* c) {
+  // Pillow: scale = in/out; filterscale = max(scale, 1); support = 1.0 * filterscale (bilinear)
+  const double scale = __ddiv_rn((double)in_size, (double)out_size);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = filterscale;  // bilinear support 1.0
+  const double ss = __ddiv_rn(1.0, filterscale);
+  const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), scale);
+  int xmin = (int)__dadd_rn(__dadd_rn(center, -support), 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+  if (xmax > in_size) xmax = in_size;
+  const int n = xmax - xmin;  // <= 3 when up-sampling (support == 1)
+  double k[3] = {0.0, 0.0, 0.0};
+  double ww = 0.0;
+  for (int x = 0; x < n && x < 3; ++x) {
+    double a = __dmul_rn(__dadd_rn(__dadd_rn((double)(x + xmin), -center), 0.5), ss);
+    if (a < 0.0) a = -a;
+    const double w = a < 1.0 ? __dadd_rn(1.0, -a) : 0.0;
+    k[x] = w;
+    ww = __dadd_rn(ww, w);
+  }
+  c->xmin = xmin;
+  c->n = n < 3 ? n : 3;
+  for (int x = 0; x < 3; ++x) {
+    double kv = k[x];
+    if (x < n && ww != 0.0) kv = __ddiv_rn(kv, ww);
+    const double scaled = __dmul_rn(kv, (double)(1 << kPrecBits));
+    c->kk[x] = kv < 0.0 ? (int)__dadd_rn(-0.5, scaled) : (int)__dadd_rn(0.5, scaled);
+  }
+}
+
+__device__ __forceinline__ int clip8(int v) {
+  v >>= kPrecBits;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// grid (S / rows_per_block, B); each block produces rows_per_block output rows of one image.
+__global__ void __launch_bounds__(256) cropresize_kernel(ug_cropresize_desc d, int rows_per_block) {
+  __shared__ AxisCoef s_h[256];
+  __shared__ AxisCoef s_v[32];
+  const int n = blockIdx.y;
+  const int oy0 = blockIdx.x * rows_per_block;
+  const int x0 = d.boxes[n * 4 + 0], y0 = d.boxes[n * 4 + 1];
+  const int cw = d.boxes[n * 4 + 2] - x0, ch = d.boxes[n * 4 + 3] - y0;
+  for (int i = threadIdx.x; i < d.S; i += blockDim.x) pil_coef(cw, d.S, i, &s_h[i]);
+  if (threadIdx.x < rows_per_block && oy0 + threadIdx.x < d.S) pil_coef(ch, d.S, oy0 + threadIdx.x, &s_v[threadIdx.x]);
+  __syncthreads();
+  const float* img = d.img + (long long)n * 3 * d.H * d.W;
+  const int total = rows_per_block * d.S;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    const int ry = t / d.S, ox = t - ry * d.S;
+    const int oy = oy0 + ry;
+    if (oy >= d.S) break;
+    const AxisCoef hc = s_h[ox];
+    const AxisCoef vc = s_v[ry];
+    unsigned char res[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* plane = img + (long long)(2 - c) * d.H * d.W;  // cv2.COLOR_BGR2RGB: channel flip
+      int acc_v = 1 << (kPrecBits - 1);
+      for (int j = 0; j < vc.n; ++j) {
+        const float* srow = plane + (long long)(y0 + vc.xmin + j) * d.W + x0 + hc.xmin;
+        int acc_h = 1 << (kPrecBits - 1);
+        for (int i = 0; i < hc.n; ++i) {
+          const int u8 = ((int)__fmul_rn(__ldg(srow + i), 255.0f)) & 255;  // (roi*255).astype(uint8): fp32 mul, truncate
+          acc_h += u8 * hc.kk[i];
+        }
+        acc_v += clip8(acc_h) * vc.kk[j];
+      }
+      res[c] = (unsigned char)clip8(acc_v);
+    }
+    unsigned char* o = d.out_u8 + (((long long)n * d.S + oy) * d.S + ox) * 3;
+    o[0] = res[0];
+    o[1] = res[1];
+    o[2] = res[2];
+  }
+}
+
+int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s) {
+  if (!d->img || !d->boxes || !d->out_u8 || d->S <= 0 || d->S > 256 || d->B <= 0)
+    return set_error(h, UG_EINVAL, "cropresize: bad args (S <= 256)");
+  const int rows = 8;
+  cropresize_kernel<<<dim3(cdiv(d->S, rows), d->B), 256, 0, s>>>(*d, rows);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "cropresize launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// GoogLeNet conv1 im2col (7x7, stride 2, pad 3) with to_tensor and _transform_input folded in.
+__global__ void __launch_bounds__(256) g1_im2col_kernel(const unsigned char* __restrict__ u8, uint4* __restrict__ out,
+                                                        int B, int S) {
+  const int OS = S / 2;
+  const long long total = (long long)B * OS * OS * 24;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int g = (int)(t % 24);
+  long long pp = t / 24;
+  const int ox = (int)(pp % OS);
+  pp /= OS;
+  const int oy = (int)(pp % OS);
+  const int n = (int)(pp / OS);
+  // torchvision GoogLeNet._transform_input: x_c * (std_c / 0.5) + (mean_c - 0.5) / 0.5
+  const float sc[3] = {0.229f / 0.5f, 0.224f / 0.5f, 0.225f / 0.5f};
+  const float sh[3] = {(0.485f - 0.5f) / 0.5f, (0.456f - 0.5f) / 0.5f, (0.406f - 0.5f) / 0.5f};
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = g * 8 + j;
+    float val = 0.0f;
+    if (col < 147) {
+      const int tap = col / 3, c = col - tap * 3;
+      const int r = tap / 7, s = tap - r * 7;
+      const int iy = 2 * oy + r - 3, ix = 2 * ox + s - 3;
+      if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
+        const float px = (float)u8[(((long long)n * S + iy) * S + ix) * 3 + c] / 255.0f;
+        val = px * sc[c] + sh[c];
+      }
+    }
+    v[j] = val;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  out[t] = o;
+}
+
+int launch_g1_im2col(ug_engine* h, const ug_g1_im2col_desc* d, cudaStream_t s) {
+  if (!d->u8 || !d->out || d->B <= 0 || d->S <= 0 || d->S % 2) return set_error(h, UG_EINVAL, "g1_im2col: bad args");
+  const long long total = (long long)d->B * (d->S / 2) * (d->S / 2) * 24;
+  g1_im2col_kernel<<<cdiv(total, 256), 256, 0, s>>>(d->u8, reinterpret_cast<uint4*>(d->out), d->B, d->S);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "g1_im2col launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// GoogLeNet head: global average pool + fc, one block per image.
+__global__ void __launch_bounds__(256) head_kernel(ug_head_desc d) {
+  __shared__ float s_avg[1024];
+  const int n = blockIdx.x;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d.in) + (long long)n * d.HW * d.C;
+  for (int c2 = threadIdx.x; c2 < d.C / 2; c2 += blockDim.x) {
+    float a = 0.0f, b = 0.0f;
+    for (int p = 0; p < d.HW; ++p) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(in + (long long)p * d.C + c2 * 2);
+      a += bf16_lo(w);
+      b += bf16_hi(w);
+    }
+    s_avg[c2 * 2] = a / (float)d.HW;
+    s_avg[c2 * 2 + 1] = b / (float)d.HW;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < d.ncls; k += 8) {
+    float a = 0.0f;
+    for (int c = lane; c < d.C; c += 32) a += d.w[(long long)k * d.C + c] * s_avg[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) d.logits[(long long)n * d.ncls + k] = a + d.b[k];
+  }
+}
+
+int launch_head(ug_engine* h, const ug_head_desc* d, cudaStream_t s) {
+  if (!d->in || !d->w || !d->b || !d->logits || d->C > 1024 || d->C % 2 || d->HW <= 0 || d->ncls <= 0)
+    return set_error(h, UG_EINVAL, "head: bad args (C <= 1024)");
+  head_kernel<<<d->B, 256, 0, s>>>(*d);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "head launch");
+}
+
+}  // namespace ug

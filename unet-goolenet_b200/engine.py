@@ -1,0 +1,220 @@
+"""ctypes binding of libugnet.so (include/ugnet.h).
+
+The library is the only compute path: if it cannot be loaded, or no sm_100 device is present when an
+engine is created, this module raises — there is no CPU or PyTorch fallback.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libugnet.so")
+
+UG_OK = 0
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+EPI_STORE, EPI_ADD, EPI_GATE, EPI_OUTC = 0, 1, 2, 3
+(OP_CONV, OP_INC_IM2COL, OP_POOL, OP_LAYERNORM, OP_ATTN, OP_CHANSTATS, OP_GATE, OP_BBOX, OP_CROPRESIZE,
+ OP_G1_IM2COL, OP_HEAD) = range(1, 12)
+
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("inp", _vp), ("in_cstride", _i), ("Cin", _i), ("B", _i), ("H", _i), ("W", _i),
+                ("R", _i), ("S", _i), ("pad", _i), ("w", _vp), ("N", _i), ("scale", _vp), ("bias", _vp),
+                ("act", _i), ("mode", _i), ("out", _vp), ("out_cstride", _i), ("up", _i), ("convt_cout", _i),
+                ("add", _vp), ("add_bstride", _ll), ("add_cstride", _i), ("gate", _vp), ("outc_w", _vp),
+                ("outc_b", _f), ("logits", _vp), ("mask", _vp),
+                ("TW", _i), ("TH", _i), ("TN", _i), ("BN", _i), ("stages", _i)]
+
+
+class IncIm2colDesc(C.Structure):
+    _fields_ = [("x", _vp), ("out", _vp), ("B", _i), ("H", _i), ("W", _i)]
+
+
+class PoolDesc(C.Structure):
+    _fields_ = [("inp", _vp), ("in_cstride", _i), ("out", _vp), ("out_cstride", _i), ("C", _i), ("B", _i),
+                ("H", _i), ("W", _i), ("OH", _i), ("OW", _i), ("k", _i), ("stride", _i), ("pad", _i)]
+
+
+class LayerNormDesc(C.Structure):
+    _fields_ = [("inp", _vp), ("out", _vp), ("gamma", _vp), ("beta", _vp), ("M", _i), ("C", _i), ("eps", _f)]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [("q", _vp), ("k", _vp), ("v", _vp), ("q_stride", _i), ("k_stride", _i), ("v_stride", _i),
+                ("out", _vp), ("out_stride", _i), ("B", _i), ("S", _i), ("heads", _i), ("scale", _f)]
+
+
+class ChanStatsDesc(C.Structure):
+    _fields_ = [("inp", _vp), ("in_cstride", _i), ("C", _i), ("B", _i), ("HW", _i), ("splits", _i),
+                ("psum", _vp), ("pmax", _vp)]
+
+
+class GateDesc(C.Structure):
+    _fields_ = [("psum", _vp), ("pmax", _vp), ("w1", _vp), ("b1", _vp), ("w2", _vp), ("b2", _vp), ("w3", _vp),
+                ("b3", _vp), ("g", _vp), ("B", _i), ("C", _i), ("HW", _i), ("splits", _i)]
+
+
+class BBoxDesc(C.Structure):
+    _fields_ = [("mask", _vp), ("boxes", _vp), ("B", _i), ("H", _i), ("W", _i), ("padding", _i)]
+
+
+class CropResizeDesc(C.Structure):
+    _fields_ = [("img", _vp), ("boxes", _vp), ("out_u8", _vp), ("B", _i), ("H", _i), ("W", _i), ("S", _i)]
+
+
+class G1Im2colDesc(C.Structure):
+    _fields_ = [("u8", _vp), ("out", _vp), ("B", _i), ("S", _i)]
+
+
+class HeadDesc(C.Structure):
+    _fields_ = [("inp", _vp), ("w", _vp), ("b", _vp), ("logits", _vp), ("B", _i), ("HW", _i), ("C", _i),
+                ("ncls", _i)]
+
+
+class _OpUnion(C.Union):
+    _fields_ = [("conv", ConvDesc), ("inc", IncIm2colDesc), ("pool", PoolDesc), ("ln", LayerNormDesc),
+                ("attn", AttnDesc), ("stats", ChanStatsDesc), ("gate", GateDesc), ("bbox", BBoxDesc),
+                ("crop", CropResizeDesc), ("g1", G1Im2colDesc), ("head", HeadDesc)]
+
+
+class Op(C.Structure):
+    _fields_ = [("kind", _i), ("reserved", _i), ("u", _OpUnion)]
+
+
+class Copy(C.Structure):
+    _fields_ = [("dst", _vp), ("src", _vp), ("bytes", C.c_size_t)]
+
+
+_KIND_FIELD = {OP_CONV: "conv", OP_INC_IM2COL: "inc", OP_POOL: "pool", OP_LAYERNORM: "ln", OP_ATTN: "attn",
+               OP_CHANSTATS: "stats", OP_GATE: "gate", OP_BBOX: "bbox", OP_CROPRESIZE: "crop",
+               OP_G1_IM2COL: "g1", OP_HEAD: "head"}
+_DESC_KIND = {ConvDesc: OP_CONV, IncIm2colDesc: OP_INC_IM2COL, PoolDesc: OP_POOL, LayerNormDesc: OP_LAYERNORM,
+              AttnDesc: OP_ATTN, ChanStatsDesc: OP_CHANSTATS, GateDesc: OP_GATE, BBoxDesc: OP_BBOX,
+              CropResizeDesc: OP_CROPRESIZE, G1Im2colDesc: OP_G1_IM2COL, HeadDesc: OP_HEAD}
+_SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_INC_IM2COL: "ug_inc_im2col", OP_POOL: "ug_pool",
+                 OP_LAYERNORM: "ug_layernorm", OP_ATTN: "ug_attention", OP_CHANSTATS: "ug_chanstats",
+                 OP_GATE: "ug_gate", OP_BBOX: "ug_bbox", OP_CROPRESIZE: "ug_cropresize",
+                 OP_G1_IM2COL: "ug_g1_im2col", OP_HEAD: "ug_head"}
+
+EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
+                    *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
+                    "ug_program_destroy", "ug_program_run_host"]
+
+_lib = None
+
+
+def load_library():
+    """Load libugnet.so (built in-tree by __graft_entry__.build() / csrc/Makefile). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                           f"g.build()'` (there is no fallback path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.ug_version.restype = _i
+    lib.ug_create.argtypes = [_i, C.POINTER(_vp)]
+    lib.ug_destroy.argtypes = [_vp]
+    lib.ug_last_error.argtypes = [_vp]
+    lib.ug_last_error.restype = C.c_char_p
+    lib.ug_launch_count.argtypes = [_vp]
+    lib.ug_launch_count.restype = _ll
+    for name in _SINGLE_ENTRY.values():
+        getattr(lib, name).argtypes = [_vp, _vp, _vp]
+    lib.ug_program_create.argtypes = [_vp, _vp, _i, C.POINTER(_vp)]
+    lib.ug_program_run.argtypes = [_vp, _vp, _vp]
+    lib.ug_program_num_launches.argtypes = [_vp]
+    lib.ug_program_destroy.argtypes = [_vp, _vp]
+    lib.ug_program_run_host.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _vp]
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device/host pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+class Program:
+    """A prepared op list (tensor maps and launch geometry built once); run() only launches kernels."""
+
+    def __init__(self, engine, descs, keepalive=()):
+        self.engine = engine
+        self.keepalive = list(keepalive)
+        arr = (Op * len(descs))()
+        for i, d in enumerate(descs):
+            kind = _DESC_KIND[type(d)]
+            arr[i].kind = kind
+            setattr(arr[i].u, _KIND_FIELD[kind], d)
+        self._ops = arr
+        self.handle = _vp()
+        engine._check(engine.lib.ug_program_create(engine.handle, C.byref(arr), len(descs), C.byref(self.handle)))
+        self.num_launches = engine.lib.ug_program_num_launches(self.handle)
+
+    def run(self, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        self.engine._check(self.engine.lib.ug_program_run(self.engine.handle, self.handle, s))
+
+    def run_host(self, h2d, d2h, stream=None):
+        """h2d / d2h: lists of (dst_tensor, src_tensor); copies + run + copies + stream sync, all in C."""
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        a = (Copy * max(1, len(h2d)))()
+        for i, (dst, src) in enumerate(h2d):
+            a[i] = Copy(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size())
+        b = (Copy * max(1, len(d2h)))()
+        for i, (dst, src) in enumerate(d2h):
+            b[i] = Copy(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size())
+        self.engine._check(self.engine.lib.ug_program_run_host(self.engine.handle, self.handle, C.byref(a), len(h2d),
+                                                               C.byref(b), len(d2h), s))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.engine.lib.ug_program_destroy(self.engine.handle, self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Engine:
+    """One handle per CUDA device."""
+
+    _per_device = {}
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("ugnet: no CUDA device visible; the engine has no CPU path")
+        self.device = int(device)
+        self.handle = _vp()
+        rc = self.lib.ug_create(self.device, C.byref(self.handle))
+        if rc != UG_OK:
+            raise RuntimeError(f"ug_create(device={device}) failed with code {rc} (needs an sm_100 GPU)")
+
+    @classmethod
+    def get(cls, device=0):
+        dev = torch.device(device).index if not isinstance(device, int) else device
+        dev = 0 if dev is None else dev
+        if dev not in cls._per_device:
+            cls._per_device[dev] = cls(dev)
+        return cls._per_device[dev]
+
+    def _check(self, rc):
+        if rc != UG_OK:
+            msg = self.lib.ug_last_error(self.handle)
+            raise RuntimeError(f"ugnet error {rc}: {msg.decode() if msg else ''}")
+
+    def run_op(self, desc, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        fn = getattr(self.lib, _SINGLE_ENTRY[_DESC_KIND[type(desc)]])
+        self._check(fn(self.handle, C.byref(desc), s))
+
+    def program(self, descs, keepalive=()):
+        return Program(self, descs, keepalive)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.ug_launch_count(self.handle))

@@ -1,0 +1,48 @@
+"""Weight preparation for the engine: eval-mode BatchNorm folding (fp32) and bf16 K-major GEMM packing.
+
+BN fold: scale = gamma / sqrt(var + eps); bias' = beta + (b_conv - mean) * scale.
+Packed conv weight: [Npad][R*S*Cin_pad] bf16, K index = (r*S + s)*Cin_pad + c (see ug_conv_desc).
+"""
+import torch
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def choose_bn(n_out, convt_cout=None):
+    """N-tile of the implicit-GEMM kernel (multiple of 16, <= 128 by default)."""
+    if convt_cout is not None:
+        return min(128, convt_cout)
+    return 128 if n_out >= 128 else round_up(n_out, 16)
+
+
+def fold_bn(conv_bias, gamma, beta, mean, var, eps):
+    scale = gamma.double() / torch.sqrt(var.double() + eps)
+    b = conv_bias.double() if conv_bias is not None else torch.zeros_like(mean, dtype=torch.float64)
+    bias = beta.double() + (b - mean.double()) * scale
+    return scale.float().contiguous(), bias.float().contiguous()
+
+
+def pack_conv_weight(w, bn):
+    """w: [Cout, Cin, R, S] (fp32) -> bf16 [round_up(Cout, bn)][R*S*round_up(Cin, 64)]."""
+    cout, cin, r, s = w.shape
+    cin_pad = round_up(cin, 64)
+    npad = round_up(cout, bn)
+    out = torch.zeros(npad, r, s, cin_pad, dtype=torch.float32, device=w.device)
+    out[:cout, :, :, :cin] = w.permute(0, 2, 3, 1).float()
+    return out.reshape(npad, r * s * cin_pad).to(torch.bfloat16).contiguous()
+
+
+def pack_linear_weight(w, bn):
+    """w: [out, in] -> bf16 [round_up(out, bn)][round_up(in, 64)]."""
+    return pack_conv_weight(w[:, :, None, None], bn)
+
+
+def pack_convt_weight(w, bias, bn):
+    """ConvTranspose2d(k=2, s=2) weight [Cin, Cout, 2, 2] -> GEMM weight with N = 4*Cout ordered (kh, kw, co),
+    plus the bias replicated for the four taps."""
+    cin, cout, kh, kw = w.shape
+    assert kh == 2 and kw == 2
+    g = w.permute(2, 3, 1, 0).reshape(4 * cout, cin)  # row (kh*2+kw)*cout + co, col ci
+    return pack_linear_weight(g, bn), bias.float().repeat(4).contiguous()
