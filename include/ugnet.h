@@ -151,13 +151,15 @@ typedef struct ug_cropresize_desc {
   int B, H, W, S;
 } ug_cropresize_desc;
 
-/* u8 [B][224][224][3] -> bf16 [B*112*112][192] im2col of GoogLeNet conv1 (7x7, stride 2, pad 3) with
+/* u8 [B][S][S][3] -> bf16 [B*(S/2)^2][192] im2col of GoogLeNet conv1 (7x7, stride 2, pad 3) with
  * to_tensor (/255) and torchvision _transform_input applied per channel before zero padding;
- * column (r*7+s)*3+c, columns 147..191 zero. */
+ * column (r*7+s)*3+c, columns 147..191 zero.  If `f32` is non-NULL the source is instead a float NCHW
+ * [B,3,S,S] image already in [0,1] (GoogLeNetClassifier.forward on an arbitrary float tensor). */
 typedef struct ug_g1_im2col_desc {
   const unsigned char* u8;
   void* out;
   int B, S;
+  const float* f32;
 } ug_g1_im2col_desc;
 
 /* AdaptiveAvgPool2d(1) + Linear(C, ncls): in NHWC bf16 [B][HW][C], w fp32 [ncls][C], logits fp32 [B][ncls]. */

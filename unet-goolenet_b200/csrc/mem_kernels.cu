@@ -570,7 +570,8 @@ int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s)
 
 // ------------------------------------------------------------------------------------------------
 // GoogLeNet conv1 im2col (7x7, stride 2, pad 3) with to_tensor and _transform_input folded in.
-__global__ void __launch_bounds__(256) g1_im2col_kernel(const unsigned char* __restrict__ u8, uint4* __restrict__ out,
+__global__ void __launch_bounds__(256) g1_im2col_kernel(const unsigned char* __restrict__ u8,
+                                                        const float* __restrict__ f32, uint4* __restrict__ out,
                                                         int B, int S) {
   const int OS = S / 2;
   const long long total = (long long)B * OS * OS * 24;
@@ -595,7 +596,8 @@ __global__ void __launch_bounds__(256) g1_im2col_kernel(const unsigned char* __r
       const int r = tap / 7, s = tap - r * 7;
       const int iy = 2 * oy + r - 3, ix = 2 * ox + s - 3;
       if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
-        const float px = (float)u8[(((long long)n * S + iy) * S + ix) * 3 + c] / 255.0f;
+        const float px = f32 ? __ldg(f32 + (((long long)n * 3 + c) * S + iy) * S + ix)
+                             : (float)u8[(((long long)n * S + iy) * S + ix) * 3 + c] / 255.0f;
         val = px * sc[c] + sh[c];
       }
     }
@@ -610,9 +612,10 @@ __global__ void __launch_bounds__(256) g1_im2col_kernel(const unsigned char* __r
 }
 
 int launch_g1_im2col(ug_engine* h, const ug_g1_im2col_desc* d, cudaStream_t s) {
-  if (!d->u8 || !d->out || d->B <= 0 || d->S <= 0 || d->S % 2) return set_error(h, UG_EINVAL, "g1_im2col: bad args");
+  if ((!d->u8 && !d->f32) || !d->out || d->B <= 0 || d->S <= 0 || d->S % 2)
+    return set_error(h, UG_EINVAL, "g1_im2col: bad args");
   const long long total = (long long)d->B * (d->S / 2) * (d->S / 2) * 24;
-  g1_im2col_kernel<<<cdiv(total, 256), 256, 0, s>>>(d->u8, reinterpret_cast<uint4*>(d->out), d->B, d->S);
+  g1_im2col_kernel<<<cdiv(total, 256), 256, 0, s>>>(d->u8, d->f32, reinterpret_cast<uint4*>(d->out), d->B, d->S);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "g1_im2col launch");
 }

@@ -66,7 +66,7 @@ class CropResizeDesc(C.Structure):
 
 
 class G1Im2colDesc(C.Structure):
-    _fields_ = [("u8", _vp), ("out", _vp), ("B", _i), ("S", _i)]
+    _fields_ = [("u8", _vp), ("out", _vp), ("B", _i), ("S", _i), ("f32", _vp)]
 
 
 class HeadDesc(C.Structure):

@@ -1,0 +1,53 @@
+"""Entry-point mirrors of the reference's two inference scripts.
+
+  inference_all_seg  <- 分割/predict.py:11-51  (UNet over a loader; masks returned / optionally painted)
+  inference_all_cls  <- 分类/test.py:74-96     (GoogLeNet over a loader of ROI crops; sorted result.txt)
+
+Same arguments and on-disk outputs as the reference functions for the parts on the hot path; the reference's
+Excel dump (predict.py:50-51) is host I/O outside the path and is not reproduced."""
+import os
+
+import numpy as np
+import torch
+
+
+@torch.no_grad()
+def inference_all_cls(model, test_loader, device, save_dir="test_results"):
+    model.eval()
+    os.makedirs(save_dir, exist_ok=True)
+    records = []
+    for data in test_loader:
+        imgs = data["image"].float().to(device)
+        cl_out = model(imgs)
+        pred = torch.argmax(torch.softmax(cl_out, dim=1), dim=1).cpu().numpy()
+        for i in range(imgs.size(0)):
+            records.append(f"{data['filename'][i].replace('.png', '')} {int(pred[i])}")
+    records.sort(key=lambda x: int(x.split()[0].replace(".jpg", "").replace(".png", "")))
+    with open(os.path.join(save_dir, "result.txt"), "w") as f:
+        for line in records:
+            f.write(line + "\n")
+    return records
+
+
+@torch.no_grad()
+def inference_all_seg(model, test_loader, device, save_dir=None):
+    """Returns {filename: uint8 mask [224,224]}; with save_dir, also paints each mask as the reference does
+    (red where mask == 1 on a black RGB canvas, predict.py:32-45) using a vectorised NumPy write."""
+    model.eval()
+    out = {}
+    for data in test_loader:
+        imgs = data["image"].float().to(device)
+        _, masks, _ = model.forward_mask_boxes(imgs)
+        masks = masks.cpu().numpy()
+        for i, name in enumerate(data["filename"]):
+            out[name] = masks[i]
+            if save_dir is not None:
+                from PIL import Image
+                os.makedirs(save_dir, exist_ok=True)
+                canvas = np.zeros(masks[i].shape + (3,), np.uint8)
+                canvas[masks[i] == 1] = (255, 0, 0)
+                Image.fromarray(canvas).save(os.path.join(save_dir, name if name.endswith(".png") else name + ".png"))
+    return out
+
+
+inference_all = inference_all_cls

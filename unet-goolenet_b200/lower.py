@@ -1,0 +1,473 @@
+"""Lowering of the reference networks to engine op lists ("programs").
+
+Each builder walks a reference-format state_dict, folds/packs the weights once (pack.py) and, per batch size,
+lays out the NHWC bf16 activation workspace in HBM and emits the op descriptors of include/ugnet.h:
+
+  UNetTaskAligWeight.forward (basicUnet.py:406-437)      -> UNetRunner._emit_unet
+  roi.py:22-49 (threshold, bbox, crop, quantise, resize) -> fused into the UNet tail + bbox/cropresize ops
+  GoogLeNetClassifier.forward (test.py:64-73)            -> GoogLeNetRunner._emit_googlenet
+  whole two-stage path                                   -> PipelineRunner
+
+Dead compute of the reference forward is skipped: the `x` output of the bottleneck (attention1, the first
+cross_attention_cl call, x_mlp_norm, x_feed) feeds only a discarded result (basicUnet.py:418).
+"""
+import torch
+
+from . import engine as E
+from . import pack
+
+IMG = 224
+
+
+class View:
+    """A channel slice [off, off+C) of an NHWC bf16 buffer with `cstride` channels per pixel."""
+
+    def __init__(self, t, C=None, off=0, cstride=None):
+        self.t = t
+        self.cstride = cstride if cstride is not None else t.shape[-1]
+        self.off = off
+        self.C = C if C is not None else self.cstride - off
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + 2 * self.off
+
+    def slice(self, off, C):
+        return View(self.t, C, self.off + off, self.cstride)
+
+
+def _f32(t, dev):
+    return t.detach().to(dev, torch.float32).contiguous()
+
+
+class _Builder:
+    """Shared helpers: weight cache on the device + op emission."""
+
+    def __init__(self, sd, dev):
+        self.sd = sd
+        self.dev = dev
+        self.w = {}          # packed tensors kept alive for the lifetime of the runner
+        self.engine = E.Engine.get(dev)
+
+    # ---- weights -------------------------------------------------------------------------------
+    def conv_bn(self, key, conv, bn, eps, bias_key=None):
+        """Pack conv weight `conv`.weight and fold BatchNorm `bn`.* (eval) into fp32 scale/bias."""
+        if key in self.w:
+            return self.w[key]
+        sd = self.sd
+        wt = _f32(sd[conv + ".weight"], self.dev)
+        cb = _f32(sd[conv + ".bias"], self.dev) if (conv + ".bias") in sd else None
+        scale, bias = pack.fold_bn(cb, _f32(sd[bn + ".weight"], self.dev), _f32(sd[bn + ".bias"], self.dev),
+                                   _f32(sd[bn + ".running_mean"], self.dev), _f32(sd[bn + ".running_var"], self.dev),
+                                   eps)
+        bn_tile = pack.choose_bn(wt.shape[0])
+        self.w[key] = dict(w=pack.pack_conv_weight(wt, bn_tile), scale=scale, bias=bias, N=wt.shape[0],
+                           Cin=wt.shape[1], R=wt.shape[2], BN=bn_tile)
+        return self.w[key]
+
+    def linear(self, key, weights, bias=None):
+        """Pack (a vertical concatenation of) nn.Linear weights [out, in]."""
+        if key in self.w:
+            return self.w[key]
+        wt = torch.cat([_f32(self.sd[k], self.dev) for k in weights], 0)
+        b = _f32(self.sd[bias], self.dev) if bias else None
+        bn_tile = pack.choose_bn(wt.shape[0])
+        self.w[key] = dict(w=pack.pack_linear_weight(wt, bn_tile), scale=None, bias=b, N=wt.shape[0],
+                           Cin=wt.shape[1], R=1, BN=bn_tile)
+        return self.w[key]
+
+    # ---- ops -----------------------------------------------------------------------------------
+    def conv(self, ops, wd, x, geom, out=None, act=E.ACT_RELU, mode=E.EPI_STORE, up=1, add=None, add_bstride=0,
+             gate=None, outc=None):
+        B, H, W = geom
+        d = E.ConvDesc()
+        d.inp, d.in_cstride, d.Cin = x.ptr, x.cstride, wd["Cin"]
+        assert x.C == wd["Cin"], (x.C, wd["Cin"])
+        d.B, d.H, d.W = B, H, W
+        d.R = d.S = wd["R"]
+        d.pad = (wd["R"] - 1) // 2
+        d.w, d.N = wd["w"].data_ptr(), wd["N"]
+        d.scale, d.bias = E.ptr(wd["scale"]), E.ptr(wd["bias"])
+        d.act, d.mode = act, mode
+        if out is not None:
+            d.out, d.out_cstride = out.ptr, out.cstride
+        d.up = up
+        d.convt_cout = wd["N"] // 4 if up == 2 else 0
+        d.BN = wd["BN"]
+        if add is not None:
+            d.add, d.add_cstride, d.add_bstride = add.ptr, add.cstride, add_bstride
+        if gate is not None:
+            d.gate = gate.data_ptr()
+        if outc is not None:
+            d.outc_w, d.outc_b = outc["w"].data_ptr(), outc["b"]
+            d.logits, d.mask = outc["logits"].data_ptr(), outc["mask"].data_ptr()
+        ops.append(d)
+
+    def buf(self, *shape, dtype=torch.bfloat16):
+        return torch.empty(shape, device=self.dev, dtype=dtype)
+
+
+# =================================================================================================== UNet
+class UNetRunner(_Builder):
+    """Engine-side UNetTaskAligWeight(3, 1): packed weights + one compiled program per batch size."""
+
+    EPS = 1e-5
+    STATS_SPLITS = 16
+
+    def __init__(self, sd, dev, max_batch=64):
+        super().__init__(sd, torch.device(dev))
+        self.max_batch = max_batch
+        self.plans = {}
+        self._pack()
+
+    # ---------------------------------------------------------------------------- weights
+    def _pack(self):
+        sd, dev = self.sd, self.dev
+        # inc: 3x3 conv on 3 channels as a K=64 GEMM over the im2col matrix, column = (r*3+s)*3 + c
+        wt = _f32(sd["inc.conv.weight"], dev)                       # [64, 3, 3, 3]
+        scale, bias = pack.fold_bn(_f32(sd["inc.conv.bias"], dev), _f32(sd["inc.norm.weight"], dev),
+                                   _f32(sd["inc.norm.bias"], dev), _f32(sd["inc.norm.running_mean"], dev),
+                                   _f32(sd["inc.norm.running_var"], dev), self.EPS)
+        gemm = wt.permute(0, 2, 3, 1).reshape(64, 27)
+        self.w["inc"] = dict(w=pack.pack_linear_weight(gemm, 64), scale=scale, bias=bias, N=64, Cin=64, R=1, BN=64)
+        for blk in ("down1", "down2", "down3", "down4"):
+            for i in (0, 1):
+                self.conv_bn(f"{blk}.{i}", f"{blk}.nConvs.{i}.conv", f"{blk}.nConvs.{i}.norm", self.EPS)
+        for name in ("conv_cl", "conv_seg"):
+            self.conv_bn(f"task2.{name}", f"task2.{name}.0", f"task2.{name}.1", self.EPS)
+            pos = _f32(sd[f"task2.pos_embedding_decoder_{name[5:]}"], dev)[0]       # [512,14,14]
+            self.w[f"pos_{name}"] = pos.permute(1, 2, 0).contiguous().to(torch.bfloat16)   # [14,14,512]
+        L = "task2.layers.0."
+        self.linear("qkv2", [L + "attention2.to_qkv.weight"])
+        self.linear("out2", [L + "attention2.to_out.0.weight"], L + "attention2.to_out.0.bias")
+        self.linear("cq", [L + "cross_attention_cl.to_q.weight"])
+        self.linear("ckv", [L + "cross_attention_cl.to_k.weight", L + "cross_attention_cl.to_v.weight"])
+        self.linear("cout", [L + "cross_attention_cl.to_out.0.weight"], L + "cross_attention_cl.to_out.0.bias")
+        self.linear("ff1", [L + "m_feed.net.0.weight"], L + "m_feed.net.0.bias")
+        self.linear("ff2", [L + "m_feed.net.3.weight"], L + "m_feed.net.3.bias")
+        for n in ("x_att_norm", "m_att_norm", "m_mlp_norm"):
+            self.w[n] = (_f32(sd[L + n + ".weight"], dev), _f32(sd[L + n + ".bias"], dev))
+        for blk in ("up4", "up3", "up2", "up1"):
+            wt = _f32(sd[blk + ".up.weight"], dev)                  # [Cin, Cout, 2, 2]
+            cout = wt.shape[1]
+            bn_tile = pack.choose_bn(4 * cout, cout)
+            wp, b4 = pack.pack_convt_weight(wt, _f32(sd[blk + ".up.bias"], dev), bn_tile)
+            self.w[blk + ".up"] = dict(w=wp, scale=None, bias=b4, N=4 * cout, Cin=wt.shape[0], R=1, BN=bn_tile)
+            for i in (0, 1):
+                self.conv_bn(f"{blk}.{i}", f"{blk}.nConvs.{i}.conv", f"{blk}.nConvs.{i}.norm", self.EPS)
+            for e in ("conv1_e", "conv2_e"):
+                self.conv_bn(f"{blk}.{e}", f"{blk}.cca.{e}.0.conv", f"{blk}.cca.{e}.0.norm", self.EPS)
+            C = cout
+            self.w[blk + ".gate"] = dict(
+                w1=_f32(sd[blk + ".cca.fc_avg.weight"], dev).reshape(C // 2, C).contiguous(),
+                b1=_f32(sd[blk + ".cca.fc_avg.bias"], dev),
+                w2=_f32(sd[blk + ".cca.fc_max.weight"], dev).reshape(C // 2, C).contiguous(),
+                b2=_f32(sd[blk + ".cca.fc_max.bias"], dev),
+                w3=_f32(sd[blk + ".cca.fc_avg_max_sfot.weight"], dev).reshape(C, C // 2).contiguous(),
+                b3=_f32(sd[blk + ".cca.fc_avg_max_sfot.bias"], dev))
+        self.w["outc"] = dict(w=_f32(sd["outc.weight"], dev).reshape(64).contiguous(),
+                              b=float(sd["outc.bias"].float().item()))
+
+    # ---------------------------------------------------------------------------- program
+    def _emit_unet(self, B, ws, ops):
+        """Append the ops of one UNet forward at batch B; `ws` receives the workspace tensors."""
+        buf = self.buf
+        ws["x_in"] = buf(B, 3, IMG, IMG, dtype=torch.float32)
+        ws["logits"] = buf(B, 1, IMG, IMG, dtype=torch.float32)
+        ws["mask"] = buf(B, IMG, IMG, dtype=torch.uint8)
+        # ---- encoder (basicUnet.py:409-416)
+        a0 = buf(B * IMG * IMG, 64)
+        ops.append(E.IncIm2colDesc(ws["x_in"].data_ptr(), a0.data_ptr(), B, IMG, IMG))
+        x1 = buf(B, IMG, IMG, 64)
+        self.conv(ops, self.w["inc"], View(a0), (1, 1, B * IMG * IMG), View(x1))
+        skips = [x1]
+        cur, size, cin = x1, IMG, 64
+        for blk, cout in (("down1", 128), ("down2", 256), ("down3", 512), ("down4", 512)):
+            half = size // 2
+            p = buf(B, half, half, cin)
+            ops.append(E.PoolDesc(cur.data_ptr(), cin, p.data_ptr(), cin, cin, B, size, size, half, half, 2, 2, 0))
+            t0 = buf(B, half, half, cout)
+            self.conv(ops, self.w[blk + ".0"], View(p), (B, half, half), View(t0))
+            t1 = buf(B, half, half, cout)
+            self.conv(ops, self.w[blk + ".1"], View(t0), (B, half, half), View(t1))
+            cur, size, cin = t1, half, cout
+            skips.append(t1)
+            ws[blk] = t1
+        ws["x1"] = x1
+        out0 = skips.pop()                                           # [B,14,14,512]
+        # ---- bottleneck (tasks.py:218-231, Multi_Attention :166-184), live `m` branch only
+        T = B * 196
+        X, M = buf(T, 512), buf(T, 512)
+        g14 = (B, 14, 14)
+        self.conv(ops, self.w["task2.conv_cl"], View(out0), g14, View(X), mode=E.EPI_ADD,
+                  add=View(self.w["pos_conv_cl"]), add_bstride=0)
+        self.conv(ops, self.w["task2.conv_seg"], View(out0), g14, View(M), mode=E.EPI_ADD,
+                  add=View(self.w["pos_conv_seg"]), add_bstride=0)
+        xn, mn = buf(T, 512), buf(T, 512)
+        for src, dst, n in ((X, xn, "x_att_norm"), (M, mn, "m_att_norm")):
+            ops.append(E.LayerNormDesc(src.data_ptr(), dst.data_ptr(), self.w[n][0].data_ptr(),
+                                       self.w[n][1].data_ptr(), T, 512, 1e-5))
+        flat = (1, 1, T)
+        scale = 512 ** -0.5                                          # tasks.py:126 / :63 (dim ** -0.5)
+        qkv = buf(T, 1536)
+        self.conv(ops, self.w["qkv2"], View(mn), flat, View(qkv), act=E.ACT_NONE)
+        att = buf(T, 512)
+        ops.append(E.AttnDesc(qkv.data_ptr(), qkv.data_ptr() + 2 * 512, qkv.data_ptr() + 2 * 1024, 1536, 1536,
+                              1536, att.data_ptr(), 512, B, 196, 8, scale))
+        m1 = buf(T, 512)                                             # m + m_att
+        self.conv(ops, self.w["out2"], View(att), flat, View(m1), act=E.ACT_NONE, mode=E.EPI_ADD, add=View(M))
+        cq, ckv = buf(T, 512), buf(T, 1024)
+        self.conv(ops, self.w["cq"], View(mn), flat, View(cq), act=E.ACT_NONE)
+        self.conv(ops, self.w["ckv"], View(xn), flat, View(ckv), act=E.ACT_NONE)
+        catt = buf(T, 512)
+        ops.append(E.AttnDesc(cq.data_ptr(), ckv.data_ptr(), ckv.data_ptr() + 2 * 512, 512, 1024, 1024,
+                              catt.data_ptr(), 512, B, 196, 8, scale))
+        m_in = buf(T, 512)                                           # m_att + m_cross + m
+        self.conv(ops, self.w["cout"], View(catt), flat, View(m_in), act=E.ACT_NONE, mode=E.EPI_ADD, add=View(m1))
+        mln = buf(T, 512)
+        ops.append(E.LayerNormDesc(m_in.data_ptr(), mln.data_ptr(), self.w["m_mlp_norm"][0].data_ptr(),
+                                   self.w["m_mlp_norm"][1].data_ptr(), T, 512, 1e-5))
+        hid = buf(T, 2048)
+        self.conv(ops, self.w["ff1"], View(mln), flat, View(hid), act=E.ACT_GELU)
+        tok = buf(B, 14, 14, 512)                                    # m_mlp_in + m_feed == NHWC [B,14,14,512]
+        self.conv(ops, self.w["ff2"], View(hid), flat, View(tok), act=E.ACT_NONE, mode=E.EPI_ADD, add=View(m_in))
+        ws["bottleneck"] = tok
+        # ---- decoder (UpBlockAlig.forward basicUnet.py:124-128, CoordAtt3.forward :215-231)
+        prev, psize = tok, 14
+        for blk, C, cout in (("up4", 512, 256), ("up3", 256, 128), ("up2", 128, 64), ("up1", 64, 64)):
+            skip = skips.pop()
+            size = psize * 2
+            geom = (B, size, size)
+            cat = buf(B, size, size, 2 * C)                         # torch.cat([up, gated_skip], 1)
+            self.conv(ops, self.w[blk + ".up"], View(prev), (B, psize, psize), View(cat, C, 0), act=E.ACT_NONE,
+                      up=2)
+            e1 = buf(B, size, size, C)
+            self.conv(ops, self.w[blk + ".conv1_e"], View(skip), geom, View(e1))
+            S = self.STATS_SPLITS
+            psum, pmax = buf(B, S, C, dtype=torch.float32), buf(B, S, C, dtype=torch.float32)
+            ops.append(E.ChanStatsDesc(e1.data_ptr(), C, C, B, size * size, S, psum.data_ptr(), pmax.data_ptr()))
+            gw = self.w[blk + ".gate"]
+            g = buf(B, C, dtype=torch.float32)
+            ops.append(E.GateDesc(psum.data_ptr(), pmax.data_ptr(), gw["w1"].data_ptr(), gw["b1"].data_ptr(),
+                                  gw["w2"].data_ptr(), gw["b2"].data_ptr(), gw["w3"].data_ptr(), gw["b3"].data_ptr(),
+                                  g.data_ptr(), B, C, size * size, S))
+            self.conv(ops, self.w[blk + ".conv2_e"], View(cat, C, 0), geom, View(cat, C, C), mode=E.EPI_GATE,
+                      add=View(e1), add_bstride=size * size * C, gate=g)
+            n0 = buf(B, size, size, cout)
+            self.conv(ops, self.w[blk + ".0"], View(cat), geom, View(n0))
+            if blk == "up1":                                         # outc + sigmoid + threshold fused (:435)
+                self.conv(ops, self.w[blk + ".1"], View(n0), geom, None, mode=E.EPI_OUTC,
+                          outc=dict(w=self.w["outc"]["w"], b=self.w["outc"]["b"], logits=ws["logits"],
+                                    mask=ws["mask"]))
+            else:
+                n1 = buf(B, size, size, cout)
+                self.conv(ops, self.w[blk + ".1"], View(n0), geom, View(n1))
+                prev = n1
+                ws[blk] = n1
+            psize = size
+            ws.setdefault("keep", []).extend([cat, e1, psum, pmax, g, n0])
+        ws.setdefault("keep", []).extend([a0, X, M, xn, mn, qkv, att, m1, cq, ckv, catt, m_in, mln, hid, out0])
+
+    def _emit_bbox(self, B, ws, ops, padding=30):
+        ws["boxes"] = self.buf(B, 4, dtype=torch.int32)
+        ops.append(E.BBoxDesc(ws["mask"].data_ptr(), ws["boxes"].data_ptr(), B, IMG, IMG, padding))
+
+    def plan(self, B, padding=30):
+        key = (B, padding)
+        if key not in self.plans:
+            ws, ops = {}, []
+            self._emit_unet(B, ws, ops)
+            self._emit_bbox(B, ws, ops, padding)
+            ws["program"] = self.engine.program(ops)
+            self.plans[key] = ws
+        return self.plans[key]
+
+    @torch.no_grad()
+    def forward(self, x, with_mask_boxes=False, padding=30):
+        if x.device.type != "cuda":
+            raise RuntimeError("ugnet: input must be a CUDA tensor (no CPU path)")
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != IMG or x.shape[3] != IMG:
+            raise ValueError(f"expected [B,3,{IMG},{IMG}] input (the network is locked to {IMG}x{IMG} by its "
+                             f"14x14 positional embedding), got {tuple(x.shape)}")
+        outs = ([], [], [])
+        for s in range(0, x.shape[0], self.max_batch):
+            xb = x[s:s + self.max_batch]
+            ws = self.plan(xb.shape[0], padding)
+            ws["x_in"].copy_(xb)                                     # also performs x.float() (:408)
+            ws["program"].run()
+            outs[0].append(ws["logits"].clone())
+            if with_mask_boxes:
+                outs[1].append(ws["mask"].clone())
+                outs[2].append(ws["boxes"].clone())
+        logits = torch.cat(outs[0]) if len(outs[0]) > 1 else outs[0][0]
+        if with_mask_boxes:
+            return logits, torch.cat(outs[1]), torch.cat(outs[2])
+        return logits
+
+
+# ============================================================================================== GoogLeNet
+_INCEPTION_CFG = {  # name: (cin, ch1x1, ch3x3red, ch3x3, ch5x5red, ch5x5, pool_proj, spatial)
+    "inception3a": (192, 64, 96, 128, 16, 32, 32, 28), "inception3b": (256, 128, 128, 192, 32, 96, 64, 28),
+    "inception4a": (480, 192, 96, 208, 16, 48, 64, 14), "inception4b": (512, 160, 112, 224, 24, 64, 64, 14),
+    "inception4c": (512, 128, 128, 256, 24, 64, 64, 14), "inception4d": (512, 112, 144, 288, 32, 64, 64, 14),
+    "inception4e": (528, 256, 160, 320, 32, 128, 128, 14), "inception5a": (832, 256, 160, 320, 32, 128, 128, 7),
+    "inception5b": (832, 384, 192, 384, 48, 128, 128, 7)}
+
+
+class GoogLeNetRunner(_Builder):
+    """Engine-side GoogLeNetClassifier (torchvision GoogLeNet, transform_input=True, no aux heads)."""
+
+    EPS = 1e-3
+
+    def __init__(self, sd, dev, max_batch=256, prefix="googlenet."):
+        super().__init__({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, torch.device(dev))
+        self.max_batch = max_batch
+        self.plans = {}
+        self._pack()
+
+    def _pack(self):
+        sd, dev = self.sd, self.dev
+        # conv1 7x7 s2 as a K=192 GEMM over the im2col matrix, column = (r*7+s)*3 + c
+        wt = _f32(sd["conv1.conv.weight"], dev)                     # [64,3,7,7]
+        scale, bias = pack.fold_bn(None, _f32(sd["conv1.bn.weight"], dev), _f32(sd["conv1.bn.bias"], dev),
+                                   _f32(sd["conv1.bn.running_mean"], dev), _f32(sd["conv1.bn.running_var"], dev),
+                                   self.EPS)
+        gemm = wt.permute(0, 2, 3, 1).reshape(64, 147)
+        self.w["conv1"] = dict(w=pack.pack_linear_weight(gemm, 64), scale=scale, bias=bias, N=64, Cin=192, R=1,
+                               BN=64)
+        self.conv_bn("conv2", "conv2.conv", "conv2.bn", self.EPS)
+        self.conv_bn("conv3", "conv3.conv", "conv3.bn", self.EPS)
+        for name in _INCEPTION_CFG:
+            for br in ("branch1", "branch2.0", "branch2.1", "branch3.0", "branch3.1", "branch4.1"):
+                self.conv_bn(f"{name}.{br}", f"{name}.{br}.conv", f"{name}.{br}.bn", self.EPS)
+        self.w["fc"] = (_f32(sd["fc.weight"], dev), _f32(sd["fc.bias"], dev))
+        self.ncls = self.w["fc"][0].shape[0]
+
+    def _emit_googlenet(self, B, ws, ops, u8=None, f32=None):
+        """u8: [B,224,224,3] uint8 crops (HWC, channel order as the reference's roi_rgb), or f32: float NCHW."""
+        buf = self.buf
+        a1 = buf(B * 112 * 112, 192)
+        ops.append(E.G1Im2colDesc(E.ptr(u8), a1.data_ptr(), B, IMG, E.ptr(f32)))
+        c1 = buf(B, 112, 112, 64)
+        self.conv(ops, self.w["conv1"], View(a1), (1, 1, B * 112 * 112), View(c1))
+        p1 = buf(B, 56, 56, 64)
+        ops.append(E.PoolDesc(c1.data_ptr(), 64, p1.data_ptr(), 64, 64, B, 112, 112, 56, 56, 3, 2, 0))
+        c2 = buf(B, 56, 56, 64)
+        self.conv(ops, self.w["conv2"], View(p1), (1, 1, B * 56 * 56), View(c2))
+        c3 = buf(B, 56, 56, 192)
+        self.conv(ops, self.w["conv3"], View(c2), (B, 56, 56), View(c3))
+        cur = buf(B, 28, 28, 192)
+        ops.append(E.PoolDesc(c3.data_ptr(), 192, cur.data_ptr(), 192, 192, B, 56, 56, 28, 28, 3, 2, 0))
+        keep = [a1, c1, p1, c2, c3, cur]
+        size = 28
+        for name, (cin, c1x1, c3r, c3x3, c5r, c5x5, pp, sp) in _INCEPTION_CFG.items():
+            if sp != size:                                           # maxpool3 (3,s2,ceil) / maxpool4 (2,s2,ceil)
+                k = 3 if sp == 14 else 2
+                nxt = buf(B, sp, sp, cin)
+                ops.append(E.PoolDesc(cur.data_ptr(), cin, nxt.data_ptr(), cin, cin, B, size, size, sp, sp, k, 2, 0))
+                keep.append(nxt)
+                cur, size = nxt, sp
+            cout = c1x1 + c3x3 + c5x5 + pp
+            out = buf(B, sp, sp, cout)                               # torch.cat([b1,b2,b3,b4],1) target
+            flat = (1, 1, B * sp * sp)
+            geom = (B, sp, sp)
+            xin = View(cur)
+            self.conv(ops, self.w[name + ".branch1"], xin, flat, View(out, c1x1, 0))
+            r2 = buf(B, sp, sp, c3r)
+            self.conv(ops, self.w[name + ".branch2.0"], xin, flat, View(r2))
+            self.conv(ops, self.w[name + ".branch2.1"], View(r2), geom, View(out, c3x3, c1x1))
+            r3 = buf(B, sp, sp, c5r)
+            self.conv(ops, self.w[name + ".branch3.0"], xin, flat, View(r3))
+            self.conv(ops, self.w[name + ".branch3.1"], View(r3), geom, View(out, c5x5, c1x1 + c3x3))
+            pl = buf(B, sp, sp, cin)
+            ops.append(E.PoolDesc(cur.data_ptr(), cin, pl.data_ptr(), cin, cin, B, sp, sp, sp, sp, 3, 1, 1))
+            self.conv(ops, self.w[name + ".branch4.1"], View(pl), flat, View(out, pp, c1x1 + c3x3 + c5x5))
+            keep += [out, r2, r3, pl]
+            ws[name] = out
+            cur = out
+        ws["cls_logits"] = buf(B, self.ncls, dtype=torch.float32)
+        ops.append(E.HeadDesc(cur.data_ptr(), self.w["fc"][0].data_ptr(), self.w["fc"][1].data_ptr(),
+                              ws["cls_logits"].data_ptr(), B, 49, 1024, self.ncls))
+        ws.setdefault("keep", []).extend(keep)
+
+    def plan(self, B, kind="f32"):
+        key = (B, kind)
+        if key not in self.plans:
+            ws, ops = {}, []
+            if kind == "u8":
+                ws["in"] = self.buf(B, IMG, IMG, 3, dtype=torch.uint8)
+                self._emit_googlenet(B, ws, ops, u8=ws["in"])
+            else:
+                ws["in"] = self.buf(B, 3, IMG, IMG, dtype=torch.float32)
+                self._emit_googlenet(B, ws, ops, f32=ws["in"])
+            ws["program"] = self.engine.program(ops)
+            self.plans[key] = ws
+        return self.plans[key]
+
+    def _run(self, x, kind):
+        if x.device.type != "cuda":
+            raise RuntimeError("ugnet: input must be a CUDA tensor (no CPU path)")
+        outs = []
+        for s in range(0, x.shape[0], self.max_batch):
+            xb = x[s:s + self.max_batch]
+            ws = self.plan(xb.shape[0], kind)
+            ws["in"].copy_(xb)
+            ws["program"].run()
+            outs.append(ws["cls_logits"].clone())
+        return torch.cat(outs) if len(outs) > 1 else outs[0]
+
+    @torch.no_grad()
+    def forward_u8(self, u8):
+        """u8: uint8 [B,224,224,3] crops (what the ROI stage produces) -> logits [B, ncls]."""
+        return self._run(u8, "u8")
+
+    @torch.no_grad()
+    def forward(self, x):
+        """x: float [B,3,224,224] in [0,1] (test.py:82-84) -> logits [B, ncls]."""
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != IMG or x.shape[3] != IMG:
+            raise ValueError(f"expected [B,3,{IMG},{IMG}] input, got {tuple(x.shape)}")
+        return self._run(x, "f32")
+
+
+# =============================================================================================== pipeline
+class PipelineRunner:
+    """UNet -> threshold -> bbox -> crop/resize -> GoogLeNet as one program per batch (no host round trip)."""
+
+    def __init__(self, unet_sd, googlenet_sd, dev, micro_batch=64, padding=30):
+        self.dev = torch.device(dev)
+        self.unet = UNetRunner(unet_sd, self.dev, max_batch=micro_batch)
+        self.gnet = GoogLeNetRunner(googlenet_sd, self.dev, max_batch=micro_batch)
+        self.engine = self.unet.engine
+        self.micro_batch = micro_batch
+        self.padding = padding
+        self.plans = {}
+
+    def plan(self, B):
+        if B not in self.plans:
+            ws, ops = {}, []
+            self.unet._emit_unet(B, ws, ops)
+            self.unet._emit_bbox(B, ws, ops, self.padding)
+            ws["u8"] = self.unet.buf(B, IMG, IMG, 3, dtype=torch.uint8)
+            ops.append(E.CropResizeDesc(ws["x_in"].data_ptr(), ws["boxes"].data_ptr(), ws["u8"].data_ptr(), B, IMG,
+                                        IMG, IMG))
+            self.gnet._emit_googlenet(B, ws, ops, u8=ws["u8"])
+            ws["program"] = self.engine.program(ops)
+            self.plans[B] = ws
+        return self.plans[B]
+
+    @torch.no_grad()
+    def __call__(self, imgs, return_logits=False):
+        """imgs: float [B,3,224,224] CUDA -> (masks u8 [B,224,224], boxes i32 [B,4], cls_logits f32 [B,6])."""
+        masks, boxes, cls, seg = [], [], [], []
+        for s in range(0, imgs.shape[0], self.micro_batch):
+            xb = imgs[s:s + self.micro_batch]
+            ws = self.plan(xb.shape[0])
+            ws["x_in"].copy_(xb)
+            ws["program"].run()
+            masks.append(ws["mask"].clone())
+            boxes.append(ws["boxes"].clone())
+            cls.append(ws["cls_logits"].clone())
+            if return_logits:
+                seg.append(ws["logits"].clone())
+        out = (torch.cat(masks), torch.cat(boxes), torch.cat(cls))
+        return out + (torch.cat(seg),) if return_logits else out
