@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — seg+crop+cls images/sec of the two-stage path (UNet -> mask -> bbox -> crop/resize -> GoogLeNet).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched per rank by torch.distributed.run)
+  python bench.py --impl reference ...                      (the reference's CPU arithmetic: the oracle port)
+
+A step is one pass of the whole path over this rank's batch of synthetic 224x224 images (default 256 per GPU,
+run as micro-batches of 64 — BASELINE.json config 4/5: 512 images on 2 GPUs, 2048 on 8), followed for N>1 by
+the path's only collective: an NCCL all-gather of masks and class logits.  Weak scaling: per-GPU work is fixed.
+
+  value     device-timed whole-job images/s, inputs already resident in HBM (staging buffer of the program)
+  e2e       same metric through the C-ABI host entry (ug_program_run_host): pinned host inputs copied H2D and
+            masks/boxes/logits copied D2H inside the timed region, every step
+  roofline  tensor-pipe roofline of the dominant kernel (conv_gemm_kernel): algorithmic conv/linear FLOPs per
+            step / summed device time of its launches (event pair per launch, measured live in a separate
+            profiling pass of the same program), against MEASURED_PEAKS.json bf16_tflops_sustained
+  cpu_baseline  the oracle (CPU restatement of the reference, kind "port") on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "seg+crop+cls images/sec"
+UNIT = "images/s"
+FLOP_PER_IMAGE = 81.53e9   # live algorithmic FLOPs of the whole path per image
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def synth_batch(n, seed, device):
+    """Seeded synthetic ultrasound-like images generated on the device: low-frequency background, one dark
+    ellipse, speckle; 3 identical channels in [0,1]."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    S = 224
+    coarse = torch.rand((n, 1, 6, 6), generator=g, device=device)
+    bg = 0.45 + 0.35 * (torch.nn.functional.interpolate(coarse, size=(S, S), mode="bicubic") - 0.5)
+    yy, xx = torch.meshgrid(torch.arange(S, device=device), torch.arange(S, device=device), indexing="ij")
+    c = (torch.rand((n, 2), generator=g, device=device) * 0.5 + 0.25) * S
+    a = (torch.rand((n,), generator=g, device=device) * 0.2 + 0.08) * S
+    b = a * (torch.rand((n,), generator=g, device=device) * 0.6 + 0.4)
+    inside = (((xx[None] - c[:, 0, None, None]) / a[:, None, None]) ** 2 +
+              ((yy[None] - c[:, 1, None, None]) / b[:, None, None]) ** 2) <= 1.0
+    img = torch.where(inside[:, None], bg * 0.3, bg) + torch.randn((n, 1, S, S), generator=g, device=device) * 0.12
+    return img.clamp_(0, 1).expand(n, 3, S, S).contiguous()
+
+
+def conv_flops(descs):
+    """Algorithmic FLOPs (2*M*N*K with true, unpadded dims) of the conv/linear ops of a program."""
+    from ugnet_b200 import engine as E
+    total, per_op = 0.0, []
+    for d in descs:
+        if isinstance(d, E.ConvDesc):
+            # im2col-fed GEMMs carry zero-padded K columns: algo_k is the true reduction length (inc 27, conv1 147)
+            f = 2.0 * d.B * d.H * d.W * d.N * getattr(d, "algo_k", d.Cin * d.R * d.S)
+            per_op.append(f)
+            total += f
+        else:
+            per_op.append(0.0)
+    return total, per_op
+
+
+def run_reference_arm(args, rank):
+    """The reference's CPU arithmetic for the path (the oracle port; the Python reference itself cannot travel
+    to the GPU box), all host threads, one bounded sample of the workload per step."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from oracle import fixtures, googlenet_ref, roi_ref, unet_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = args.cpu_sample
+    usd = fixtures.procedural_state(fixtures.unet_template(), seed=7)
+    gsd = fixtures.procedural_state(fixtures.googlenet_template(), seed=11)
+    imgs, _, _ = fixtures.synth_images(sample, seed=1234)
+    x = torch.from_numpy(imgs)
+
+    def step():
+        with torch.no_grad():
+            logits = unet_ref.unet_forward(usd, x)
+            masks = unet_ref.mask_from_logits(logits)[:, 0].numpy()
+            crops = np.stack([roi_ref.roi_tensor(imgs[i], masks[i])[0] for i in range(sample)])
+            return googlenet_ref.googlenet_forward(gsd, torch.from_numpy(crops))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    desc = f"{sample} images/step of the same synthetic workload, fp32, oracle port of the reference path"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "end-to-end UNet->bbox crop->GoogLeNet, 224x224 (BASELINE configs[3]/[4] shape)",
+                   "sample_images_per_step": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline(sample, budget_s=20.0):
+    import numpy as np
+    import torch
+    from oracle import fixtures, googlenet_ref, roi_ref, unet_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    usd = fixtures.procedural_state(fixtures.unet_template(), seed=7)
+    gsd = fixtures.procedural_state(fixtures.googlenet_template(), seed=11)
+    imgs, _, _ = fixtures.synth_images(sample, seed=1234)
+    x = torch.from_numpy(imgs)
+
+    def step():
+        with torch.no_grad():
+            logits = unet_ref.unet_forward(usd, x)
+            masks = unet_ref.mask_from_logits(logits)[:, 0].numpy()
+            crops = np.stack([roi_ref.roi_tensor(imgs[i], masks[i])[0] for i in range(sample)])
+            googlenet_ref.googlenet_forward(gsd, torch.from_numpy(crops))
+
+    step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 20:
+            break
+    return {"value": sample * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} x {sample} images of the same synthetic workload through the oracle (fp32 PyTorch CPU "
+                      f"restatement of the reference path), {dt:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--micro-batch", type=int, default=64)
+    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ugnet_b200  # noqa: F401
+    from ugnet_b200.googlenet import GoogLeNetClassifier
+    from ugnet_b200.lower import PipelineRunner
+    from ugnet_b200.nets import UNetTaskAligWeight
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    PB, MB = args.batch, args.micro_batch
+    assert PB % MB == 0
+
+    torch.manual_seed(1234)                                   # identical random-init replica on every rank
+    unet_sd = UNetTaskAligWeight(3, 1).state_dict()
+    gnet_sd = GoogLeNetClassifier(6).state_dict()
+    pipe = PipelineRunner(unet_sd, gnet_sd, dev, micro_batch=MB)
+    eng = pipe.engine
+    ws = pipe.plan(MB)
+    prog = ws["program"]
+    n_mb = PB // MB
+    imgs = synth_batch(PB, 1234 + rank, dev)                  # this rank's slice of the global batch (HBM-resident)
+    out_masks = torch.empty((PB, 224, 224), dtype=torch.uint8, device=dev)
+    out_cls = torch.empty((PB, 6), dtype=torch.float32, device=dev)
+    if world > 1:
+        g_masks = torch.empty((world * PB, 224, 224), dtype=torch.uint8, device=dev)
+        g_cls = torch.empty((world * PB, 6), dtype=torch.float32, device=dev)
+
+    def step_device():
+        for m in range(n_mb):
+            ws["x_in"].copy_(imgs[m * MB:(m + 1) * MB])
+            prog.run()
+            out_masks[m * MB:(m + 1) * MB].copy_(ws["mask"])
+            out_cls[m * MB:(m + 1) * MB].copy_(ws["cls_logits"])
+        if world > 1:                                          # the path's only collective (NVLink all-gather)
+            dist.all_gather_into_tensor(g_masks, out_masks)
+            dist.all_gather_into_tensor(g_cls, out_cls)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(W):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    ms = timed(step_device, args.steps)
+    launches = eng.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * PB * args.steps / (ms / 1e3)
+
+    # ---- end to end through the C-ABI host entry: pinned host buffers, H2D + D2H every step
+    h_in = torch.empty((PB, 3, 224, 224), dtype=torch.float32).pin_memory()
+    h_in.copy_(imgs.cpu())
+    h_masks = torch.empty((PB, 224, 224), dtype=torch.uint8).pin_memory()
+    h_boxes = torch.empty((PB, 4), dtype=torch.int32).pin_memory()
+    h_cls = torch.empty((PB, 6), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        for m in range(n_mb):
+            sl = slice(m * MB, (m + 1) * MB)
+            prog.run_host([(ws["x_in"], h_in[sl])],
+                          [(h_masks[sl], ws["mask"]), (h_boxes[sl], ws["boxes"]), (h_cls[sl], ws["cls_logits"])])
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * PB * args.steps / (ms_e2e / 1e3)
+    h2d = PB * 3 * 224 * 224 * 4
+    d2h = PB * (224 * 224 + 16 + 24)
+
+    # ---- roofline of the dominant kernel: per-launch event timing of the same program (profiling pass)
+    peak_tf, peak_hbm, peak_src = _peaks()
+    total_flop, per_op_flop = conv_flops(prog.descs)
+    per_op_ms = [0.0] * prog.num_launches
+    reps = 3
+    prog.run_timed()
+    for _ in range(reps):
+        for i, t in enumerate(prog.run_timed()):
+            per_op_ms[i] += t / reps
+    from ugnet_b200 import engine as E
+    conv_ms = sum(t for t, d in zip(per_op_ms, prog.descs) if isinstance(d, E.ConvDesc))
+    n_conv = sum(isinstance(d, E.ConvDesc) for d in prog.descs)
+    achieved = total_flop / (conv_ms / 1e3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf, "traffic": None,
+                "kernel": "conv_gemm_kernel", "launches_per_microbatch": n_conv,
+                "avg_launch_ms": conv_ms / n_conv, "share_of_step": conv_ms / sum(per_op_ms),
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "end-to-end UNet->bbox crop->GoogLeNet at 224x224 (BASELINE.json configs[3]/[4]: "
+                                   "batch sharded across GPUs), random-init weights",
+                       "images_per_gpu_per_step": PB, "micro_batch": MB, "global_batch": world * PB,
+                       "collective": "nccl all_gather(masks u8, logits f32)" if world > 1 else "none",
+                       "l2": "per-step inputs (154 MB fp32) and activations (GBs) exceed the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "model_tflops": value * FLOP_PER_IMAGE / 1e12 / world,
+            "roofline": roofline, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+        # per-op breakdown for profiles/ (not part of the contract line)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        kinds = {}
+        for t, d in zip(per_op_ms, prog.descs):
+            kinds[type(d).__name__] = kinds.get(type(d).__name__, 0.0) + t
+        with open(os.path.join(ROOT, "gpurun_out", f"bench_breakdown_n{world}.json"), "w") as f:
+            json.dump({"per_kind_ms_per_microbatch": kinds, "micro_batch": MB,
+                       "per_op": [{"i": i, "kind": type(d).__name__, "ms": t, "gflop": fl / 1e9,
+                                   "tflops": (fl / (t / 1e3) / 1e12) if fl and t > 0 else None,
+                                   "shape": ([d.B, d.H, d.W, d.Cin, d.N, d.R] if isinstance(d, E.ConvDesc) else None)}
+                                  for i, (t, d, fl) in enumerate(zip(per_op_ms, prog.descs, per_op_flop))]}, f, indent=1)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

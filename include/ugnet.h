@@ -227,6 +227,9 @@ int ug_head(ug_handle h, const ug_head_desc* d, void* stream);
 int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out);
 int ug_program_run(ug_handle h, ug_program p, void* stream);
 int ug_program_num_launches(ug_program p);
+/* Profiling aid: run with a CUDA event pair around every op, synchronize, and return the device time of each
+ * op in milliseconds (ms_per_op has ug_program_num_launches(p) entries). */
+int ug_program_run_timed(ug_handle h, ug_program p, void* stream, float* ms_per_op);
 int ug_program_destroy(ug_handle h, ug_program p);
 
 /* Host-buffer convenience used for end-to-end timing: H2D copies, run, D2H copies, all on `stream`,

@@ -111,7 +111,7 @@ def _train(sd, loss_fn, batches, lr, device):
         loss = loss_fn(params, batch)
         loss.backward()
         opt.step()
-        last = float(loss)
+        last = float(loss.detach())
     return {k: v.detach() for k, v in params.items()}, last
 
 
@@ -177,7 +177,7 @@ def roi_crops_from_masks(imgs, masks):
     return np.stack([roi_ref.roi_tensor(imgs[i], masks[i])[0] for i in range(len(imgs))])
 
 
-def trained_googlenet_state(device="cpu", steps=80, batch=16, seed=4321, lr=1e-3, cache=True, verbose=False):
+def trained_googlenet_state(device="cpu", steps=300, batch=16, seed=4321, lr=1e-3, cache=True, verbose=False):
     path = os.path.join(CACHE_DIR, f"googlenet_trained_s{seed}_n{steps}_b{batch}.pt")
     if cache and os.path.exists(path):
         return torch.load(path, map_location="cpu")["net"]

@@ -148,6 +148,27 @@ int ug_program_run(ug_handle h, ug_program p, void* stream) {
   return UG_OK;
 }
 
+int ug_program_run_timed(ug_handle h, ug_program p, void* stream, float* ms_per_op) {
+  if (!h || !p || !ms_per_op) return UG_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = p->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return set_error(h, UG_ECUDA, "cudaEventCreate failed");
+  int rc = UG_OK;
+  cudaEventRecord(ev[0], s);
+  for (size_t i = 0; i < n && rc == UG_OK; ++i) {
+    const PreparedOp& po = p->ops[i];
+    rc = (po.kind == UG_OP_CONV) ? conv_launch(h, &po.conv, s) : run_simple(h, &po.op, s);
+    cudaEventRecord(ev[i + 1], s);
+  }
+  if (rc == UG_OK) rc = check_cuda(h, cudaStreamSynchronize(s), "stream synchronize");
+  if (rc == UG_OK)
+    for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
 int ug_program_num_launches(ug_program p) { return p ? (int)p->ops.size() : 0; }
 
 int ug_program_destroy(ug_handle h, ug_program p) {

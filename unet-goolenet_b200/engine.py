@@ -101,7 +101,7 @@ _SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_INC_IM2COL: "ug_inc_im2col", OP_POOL: "u
 
 EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
-                    "ug_program_destroy", "ug_program_run_host"]
+                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_timed"]
 
 _lib = None
 
@@ -127,6 +127,7 @@ def load_library():
     lib.ug_program_create.argtypes = [_vp, _vp, _i, C.POINTER(_vp)]
     lib.ug_program_run.argtypes = [_vp, _vp, _vp]
     lib.ug_program_num_launches.argtypes = [_vp]
+    lib.ug_program_run_timed.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_float)]
     lib.ug_program_destroy.argtypes = [_vp, _vp]
     lib.ug_program_run_host.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _vp]
     _lib = lib
@@ -144,6 +145,7 @@ class Program:
     def __init__(self, engine, descs, keepalive=()):
         self.engine = engine
         self.keepalive = list(keepalive)
+        self.descs = list(descs)
         arr = (Op * len(descs))()
         for i, d in enumerate(descs):
             kind = _DESC_KIND[type(d)]
@@ -157,6 +159,13 @@ class Program:
     def run(self, stream=None):
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         self.engine._check(self.engine.lib.ug_program_run(self.engine.handle, self.handle, s))
+
+    def run_timed(self, stream=None):
+        """Per-op device times in ms (event pair around every op; profiling aid, not the benchmark path)."""
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        ms = (C.c_float * self.num_launches)()
+        self.engine._check(self.engine.lib.ug_program_run_timed(self.engine.handle, self.handle, s, ms))
+        return list(ms)
 
     def run_host(self, h2d, d2h, stream=None):
         """h2d / d2h: lists of (dst_tensor, src_tensor); copies + run + copies + stream sync, all in C."""

@@ -81,6 +81,7 @@ class _Builder:
              gate=None, outc=None):
         B, H, W = geom
         d = E.ConvDesc()
+        d.algo_k = wd.get("algo_k", wd["Cin"] * wd["R"] * wd["R"])   # true reduction length (for FLOP accounting)
         d.inp, d.in_cstride, d.Cin = x.ptr, x.cstride, wd["Cin"]
         assert x.C == wd["Cin"], (x.C, wd["Cin"])
         d.B, d.H, d.W = B, H, W
@@ -129,7 +130,8 @@ class UNetRunner(_Builder):
                                    _f32(sd["inc.norm.bias"], dev), _f32(sd["inc.norm.running_mean"], dev),
                                    _f32(sd["inc.norm.running_var"], dev), self.EPS)
         gemm = wt.permute(0, 2, 3, 1).reshape(64, 27)
-        self.w["inc"] = dict(w=pack.pack_linear_weight(gemm, 64), scale=scale, bias=bias, N=64, Cin=64, R=1, BN=64)
+        self.w["inc"] = dict(w=pack.pack_linear_weight(gemm, 64), scale=scale, bias=bias, N=64, Cin=64, R=1, BN=64,
+                             algo_k=27)
         for blk in ("down1", "down2", "down3", "down4"):
             for i in (0, 1):
                 self.conv_bn(f"{blk}.{i}", f"{blk}.nConvs.{i}.conv", f"{blk}.nConvs.{i}.norm", self.EPS)
@@ -334,7 +336,7 @@ class GoogLeNetRunner(_Builder):
                                    self.EPS)
         gemm = wt.permute(0, 2, 3, 1).reshape(64, 147)
         self.w["conv1"] = dict(w=pack.pack_linear_weight(gemm, 64), scale=scale, bias=bias, N=64, Cin=192, R=1,
-                               BN=64)
+                               BN=64, algo_k=147)
         self.conv_bn("conv2", "conv2.conv", "conv2.bn", self.EPS)
         self.conv_bn("conv3", "conv3.conv", "conv3.bn", self.EPS)
         for name in _INCEPTION_CFG:
