@@ -70,6 +70,8 @@ typedef struct ug_conv_desc {
   float* logits;
   unsigned char* mask;
   int TW, TH, TN, BN, stages; /* tiling; 0 = engine chooses */
+  int variant;                /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel (TMEM multi-buffered
+                                 accumulators, TMA-store epilogue) */
 } ug_conv_desc;
 
 /* x: fp32 NCHW [B,3,H,W] -> out: bf16 [B*H*W][64], column (r*3+s)*3+c = x[n,c,y+r-1,x+s-1] (0 outside),
@@ -209,6 +211,12 @@ int ug_destroy(ug_handle h);
 const char* ug_last_error(ug_handle h);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 long long ug_launch_count(ug_handle h);
+
+/* Profiling aid for the persistent conv kernel: runs the op with per-role cycle counters enabled and returns,
+ * averaged over CTAs, {producer wait-for-free-slot, producer total, MMA wait-for-data, MMA wait-for-accumulator,
+ * epilogue wait-for-accumulator, epilogue wait-for-staging, epilogue math, epilogue store} in SM cycles,
+ * plus out[8] = number of CTAs, out[9] = tiles per CTA (rounded up).  Synchronizes the stream. */
+int ug_conv_profile(ug_handle h, const ug_conv_desc* d, void* stream, double* out10);
 
 /* Single ops (validated, tensor maps built per call) — used by the unit parity tests. */
 int ug_conv(ug_handle h, const ug_conv_desc* d, void* stream);

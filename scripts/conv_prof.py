@@ -1,0 +1,68 @@
+"""Sweep the conv kernel over the hot layer shapes at batch 64: time per config + per-role cycle counters."""
+import json
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ugnet_b200  # noqa
+from ugnet_b200 import engine as E, pack
+
+eng = E.Engine.get(0)
+g = torch.Generator(device="cuda").manual_seed(0)
+
+
+def make(B, H, W, Cin, N, R, mode=0, bn=None, stages=0, variant=0, tile=None):
+    x = torch.randn((B, H, W, Cin), generator=g, device="cuda").to(torch.bfloat16)
+    wt = torch.randn((N, Cin, R, R), generator=g, device="cuda") * (Cin * R * R) ** -0.5
+    BN = bn or pack.choose_bn(N)
+    wp = pack.pack_conv_weight(wt, BN)
+    out = torch.empty((B, H, W, N), device="cuda", dtype=torch.bfloat16)
+    scale = torch.ones(N, device="cuda"); bias = torch.zeros(N, device="cuda")
+    d = E.ConvDesc()
+    d.inp = x.data_ptr(); d.in_cstride = Cin; d.Cin = Cin; d.B, d.H, d.W = B, H, W
+    d.R = d.S = R; d.pad = (R - 1) // 2; d.w = wp.data_ptr(); d.N = N
+    d.scale = scale.data_ptr(); d.bias = bias.data_ptr(); d.act = 1; d.mode = mode
+    d.out = out.data_ptr(); d.out_cstride = N; d.up = 1; d.BN = BN; d.stages = stages; d.variant = variant
+    if tile: d.TW, d.TH, d.TN = tile
+    keep = [x, wp, out, scale, bias]
+    if mode == 2:
+        add = torch.randn((B, H, W, N), generator=g, device="cuda").to(torch.bfloat16)
+        gate = torch.rand((B, N), device="cuda")
+        d.add = add.data_ptr(); d.add_cstride = N; d.add_bstride = H * W * N; d.gate = gate.data_ptr()
+        keep += [add, gate]
+    return d, keep
+
+
+def timeit(d, n=5):
+    for _ in range(2):
+        eng.run_op(d)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        eng.run_op(d)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+SHAPES = [(64, 224, 224, 64, 64, 3), (64, 112, 112, 128, 128, 3), (64, 56, 56, 256, 256, 3), (64, 28, 28, 512, 512, 3),
+          (64, 14, 14, 512, 512, 3), (64, 224, 224, 128, 64, 3)]
+if len(sys.argv) > 1:
+    SHAPES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+CONFIGS = [dict(variant=1), dict(variant=0), dict(variant=0, stages=3), dict(variant=0, bn=256), dict(variant=0, bn=64)]
+for shp in SHAPES:
+    B, H, W, Cin, N, R = shp
+    fl = 2.0 * B * H * W * N * Cin * R * R
+    for cfg in CONFIGS:
+        if cfg.get("bn", 0) > N:
+            continue
+        try:
+            d, keep = make(*shp, **cfg)
+            ms = timeit(d)
+            line = f"{shp} {cfg}: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s"
+            if cfg.get("variant", 0) == 0:
+                pr = eng.conv_profile(d)
+                line += " | " + " ".join(f"{k}={v:.0f}" for k, v in pr.items())
+            print(line, flush=True)
+        except Exception as ex:
+            print(shp, cfg, "ERR", ex, flush=True)

@@ -13,7 +13,7 @@ def _mk(shape, gen, scale=1.0):
 
 
 def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_extra=0, in_off=0, out_off=0,
-             seed=0, tile=None, bn=None, stages=0, add_broadcast=False):
+             seed=0, tile=None, bn=None, stages=0, add_broadcast=False, variant=0):
     from ugnet_b200 import engine as E
     from ugnet_b200 import pack
     g = torch.Generator(device="cuda").manual_seed(seed)
@@ -47,7 +47,7 @@ def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_ex
     d.act = act; d.mode = mode
     d.out = obuf.data_ptr() + 2 * out_off; d.out_cstride = out_cs
     d.up = up; d.convt_cout = cout if up == 2 else 0
-    d.BN = BN; d.stages = stages
+    d.BN = BN; d.stages = stages; d.variant = variant
     if tile:
         d.TW, d.TH, d.TN = tile
     addt = gate = outw = logits = mask = None
@@ -124,6 +124,18 @@ CASES = [
     dict(B=2, H=32, W=48, Cin=64, N=64, R=3, mode=3),              # fused outc + threshold
     dict(B=1, H=16, W=16, Cin=64, N=64, R=3, tile=(16, 8, 1), stages=2),
     dict(B=1, H=16, W=16, Cin=128, N=256, R=3, bn=256, stages=3),  # BN=256
+    dict(B=4, H=56, W=56, Cin=128, N=512, R=3, bn=256),            # BN=256, single staging buffer, many tiles
+    dict(B=8, H=28, W=28, Cin=64, N=64, R=3, mode=2, variant=2),   # persistent: gate combine, several tiles per CTA
+    dict(B=3, H=14, W=14, Cin=256, N=208, R=3, out_extra=48, out_off=16, variant=2),   # persistent: ragged n-tile
+    dict(B=1, H=224, W=224, Cin=64, N=64, R=3, variant=2),        # persistent: 392 tiles over 148 CTAs
+    dict(B=2, H=32, W=48, Cin=64, N=64, R=3, mode=3, variant=2),   # persistent: fused outc
+    dict(B=2, H=14, W=14, Cin=512, N=2048, R=1, up=2, act=0, variant=2),  # persistent: ConvTranspose direct stores
+    dict(B=1, H=1, W=392, Cin=512, N=2048, R=1, act=2, variant=2),  # persistent: GELU
+    # legacy one-tile-per-CTA variant stays covered
+    dict(B=2, H=28, W=28, Cin=128, N=256, R=3, variant=1),
+    dict(B=2, H=14, W=14, Cin=512, N=2048, R=1, up=2, act=0, variant=1),
+    dict(B=2, H=32, W=48, Cin=64, N=64, R=3, mode=3, variant=1),
+    dict(B=2, H=28, W=28, Cin=512, N=512, R=3, mode=2, variant=1),
 ]
 
 

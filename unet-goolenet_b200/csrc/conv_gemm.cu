@@ -24,6 +24,17 @@ namespace ug {
 static constexpr int kThreads = 192;
 static constexpr int kABytesPerStage = 128 * 128;  // 128 rows x 64 bf16
 
+// kAct is a template parameter on purpose: with a run-time activation switch the compiler if-converts the erf
+// polynomial of GELU into predicated code inside the unrolled per-element loop, and every ReLU epilogue then
+// issues ~40 dead instructions per element (measured: ~1500 cycles per 16-column chunk).
+template <int kAct>
+__device__ __forceinline__ float apply_act(float t) {
+  if constexpr (kAct == UG_ACT_RELU) return fmaxf(t, 0.0f);
+  else if constexpr (kAct == UG_ACT_GELU) return gelu_erf(t);
+  else return t;
+}
+
+template <int kAct>
 __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const ConvKParams p) {
@@ -162,10 +173,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
       float f[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float t = __uint_as_float(v[j]) * sScale[c0 + j] + sBias[c0 + j];
-        if (p.act == UG_ACT_RELU) t = fmaxf(t, 0.0f);
-        else if (p.act == UG_ACT_GELU) t = gelu_erf(t);
-        f[j] = t;
+        f[j] = apply_act<kAct>(__uint_as_float(v[j]) * sScale[c0 + j] + sBias[c0 + j]);
       }
       if (p.mode == UG_EPI_OUTC) {
 #pragma unroll
@@ -210,6 +218,296 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
       // torch.sigmoid(seg_out) > 0.5 evaluated in fp32 (roi.py:22-23, predict.py:26-27)
       const float sg = 1.0f / (1.0f + expf(-logit));
       p.mask[o] = sg > 0.5f ? 1 : 0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM loops over (n-tile, pixel-tile) pairs.  The TMA producer and the MMA
+// issuer run ahead across tile boundaries; accumulators are multi-buffered in TMEM (acc_stages x BN columns)
+// so the epilogue of tile i overlaps the main loop of tile i+1; plain/ADD/GATE epilogues stage the bf16 tile
+// in 128B-swizzled smem and write it with one TMA store per 64 channels (clipping handles ragged edges).
+template <int kAct>
+__device__ __forceinline__ void epi_math16(const uint32_t (&v)[16], float (&f)[16], const float* sScale,
+                                           const float* sBias, int col) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = apply_act<kAct>(__uint_as_float(v[j]) * sScale[col + j] + sBias[col + j]);
+}
+
+__device__ __forceinline__ void epi_add_gate8(const ConvKParams& p, float* f, const __nv_bfloat16* add_ptr,
+                                              const float* gate_ptr) {
+  const uint4 a = *reinterpret_cast<const uint4*>(add_ptr);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float e0 = bf16_lo(aw[j]), e1 = bf16_hi(aw[j]);
+    if (p.mode == UG_EPI_ADD) {
+      f[2 * j] += e0;
+      f[2 * j + 1] += e1;
+    } else {
+      f[2 * j] = e0 + f[2 * j] * (1.0f + __ldg(gate_ptr + 2 * j));
+      f[2 * j + 1] = e1 + f[2 * j + 1] * (1.0f + __ldg(gate_ptr + 2 * j + 1));
+    }
+  }
+}
+
+template <int kAct>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                           const __grid_constant__ CUtensorMap tmB,
+                                                                           const __grid_constant__ CUtensorMap tmO,
+                                                                           const ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_stage_bytes = p.BN * 128;
+  const int n_sub = (p.BN + 63) / 64;
+  const int obuf_bytes = p.tma_store ? n_sub * kABytesPerStage : 0;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + p.stages * kABytesPerStage;
+  uint8_t* sO = sB + p.stages * b_stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sO + p.obufs * obuf_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* acc_full = empty + p.stages;
+  uint64_t* acc_empty = acc_full + p.acc_stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + p.acc_stages);
+  float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);
+  float* sBias = sScale + p.npad;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (p.tma_store) prefetch_tmap(&tmO);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < p.acc_stages; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, p.tmem_cols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.npad; i += kThreads) {
+    sScale[i] = (i < p.N) ? (p.scale ? p.scale[i] : 1.0f) : 0.0f;
+    sBias[i] = (i < p.N && p.bias) ? p.bias[i] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
+      long long w_empty = 0;
+      const long long t_start = clock64();
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+        const int x0 = (mt % p.tiles_x) * p.TW;
+        const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.TH;
+        const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.TN;
+        int it = 0;
+        for (int tap = 0; tap < p.R * p.S; ++tap) {
+          const int r = tap / p.S, s = tap % p.S;
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            const long long tw0 = p.prof ? clock64() : 0;
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (p.prof) w_empty += clock64() - tw0;
+            mbar_arrive_expect_tx(&full[stage], tx_bytes);
+            tma_load_4d(sA + stage * kABytesPerStage, &tmA, &full[stage], kc * 64, x0 + s - p.pad, y0 + r - p.pad, n0);
+            tma_load_2d(sB + stage * b_stage_bytes, &tmB, &full[stage], it * 64, nt * p.BN);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+      if (p.prof) {
+        p.prof[blockIdx.x * 8 + 0] = w_empty;
+        p.prof[blockIdx.x * 8 + 1] = clock64() - t_start;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      long long w_full = 0, w_acc = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        long long tw0 = p.prof ? clock64() : 0;
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        if (p.prof) w_acc += clock64() - tw0;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.BN;
+        for (int it = 0; it < p.num_k; ++it) {
+          tw0 = p.prof ? clock64() : 0;
+          mbar_wait(&full[stage], phase);
+          if (p.prof) w_full += clock64() - tw0;
+          tc_fence_after();
+          const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytesPerStage));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * b_stage_bytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[acc]);
+        if (++acc == p.acc_stages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (p.prof) {
+        p.prof[blockIdx.x * 8 + 2] = w_full;
+        p.prof[blockIdx.x * 8 + 3] = w_acc;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps, 1 pixel / thread)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int etid = threadIdx.x - 64;  // 0..127
+    long long w_accfull = 0, w_obuf = 0, t_proc = 0, t_store = 0;
+    const int tx = row % p.TW;
+    const int trest = row / p.TW;
+    const int ty = trest % p.TH;
+    const int tn = trest / p.TH;
+    const bool row_in_tile = row < p.TW * p.TH * p.TN;
+    int acc = 0, obuf = 0;
+    uint32_t acc_phase = 0;
+
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+      const int x0 = (mt % p.tiles_x) * p.TW;
+      const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.TH;
+      const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.TN;
+      const int ncol0 = nt * p.BN;
+      const int x = x0 + tx, y = y0 + ty, n = n0 + tn;
+      const bool valid = row_in_tile && (x < p.W) && (y < p.H) && (n < p.B);
+
+      int dy = 0, dx = 0, cbase = ncol0;
+      if (p.up == 2) {
+        const int qd = ncol0 / p.convt_cout;
+        dy = qd >> 1;
+        dx = qd & 1;
+        cbase = ncol0 % p.convt_cout;
+      }
+      const int oy = y * p.up + dy, ox = x * p.up + dx;
+      const long long pix = (long long)oy * p.OW + ox;
+      __nv_bfloat16* out_row =
+          reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)n * p.OH * p.OW + pix) * p.out_cstride + cbase;
+      const __nv_bfloat16* add_row =
+          reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)n * p.add_bstride + pix * p.add_cstride + cbase;
+      const float* gate_row = p.gate + (long long)n * p.N + ncol0;
+      uint8_t* so_row = sO + obuf * obuf_bytes + row * 128;
+
+      long long tw0 = p.prof ? clock64() : 0;
+      mbar_wait(&acc_full[acc], acc_phase);
+      if (p.prof) { const long long c = clock64(); w_accfull += c - tw0; tw0 = c; }
+      tc_fence_after();
+      if (p.tma_store) {
+        // the TMA store that last read this staging buffer must have finished reading it
+        if (etid == 0) {
+          if (p.obufs == 2) bulk_wait_group_read<1>();
+          else bulk_wait_group_read<0>();
+        }
+        named_bar_sync(1, 128);
+      }
+      if (p.prof) { const long long c = clock64(); w_obuf += c - tw0; tw0 = c; }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.BN;
+      float dot = 0.0f;
+      const int ncols = min(p.BN, p.N - ncol0);  // valid columns of this n-tile (multiple of 8)
+
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld16(taddr, v);
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        tmem_ld_wait();
+        float f[16];
+        epi_math16<kAct>(v, f, sScale, sBias, ncol0 + c0);
+        __syncwarp();
+        if (c0 + 16 < ncols) tmem_ld16(taddr + c0 + 16, v);  // next chunk in flight while this one is processed
+        if (p.mode == UG_EPI_OUTC) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dot += f[j] * __ldg(p.outc_w + ncol0 + c0 + j);
+          continue;
+        }
+        const int groups = (c0 + 16 <= ncols) ? 2 : 1;
+        if ((p.mode == UG_EPI_ADD || p.mode == UG_EPI_GATE) && valid) {
+          for (int g = 0; g < groups; ++g) epi_add_gate8(p, f + g * 8, add_row + c0 + g * 8, gate_row + c0 + g * 8);
+        }
+        for (int g = 0; g < groups; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+          o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+          o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+          o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+          if (p.tma_store) {
+            const int col = c0 + g * 8;
+            const int sub = col >> 6, chunk = (col & 63) >> 3;
+            *reinterpret_cast<uint4*>(so_row + sub * kABytesPerStage + ((chunk ^ (row & 7)) << 4)) = o;
+          } else if (valid) {
+            *reinterpret_cast<uint4*>(out_row + c0 + g * 8) = o;
+          }
+        }
+      }
+      // all TMEM reads of this accumulator are complete: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (p.prof) { const long long c = clock64(); t_proc += c - tw0; tw0 = c; }
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      if (p.mode == UG_EPI_OUTC) {
+        if (valid) {
+          const float logit = dot + p.outc_b;
+          const long long o = ((long long)n * p.H + y) * p.W + x;
+          p.logits[o] = logit;
+          const float sg = 1.0f / (1.0f + expf(-logit));  // torch.sigmoid(seg_out) > 0.5 in fp32
+          p.mask[o] = sg > 0.5f ? 1 : 0;
+        }
+      } else if (p.tma_store) {
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(1, 128);
+        if (etid == 0) {
+          for (int sub = 0; sub * 64 < ncols; ++sub)
+            tma_store_4d(&tmO, sO + obuf * obuf_bytes + sub * kABytesPerStage, ncol0 + sub * 64, x0, y0, n0);
+          bulk_commit_group();
+        }
+        if (p.obufs == 2) obuf ^= 1;
+      }
+      if (p.prof) t_store += clock64() - tw0;
+    }
+    if (p.tma_store && etid == 0) bulk_wait_group_all();
+    if (p.prof && etid == 0) {
+      p.prof[blockIdx.x * 8 + 4] = w_accfull;
+      p.prof[blockIdx.x * 8 + 5] = w_obuf;
+      p.prof[blockIdx.x * 8 + 6] = t_proc;
+      p.prof[blockIdx.x * 8 + 7] = t_store;
     }
   }
 
@@ -268,6 +566,7 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   if (!d->in || !d->w) return set_error(h, UG_EINVAL, "conv: null in/w pointer");
   if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->N <= 0)
     return set_error(h, UG_EINVAL, "conv: non-positive shape");
+  if (d->act < UG_ACT_NONE || d->act > UG_ACT_GELU) return set_error(h, UG_EINVAL, "conv: unknown activation");
   if (d->R <= 0 || d->S <= 0 || 2 * d->pad != d->R - 1 || d->R != d->S)
     return set_error(h, UG_EINVAL, "conv: only square stride-1 'same' filters (2*pad == R-1) are supported");
   if (d->in_cstride % 8 || (reinterpret_cast<uintptr_t>(d->in) & 15))
@@ -312,13 +611,35 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   const int n_tiles = ceil_div(d->N, BN);
   const long long ktot = (long long)d->R * d->S * cin_pad;
 
+  // variant: 0 = auto (persistent kernel for BN == 256, otherwise one tile per CTA, as measured in
+  // profiles/r01_conv_sweep.txt), 1 = one tile per CTA, 2 = persistent.
+  const int variant = d->variant == 1 ? 1 : (d->variant == 2 ? 0 : (BN == 256 ? 0 : 1));
+  const int m_tiles_total = ceil_div(d->W, TW) * ceil_div(d->H, TH) * ceil_div(d->B, TN);
+  const int tma_store = (variant == 0 && up == 1 && d->mode != UG_EPI_OUTC) ? 1 : 0;
+  const int n_sub = ceil_div(BN, 64);
+  const int obuf_bytes = tma_store ? n_sub * kABytesPerStage : 0;
+  const int acc_stages = std::max(1, std::min(4, 512 / BN));
+  const int npad = n_tiles * BN;
+  int obufs = tma_store ? 2 : 0;
   int stages = d->stages;
-  if (stages <= 0) {
-    const int per_stage = kABytesPerStage + BN * 128;
-    stages = (108 * 1024) / per_stage;  // two CTAs per SM
+  const int per_stage = kABytesPerStage + BN * 128;
+  if (variant == 1) {
+    if (stages <= 0) {
+      stages = (108 * 1024) / per_stage;  // two CTAs per SM
+      stages = std::max(2, std::min(stages, 8));
+    }
+    stages = std::min(stages, std::max(2, num_k));
+  } else {
+    const int fixed = 1024 + 8 * (2 * 8 + 2 * acc_stages) + 16 + 2 * npad * (int)sizeof(float);
+    const int budget = 227 * 1024 - fixed;
+    int fit = (budget - obufs * obuf_bytes) / per_stage;
+    if (tma_store && fit < 4) {
+      obufs = 1;
+      fit = (budget - obuf_bytes) / per_stage;
+    }
+    if (stages <= 0 || stages > fit) stages = fit;
     stages = std::max(2, std::min(stages, 8));
   }
-  stages = std::min(stages, std::max(2, num_k));
 
   ConvKParams& p = L->p;
   memset(&p, 0, sizeof(p));
@@ -343,6 +664,27 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   p.add = d->add; p.add_bstride = d->add_bstride; p.add_cstride = d->add_cstride;
   p.gate = d->gate; p.outc_w = d->outc_w; p.outc_b = d->outc_b;
   p.logits = d->logits; p.mask = d->mask;
+  p.m_tiles = m_tiles_total; p.n_tiles = n_tiles; p.acc_stages = acc_stages;
+  p.tma_store = tma_store; p.obufs = obufs; p.npad = npad;
+  L->variant = variant;
+  if (variant == 0) {
+    int tcols = 32;
+    while (tcols < acc_stages * BN) tcols <<= 1;
+    p.tmem_cols = tcols;
+  }
+  if (tma_store) {
+    cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->out_cstride * 2, (cuuint64_t)d->W * d->out_cstride * 2,
+                             (cuuint64_t)d->H * d->W * d->out_cstride * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&L->tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv: output tensor map encode failed (%d)", (int)r);
+  } else {
+    memset(&L->tmO, 0, sizeof(L->tmO));
+  }
 
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
@@ -365,8 +707,15 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv: weight tensor map encode failed (%d)", (int)r);
   }
-  L->grid = dim3((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)n_tiles, 1);
-  L->smem = 1024 + (size_t)stages * (kABytesPerStage + BN * 128) + 8 * (2 * stages + 1) + 8 + 2 * BN * sizeof(float);
+  if (variant == 1) {
+    L->grid = dim3((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)n_tiles, 1);
+    L->smem = 1024 + (size_t)stages * per_stage + 8 * (2 * stages + 1) + 8 + 2 * BN * sizeof(float);
+  } else {
+    const long long total = (long long)m_tiles_total * n_tiles;
+    L->grid = dim3((unsigned)std::min<long long>(total, h->num_sms), 1, 1);
+    L->smem = 1024 + (size_t)stages * per_stage + (size_t)obufs * obuf_bytes + 8 * (2 * stages + 2 * acc_stages) + 16 +
+              2 * (size_t)npad * sizeof(float);
+  }
   if (L->smem > 227 * 1024) return set_error(h, UG_EINVAL, "conv: shared memory request %zu too large", L->smem);
   return UG_OK;
 }
@@ -374,14 +723,34 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
 int conv_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_gemm_kernel)");
+    cudaError_t e = cudaSuccess;
+    const int kMax = 227 * 1024;
+    const void* fns[] = {(const void*)conv_gemm_kernel<UG_ACT_NONE>,
+                         (const void*)conv_gemm_kernel<UG_ACT_RELU>,
+                         (const void*)conv_gemm_kernel<UG_ACT_GELU>,
+                         (const void*)conv_gemm_persistent_kernel<UG_ACT_NONE>,
+                         (const void*)conv_gemm_persistent_kernel<UG_ACT_RELU>,
+                         (const void*)conv_gemm_persistent_kernel<UG_ACT_GELU>};
+    for (const void* f : fns)
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_gemm kernels)");
     attr_set = true;
   }
-  conv_gemm_kernel<<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->p);
+  const int act = L->p.act;
+  if (L->variant == 1) {
+    if (act == UG_ACT_RELU) conv_gemm_kernel<UG_ACT_RELU><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->p);
+    else if (act == UG_ACT_GELU) conv_gemm_kernel<UG_ACT_GELU><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->p);
+    else conv_gemm_kernel<UG_ACT_NONE><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->p);
+  } else {
+    if (act == UG_ACT_RELU)
+      conv_gemm_persistent_kernel<UG_ACT_RELU><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p);
+    else if (act == UG_ACT_GELU)
+      conv_gemm_persistent_kernel<UG_ACT_GELU><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p);
+    else
+      conv_gemm_persistent_kernel<UG_ACT_NONE><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p);
+  }
   h->launches++;
-  return check_cuda(h, cudaGetLastError(), "conv_gemm_kernel launch");
+  return check_cuda(h, cudaGetLastError(), "conv_gemm kernel launch");
 }
 
 }  // namespace ug

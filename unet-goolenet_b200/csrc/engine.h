@@ -35,15 +35,20 @@ struct ConvKParams {
   float outc_b;
   float* logits;
   unsigned char* mask;
+  // persistent variant
+  int m_tiles, n_tiles, acc_stages, tma_store, obufs, npad;
+  long long* prof;  // optional per-CTA cycle counters [grid][8] (debug / profiling builds of the plan)
 };
 
 // A fully prepared launch of the implicit-GEMM kernel.
 struct ConvLaunch {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmO;  // output map for the TMA-store epilogue (persistent variant)
   ConvKParams p;
   dim3 grid;
   size_t smem;
+  int variant;  // 0 = persistent (default), 1 = one tile per CTA
 };
 
 int set_error(ug_engine* h, int code, const char* fmt, ...);

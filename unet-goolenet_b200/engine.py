@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
                 ("act", _i), ("mode", _i), ("out", _vp), ("out_cstride", _i), ("up", _i), ("convt_cout", _i),
                 ("add", _vp), ("add_bstride", _ll), ("add_cstride", _i), ("gate", _vp), ("outc_w", _vp),
                 ("outc_b", _f), ("logits", _vp), ("mask", _vp),
-                ("TW", _i), ("TH", _i), ("TN", _i), ("BN", _i), ("stages", _i)]
+                ("TW", _i), ("TH", _i), ("TN", _i), ("BN", _i), ("stages", _i), ("variant", _i)]
 
 
 class IncIm2colDesc(C.Structure):
@@ -101,7 +101,7 @@ _SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_INC_IM2COL: "ug_inc_im2col", OP_POOL: "u
 
 EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
-                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_timed"]
+                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_timed", "ug_conv_profile"]
 
 _lib = None
 
@@ -124,6 +124,7 @@ def load_library():
     lib.ug_launch_count.restype = _ll
     for name in _SINGLE_ENTRY.values():
         getattr(lib, name).argtypes = [_vp, _vp, _vp]
+    lib.ug_conv_profile.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_double)]
     lib.ug_program_create.argtypes = [_vp, _vp, _i, C.POINTER(_vp)]
     lib.ug_program_run.argtypes = [_vp, _vp, _vp]
     lib.ug_program_num_launches.argtypes = [_vp]
@@ -220,6 +221,15 @@ class Engine:
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         fn = getattr(self.lib, _SINGLE_ENTRY[_DESC_KIND[type(desc)]])
         self._check(fn(self.handle, C.byref(desc), s))
+
+    def conv_profile(self, desc, stream=None):
+        """Per-role cycle counters of the persistent conv kernel for one op (see ug_conv_profile)."""
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        out = (C.c_double * 10)()
+        self._check(self.lib.ug_conv_profile(self.handle, C.byref(desc), s, out))
+        keys = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_acc", "epi_wait_acc", "epi_wait_obuf",
+                "epi_math", "epi_store", "ctas", "tiles_per_cta"]
+        return dict(zip(keys, list(out)))
 
     def program(self, descs, keepalive=()):
         return Program(self, descs, keepalive)

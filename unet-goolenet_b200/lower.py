@@ -60,7 +60,7 @@ class _Builder:
         scale, bias = pack.fold_bn(cb, _f32(sd[bn + ".weight"], self.dev), _f32(sd[bn + ".bias"], self.dev),
                                    _f32(sd[bn + ".running_mean"], self.dev), _f32(sd[bn + ".running_var"], self.dev),
                                    eps)
-        bn_tile = pack.choose_bn(wt.shape[0])
+        bn_tile = pack.choose_bn(wt.shape[0], r=wt.shape[2])
         self.w[key] = dict(w=pack.pack_conv_weight(wt, bn_tile), scale=scale, bias=bias, N=wt.shape[0],
                            Cin=wt.shape[1], R=wt.shape[2], BN=bn_tile)
         return self.w[key]

@@ -10,10 +10,13 @@ def round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def choose_bn(n_out, convt_cout=None):
-    """N-tile of the implicit-GEMM kernel (multiple of 16, <= 128 by default)."""
+def choose_bn(n_out, convt_cout=None, r=1):
+    """N-tile of the implicit-GEMM kernel (multiple of 16).  3x3 layers whose output width is a multiple of
+    256 use BN=256 (persistent kernel; halves the activation-tile traffic per FLOP), otherwise 128."""
     if convt_cout is not None:
         return min(128, convt_cout)
+    if r == 3 and n_out % 256 == 0:
+        return 256
     return 128 if n_out >= 128 else round_up(n_out, 16)
 
 
