@@ -71,7 +71,9 @@ typedef struct ug_conv_desc {
   unsigned char* mask;
   int TW, TH, TN, BN, stages; /* tiling; 0 = engine chooses */
   int variant;                /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel (TMEM multi-buffered
-                                 accumulators, TMA-store epilogue) */
+                                 accumulators, TMA-store epilogue); 3 / 4 = 3x3 halo kernel with 2 / 1
+                                 CTAs per SM (activation tile fetched once per 64-channel chunk for all
+                                 nine taps; see csrc/conv3x3_halo.cu) */
 } ug_conv_desc;
 
 /* x: fp32 NCHW [B,3,H,W] -> out: bf16 [B*H*W][64], column (r*3+s)*3+c = x[n,c,y+r-1,x+s-1] (0 outside),
@@ -217,6 +219,11 @@ long long ug_launch_count(ug_handle h);
  * epilogue wait-for-accumulator, epilogue wait-for-staging, epilogue math, epilogue store} in SM cycles,
  * plus out[8] = number of CTAs, out[9] = tiles per CTA (rounded up).  Synchronizes the stream. */
 int ug_conv_profile(ug_handle h, const ug_conv_desc* d, void* stream, double* out10);
+
+/* Micro-benchmark (sizing aid, not on the product path): average SM cycles per tcgen05.mma (M=128, N, K=16)
+ * with n_acc interleaved TMEM accumulators and ctas_per_sm co-resident CTAs. */
+int ug_mma_microbench(ug_handle h, int N, int n_acc, int iters, int ctas_per_sm, int distinct_ab,
+                      double* cycles_per_mma);
 
 /* Single ops (validated, tensor maps built per call) — used by the unit parity tests. */
 int ug_conv(ug_handle h, const ug_conv_desc* d, void* stream);

@@ -49,7 +49,7 @@ SHAPES = [(64, 224, 224, 64, 64, 3), (64, 112, 112, 128, 128, 3), (64, 56, 56, 2
           (64, 14, 14, 512, 512, 3), (64, 224, 224, 128, 64, 3)]
 if len(sys.argv) > 1:
     SHAPES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
-CONFIGS = [dict(variant=1), dict(variant=0), dict(variant=0, stages=3), dict(variant=0, bn=256), dict(variant=0, bn=64)]
+CONFIGS = [dict(variant=1), dict(variant=2, bn=256), dict(variant=3), dict(variant=4), dict(variant=3, bn=64), dict(variant=4, bn=256)]
 for shp in SHAPES:
     B, H, W, Cin, N, R = shp
     fl = 2.0 * B * H * W * N * Cin * R * R
@@ -60,7 +60,7 @@ for shp in SHAPES:
             d, keep = make(*shp, **cfg)
             ms = timeit(d)
             line = f"{shp} {cfg}: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s"
-            if cfg.get("variant", 0) == 0:
+            if cfg.get("variant", 0) == 2:
                 pr = eng.conv_profile(d)
                 line += " | " + " ".join(f"{k}={v:.0f}" for k, v in pr.items())
             print(line, flush=True)

@@ -131,7 +131,20 @@ CASES = [
     dict(B=2, H=32, W=48, Cin=64, N=64, R=3, mode=3, variant=2),   # persistent: fused outc
     dict(B=2, H=14, W=14, Cin=512, N=2048, R=1, up=2, act=0, variant=2),  # persistent: ConvTranspose direct stores
     dict(B=1, H=1, W=392, Cin=512, N=2048, R=1, act=2, variant=2),  # persistent: GELU
+    # 3x3 halo kernel: two CTAs per SM (3) and one CTA per SM with resident weights where they fit (4)
+    dict(B=2, H=28, W=28, Cin=128, N=256, R=3, variant=3),
+    dict(B=1, H=224, W=224, Cin=64, N=64, R=3, variant=3),
+    dict(B=2, H=56, W=56, Cin=256, N=128, R=3, mode=2, variant=3),
+    dict(B=2, H=32, W=48, Cin=64, N=64, R=3, mode=3, variant=3),
+    dict(B=2, H=14, W=14, Cin=24, N=64, R=3, in_extra=40, in_off=16, variant=3),
+    dict(B=3, H=14, W=14, Cin=256, N=208, R=3, out_extra=48, out_off=16, variant=3),
+    dict(B=2, H=20, W=36, Cin=192, N=96, R=3, mode=1, variant=3),
+    dict(B=2, H=16, W=16, Cin=64, N=64, R=3, variant=4),          # weights resident in smem
+    dict(B=2, H=56, W=56, Cin=256, N=512, R=3, bn=256, variant=4),
+    dict(B=5, H=7, W=7, Cin=160, N=320, R=3, variant=3),           # GoogLeNet 5a-like, tiny map
     # legacy one-tile-per-CTA variant stays covered
+    dict(B=2, H=16, W=16, Cin=64, N=64, R=3, variant=1),
+    dict(B=2, H=56, W=56, Cin=256, N=128, R=3, variant=1),
     dict(B=2, H=28, W=28, Cin=128, N=256, R=3, variant=1),
     dict(B=2, H=14, W=14, Cin=512, N=2048, R=1, up=2, act=0, variant=1),
     dict(B=2, H=32, W=48, Cin=64, N=64, R=3, mode=3, variant=1),

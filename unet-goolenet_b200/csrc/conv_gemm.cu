@@ -16,23 +16,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
-#include "common.cuh"
-#include "engine.h"
+#include "conv_common.cuh"
 
 namespace ug {
 
-static constexpr int kThreads = 192;
-static constexpr int kABytesPerStage = 128 * 128;  // 128 rows x 64 bf16
-
-// kAct is a template parameter on purpose: with a run-time activation switch the compiler if-converts the erf
-// polynomial of GELU into predicated code inside the unrolled per-element loop, and every ReLU epilogue then
-// issues ~40 dead instructions per element (measured: ~1500 cycles per 16-column chunk).
-template <int kAct>
-__device__ __forceinline__ float apply_act(float t) {
-  if constexpr (kAct == UG_ACT_RELU) return fmaxf(t, 0.0f);
-  else if constexpr (kAct == UG_ACT_GELU) return gelu_erf(t);
-  else return t;
-}
 
 template <int kAct>
 __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -232,30 +219,6 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
 // issuer run ahead across tile boundaries; accumulators are multi-buffered in TMEM (acc_stages x BN columns)
 // so the epilogue of tile i overlaps the main loop of tile i+1; plain/ADD/GATE epilogues stage the bf16 tile
 // in 128B-swizzled smem and write it with one TMA store per 64 channels (clipping handles ragged edges).
-template <int kAct>
-__device__ __forceinline__ void epi_math16(const uint32_t (&v)[16], float (&f)[16], const float* sScale,
-                                           const float* sBias, int col) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) f[j] = apply_act<kAct>(__uint_as_float(v[j]) * sScale[col + j] + sBias[col + j]);
-}
-
-__device__ __forceinline__ void epi_add_gate8(const ConvKParams& p, float* f, const __nv_bfloat16* add_ptr,
-                                              const float* gate_ptr) {
-  const uint4 a = *reinterpret_cast<const uint4*>(add_ptr);
-  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float e0 = bf16_lo(aw[j]), e1 = bf16_hi(aw[j]);
-    if (p.mode == UG_EPI_ADD) {
-      f[2 * j] += e0;
-      f[2 * j + 1] += e1;
-    } else {
-      f[2 * j] = e0 + f[2 * j] * (1.0f + __ldg(gate_ptr + 2 * j));
-      f[2 * j + 1] = e1 + f[2 * j + 1] * (1.0f + __ldg(gate_ptr + 2 * j + 1));
-    }
-  }
-}
-
 template <int kAct>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                            const __grid_constant__ CUtensorMap tmB,
@@ -522,7 +485,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
   void* p = nullptr;
@@ -598,6 +561,17 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
     if (!d->add || d->add_cstride % 8 || d->add_bstride % 8 || (reinterpret_cast<uintptr_t>(d->add) & 15))
       return set_error(h, UG_EINVAL, "conv: add tensor must be 16B aligned with strides multiple of 8");
     if (d->mode == UG_EPI_GATE && !d->gate) return set_error(h, UG_EINVAL, "conv: GATE epilogue needs gate");
+  }
+
+  if (d->variant == 3 || d->variant == 4) return conv_halo_prepare(h, d, BN, d->variant == 3 ? 2 : 1, L);
+  if (d->variant == 0 && d->R == 3 && up == 1) {
+    // measured choice (profiles/r01_conv_sweep.txt): halo kernel with two CTAs per SM for BN <= 128 on maps of
+    // at least 28x28, halo kernel with one CTA per SM for BN = 256 on maps of at least 56x56
+    int rc = UG_EUNSUPPORTED;
+    if (BN <= 128 && d->H * d->W >= 784) rc = conv_halo_prepare(h, d, BN, 2, L);
+    else if (BN == 256 && d->H * d->W >= 3136) rc = conv_halo_prepare(h, d, BN, 1, L);
+    if (rc == UG_OK) return rc;
+    if (rc != UG_EUNSUPPORTED) return rc;
   }
 
   int TW = d->TW, TH = d->TH, TN = d->TN;
@@ -736,6 +710,7 @@ int conv_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_gemm kernels)");
     attr_set = true;
   }
+  if (L->variant == 3) return conv_halo_launch(h, L, s);
   const int act = L->p.act;
   if (L->variant == 1) {
     if (act == UG_ACT_RELU) conv_gemm_kernel<UG_ACT_RELU><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->p);

@@ -48,7 +48,8 @@ struct ConvLaunch {
   ConvKParams p;
   dim3 grid;
   size_t smem;
-  int variant;  // 0 = persistent (default), 1 = one tile per CTA
+  int variant;  // 0 = persistent, 1 = one tile per CTA, 3 = 3x3 halo kernel
+  int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres;
 };
 
 int set_error(ug_engine* h, int code, const char* fmt, ...);
@@ -56,6 +57,8 @@ int check_cuda(ug_engine* h, cudaError_t e, const char* what);
 
 int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
 int conv_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
+int conv_halo_prepare(ug_engine* h, const ug_conv_desc* d, int BN, int mode, ConvLaunch* out);
+int conv_halo_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 
 int launch_inc_im2col(ug_engine* h, const ug_inc_im2col_desc* d, cudaStream_t s);
 int launch_pool(ug_engine* h, const ug_pool_desc* d, cudaStream_t s);

@@ -1,0 +1,89 @@
+// Micro-benchmarks used to size the conv kernels (not on the product path):
+//   ug_mma_microbench: cycles per tcgen05.mma (M=128, N, K=16, bf16, both operands in 128B-swizzled smem) when
+//   `n_acc` independent TMEM accumulators are interleaved and `n_cta` CTAs share an SM.
+#include "conv_common.cuh"
+
+namespace ug {
+
+__global__ void __launch_bounds__(128) mma_bench_kernel(int N, int n_acc, int iters, int distinct_ab, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  // A: 4 tiles x 16 KB, B: 4 tiles x N*128 B (zero-filled: values are irrelevant for timing)
+  for (int i = threadIdx.x; i < (4 * 16384 + 4 * N * 128) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  int cols = 32;
+  while (cols < n_acc * N) cols <<= 1;
+  if (warp == 1) {
+    tmem_alloc(&tmem_ptr, cols);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+  if (warp == 0 && lane == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 4 * 16384);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int buf = distinct_ab ? (it & 3) : 0;
+      const uint64_t ad = umma_desc_sw128(a0 + buf * 16384);
+      const uint64_t bd = umma_desc_sw128(b0 + buf * N * 128);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        for (int g = 0; g < n_acc; ++g) umma_bf16(tmem_base + g * N, ad + 2 * k, bd + 2 * k, idesc, 1u);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, cols);
+}
+
+}  // namespace ug
+
+extern "C" int ug_mma_microbench(ug_handle h, int N, int n_acc, int iters, int ctas_per_sm, int distinct_ab,
+                                 double* cycles_per_mma) {
+  if (!h || !cycles_per_mma || N % 16 || N < 16 || N > 256 || n_acc < 1 || n_acc * N > 512) return UG_EINVAL;
+  using namespace ug;
+  const int ctas = h->num_sms * ctas_per_sm;
+  long long* dev = nullptr;
+  if (cudaMalloc(&dev, sizeof(long long) * ctas) != cudaSuccess) return UG_ENOMEM;
+  const size_t smem = 1024 + 4 * 16384 + 4 * (size_t)N * 128;
+  cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaMemset(dev, 0, sizeof(long long) * ctas);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  mma_bench_kernel<<<ctas, 128, smem>>>(N, n_acc, 10, distinct_ab, dev);  // warm-up
+  cudaEventRecord(e0);
+  mma_bench_kernel<<<ctas, 128, smem>>>(N, n_acc, iters, distinct_ab, dev);
+  cudaEventRecord(e1);
+  int rc = check_cuda(h, cudaGetLastError(), "mma_bench launch");
+  if (rc == UG_OK) rc = check_cuda(h, cudaDeviceSynchronize(), "mma_bench");
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cycles_per_mma[1] = ms;  // wall time of the launch: tells whether co-resident CTAs overlapped
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc == UG_OK) {
+    std::vector<long long> host(ctas);
+    cudaMemcpy(host.data(), dev, sizeof(long long) * ctas, cudaMemcpyDeviceToHost);
+    double s = 0;
+    for (long long v : host) s += (double)v;
+    *cycles_per_mma = s / ctas / ((double)iters * 4 * n_acc);
+  }
+  cudaFree(dev);
+  return rc;
+}

@@ -101,7 +101,7 @@ _SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_INC_IM2COL: "ug_inc_im2col", OP_POOL: "u
 
 EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
-                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_timed", "ug_conv_profile"]
+                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_timed", "ug_conv_profile", "ug_mma_microbench"]
 
 _lib = None
 
@@ -124,6 +124,7 @@ def load_library():
     lib.ug_launch_count.restype = _ll
     for name in _SINGLE_ENTRY.values():
         getattr(lib, name).argtypes = [_vp, _vp, _vp]
+    lib.ug_mma_microbench.argtypes = [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]
     lib.ug_conv_profile.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_double)]
     lib.ug_program_create.argtypes = [_vp, _vp, _i, C.POINTER(_vp)]
     lib.ug_program_run.argtypes = [_vp, _vp, _vp]
