@@ -135,6 +135,7 @@ typedef struct ug_gate_desc {
   const float *w1, *b1, *w2, *b2, *w3, *b3;
   float* g;
   int B, C, HW, splits;
+  float* hid; /* scratch fp32 [B][C/2] (hidden layer, written then read by the two launches of this op) */
 } ug_gate_desc;
 
 /* mask u8 [B,H,W] -> boxes int32 [B][4] = {x_min, y_min, x_max, y_max} with roi.py:25-36 semantics

@@ -88,8 +88,10 @@ def test_chanstats_gate(engine, C, HW):
     b2 = torch.randn((C // 2,), generator=g, device="cuda")
     b3 = torch.randn((C,), generator=g, device="cuda")
     gout = torch.empty((B, C), device="cuda")
+    hid_buf = torch.empty((B, C // 2), device="cuda")
     engine.run_op(E.GateDesc(psum.data_ptr(), pmax.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                             b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), gout.data_ptr(), B, C, HW, splits))
+                             b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), gout.data_ptr(), B, C, HW, splits,
+                             hid_buf.data_ptr()))
     xf = x.float()
     avg, mx = xf.mean(1), xf.amax(1)
     assert torch.allclose(psum.sum(1) / HW, avg, rtol=1e-4, atol=1e-5)

@@ -151,9 +151,9 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float dot = 0.0f;
 
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      if (ncol0 + c0 >= p.N) break;  // warp-uniform
-      __syncwarp();                  // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
+    const int ncols = min(p.BN, p.N - ncol0);
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
       uint32_t v[16];
       tmem_ld16(taddr + c0, v);
       tmem_ld_wait();
@@ -167,27 +167,9 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         for (int j = 0; j < 16; ++j) dot += f[j] * __ldg(p.outc_w + ncol0 + c0 + j);
         continue;
       }
-      const int groups = !valid ? 0 : ((ncol0 + c0 + 16 <= p.N) ? 2 : 1);  // N is a multiple of 8
-      if (p.mode == UG_EPI_ADD || p.mode == UG_EPI_GATE) {
-        for (int g = 0; g < groups; ++g) {
-          const uint4 a = *reinterpret_cast<const uint4*>(add_row + c0 + g * 8);
-          const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float e0 = bf16_lo(aw[j]), e1 = bf16_hi(aw[j]);
-            float& f0 = f[g * 8 + 2 * j];
-            float& f1 = f[g * 8 + 2 * j + 1];
-            if (p.mode == UG_EPI_ADD) {
-              f0 += e0;
-              f1 += e1;
-            } else {
-              const float g0 = __ldg(gate_row + c0 + g * 8 + 2 * j);
-              const float g1 = __ldg(gate_row + c0 + g * 8 + 2 * j + 1);
-              f0 = e0 + f0 * (1.0f + g0);
-              f1 = e1 + f1 * (1.0f + g1);
-            }
-          }
-        }
+      const int groups = (c0 + 16 <= ncols) ? 2 : 1;  // N is a multiple of 8
+      if ((p.mode == UG_EPI_ADD || p.mode == UG_EPI_GATE) && valid) {
+        for (int g = 0; g < groups; ++g) epi_add_gate8(p, f + g * 8, add_row + c0 + g * 8, gate_row + c0 + g * 8);
       }
       for (int g = 0; g < groups; ++g) {
         uint4 o;
@@ -195,7 +177,9 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
         o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
         o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-        *reinterpret_cast<uint4*>(out_row + c0 + g * 8) = o;
+        // direct stores: each thread writes 16-byte pieces of its own pixel row.  A smem-staged, coalesced
+        // copy-out was measured slower here (profiles/r01_notes.md): L2 merges the partial-line writes.
+        if (valid) *reinterpret_cast<uint4*>(out_row + c0 + g * 8) = o;
       }
     }
     if (p.mode == UG_EPI_OUTC && valid) {
@@ -228,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_stage_bytes = p.BN * 128;
   const int n_sub = (p.BN + 63) / 64;
-  const int obuf_bytes = p.tma_store ? n_sub * kABytesPerStage : 0;
+  const int obuf_bytes = (p.tma_store || p.stage_copy) ? n_sub * kABytesPerStage : 0;
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.stages * kABytesPerStage;
   uint8_t* sO = sB + p.stages * b_stage_bytes;
@@ -427,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
           o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
           o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
           o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-          if (p.tma_store) {
+          if (p.tma_store || p.stage_copy) {
             const int col = c0 + g * 8;
             const int sub = col >> 6, chunk = (col & 63) >> 3;
             *reinterpret_cast<uint4*>(so_row + sub * kABytesPerStage + ((chunk ^ (row & 7)) << 4)) = o;
@@ -462,6 +446,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
           bulk_commit_group();
         }
         if (p.obufs == 2) obuf ^= 1;
+      } else if (p.stage_copy) {
+        // ConvTranspose pixel shuffle: every output pixel owns a contiguous run of `ncols` channels, so the
+        // staged tile is copied out with 16-byte stores that are contiguous across neighbouring threads.
+        named_bar_sync(1, 128);
+        const int cpr = ncols >> 3;  // 16-byte chunks per row
+        const int nrows = p.TW * p.TH * p.TN;
+        const uint8_t* sbuf = sO + obuf * obuf_bytes;
+        for (int idx = etid; idx < nrows * cpr; idx += 128) {
+          const int r2 = idx / cpr, ch = idx - r2 * cpr;
+          const int tx2 = r2 % p.TW, rest = r2 / p.TW;
+          const int x2 = x0 + tx2, y2 = y0 + rest % p.TH, n2 = n0 + rest / p.TH;
+          if (x2 >= p.W || y2 >= p.H || n2 >= p.B) continue;
+          const long long opix = (long long)(y2 * p.up + dy) * p.OW + (x2 * p.up + dx);
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                               ((long long)n2 * p.OH * p.OW + opix) * p.out_cstride + cbase + ch * 8;
+          const uint4 val = *reinterpret_cast<const uint4*>(sbuf + (ch >> 3) * kABytesPerStage + r2 * 128 +
+                                                            (((ch & 7) ^ (r2 & 7)) << 4));
+          *reinterpret_cast<uint4*>(dst) = val;
+        }
+        obuf ^= 1;  // two staging buffers: the barrier of the next tile orders reuse
       }
       if (p.prof) t_store += clock64() - tw0;
     }
@@ -590,11 +594,12 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   const int variant = d->variant == 1 ? 1 : (d->variant == 2 ? 0 : (BN == 256 ? 0 : 1));
   const int m_tiles_total = ceil_div(d->W, TW) * ceil_div(d->H, TH) * ceil_div(d->B, TN);
   const int tma_store = (variant == 0 && up == 1 && d->mode != UG_EPI_OUTC) ? 1 : 0;
+  const int stage_copy = (variant == 0 && up == 2) ? 1 : 0;
   const int n_sub = ceil_div(BN, 64);
-  const int obuf_bytes = tma_store ? n_sub * kABytesPerStage : 0;
+  const int obuf_bytes = (tma_store || stage_copy) ? n_sub * kABytesPerStage : 0;
   const int acc_stages = std::max(1, std::min(4, 512 / BN));
   const int npad = n_tiles * BN;
-  int obufs = tma_store ? 2 : 0;
+  int obufs = (variant == 0 && (tma_store || stage_copy)) ? 2 : 0;
   int stages = d->stages;
   const int per_stage = kABytesPerStage + BN * 128;
   if (variant == 1) {
@@ -639,7 +644,7 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   p.gate = d->gate; p.outc_w = d->outc_w; p.outc_b = d->outc_b;
   p.logits = d->logits; p.mask = d->mask;
   p.m_tiles = m_tiles_total; p.n_tiles = n_tiles; p.acc_stages = acc_stages;
-  p.tma_store = tma_store; p.obufs = obufs; p.npad = npad;
+  p.tma_store = tma_store; p.obufs = obufs; p.npad = npad; p.stage_copy = stage_copy;
   L->variant = variant;
   if (variant == 0) {
     int tcols = 32;

@@ -37,6 +37,7 @@ struct ConvKParams {
   unsigned char* mask;
   // persistent variant
   int m_tiles, n_tiles, acc_stages, tma_store, obufs, npad;
+  int stage_copy;  // ConvTranspose scatter: stage the tile in smem, then coalesced cooperative copy-out
   long long* prof;  // optional per-CTA cycle counters [grid][8] (debug / profiling builds of the plan)
 };
 

@@ -345,10 +345,14 @@ int launch_chanstats(ug_engine* h, const ug_chanstats_desc* d, cudaStream_t s) {
   return check_cuda(h, cudaGetLastError(), "chanstats launch");
 }
 
-// stage 2 + gate MLP: one block per image.
-__global__ void __launch_bounds__(256) gate_kernel(ug_gate_desc d) {
-  __shared__ float s_avg[512], s_max[512], s_hid[256];
-  const int n = blockIdx.x;
+// stage 2 + gate MLP.  Two launches so that each image is spread over kGateSplit blocks:
+//   gate_hidden_kernel: fold the partial sums/maxima, hid = relu(W1 avg + b1) + relu(W2 max + b2)   (slice of hid)
+//   gate_out_kernel:    g = sigmoid(W3 hid + b3)                                                     (slice of g)
+static constexpr int kGateSplit = 8;
+
+__global__ void __launch_bounds__(256) gate_hidden_kernel(ug_gate_desc d, float* __restrict__ hid_out) {
+  __shared__ float s_avg[512], s_max[512];
+  const int n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
     float a = 0.0f, b = -FLT_MAX;
@@ -362,23 +366,35 @@ __global__ void __launch_bounds__(256) gate_kernel(ug_gate_desc d) {
   }
   __syncthreads();
   const int hid = d.C / 2;
-  for (int j = warp; j < hid; j += 8) {
+  const int per = (hid + kGateSplit - 1) / kGateSplit;
+  const int j0 = blockIdx.x * per, j1 = min(hid, j0 + per);
+  for (int j = j0 + warp; j < j1; j += 8) {
     float a = 0.0f, b = 0.0f;
     for (int c = lane; c < d.C; c += 32) {
-      a += d.w1[(long long)j * d.C + c] * s_avg[c];
-      b += d.w2[(long long)j * d.C + c] * s_max[c];
+      a += __ldg(d.w1 + (long long)j * d.C + c) * s_avg[c];
+      b += __ldg(d.w2 + (long long)j * d.C + c) * s_max[c];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       a += __shfl_xor_sync(0xffffffffu, a, o);
       b += __shfl_xor_sync(0xffffffffu, b, o);
     }
-    if (lane == 0) s_hid[j] = fmaxf(a + d.b1[j], 0.0f) + fmaxf(b + d.b2[j], 0.0f);
+    if (lane == 0) hid_out[(long long)n * hid + j] = fmaxf(a + d.b1[j], 0.0f) + fmaxf(b + d.b2[j], 0.0f);
   }
+}
+
+__global__ void __launch_bounds__(256) gate_out_kernel(ug_gate_desc d, const float* __restrict__ hid_in) {
+  __shared__ float s_hid[256];
+  const int n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hid = d.C / 2;
+  for (int j = threadIdx.x; j < hid; j += blockDim.x) s_hid[j] = hid_in[(long long)n * hid + j];
   __syncthreads();
-  for (int c = warp; c < d.C; c += 8) {
+  const int per = (d.C + kGateSplit - 1) / kGateSplit;
+  const int c0 = blockIdx.x * per, c1 = min(d.C, c0 + per);
+  for (int c = c0 + warp; c < c1; c += 8) {
     float a = 0.0f;
-    for (int j = lane; j < hid; j += 32) a += d.w3[(long long)c * hid + j] * s_hid[j];
+    for (int j = lane; j < hid; j += 32) a += __ldg(d.w3 + (long long)c * hid + j) * s_hid[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) d.g[(long long)n * d.C + c] = 1.0f / (1.0f + expf(-(a + d.b3[c])));
@@ -386,11 +402,12 @@ __global__ void __launch_bounds__(256) gate_kernel(ug_gate_desc d) {
 }
 
 int launch_gate(ug_engine* h, const ug_gate_desc* d, cudaStream_t s) {
-  if (!d->psum || !d->pmax || !d->w1 || !d->w2 || !d->w3 || !d->b1 || !d->b2 || !d->b3 || !d->g || d->C > 512 ||
-      d->C % 2 || d->HW <= 0 || d->splits <= 0)
-    return set_error(h, UG_EINVAL, "gate: bad args (C <= 512)");
-  gate_kernel<<<d->B, 256, 0, s>>>(*d);
-  h->launches++;
+  if (!d->psum || !d->pmax || !d->w1 || !d->w2 || !d->w3 || !d->b1 || !d->b2 || !d->b3 || !d->g || !d->hid ||
+      d->C > 512 || d->C % 2 || d->HW <= 0 || d->splits <= 0)
+    return set_error(h, UG_EINVAL, "gate: bad args (C <= 512, hid scratch required)");
+  gate_hidden_kernel<<<dim3(kGateSplit, d->B), 256, 0, s>>>(*d, d->hid);
+  gate_out_kernel<<<dim3(kGateSplit, d->B), 256, 0, s>>>(*d, d->hid);
+  h->launches += 2;
   return check_cuda(h, cudaGetLastError(), "gate launch");
 }
 
@@ -570,52 +587,65 @@ int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s)
 
 // ------------------------------------------------------------------------------------------------
 // GoogLeNet conv1 im2col (7x7, stride 2, pad 3) with to_tensor and _transform_input folded in.
+// One block per (image, output row, segment of 56 output pixels): the 7 input rows it needs are staged in shared
+// memory as transformed floats (zero outside the image: padding is applied after the affine), then each thread
+// emits 16-byte groups; column (r*7+s)*3+c of pixel px is smem[r][6*px + s*3 + c], i.e. contiguous in (s,c).
+static constexpr int kG1Seg = 56;
+static constexpr int kG1RowFloats = (2 * kG1Seg + 5) * 3;  // 117 input pixels x 3 channels
+
 __global__ void __launch_bounds__(256) g1_im2col_kernel(const unsigned char* __restrict__ u8,
                                                         const float* __restrict__ f32, uint4* __restrict__ out,
                                                         int B, int S) {
+  __shared__ float sm[7][kG1RowFloats];
   const int OS = S / 2;
-  const long long total = (long long)B * OS * OS * 24;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int g = (int)(t % 24);
-  long long pp = t / 24;
-  const int ox = (int)(pp % OS);
-  pp /= OS;
-  const int oy = (int)(pp % OS);
-  const int n = (int)(pp / OS);
+  const int segs = (OS + kG1Seg - 1) / kG1Seg;
+  const int seg = blockIdx.x % segs;
+  const int oy = (blockIdx.x / segs) % OS;
+  const int n = blockIdx.x / (segs * OS);
+  const int ox0 = seg * kG1Seg;
+  const int ix0 = 2 * ox0 - 3;
   // torchvision GoogLeNet._transform_input: x_c * (std_c / 0.5) + (mean_c - 0.5) / 0.5
   const float sc[3] = {0.229f / 0.5f, 0.224f / 0.5f, 0.225f / 0.5f};
   const float sh[3] = {(0.485f - 0.5f) / 0.5f, (0.456f - 0.5f) / 0.5f, (0.406f - 0.5f) / 0.5f};
-  float v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int col = g * 8 + j;
+  for (int i = threadIdx.x; i < 7 * kG1RowFloats; i += blockDim.x) {
+    const int r = i / kG1RowFloats, e = i - r * kG1RowFloats;
+    const int px = e / 3, c = e - px * 3;
+    const int iy = 2 * oy + r - 3, ix = ix0 + px;
     float val = 0.0f;
-    if (col < 147) {
-      const int tap = col / 3, c = col - tap * 3;
-      const int r = tap / 7, s = tap - r * 7;
-      const int iy = 2 * oy + r - 3, ix = 2 * ox + s - 3;
-      if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
-        const float px = f32 ? __ldg(f32 + (((long long)n * 3 + c) * S + iy) * S + ix)
-                             : (float)u8[(((long long)n * S + iy) * S + ix) * 3 + c] / 255.0f;
-        val = px * sc[c] + sh[c];
-      }
+    if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
+      const float v = f32 ? __ldg(f32 + (((long long)n * 3 + c) * S + iy) * S + ix)
+                          : (float)u8[(((long long)n * S + iy) * S + ix) * 3 + c] / 255.0f;
+      val = v * sc[c] + sh[c];
     }
-    v[j] = val;
+    sm[r][e] = val;
   }
-  uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]);
-  o.y = pack_bf16x2(v[2], v[3]);
-  o.z = pack_bf16x2(v[4], v[5]);
-  o.w = pack_bf16x2(v[6], v[7]);
-  out[t] = o;
+  __syncthreads();
+  const int npx = min(kG1Seg, OS - ox0);
+  uint4* orow = out + (((long long)n * OS + oy) * OS + ox0) * 24;
+  for (int t = threadIdx.x; t < npx * 24; t += blockDim.x) {
+    const int px = t / 24, g = t - px * 24;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = g * 8 + j;
+      const int r = col / 21, rem = col - r * 21;
+      v[j] = col < 147 ? sm[r][6 * px + rem] : 0.0f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    orow[t] = o;
+  }
 }
 
 int launch_g1_im2col(ug_engine* h, const ug_g1_im2col_desc* d, cudaStream_t s) {
   if ((!d->u8 && !d->f32) || !d->out || d->B <= 0 || d->S <= 0 || d->S % 2)
     return set_error(h, UG_EINVAL, "g1_im2col: bad args");
-  const long long total = (long long)d->B * (d->S / 2) * (d->S / 2) * 24;
-  g1_im2col_kernel<<<cdiv(total, 256), 256, 0, s>>>(d->u8, d->f32, reinterpret_cast<uint4*>(d->out), d->B, d->S);
+  const int OS = d->S / 2;
+  const int segs = (OS + kG1Seg - 1) / kG1Seg;
+  g1_im2col_kernel<<<d->B * OS * segs, 256, 0, s>>>(d->u8, d->f32, reinterpret_cast<uint4*>(d->out), d->B, d->S);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "g1_im2col launch");
 }

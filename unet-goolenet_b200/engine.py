@@ -54,7 +54,7 @@ class ChanStatsDesc(C.Structure):
 
 class GateDesc(C.Structure):
     _fields_ = [("psum", _vp), ("pmax", _vp), ("w1", _vp), ("b1", _vp), ("w2", _vp), ("b2", _vp), ("w3", _vp),
-                ("b3", _vp), ("g", _vp), ("B", _i), ("C", _i), ("HW", _i), ("splits", _i)]
+                ("b3", _vp), ("g", _vp), ("B", _i), ("C", _i), ("HW", _i), ("splits", _i), ("hid", _vp)]
 
 
 class BBoxDesc(C.Structure):

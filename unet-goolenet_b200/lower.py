@@ -249,10 +249,10 @@ class UNetRunner(_Builder):
             psum, pmax = buf(B, S, C, dtype=torch.float32), buf(B, S, C, dtype=torch.float32)
             ops.append(E.ChanStatsDesc(e1.data_ptr(), C, C, B, size * size, S, psum.data_ptr(), pmax.data_ptr()))
             gw = self.w[blk + ".gate"]
-            g = buf(B, C, dtype=torch.float32)
+            g, hid = buf(B, C, dtype=torch.float32), buf(B, C // 2, dtype=torch.float32)
             ops.append(E.GateDesc(psum.data_ptr(), pmax.data_ptr(), gw["w1"].data_ptr(), gw["b1"].data_ptr(),
                                   gw["w2"].data_ptr(), gw["b2"].data_ptr(), gw["w3"].data_ptr(), gw["b3"].data_ptr(),
-                                  g.data_ptr(), B, C, size * size, S))
+                                  g.data_ptr(), B, C, size * size, S, hid.data_ptr()))
             self.conv(ops, self.w[blk + ".conv2_e"], View(cat, C, 0), geom, View(cat, C, C), mode=E.EPI_GATE,
                       add=View(e1), add_bstride=size * size * C, gate=g)
             n0 = buf(B, size, size, cout)
@@ -267,7 +267,7 @@ class UNetRunner(_Builder):
                 prev = n1
                 ws[blk] = n1
             psize = size
-            ws.setdefault("keep", []).extend([cat, e1, psum, pmax, g, n0])
+            ws.setdefault("keep", []).extend([cat, e1, psum, pmax, g, hid, n0])
         ws.setdefault("keep", []).extend([a0, X, M, xn, mn, qkv, att, m1, cq, ckv, catt, m_in, mln, hid, out0])
 
     def _emit_bbox(self, B, ws, ops, padding=30):
