@@ -221,27 +221,21 @@ def main():
     torch.manual_seed(1234)                                   # identical random-init replica on every rank
     unet_sd = UNetTaskAligWeight(3, 1).state_dict()
     gnet_sd = GoogLeNetClassifier(6).state_dict()
-    pipe = PipelineRunner(unet_sd, gnet_sd, dev, micro_batch=MB)
+    pipe = PipelineRunner(unet_sd, gnet_sd, dev, micro_batch=MB, cls_batch=PB)
     eng = pipe.engine
-    ws = pipe.plan(MB)
+    ws = pipe.plan(PB)            # one program per step: PB/MB UNet micro-batches + one GoogLeNet pass over PB crops
     prog = ws["program"]
-    n_mb = PB // MB
-    imgs = synth_batch(PB, 1234 + rank, dev)                  # this rank's slice of the global batch (HBM-resident)
-    out_masks = torch.empty((PB, 224, 224), dtype=torch.uint8, device=dev)
-    out_cls = torch.empty((PB, 6), dtype=torch.float32, device=dev)
+    imgs = synth_batch(PB, 1234 + rank, dev)                  # this rank's slice of the global batch
+    ws["x_in"].copy_(imgs)                                    # HBM-resident input of the program
     if world > 1:
         g_masks = torch.empty((world * PB, 224, 224), dtype=torch.uint8, device=dev)
         g_cls = torch.empty((world * PB, 6), dtype=torch.float32, device=dev)
 
     def step_device():
-        for m in range(n_mb):
-            ws["x_in"].copy_(imgs[m * MB:(m + 1) * MB])
-            prog.run()
-            out_masks[m * MB:(m + 1) * MB].copy_(ws["mask"])
-            out_cls[m * MB:(m + 1) * MB].copy_(ws["cls_logits"])
+        prog.run()
         if world > 1:                                          # the path's only collective (NVLink all-gather)
-            dist.all_gather_into_tensor(g_masks, out_masks)
-            dist.all_gather_into_tensor(g_cls, out_cls)
+            dist.all_gather_into_tensor(g_masks, ws["mask"])
+            dist.all_gather_into_tensor(g_cls, ws["cls_logits"])
 
     def timed(fn, steps):
         torch.cuda.synchronize()
@@ -279,10 +273,8 @@ def main():
     h_cls = torch.empty((PB, 6), dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        for m in range(n_mb):
-            sl = slice(m * MB, (m + 1) * MB)
-            prog.run_host([(ws["x_in"], h_in[sl])],
-                          [(h_masks[sl], ws["mask"]), (h_boxes[sl], ws["boxes"]), (h_cls[sl], ws["cls_logits"])])
+        prog.run_host([(ws["x_in"], h_in)],
+                      [(h_masks, ws["mask"]), (h_boxes, ws["boxes"]), (h_cls, ws["cls_logits"])])
 
     for _ in range(2):
         step_e2e()
@@ -306,7 +298,7 @@ def main():
     achieved = total_flop / (conv_ms / 1e3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": None,
-                "kernel": "conv_gemm_kernel", "launches_per_microbatch": n_conv,
+                "kernel": "conv_gemm_kernel", "launches_per_step": n_conv,
                 "avg_launch_ms": conv_ms / n_conv, "share_of_step": conv_ms / sum(per_op_ms),
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"}
 
@@ -334,7 +326,7 @@ def main():
         for t, d in zip(per_op_ms, prog.descs):
             kinds[type(d).__name__] = kinds.get(type(d).__name__, 0.0) + t
         with open(os.path.join(ROOT, "gpurun_out", f"bench_breakdown_n{world}.json"), "w") as f:
-            json.dump({"per_kind_ms_per_microbatch": kinds, "micro_batch": MB,
+            json.dump({"per_kind_ms_per_step": kinds, "images_per_step": PB, "micro_batch": MB,
                        "per_op": [{"i": i, "kind": type(d).__name__, "ms": t, "gflop": fl / 1e9,
                                    "tflops": (fl / (t / 1e3) / 1e12) if fl and t > 0 else None,
                                    "shape": ([d.B, d.H, d.W, d.Cin, d.N, d.R] if isinstance(d, E.ConvDesc) else None)}

@@ -115,6 +115,7 @@ typedef struct ug_attn_desc {
   int out_stride;
   int B, S, heads;
   float scale;
+  int variant; /* 0 = auto (mma.sync tensor-core kernel for S <= 208), 1 = fp32 CUDA-core kernel */
 } ug_attn_desc;
 
 /* AdaptiveAvgPool2d(1)/AdaptiveMaxPool2d(1) of an NHWC bf16 map (basicUnet.py:217-218), stage 1: each of

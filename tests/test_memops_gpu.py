@@ -56,20 +56,22 @@ def test_layernorm(engine):
     assert ((out.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-3).all()
 
 
-def test_attention(engine):
+@pytest.mark.parametrize("S,variant", [(196, 0), (196, 1), (50, 0), (208, 0), (240, 0)])
+def test_attention(engine, S, variant):
     from ugnet_b200 import engine as E
     g = _gen(4)
-    B, S, heads = 3, 196, 8
+    B, heads = 3, 8
     qkv = torch.randn((B * S, 1536), generator=g, device="cuda").to(torch.bfloat16)
     out = torch.empty((B * S, 512), device="cuda", dtype=torch.bfloat16)
     scale = 512 ** -0.5
     d = E.AttnDesc(qkv.data_ptr(), qkv.data_ptr() + 2 * 512, qkv.data_ptr() + 2 * 1024, 1536, 1536, 1536,
-                   out.data_ptr(), 512, B, S, heads, scale)
+                   out.data_ptr(), 512, B, S, heads, scale, variant)
     engine.run_op(d)
     q, k, v = [t.float().reshape(B, S, heads, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1)]
     att = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
     ref = (att @ v).permute(0, 2, 1, 3).reshape(B * S, 512)
-    assert ((out.float() - ref).abs() <= 2.0 ** -7 * ref.abs() + 2e-3).all()
+    # P is rounded to bf16 before the PV product in the tensor-core kernel: 2^-7 relative + small absolute
+    assert ((out.float() - ref).abs() <= 2.0 ** -7 * ref.abs() + 4e-3).all()
 
 
 @pytest.mark.parametrize("C,HW", [(64, 224 * 224), (128, 112 * 112), (256, 56 * 56), (512, 28 * 28)])

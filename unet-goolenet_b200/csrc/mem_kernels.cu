@@ -266,19 +266,148 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(ug_attn_desc d)
   }
 }
 
+// Tensor-core attention for S <= 208 tokens (the 14x14 bottleneck: S = 196), dim_head = 64.
+// One CTA (4 warps) per (image, head).  K (row-major, padded pitch) and V^T are staged in shared memory; each warp
+// owns 16-query slabs: S = Q K^T with mma.sync m16n8k16 (bf16 in, fp32 accumulate; the matrices are far too
+// small for tcgen05 tiles), fp32 softmax on the accumulator fragments, P re-used in registers as the A operand
+// of O = P V (accumulator layout of the first MMA == A-fragment layout of the second).
+static constexpr int kAttnSP = 208;           // padded sequence length (multiple of 16)
+static constexpr int kAttnKPitch = 72;        // bf16 elements per sK row  (144 B: conflict-free fragment loads)
+static constexpr int kAttnVPitch = kAttnSP + 8;  // bf16 elements per sVt row (432 B)
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) attention_mma_kernel(ug_attn_desc d) {
+  extern __shared__ uint4 attn_smem[];
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(attn_smem);   // [kAttnSP][kAttnKPitch]
+  __nv_bfloat16* sVt = sK + kAttnSP * kAttnKPitch;                    // [64][kAttnVPitch]
+  const int b = blockIdx.x / d.heads;
+  const int hd = blockIdx.x % d.heads;
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(d.q);
+  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(d.k);
+  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(d.v);
+  for (int i = threadIdx.x; i < kAttnSP * 8; i += blockDim.x) {
+    const int row = i >> 3, part = i & 7;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (row < d.S) {
+      const long long tok = (long long)b * d.S + row;
+      kv = *reinterpret_cast<const uint4*>(k + tok * d.k_stride + hd * 64 + part * 8);
+      vv = *reinterpret_cast<const uint4*>(v + tok * d.v_stride + hd * 64 + part * 8);
+    }
+    *reinterpret_cast<uint4*>(sK + row * kAttnKPitch + part * 8) = kv;
+    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sVt[(part * 8 + e) * kAttnVPitch + row] = ve[e];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float sl2 = d.scale * 1.4426950408889634f;
+  const int nslabs = (d.S + 15) / 16;
+  for (int slab = warp; slab < nslabs; slab += 4) {
+    const int r0 = slab * 16 + g, r1 = r0 + 8;
+    const long long tok0 = (long long)b * d.S + r0, tok1 = (long long)b * d.S + r1;
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int c = hd * 64 + kk * 16 + 2 * t;
+      qa[kk][0] = r0 < d.S ? __ldg(reinterpret_cast<const uint32_t*>(q + tok0 * d.q_stride + c)) : 0u;
+      qa[kk][1] = r1 < d.S ? __ldg(reinterpret_cast<const uint32_t*>(q + tok1 * d.q_stride + c)) : 0u;
+      qa[kk][2] = r0 < d.S ? __ldg(reinterpret_cast<const uint32_t*>(q + tok0 * d.q_stride + c + 8)) : 0u;
+      qa[kk][3] = r1 < d.S ? __ldg(reinterpret_cast<const uint32_t*>(q + tok1 * d.q_stride + c + 8)) : 0u;
+    }
+    float sc[kAttnSP / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < kAttnSP / 8; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.0f;
+      const __nv_bfloat16* krow = sK + (nt * 8 + g) * kAttnKPitch + 2 * t;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + kk * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + kk * 16 + 8);
+        mma_bf16_16816(sc[nt], qa[kk], b0, b1);
+      }
+    }
+    // fp32 softmax over the key axis (columns nt*8 + 2t, +1); rows g (c0,c1) and g+8 (c2,c3)
+    float m0 = -FLT_MAX, m1 = -FLT_MAX;
+#pragma unroll
+    for (int nt = 0; nt < kAttnSP / 8; ++nt) {
+      const int col = nt * 8 + 2 * t;
+      if (col >= d.S) sc[nt][0] = sc[nt][2] = -FLT_MAX;
+      if (col + 1 >= d.S) sc[nt][1] = sc[nt][3] = -FLT_MAX;
+      m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+      m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+    for (int nt = 0; nt < kAttnSP / 8; ++nt) {
+      sc[nt][0] = exp2f((sc[nt][0] - m0) * sl2);
+      sc[nt][1] = exp2f((sc[nt][1] - m0) * sl2);
+      sc[nt][2] = exp2f((sc[nt][2] - m1) * sl2);
+      sc[nt][3] = exp2f((sc[nt][3] - m1) * sl2);
+      l0 += sc[nt][0] + sc[nt][1];
+      l1 += sc[nt][2] + sc[nt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.0f;
+#pragma unroll
+    for (int kk = 0; kk < kAttnSP / 16; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+      pa[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+      pa[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const __nv_bfloat16* vrow = sVt + (nt * 8 + g) * kAttnVPitch + kk * 16 + 2 * t;
+        mma_bf16_16816(o[nt], pa, *reinterpret_cast<const uint32_t*>(vrow), *reinterpret_cast<const uint32_t*>(vrow + 8));
+      }
+    }
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = hd * 64 + nt * 8 + 2 * t;
+      if (r0 < d.S) *reinterpret_cast<uint32_t*>(out + tok0 * d.out_stride + c) = pack_bf16x2(o[nt][0] * i0, o[nt][1] * i0);
+      if (r1 < d.S) *reinterpret_cast<uint32_t*>(out + tok1 * d.out_stride + c) = pack_bf16x2(o[nt][2] * i1, o[nt][3] * i1);
+    }
+  }
+}
+
 int launch_attention(ug_engine* h, const ug_attn_desc* d, cudaStream_t s) {
   if (!d->q || !d->k || !d->v || !d->out || d->S <= 0 || d->S > kAttnThreads || d->heads <= 0 || d->B <= 0)
     return set_error(h, UG_EINVAL, "attention: bad args (S <= 256)");
   if (d->q_stride % 8 || d->k_stride % 8 || d->v_stride % 8 || d->out_stride % 8)
     return set_error(h, UG_EINVAL, "attention: row strides must be multiples of 8");
-  const size_t smem = (size_t)d->S * 8 * sizeof(uint4) * 2;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(attention_kernel)");
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(attention kernels)");
     attr_set = true;
   }
-  attention_kernel<<<d->B * d->heads, kAttnThreads, smem, s>>>(*d);
+  if (d->S <= kAttnSP && d->variant == 0) {
+    const size_t smem = (size_t)(kAttnSP * kAttnKPitch + 64 * kAttnVPitch) * sizeof(__nv_bfloat16);
+    attention_mma_kernel<<<d->B * d->heads, 128, smem, s>>>(*d);
+  } else {  // generic fp32 CUDA-core path (S up to 256)
+    const size_t smem = (size_t)d->S * 8 * sizeof(uint4) * 2;
+    attention_kernel<<<d->B * d->heads, kAttnThreads, smem, s>>>(*d);
+  }
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "attention launch");
 }

@@ -44,7 +44,7 @@ class LayerNormDesc(C.Structure):
 
 class AttnDesc(C.Structure):
     _fields_ = [("q", _vp), ("k", _vp), ("v", _vp), ("q_stride", _i), ("k_stride", _i), ("v_stride", _i),
-                ("out", _vp), ("out_stride", _i), ("B", _i), ("S", _i), ("heads", _i), ("scale", _f)]
+                ("out", _vp), ("out_stride", _i), ("B", _i), ("S", _i), ("heads", _i), ("scale", _f), ("variant", _i)]
 
 
 class ChanStatsDesc(C.Structure):

@@ -105,7 +105,30 @@ class _Builder:
         ops.append(d)
 
     def buf(self, *shape, dtype=torch.bfloat16):
-        return torch.empty(shape, device=self.dev, dtype=dtype)
+        """Workspace allocation.  Inside `with self.sharing(pool)` the i-th request of every pass returns the
+        same tensor (the emission order is deterministic), so several op lists can share one workspace."""
+        pool = getattr(self, "_pool", None)
+        if pool is None:
+            return torch.empty(shape, device=self.dev, dtype=dtype)
+        i = self._pool_i
+        self._pool_i += 1
+        if i == len(pool):
+            pool.append(torch.empty(shape, device=self.dev, dtype=dtype))
+        t = pool[i]
+        assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, "workspace replay out of sync"
+        return t
+
+    def sharing(self, pool):
+        builder = self
+
+        class _Ctx:
+            def __enter__(self):
+                builder._pool, builder._pool_i = pool, 0
+
+            def __exit__(self, *a):
+                builder._pool = None
+
+        return _Ctx()
 
 
 # =================================================================================================== UNet
@@ -171,12 +194,14 @@ class UNetRunner(_Builder):
                               b=float(sd["outc.bias"].float().item()))
 
     # ---------------------------------------------------------------------------- program
-    def _emit_unet(self, B, ws, ops):
-        """Append the ops of one UNet forward at batch B; `ws` receives the workspace tensors."""
+    def _emit_unet(self, B, ws, ops, io=None):
+        """Append the ops of one UNet forward at batch B; `ws` receives the workspace tensors.  `io` may supply
+        pre-allocated x_in / logits / mask tensors (slices of larger buffers)."""
         buf = self.buf
-        ws["x_in"] = buf(B, 3, IMG, IMG, dtype=torch.float32)
-        ws["logits"] = buf(B, 1, IMG, IMG, dtype=torch.float32)
-        ws["mask"] = buf(B, IMG, IMG, dtype=torch.uint8)
+        io = io or {}
+        ws["x_in"] = io["x_in"] if "x_in" in io else torch.empty((B, 3, IMG, IMG), device=self.dev)
+        ws["logits"] = io["logits"] if "logits" in io else torch.empty((B, 1, IMG, IMG), device=self.dev)
+        ws["mask"] = io["mask"] if "mask" in io else torch.empty((B, IMG, IMG), device=self.dev, dtype=torch.uint8)
         # ---- encoder (basicUnet.py:409-416)
         a0 = buf(B * IMG * IMG, 64)
         ops.append(E.IncIm2colDesc(ws["x_in"].data_ptr(), a0.data_ptr(), B, IMG, IMG))
@@ -270,8 +295,8 @@ class UNetRunner(_Builder):
             ws.setdefault("keep", []).extend([cat, e1, psum, pmax, g, hid, n0])
         ws.setdefault("keep", []).extend([a0, X, M, xn, mn, qkv, att, m1, cq, ckv, catt, m_in, mln, hid, out0])
 
-    def _emit_bbox(self, B, ws, ops, padding=30):
-        ws["boxes"] = self.buf(B, 4, dtype=torch.int32)
+    def _emit_bbox(self, B, ws, ops, padding=30, boxes=None):
+        ws["boxes"] = boxes if boxes is not None else torch.empty((B, 4), device=self.dev, dtype=torch.int32)
         ops.append(E.BBoxDesc(ws["mask"].data_ptr(), ws["boxes"].data_ptr(), B, IMG, IMG, padding))
 
     def plan(self, B, padding=30):
@@ -433,38 +458,70 @@ class GoogLeNetRunner(_Builder):
 
 # =============================================================================================== pipeline
 class PipelineRunner:
-    """UNet -> threshold -> bbox -> crop/resize -> GoogLeNet as one program per batch (no host round trip)."""
+    """UNet -> threshold -> bbox -> crop/resize -> GoogLeNet as ONE program per batch (no host round trip).
 
-    def __init__(self, unet_sd, googlenet_sd, dev, micro_batch=64, padding=30):
+    Two-level batching: the UNet stage runs in micro-batches (default 64 images, ~5 GB of activations, all
+    micro-batches share one workspace) that deposit masks, boxes and uint8 crops into batch-sized buffers; the
+    much lighter GoogLeNet stage then runs once over the whole batch (default up to 256 images), which keeps its
+    many small layers above one wave of tiles."""
+
+    def __init__(self, unet_sd, googlenet_sd, dev, micro_batch=64, padding=30, cls_batch=256):
         self.dev = torch.device(dev)
         self.unet = UNetRunner(unet_sd, self.dev, max_batch=micro_batch)
-        self.gnet = GoogLeNetRunner(googlenet_sd, self.dev, max_batch=micro_batch)
+        self.gnet = GoogLeNetRunner(googlenet_sd, self.dev, max_batch=cls_batch)
         self.engine = self.unet.engine
         self.micro_batch = micro_batch
+        self.cls_batch = max(cls_batch, micro_batch) // micro_batch * micro_batch
         self.padding = padding
         self.plans = {}
+        self._pools = {}
 
     def plan(self, B):
+        """Program for a batch of B images; B must be <= micro_batch or a multiple of it."""
         if B not in self.plans:
-            ws, ops = {}, []
-            self.unet._emit_unet(B, ws, ops)
-            self.unet._emit_bbox(B, ws, ops, self.padding)
-            ws["u8"] = self.unet.buf(B, IMG, IMG, 3, dtype=torch.uint8)
-            ops.append(E.CropResizeDesc(ws["x_in"].data_ptr(), ws["boxes"].data_ptr(), ws["u8"].data_ptr(), B, IMG,
-                                        IMG, IMG))
+            mb = min(B, self.micro_batch)
+            assert B % mb == 0
+            dev = self.dev
+            ws = dict(x_in=torch.empty((B, 3, IMG, IMG), device=dev),
+                      logits=torch.empty((B, 1, IMG, IMG), device=dev),
+                      mask=torch.empty((B, IMG, IMG), device=dev, dtype=torch.uint8),
+                      boxes=torch.empty((B, 4), device=dev, dtype=torch.int32),
+                      u8=torch.empty((B, IMG, IMG, 3), device=dev, dtype=torch.uint8))
+            ops = []
+            pool = self._pools.setdefault(mb, [])
+            for s in range(0, B, mb):
+                sl = slice(s, s + mb)
+                sub = {}
+                with self.unet.sharing(pool):
+                    self.unet._emit_unet(mb, sub, ops, io=dict(x_in=ws["x_in"][sl], logits=ws["logits"][sl],
+                                                               mask=ws["mask"][sl]))
+                self.unet._emit_bbox(mb, sub, ops, self.padding, boxes=ws["boxes"][sl])
+                ops.append(E.CropResizeDesc(ws["x_in"][sl].data_ptr(), ws["boxes"][sl].data_ptr(),
+                                            ws["u8"][sl].data_ptr(), mb, IMG, IMG, IMG))
+                ws.setdefault("sub", []).append(sub)
             self.gnet._emit_googlenet(B, ws, ops, u8=ws["u8"])
             ws["program"] = self.engine.program(ops)
             self.plans[B] = ws
         return self.plans[B]
 
+    def _chunks(self, n):
+        """Split n images into plan-able chunks: multiples of micro_batch up to cls_batch, then the remainder."""
+        out, s = [], 0
+        while n - s >= self.micro_batch:
+            c = min(self.cls_batch, (n - s) // self.micro_batch * self.micro_batch)
+            out.append((s, c))
+            s += c
+        if n - s:
+            out.append((s, n - s))
+        return out
+
     @torch.no_grad()
     def __call__(self, imgs, return_logits=False):
         """imgs: float [B,3,224,224] CUDA -> (masks u8 [B,224,224], boxes i32 [B,4], cls_logits f32 [B,6])."""
         masks, boxes, cls, seg = [], [], [], []
-        for s in range(0, imgs.shape[0], self.micro_batch):
-            xb = imgs[s:s + self.micro_batch]
-            ws = self.plan(xb.shape[0])
-            ws["x_in"].copy_(xb)
+        for s, c in self._chunks(imgs.shape[0]):
+            ws = self.plan(c)
+            ws["x_in"].copy_(imgs[s:s + c])
             ws["program"].run()
             masks.append(ws["mask"].clone())
             boxes.append(ws["boxes"].clone())

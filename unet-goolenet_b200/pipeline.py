@@ -8,7 +8,7 @@ from .lower import PipelineRunner
 
 
 class TwoStagePipeline:
-    def __init__(self, unet, classifier, micro_batch=64, padding=30):
+    def __init__(self, unet, classifier, micro_batch=64, padding=30, cls_batch=256):
         """unet: nets.UNetTaskAligWeight (or a reference-format state_dict); classifier: GoogLeNetClassifier
         (or its state_dict).  Both must live on the same CUDA device."""
         usd = unet if isinstance(unet, dict) else unet.state_dict()
@@ -16,7 +16,7 @@ class TwoStagePipeline:
         dev = next(iter(usd.values())).device if isinstance(unet, dict) else unet.outc.weight.device
         if torch.device(dev).type != "cuda":
             dev = torch.device("cuda", torch.cuda.current_device())
-        self.runner = PipelineRunner(usd, gsd, dev, micro_batch=micro_batch, padding=padding)
+        self.runner = PipelineRunner(usd, gsd, dev, micro_batch=micro_batch, padding=padding, cls_batch=cls_batch)
 
     @torch.no_grad()
     def __call__(self, imgs, return_logits=False):
