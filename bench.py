@@ -105,6 +105,11 @@ def conv_flops(descs):
             f = 2.0 * d.B * d.H * d.W * d.N * getattr(d, "algo_k", d.Cin * d.R * d.S)
             per_op.append(f)
             total += f
+        elif isinstance(d, E.StemDesc):
+            # fused stem convolutions: true reduction length 27 (inc 3x3x3) / 147 (conv1 7x7x3, stride 2)
+            f = 2.0 * d.B * d.H * d.W * 64 * 27 if d.kind == 0 else 2.0 * d.B * (d.H // 2) * (d.W // 2) * 64 * 147
+            per_op.append(f)
+            total += f
         else:
             per_op.append(0.0)
     return total, per_op
@@ -293,12 +298,14 @@ def main():
         for i, t in enumerate(prog.run_timed()):
             per_op_ms[i] += t / reps
     from ugnet_b200 import engine as E
-    conv_ms = sum(t for t, d in zip(per_op_ms, prog.descs) if isinstance(d, E.ConvDesc))
-    n_conv = sum(isinstance(d, E.ConvDesc) for d in prog.descs)
+    tc_kinds = (E.ConvDesc, E.StemDesc)                       # every tcgen05 implicit-GEMM launch
+    conv_ms = sum(t for t, d in zip(per_op_ms, prog.descs) if isinstance(d, tc_kinds))
+    n_conv = sum(isinstance(d, tc_kinds) for d in prog.descs)
     achieved = total_flop / (conv_ms / 1e3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": None,
-                "kernel": "conv_gemm_kernel", "launches_per_step": n_conv,
+                "kernel": "tcgen05 implicit-GEMM conv family (conv3x3_halo_kernel, conv_gemm_kernel, "
+                          "conv_gemm_persistent_kernel, stem_conv_kernel)", "launches_per_step": n_conv,
                 "avg_launch_ms": conv_ms / n_conv, "share_of_step": conv_ms / sum(per_op_ms),
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"}
 
@@ -329,7 +336,9 @@ def main():
             json.dump({"per_kind_ms_per_step": kinds, "images_per_step": PB, "micro_batch": MB,
                        "per_op": [{"i": i, "kind": type(d).__name__, "ms": t, "gflop": fl / 1e9,
                                    "tflops": (fl / (t / 1e3) / 1e12) if fl and t > 0 else None,
-                                   "shape": ([d.B, d.H, d.W, d.Cin, d.N, d.R] if isinstance(d, E.ConvDesc) else None)}
+                                   "shape": ([d.B, d.H, d.W, d.Cin, d.N, d.R] if isinstance(d, E.ConvDesc) else
+                                             ([d.B, d.H, d.W, 3, 64, 3 if d.kind == 0 else 7]
+                                              if isinstance(d, E.StemDesc) else None))}
                                   for i, (t, d, fl) in enumerate(zip(per_op_ms, prog.descs, per_op_flop))]}, f, indent=1)
         print(json.dumps(line))
     if world > 1:

@@ -168,6 +168,26 @@ typedef struct ug_g1_im2col_desc {
   const float* f32;
 } ug_g1_im2col_desc;
 
+/* Stem convolution fused with its im2col (no im2col matrix in HBM), N = 64 output channels, folded BN + ReLU:
+ *   kind 0: UNet inc (basicUnet.py:409; ConvBatchNorm :25-40): 3x3 s1 p1 on in_f32 = fp32 NCHW [B,3,H,W]
+ *           (also performs x.float(), :408); w = bf16 [64][64], column (r*3+s)*3+c, columns 27.. zero.
+ *   kind 1: GoogLeNet conv1 (torchvision BasicConv2d 7x7 s2 p3; 分类/test.py:68-73) on in_u8 = uint8 HWC
+ *           [B,H,W,3] (the ROI crop) or, if in_f32 is non-NULL, a float NCHW [B,3,H,W] image in [0,1];
+ *           to_tensor (/255) and _transform_input are applied before the zero padding;
+ *           w = bf16 [64][192], column r*22 + s*3 + c (column r*22+21 and columns 154.. zero).
+ * out: bf16 NHWC [B,OH,OW,out_cstride], channels [0,64); OH,OW = H,W (kind 0) or H/2,W/2 (kind 1). */
+typedef struct ug_stem_desc {
+  int kind;
+  const float* in_f32;
+  const unsigned char* in_u8;
+  const void* w;
+  const float* scale;
+  const float* bias;
+  void* out;
+  int out_cstride;
+  int B, H, W;
+} ug_stem_desc;
+
 /* AdaptiveAvgPool2d(1) + Linear(C, ncls): in NHWC bf16 [B][HW][C], w fp32 [ncls][C], logits fp32 [B][ncls]. */
 typedef struct ug_head_desc {
   const void* in;
@@ -188,7 +208,8 @@ enum {
   UG_OP_BBOX = 8,
   UG_OP_CROPRESIZE = 9,
   UG_OP_G1_IM2COL = 10,
-  UG_OP_HEAD = 11
+  UG_OP_HEAD = 11,
+  UG_OP_STEM = 12
 };
 
 typedef struct ug_op {
@@ -206,6 +227,7 @@ typedef struct ug_op {
     ug_cropresize_desc crop;
     ug_g1_im2col_desc g1;
     ug_head_desc head;
+    ug_stem_desc stem;
   } u;
 } ug_op;
 
@@ -226,6 +248,9 @@ int ug_conv_profile(ug_handle h, const ug_conv_desc* d, void* stream, double* ou
  * with n_acc interleaved TMEM accumulators and ctas_per_sm co-resident CTAs. */
 int ug_mma_microbench(ug_handle h, int N, int n_acc, int iters, int ctas_per_sm, int distinct_ab,
                       double* cycles_per_mma);
+/* Same, with `issuers` (1..4) warps of one CTA each issuing their own chain(s): out2[0] = cycles per MMA of one
+ * issuer, out2[1] = launch wall time in ms. */
+int ug_mma_microbench2(ug_handle h, int N, int n_acc, int issuers, int iters, int ctas_per_sm, double* out2);
 
 /* Single ops (validated, tensor maps built per call) — used by the unit parity tests. */
 int ug_conv(ug_handle h, const ug_conv_desc* d, void* stream);
@@ -239,6 +264,7 @@ int ug_bbox(ug_handle h, const ug_bbox_desc* d, void* stream);
 int ug_cropresize(ug_handle h, const ug_cropresize_desc* d, void* stream);
 int ug_g1_im2col(ug_handle h, const ug_g1_im2col_desc* d, void* stream);
 int ug_head(ug_handle h, const ug_head_desc* d, void* stream);
+int ug_stem(ug_handle h, const ug_stem_desc* d, void* stream);
 
 /* Programs: a validated op list with tensor maps and launch geometry prepared once; run = launches only. */
 int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out);

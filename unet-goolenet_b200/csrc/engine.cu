@@ -31,6 +31,7 @@ using namespace ug;
 struct PreparedOp {
   int kind;
   ConvLaunch conv;  // valid when kind == UG_OP_CONV
+  StemLaunch stem;  // valid when kind == UG_OP_STEM
   ug_op op;         // descriptor copy for the other kinds
 };
 
@@ -52,6 +53,12 @@ static int run_simple(ug_engine* h, const ug_op* op, cudaStream_t s) {
     case UG_OP_HEAD: return launch_head(h, &op->u.head, s);
     default: return set_error(h, UG_EINVAL, "unknown op kind %d", op->kind);
   }
+}
+
+static int run_prepared(ug_engine* h, const PreparedOp& po, cudaStream_t s) {
+  if (po.kind == UG_OP_CONV) return conv_launch(h, &po.conv, s);
+  if (po.kind == UG_OP_STEM) return stem_launch(h, &po.stem, s);
+  return run_simple(h, &po.op, s);
 }
 
 extern "C" {
@@ -89,6 +96,14 @@ int ug_conv(ug_handle h, const ug_conv_desc* d, void* stream) {
   int rc = conv_prepare(h, d, &L);
   if (rc != UG_OK) return rc;
   return conv_launch(h, &L, static_cast<cudaStream_t>(stream));
+}
+
+int ug_stem(ug_handle h, const ug_stem_desc* d, void* stream) {
+  if (!h || !d) return UG_EINVAL;
+  StemLaunch L;
+  int rc = stem_prepare(h, d, &L);
+  if (rc != UG_OK) return rc;
+  return stem_launch(h, &L, static_cast<cudaStream_t>(stream));
 }
 
 int ug_conv_profile(ug_handle h, const ug_conv_desc* d, void* stream, double* out10) {
@@ -154,7 +169,15 @@ int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out)
         delete p;
         return rc;
       }
-    } else if (po.kind < UG_OP_CONV || po.kind > UG_OP_HEAD) {
+    } else if (po.kind == UG_OP_STEM) {
+      int rc = stem_prepare(h, &ops[i].u.stem, &po.stem);
+      if (rc != UG_OK) {
+        std::string msg = h->last_error;
+        set_error(h, rc, "op %d: %s", i, msg.c_str());
+        delete p;
+        return rc;
+      }
+    } else if (po.kind < UG_OP_CONV || po.kind > UG_OP_STEM) {
       delete p;
       return set_error(h, UG_EINVAL, "op %d: unknown kind %d", i, po.kind);
     }
@@ -168,7 +191,7 @@ int ug_program_run(ug_handle h, ug_program p, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (size_t i = 0; i < p->ops.size(); ++i) {
     const PreparedOp& po = p->ops[i];
-    int rc = (po.kind == UG_OP_CONV) ? conv_launch(h, &po.conv, s) : run_simple(h, &po.op, s);
+    int rc = run_prepared(h, po, s);
     if (rc != UG_OK) {
       std::string msg = h->last_error;
       return set_error(h, rc, "op %zu: %s", i, msg.c_str());
@@ -188,7 +211,7 @@ int ug_program_run_timed(ug_handle h, ug_program p, void* stream, float* ms_per_
   cudaEventRecord(ev[0], s);
   for (size_t i = 0; i < n && rc == UG_OK; ++i) {
     const PreparedOp& po = p->ops[i];
-    rc = (po.kind == UG_OP_CONV) ? conv_launch(h, &po.conv, s) : run_simple(h, &po.op, s);
+    rc = run_prepared(h, po, s);
     cudaEventRecord(ev[i + 1], s);
   }
   if (rc == UG_OK) rc = check_cuda(h, cudaStreamSynchronize(s), "stream synchronize");

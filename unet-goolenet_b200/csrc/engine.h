@@ -53,6 +53,25 @@ struct ConvLaunch {
   int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres;
 };
 
+// Stem convolution (csrc/stem_conv.cu): kernel parameters and a prepared launch.
+struct StemParams {
+  const float* in_f32;
+  const unsigned char* in_u8;
+  const float* scale;
+  const float* bias;
+  int B, H, W;  // source image
+  int OH, OW;   // output map
+  int tiles_x, tiles_y, total_tiles;
+};
+struct StemLaunch {
+  alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmO;
+  StemParams p;
+  int kind;
+  unsigned grid;
+  size_t smem;
+};
+
 int set_error(ug_engine* h, int code, const char* fmt, ...);
 int check_cuda(ug_engine* h, cudaError_t e, const char* what);
 
@@ -60,6 +79,9 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
 int conv_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 int conv_halo_prepare(ug_engine* h, const ug_conv_desc* d, int BN, int mode, ConvLaunch* out);
 int conv_halo_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
+
+int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* out);
+int stem_launch(ug_engine* h, const StemLaunch* l, cudaStream_t s);
 
 int launch_inc_im2col(ug_engine* h, const ug_inc_im2col_desc* d, cudaStream_t s);
 int launch_pool(ug_engine* h, const ug_pool_desc* d, cudaStream_t s);

@@ -51,6 +51,54 @@ __global__ void __launch_bounds__(128) mma_bench_kernel(int N, int n_acc, int it
   if (warp == 1) tmem_dealloc(tmem_base, cols);
 }
 
+
+// Second form: `issuers` warps of ONE CTA each issue their own dependent MMA chain(s) (n_acc accumulators per
+// issuer, private A tile, shared B tile).  Answers whether several issuing threads of one CTA overlap the way
+// co-resident CTAs do.  The smem footprint is small (issuers*16 KB + N*128 B) so up to 4 CTAs fit per SM.
+__global__ void __launch_bounds__(128) mma_bench2_kernel(int N, int n_acc, int issuers, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t tmem_ptr;
+  for (int i = threadIdx.x; i < (issuers * 16384 + N * 128) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+  }
+  int cols = 32;
+  while (cols < issuers * n_acc * N) cols <<= 1;
+  if (warp == 0) {
+    tmem_alloc(&tmem_ptr, cols);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+  if (warp < issuers && lane == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    const uint64_t ad = umma_desc_sw128(smem_u32(smem + warp * 16384));
+    const uint64_t bd = umma_desc_sw128(smem_u32(smem + issuers * 16384));
+    const uint32_t d0 = tmem_base + warp * n_acc * N;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        for (int g = 0; g < n_acc; ++g) umma_bf16(d0 + g * N, ad + 2 * k, bd + 2 * k, idesc, 1u);
+    }
+    umma_commit(&bar[warp]);
+    mbar_wait(&bar[warp], 0);
+    const long long t1 = clock64();
+    if (warp == 0) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, cols);
+}
+
 }  // namespace ug
 
 extern "C" int ug_mma_microbench(ug_handle h, int N, int n_acc, int iters, int ctas_per_sm, int distinct_ab,
@@ -83,6 +131,43 @@ extern "C" int ug_mma_microbench(ug_handle h, int N, int n_acc, int iters, int c
     double s = 0;
     for (long long v : host) s += (double)v;
     *cycles_per_mma = s / ctas / ((double)iters * 4 * n_acc);
+  }
+  cudaFree(dev);
+  return rc;
+}
+
+extern "C" int ug_mma_microbench2(ug_handle h, int N, int n_acc, int issuers, int iters, int ctas_per_sm,
+                                  double* out2) {
+  if (!h || !out2 || N % 16 || N < 16 || N > 256 || n_acc < 1 || issuers < 1 || issuers > 4 ||
+      issuers * n_acc * N * ctas_per_sm > 512)
+    return UG_EINVAL;
+  using namespace ug;
+  const int ctas = h->num_sms * ctas_per_sm;
+  long long* dev = nullptr;
+  if (cudaMalloc(&dev, sizeof(long long) * ctas) != cudaSuccess) return UG_ENOMEM;
+  const size_t smem = 1024 + (size_t)issuers * 16384 + (size_t)N * 128;
+  cudaFuncSetAttribute(mma_bench2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaMemset(dev, 0, sizeof(long long) * ctas);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  mma_bench2_kernel<<<ctas, 128, smem>>>(N, n_acc, issuers, 10, dev);
+  cudaEventRecord(e0);
+  mma_bench2_kernel<<<ctas, 128, smem>>>(N, n_acc, issuers, iters, dev);
+  cudaEventRecord(e1);
+  int rc = check_cuda(h, cudaGetLastError(), "mma_bench2 launch");
+  if (rc == UG_OK) rc = check_cuda(h, cudaDeviceSynchronize(), "mma_bench2");
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  out2[1] = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc == UG_OK) {
+    std::vector<long long> host(ctas);
+    cudaMemcpy(host.data(), dev, sizeof(long long) * ctas, cudaMemcpyDeviceToHost);
+    double s = 0;
+    for (long long v : host) s += (double)v;
+    out2[0] = s / ctas / ((double)iters * 4 * n_acc);  // cycles per MMA of one issuer chain set
   }
   cudaFree(dev);
   return rc;

@@ -1,0 +1,274 @@
+// Stem convolutions (the two 3-input-channel layers) as fused implicit GEMMs on tcgen05: the im2col tile is
+// built directly in shared memory from the source image, so no im2col matrix ever reaches HBM.
+//
+//   kind 0  UNet `inc`  (basicUnet.py:409, ConvBatchNorm :25-40): 3x3, stride 1, pad 1 on fp32 NCHW [B,3,H,W]
+//           K index = (r*3+s)*3+c, 27 real columns, two K=16 MMAs (columns 27..31 are written as zeros).
+//   kind 1  GoogLeNet `conv1` (torchvision BasicConv2d 7x7, stride 2, pad 3) on the uint8 HWC crop (or a float
+//           NCHW image), with to_tensor (/255) and _transform_input applied before the zero padding.
+//           K index = r*22 + s*3 + c (each filter row is a run of 21 contiguous source values padded to 22 so
+//           that runs stay 4-byte aligned), 154 columns, ten K=16 MMAs.
+//
+// One CTA = 128 threads = one 16x8 tile of output pixels (thread t <-> pixel row t of the MMA <-> TMEM lane t),
+// N = 64 output channels.  Per tile: (kind 1: stage the transformed bf16 source patch in smem) -> every thread
+// writes its im2col row into the 128B-swizzled K-major A tile -> one thread issues the MMAs -> all threads read
+// their accumulator row from TMEM, apply folded BN + ReLU, stage the bf16 tile in swizzled smem -> TMA store.
+// The phases of one CTA are serial; several co-resident CTAs per SM (5 for inc, 2 for conv1) overlap them.
+// Both layers are bound by the 64-channel output write (128 B per pixel), not by the tensor pipe.
+#include <cstring>
+#include "conv_common.cuh"
+
+namespace ug {
+
+static constexpr int kStemTW = 16, kStemTH = 8;          // output tile
+static constexpr int kG1PatchW = 2 * kStemTW + 5;        // 37 source pixels
+static constexpr int kG1PatchH = 2 * kStemTH + 5;        // 21 source rows
+static constexpr int kG1PatchPitch = 112;                // bf16 elements per patch row (111 used); 56 words keeps
+                                                         // the 4-byte run copies of a warp on distinct banks
+
+template <int kKind>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ CUtensorMap tmB,
+                                                        const __grid_constant__ CUtensorMap tmO, const StemParams p) {
+  constexpr int kAtoms = kKind == 0 ? 1 : 3;             // 64-column swizzle atoms of the A / B tiles
+  constexpr int kKSteps = kKind == 0 ? 2 : 10;           // K=16 MMAs per tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                    // kAtoms x [128 rows][128 B]
+  uint8_t* sB = sA + kAtoms * kABytesPerStage;           // kAtoms x [64 rows][128 B]
+  uint8_t* sO = sB + kAtoms * 64 * 128;                  // [128 rows][128 B] output staging
+  __nv_bfloat16* sPatch = reinterpret_cast<__nv_bfloat16*>(sO + kABytesPerStage);
+  uint8_t* tail = reinterpret_cast<uint8_t*>(sPatch) + (kKind == 1 ? kG1PatchH * kG1PatchPitch * 2 : 0);
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* acc_full = b_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);
+  float* sBias = sScale + 64;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  if (tid == 0) {
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmO);
+    mbar_init(b_full, 1);
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 64);
+    tmem_relinquish();
+  }
+  if (tid < 64) {
+    sScale[tid] = p.scale ? p.scale[tid] : 1.0f;
+    sBias[tid] = p.bias ? p.bias[tid] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (tid == 0) {  // the whole weight matrix, once per CTA
+    mbar_arrive_expect_tx(b_full, (uint32_t)(kAtoms * 64 * 128));
+    for (int a = 0; a < kAtoms; ++a) tma_load_2d(sB + a * 64 * 128, &tmB, b_full, a * 64, 0);
+  }
+
+  const int tx = tid & (kStemTW - 1);
+  const int ty = tid >> 4;
+  uint8_t* a_row = sA + tid * 128;
+  uint8_t* o_row = sO + tid * 128;
+  const int sw = tid & 7;
+  const uint32_t idesc = umma_idesc_bf16(128, 64);
+  uint32_t acc_phase = 0;
+  bool b_ready = false;
+
+  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    const int x0 = (t % p.tiles_x) * kStemTW;
+    const int y0 = ((t / p.tiles_x) % p.tiles_y) * kStemTH;
+    const int n = t / (p.tiles_x * p.tiles_y);
+
+    if constexpr (kKind == 0) {
+      // ---- inc: 27 taps straight from the fp32 NCHW image (neighbouring threads share lines through L1)
+      const float* xn = p.in_f32 + (long long)n * 3 * p.H * p.W;
+      const int px = x0 + tx, py = y0 + ty;
+      float v[32];
+#pragma unroll
+      for (int i = 27; i < 32; ++i) v[i] = 0.0f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int iy = py + r - 1;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int ix = px + s - 1;
+          const bool in = (iy >= 0) && (iy < p.H) && (ix >= 0) && (ix < p.W);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            v[(r * 3 + s) * 3 + c] = in ? __ldg(xn + ((long long)c * p.H + iy) * p.W + ix) : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+        o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+        o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+        o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(a_row + ((g ^ sw) << 4)) = o;
+      }
+    } else {
+      // ---- conv1: stage the transformed source patch (zero outside the image), then copy seven 22-element runs
+      const float sc[3] = {0.229f / 0.5f, 0.224f / 0.5f, 0.225f / 0.5f};
+      const float sh[3] = {(0.485f - 0.5f) / 0.5f, (0.456f - 0.5f) / 0.5f, (0.406f - 0.5f) / 0.5f};
+      const int iy0 = 2 * y0 - 3, ix0 = 2 * x0 - 3;
+      for (int i = tid; i < kG1PatchH * kG1PatchPitch; i += 128) {
+        const int r = i / kG1PatchPitch, e = i - r * kG1PatchPitch;
+        const int px = e / 3, c = e - px * 3;
+        const int iy = iy0 + r, ix = ix0 + px;
+        float val = 0.0f;
+        if (px < kG1PatchW && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+          const float f = p.in_f32 ? __ldg(p.in_f32 + (((long long)n * 3 + c) * p.H + iy) * p.W + ix)
+                                   : (float)p.in_u8[(((long long)n * p.H + iy) * p.W + ix) * 3 + c] / 255.0f;
+          val = f * sc[c] + sh[c];
+        }
+        sPatch[i] = __float2bfloat16_rn(val);
+      }
+      __syncthreads();
+      uint32_t w[80];
+#pragma unroll
+      for (int r = 0; r < 7; ++r) {
+        const uint32_t* src =
+            reinterpret_cast<const uint32_t*>(sPatch + (2 * ty + r) * kG1PatchPitch + 6 * tx);
+#pragma unroll
+        for (int i = 0; i < 11; ++i) w[r * 11 + i] = src[i];
+      }
+      w[77] = w[78] = w[79] = 0u;
+#pragma unroll
+      for (int j = 0; j < 20; ++j) {
+        const uint4 o = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        *reinterpret_cast<uint4*>(a_row + (j >> 3) * kABytesPerStage + (((j & 7) ^ sw) << 4)) = o;
+      }
+    }
+    // the TMA store of the previous tile must have finished reading the staging buffer before it is rewritten
+    if (tid == 0) bulk_wait_group_read<0>();
+    fence_proxy_async_smem();  // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      if (!b_ready) {
+        mbar_wait(b_full, 0);
+        b_ready = true;
+      }
+#pragma unroll
+      for (int k = 0; k < kKSteps; ++k) {
+        const uint64_t ad = umma_desc_sw128(smem_u32(sA + (k >> 2) * kABytesPerStage)) + 2 * (k & 3);
+        const uint64_t bd = umma_desc_sw128(smem_u32(sB + (k >> 2) * 64 * 128)) + 2 * (k & 3);
+        umma_bf16(tmem_base, ad, bd, idesc, k != 0 ? 1u : 0u);
+      }
+      umma_commit(acc_full);
+    }
+    mbar_wait(acc_full, acc_phase);
+    acc_phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: folded BN + ReLU, bf16, swizzled staging, TMA store of the 16x8x64 tile
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c0, v);
+      tmem_ld_wait();
+      float f[16];
+      epi_math16<UG_ACT_RELU>(v, f, sScale, sBias, c0);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+        o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+        o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+        o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(o_row + ((((c0 >> 3) + g) ^ sw) << 4)) = o;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();  // staging complete; every TMEM read of this accumulator is done
+    if (tid == 0) {
+      tma_store_4d(&tmO, sO, 0, x0, y0, n);
+      bulk_commit_group();
+    }
+  }
+  if (tid == 0) bulk_wait_group_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+
+int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* L) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return set_error(h, UG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (d->kind != 0 && d->kind != 1) return set_error(h, UG_EINVAL, "stem: kind must be 0 (inc) or 1 (conv1)");
+  if (!d->w || !d->out || d->B <= 0 || d->H <= 0 || d->W <= 0) return set_error(h, UG_EINVAL, "stem: bad args");
+  if (d->kind == 0 && !d->in_f32) return set_error(h, UG_EINVAL, "stem(inc): fp32 NCHW input required");
+  if (d->kind == 1 && !d->in_f32 && !d->in_u8) return set_error(h, UG_EINVAL, "stem(conv1): no input");
+  if (d->kind == 1 && ((d->H | d->W) & 1)) return set_error(h, UG_EINVAL, "stem(conv1): even image size required");
+  if (d->out_cstride % 8 || d->out_cstride < 64 || (reinterpret_cast<uintptr_t>(d->out) & 15) ||
+      (reinterpret_cast<uintptr_t>(d->w) & 15))
+    return set_error(h, UG_EINVAL, "stem: out/w must be 16B aligned, channel stride a multiple of 8 (>= 64)");
+  const int OH = d->kind == 0 ? d->H : d->H / 2, OW = d->kind == 0 ? d->W : d->W / 2;
+  const int katoms = d->kind == 0 ? 1 : 3;
+  memset(L, 0, sizeof(*L));
+  L->kind = d->kind;
+  StemParams& p = L->p;
+  p.in_f32 = d->in_f32; p.in_u8 = d->in_u8; p.scale = d->scale; p.bias = d->bias;
+  p.B = d->B; p.H = d->H; p.W = d->W; p.OH = OH; p.OW = OW;
+  p.tiles_x = (OW + kStemTW - 1) / kStemTW;
+  p.tiles_y = (OH + kStemTH - 1) / kStemTH;
+  p.total_tiles = p.tiles_x * p.tiles_y * d->B;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)katoms * 64, 64};
+    cuuint64_t strides[1] = {(cuuint64_t)katoms * 64 * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "stem: weight tensor map encode failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t dims[4] = {64, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->out_cstride * 2, (cuuint64_t)OW * d->out_cstride * 2,
+                             (cuuint64_t)OH * OW * d->out_cstride * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)kStemTW, (cuuint32_t)kStemTH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&L->tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "stem: output tensor map encode failed (%d)", (int)r);
+  }
+  const int ctas_per_sm = d->kind == 0 ? 5 : 2;
+  L->grid = (unsigned)std::min<long long>(p.total_tiles, (long long)h->num_sms * ctas_per_sm);
+  L->smem = 1024 + (size_t)katoms * kABytesPerStage + (size_t)katoms * 64 * 128 + kABytesPerStage +
+            (d->kind == 1 ? kG1PatchH * kG1PatchPitch * 2 : 0) + 16 + 8 + 2 * 64 * sizeof(float);
+  return UG_OK;
+}
+
+int stem_launch(ug_engine* h, const StemLaunch* L, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)stem_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         100 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute((const void*)stem_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               110 * 1024);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(stem_conv_kernel)");
+    attr_set = true;
+  }
+  if (L->kind == 0) stem_conv_kernel<0><<<L->grid, 128, L->smem, s>>>(L->tmB, L->tmO, L->p);
+  else stem_conv_kernel<1><<<L->grid, 128, L->smem, s>>>(L->tmB, L->tmO, L->p);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "stem_conv_kernel launch");
+}
+
+}  // namespace ug

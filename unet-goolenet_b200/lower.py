@@ -147,7 +147,7 @@ class UNetRunner(_Builder):
     # ---------------------------------------------------------------------------- weights
     def _pack(self):
         sd, dev = self.sd, self.dev
-        # inc: 3x3 conv on 3 channels as a K=64 GEMM over the im2col matrix, column = (r*3+s)*3 + c
+        # inc: 3x3 conv on 3 channels, GEMM weight [64][64], column = (r*3+s)*3 + c (27 real columns)
         wt = _f32(sd["inc.conv.weight"], dev)                       # [64, 3, 3, 3]
         scale, bias = pack.fold_bn(_f32(sd["inc.conv.bias"], dev), _f32(sd["inc.norm.weight"], dev),
                                    _f32(sd["inc.norm.bias"], dev), _f32(sd["inc.norm.running_mean"], dev),
@@ -203,10 +203,10 @@ class UNetRunner(_Builder):
         ws["logits"] = io["logits"] if "logits" in io else torch.empty((B, 1, IMG, IMG), device=self.dev)
         ws["mask"] = io["mask"] if "mask" in io else torch.empty((B, IMG, IMG), device=self.dev, dtype=torch.uint8)
         # ---- encoder (basicUnet.py:409-416)
-        a0 = buf(B * IMG * IMG, 64)
-        ops.append(E.IncIm2colDesc(ws["x_in"].data_ptr(), a0.data_ptr(), B, IMG, IMG))
-        x1 = buf(B, IMG, IMG, 64)
-        self.conv(ops, self.w["inc"], View(a0), (1, 1, B * IMG * IMG), View(x1))
+        x1 = buf(B, IMG, IMG, 64)                                    # inc: im2col built in smem (stem_conv.cu)
+        wi = self.w["inc"]
+        ops.append(E.StemDesc(0, ws["x_in"].data_ptr(), None, wi["w"].data_ptr(), wi["scale"].data_ptr(),
+                              wi["bias"].data_ptr(), x1.data_ptr(), 64, B, IMG, IMG))
         skips = [x1]
         cur, size, cin = x1, IMG, 64
         for blk, cout in (("down1", 128), ("down2", 256), ("down3", 512), ("down4", 512)):
@@ -293,7 +293,7 @@ class UNetRunner(_Builder):
                 ws[blk] = n1
             psize = size
             ws.setdefault("keep", []).extend([cat, e1, psum, pmax, g, hid, n0])
-        ws.setdefault("keep", []).extend([a0, X, M, xn, mn, qkv, att, m1, cq, ckv, catt, m_in, mln, hid, out0])
+        ws.setdefault("keep", []).extend([X, M, xn, mn, qkv, att, m1, cq, ckv, catt, m_in, mln, hid, out0])
 
     def _emit_bbox(self, B, ws, ops, padding=30, boxes=None):
         ws["boxes"] = boxes if boxes is not None else torch.empty((B, 4), device=self.dev, dtype=torch.int32)
@@ -354,14 +354,16 @@ class GoogLeNetRunner(_Builder):
 
     def _pack(self):
         sd, dev = self.sd, self.dev
-        # conv1 7x7 s2 as a K=192 GEMM over the im2col matrix, column = (r*7+s)*3 + c
+        # conv1 7x7 s2: GEMM weight [64][192], column r*22 + s*3 + c (each filter row padded 21 -> 22, see
+        # ug_stem_desc); 154 real columns
         wt = _f32(sd["conv1.conv.weight"], dev)                     # [64,3,7,7]
         scale, bias = pack.fold_bn(None, _f32(sd["conv1.bn.weight"], dev), _f32(sd["conv1.bn.bias"], dev),
                                    _f32(sd["conv1.bn.running_mean"], dev), _f32(sd["conv1.bn.running_var"], dev),
                                    self.EPS)
-        gemm = wt.permute(0, 2, 3, 1).reshape(64, 147)
-        self.w["conv1"] = dict(w=pack.pack_linear_weight(gemm, 64), scale=scale, bias=bias, N=64, Cin=192, R=1,
-                               BN=64, algo_k=147)
+        gemm = torch.zeros(64, 7, 22, device=dev)
+        gemm[:, :, :21] = wt.permute(0, 2, 3, 1).reshape(64, 7, 21)
+        self.w["conv1"] = dict(w=pack.pack_linear_weight(gemm.reshape(64, 154), 64), scale=scale, bias=bias, N=64,
+                               Cin=192, R=1, BN=64, algo_k=147)
         self.conv_bn("conv2", "conv2.conv", "conv2.bn", self.EPS)
         self.conv_bn("conv3", "conv3.conv", "conv3.bn", self.EPS)
         for name in _INCEPTION_CFG:
@@ -373,10 +375,10 @@ class GoogLeNetRunner(_Builder):
     def _emit_googlenet(self, B, ws, ops, u8=None, f32=None):
         """u8: [B,224,224,3] uint8 crops (HWC, channel order as the reference's roi_rgb), or f32: float NCHW."""
         buf = self.buf
-        a1 = buf(B * 112 * 112, 192)
-        ops.append(E.G1Im2colDesc(E.ptr(u8), a1.data_ptr(), B, IMG, E.ptr(f32)))
-        c1 = buf(B, 112, 112, 64)
-        self.conv(ops, self.w["conv1"], View(a1), (1, 1, B * 112 * 112), View(c1))
+        c1 = buf(B, 112, 112, 64)                                    # conv1: im2col built in smem (stem_conv.cu)
+        w1 = self.w["conv1"]
+        ops.append(E.StemDesc(1, E.ptr(f32), E.ptr(u8), w1["w"].data_ptr(), w1["scale"].data_ptr(),
+                              w1["bias"].data_ptr(), c1.data_ptr(), 64, B, IMG, IMG))
         p1 = buf(B, 56, 56, 64)
         ops.append(E.PoolDesc(c1.data_ptr(), 64, p1.data_ptr(), 64, 64, B, 112, 112, 56, 56, 3, 2, 0))
         c2 = buf(B, 56, 56, 64)
@@ -385,7 +387,7 @@ class GoogLeNetRunner(_Builder):
         self.conv(ops, self.w["conv3"], View(c2), (B, 56, 56), View(c3))
         cur = buf(B, 28, 28, 192)
         ops.append(E.PoolDesc(c3.data_ptr(), 192, cur.data_ptr(), 192, 192, B, 56, 56, 28, 28, 3, 2, 0))
-        keep = [a1, c1, p1, c2, c3, cur]
+        keep = [c1, p1, c2, c3, cur]
         size = 28
         for name, (cin, c1x1, c3r, c3x3, c5r, c5x5, pp, sp) in _INCEPTION_CFG.items():
             if sp != size:                                           # maxpool3 (3,s2,ceil) / maxpool4 (2,s2,ceil)
