@@ -73,7 +73,8 @@ typedef struct ug_conv_desc {
   int variant;                /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel (TMEM multi-buffered
                                  accumulators, TMA-store epilogue); 3 / 4 = 3x3 halo kernel with 2 / 1
                                  CTAs per SM (activation tile fetched once per 64-channel chunk for all
-                                 nine taps; see csrc/conv3x3_halo.cu) */
+                                 nine taps; see csrc/conv3x3_halo.cu); 5 = 3x3 multi-issuer kernel (one CTA per
+                                 SM, two MMA issuers sharing resident or streamed weights, conv3x3_multi.cu) */
 } ug_conv_desc;
 
 /* x: fp32 NCHW [B,3,H,W] -> out: bf16 [B*H*W][64], column (r*3+s)*3+c = x[n,c,y+r-1,x+s-1] (0 outside),
@@ -243,14 +244,21 @@ long long ug_launch_count(ug_handle h);
  * epilogue wait-for-accumulator, epilogue wait-for-staging, epilogue math, epilogue store} in SM cycles,
  * plus out[8] = number of CTAs, out[9] = tiles per CTA (rounded up).  Synchronizes the stream. */
 int ug_conv_profile(ug_handle h, const ug_conv_desc* d, void* stream, double* out10);
+/* Same for the multi-issuer 3x3 kernel (variant 5), averages over CTAs: out[0..3] = producer {wait activation slot,
+ * wait weight slot, total cycles, total ns (globaltimer)}; out[4..7] / out[8..11] = issuer 0 / 1 {wait activations,
+ * wait weights, wait accumulator, total cycles}; out[12..15] = epilogue group 0 {wait accumulator, wait staging,
+ * total cycles, tiles}. */
+int ug_conv_profile16(ug_handle h, const ug_conv_desc* d, void* stream, double* out16);
 
 /* Micro-benchmark (sizing aid, not on the product path): average SM cycles per tcgen05.mma (M=128, N, K=16)
  * with n_acc interleaved TMEM accumulators and ctas_per_sm co-resident CTAs. */
 int ug_mma_microbench(ug_handle h, int N, int n_acc, int iters, int ctas_per_sm, int distinct_ab,
                       double* cycles_per_mma);
 /* Same, with `issuers` (1..4) warps of one CTA each issuing their own chain(s): out2[0] = cycles per MMA of one
- * issuer, out2[1] = launch wall time in ms. */
-int ug_mma_microbench2(ug_handle h, int N, int n_acc, int issuers, int iters, int ctas_per_sm, double* out2);
+ * issuer, out2[1] = launch wall time in ms.  The A descriptor starts a_off bytes (multiple of 128) into its tile
+ * with 8-row groups a_sbo bytes apart (0 / 1024 = plain tile; 128..256 / 1280 = the 3x3 halo layout). */
+int ug_mma_microbench2(ug_handle h, int N, int n_acc, int issuers, int iters, int ctas_per_sm, int a_off, int a_sbo,
+                       int acc_stride /* TMEM columns between the issuers' accumulators, 0 = packed */, double* out2);
 
 /* Single ops (validated, tensor maps built per call) — used by the unit parity tests. */
 int ug_conv(ug_handle h, const ug_conv_desc* d, void* stream);

@@ -45,11 +45,16 @@ def timeit(d, n=5):
     return e0.elapsed_time(e1) / n
 
 
-SHAPES = [(64, 224, 224, 64, 64, 3), (64, 112, 112, 128, 128, 3), (64, 56, 56, 256, 256, 3), (64, 28, 28, 512, 512, 3),
-          (64, 14, 14, 512, 512, 3), (64, 224, 224, 128, 64, 3)]
+SHAPES = [(64, 224, 224, 64, 64, 3), (64, 224, 224, 128, 64, 3), (64, 112, 112, 64, 128, 3), (64, 112, 112, 128, 128, 3),
+          (64, 112, 112, 256, 64, 3), (64, 56, 56, 256, 256, 3), (64, 56, 56, 512, 128, 3), (64, 28, 28, 512, 512, 3),
+          (64, 28, 28, 1024, 256, 3), (64, 14, 14, 512, 512, 3), (256, 56, 56, 64, 192, 3), (256, 28, 28, 128, 192, 3)]
 if len(sys.argv) > 1:
     SHAPES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
-CONFIGS = [dict(variant=1), dict(variant=2, bn=256), dict(variant=3), dict(variant=4), dict(variant=3, bn=64), dict(variant=4, bn=256)]
+if __name__ != "__main__":
+    SHAPES = []
+CONFIGS = [dict(variant=2, bn=256), dict(variant=3), dict(variant=4, bn=256), dict(variant=5), dict(variant=5, mode=2)]
+if os.environ.get("UG_ABLATE"):
+    CONFIGS = [dict(variant=5)] + [dict(variant=5, stages=100 + f) for f in (1, 2, 3, 4, 7)]
 for shp in SHAPES:
     B, H, W, Cin, N, R = shp
     fl = 2.0 * B * H * W * N * Cin * R * R
@@ -63,6 +68,10 @@ for shp in SHAPES:
             if cfg.get("variant", 0) == 2:
                 pr = eng.conv_profile(d)
                 line += " | " + " ".join(f"{k}={v:.0f}" for k, v in pr.items())
+            if cfg.get("variant", 0) == 5:
+                pr = eng.conv_profile16(d)
+                line += f" | clk {pr['prod_cycles'] / max(pr['prod_ns'], 1):.3f} GHz " + " ".join(
+                    f"{k}={v:.0f}" for k, v in pr.items())
             print(line, flush=True)
         except Exception as ex:
             print(shp, cfg, "ERR", ex, flush=True)

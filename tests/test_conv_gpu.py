@@ -142,6 +142,19 @@ CASES = [
     dict(B=2, H=16, W=16, Cin=64, N=64, R=3, variant=4),          # weights resident in smem
     dict(B=2, H=56, W=56, Cin=256, N=512, R=3, bn=256, variant=4),
     dict(B=5, H=7, W=7, Cin=160, N=320, R=3, variant=3),           # GoogLeNet 5a-like, tiny map
+    # 3x3 multi-issuer kernel (one CTA per SM, two MMA issuers sharing the weights)
+    dict(B=1, H=224, W=224, Cin=64, N=64, R=3, variant=5),        # weights resident, 392 tiles over 148 CTAs
+    dict(B=3, H=16, W=8, Cin=64, N=64, R=3, variant=5),           # odd tile count: the second issuer idles once
+    dict(B=2, H=28, W=28, Cin=128, N=256, R=3, variant=5),        # streamed weights, two n-tiles
+    dict(B=1, H=24, W=8, Cin=128, N=256, R=3, variant=5),         # streamed weights + odd tile count
+    dict(B=2, H=56, W=56, Cin=256, N=128, R=3, mode=2, variant=5),   # gate combine
+    dict(B=2, H=32, W=48, Cin=64, N=64, R=3, mode=3, variant=5),  # fused outc (no staging buffers)
+    dict(B=2, H=14, W=14, Cin=24, N=64, R=3, in_extra=40, in_off=16, variant=5),
+    dict(B=3, H=14, W=14, Cin=256, N=208, R=3, out_extra=48, out_off=16, variant=5),   # ragged n-tile
+    dict(B=2, H=20, W=36, Cin=192, N=96, R=3, mode=1, variant=5),  # ragged width (TMA-store clipping)
+    dict(B=4, H=56, W=56, Cin=128, N=512, R=3, bn=256, variant=5),  # weights packed for BN=256, run with BN=128
+    dict(B=5, H=28, W=28, Cin=16, N=32, R=3, variant=5),          # GoogLeNet 3a 5x5-branch shape (resident)
+    dict(B=70, H=32, W=32, Cin=64, N=128, R=3, variant=5),        # several rounds per CTA
     # legacy one-tile-per-CTA variant stays covered
     dict(B=2, H=16, W=16, Cin=64, N=64, R=3, variant=1),
     dict(B=2, H=56, W=56, Cin=256, N=128, R=3, variant=1),

@@ -13,6 +13,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp.  Role loops (TMA producer, MMA issuer) are executed by the WHOLE warp with
+// only the asynchronous instruction itself under this predicate: inside an `if (lane == 0)` region the compiler
+// must assume divergence, keeps descriptors in vector registers and wraps every UTCHMMA / UTMALDG in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall" (~16 instructions per MMA, measured: the issuing thread, not the
+// tensor pipe, then bounds N <= 128 tiles).  With warp-uniform control flow the operands live in uniform registers.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// Warp index as a warp-uniform value (the compiler cannot prove threadIdx.x >> 5 uniform).
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -1,0 +1,548 @@
+// 3x3 convolution, one persistent CTA per SM with TWO MMA-issuing warps that share the weight tiles.
+//
+// Why: a single thread's chain of M=128 tcgen05.mma instructions retires one MMA per ~110 cycles for N <= 128
+// (profiles/r01_mma_multi_issuer.txt); two issuing warps of ONE CTA interleave exactly like two co-resident CTAs
+// (N=64: 63 cycles per MMA per SM, N=128: 73), but unlike two CTAs they can share one copy of the weights:
+//   * weights that fit (9*Cin_pad*BN*2 bytes, e.g. 72 KB for 64->64) stay RESIDENT in shared memory for the
+//     whole launch - the two-CTA halo kernel re-streamed 72 KB of weights per 16 KB output tile and was bound by
+//     the chip-wide L2->SM bandwidth (~42 B/clk/SM);
+//   * otherwise every streamed weight tile is consumed by both issuers (each for its own pixel tile) before its
+//     slot is released, which halves the weight traffic per FLOP (an effective 256 x BN CTA tile).
+//
+// Each issuer i owns a pixel-tile stream (8 x TH output pixels, activation halo tile {64 ch, 10 px, TH+2 rows}
+// fetched once per 64-channel chunk and read by all nine taps through shifted UMMA descriptors, see
+// conv3x3_halo.cu), a ring of activation stages, TMEM accumulators and a warpgroup of four epilogue warps.
+// Warp roles (384 threads): warp 0 TMA producer, warps 1-2 MMA issuers, warp 3 TMEM allocator,
+// warps 4-7 epilogue of issuer 0, warps 8-11 epilogue of issuer 1.
+#include <cstring>
+#include "conv_common.cuh"
+
+namespace ug {
+
+static constexpr int kMultiThreads = 384;
+static constexpr int kMI = 2;           // MMA issuers per CTA
+static constexpr int kMPitch = 10;      // halo tile pitch: 8 output pixels + one border pixel on each side
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+struct MultiParams {
+  int TH;             // output rows per tile (tile = 8 x TH pixels)
+  int a_stage_bytes;  // bytes of one activation stage
+  int sa, sb;         // activation stages per issuer / shared weight stages
+  int b_resident;     // whole weight matrix kept in smem (requires n_tiles == 1)
+  int m_super;        // ceil(m_tiles / kMI): pixel tiles are handed out in groups of kMI
+  int debug;          // ablation switches for profiling (results are wrong when set): 1 = no TMEM loads,
+                      // 2 = no staging stores / TMA store, 4 = activation TMA loads only for the first stages
+};
+
+template <int kAct>
+__global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                         const __grid_constant__ CUtensorMap tmB,
+                                                                         const __grid_constant__ CUtensorMap tmO,
+                                                                         const ConvKParams p, const MultiParams hp) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_tile_bytes = p.BN * 128;
+  const int obuf_bytes = p.tma_store ? kABytesPerStage : 0;  // one 64-channel sub-tile per staging buffer
+  const int nb_tiles = hp.b_resident ? 9 * p.kchunks : hp.sb;
+  uint8_t* sA = smem;                                        // [kMI][sa] activation stages
+  uint8_t* sB = sA + kMI * hp.sa * hp.a_stage_bytes;
+  uint8_t* sO = sB + nb_tiles * b_tile_bytes;                // [kMI][obufs] output staging
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sO + kMI * p.obufs * obuf_bytes);  // [kMI][sa]
+  uint64_t* a_empty = a_full + kMI * hp.sa;
+  uint64_t* b_full = a_empty + kMI * hp.sa;                  // [sb] (entry 0 only when resident)
+  uint64_t* b_empty = b_full + hp.sb;
+  uint64_t* acc_full = b_empty + hp.sb;                      // [kMI][acc_stages]
+  uint64_t* acc_empty = acc_full + kMI * p.acc_stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + kMI * p.acc_stages);
+  float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);
+  float* sBias = sScale + p.npad;
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const int total_super = hp.m_super * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (p.tma_store) prefetch_tmap(&tmO);
+    for (int i = 0; i < kMI * hp.sa; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < hp.sb; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], kMI);  // released once every issuer has consumed (or skipped) the tile
+    }
+    for (int i = 0; i < kMI * p.acc_stages; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 3) {
+    tmem_alloc(tmem_ptr, p.tmem_cols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.npad; i += kMultiThreads) {
+    sScale[i] = (i < p.N) ? (p.scale ? p.scale[i] : 1.0f) : 0.0f;
+    sBias[i] = (i < p.N && p.bias) ? p.bias[i] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      if (hp.b_resident) {
+        mbar_arrive_expect_tx(&b_full[0], (uint32_t)(9 * p.kchunks * b_tile_bytes));
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_2d(sB + (kc * 9 + tap) * b_tile_bytes, &tmB, &b_full[0], (tap * p.kchunks + kc) * 64, 0);
+      }
+      int as[kMI] = {0, 0}, bs = 0;
+      uint32_t aph[kMI] = {0, 0}, bph = 0;
+      const uint32_t a_tx = (uint32_t)(kMPitch * (hp.TH + 2) * 128);
+      long long w_a = 0, w_b = 0;
+      const long long t_start = clock64();
+      unsigned long long ns0 = 0;
+      if (p.prof) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns0));
+      for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+        const int nt = s / hp.m_super, ms = s - nt * hp.m_super;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+#pragma unroll
+          for (int i = 0; i < kMI; ++i) {
+            const int mt = ms * kMI + i;
+            if (mt >= p.m_tiles) continue;
+            const int x0 = (mt % p.tiles_x) * 8;
+            const int y0 = ((mt / p.tiles_x) % p.tiles_y) * hp.TH;
+            const int n = mt / (p.tiles_x * p.tiles_y);
+            const int slot = i * hp.sa + as[i];
+            const long long tw0 = p.prof ? clock64() : 0;
+            mbar_wait(&a_empty[slot], aph[i] ^ 1);
+            if (p.prof) w_a += clock64() - tw0;
+            if ((hp.debug & 4) && s >= (int)gridDim.x * 2) {
+              mbar_arrive(&a_full[slot]);
+            } else {
+              mbar_arrive_expect_tx(&a_full[slot], a_tx);
+              tma_load_4d(sA + slot * hp.a_stage_bytes, &tmA, &a_full[slot], kc * 64, x0 - 1, y0 - 1, n);
+            }
+            if (++as[i] == hp.sa) {
+              as[i] = 0;
+              aph[i] ^= 1;
+            }
+          }
+          if (!hp.b_resident) {
+            for (int tap = 0; tap < 9; ++tap) {
+              const long long tw0 = p.prof ? clock64() : 0;
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              if (p.prof) w_b += clock64() - tw0;
+              mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_tile_bytes);
+              tma_load_2d(sB + bs * b_tile_bytes, &tmB, &b_full[bs], (tap * p.kchunks + kc) * 64, nt * p.BN);
+              if (++bs == hp.sb) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+        }
+      }
+      if (p.prof) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1));
+        p.prof[blockIdx.x * 16 + 0] = w_a;
+        p.prof[blockIdx.x * 16 + 1] = w_b;
+        p.prof[blockIdx.x * 16 + 2] = clock64() - t_start;
+        p.prof[blockIdx.x * 16 + 3] = (long long)(ns1 - ns0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers (whole warp, one elected lane issues)
+    const int i = warp - 1;
+    const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+    int as = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, acc_phase = 0;
+    long long w_af = 0, w_bf = 0, w_acc = 0;
+    const long long t_start = clock64();
+    if (hp.b_resident) {
+      mbar_wait(&b_full[0], 0);
+      tc_fence_after();
+    }
+    const uint32_t sB_u32 = smem_u32(sB);
+    for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+      const int nt = s / hp.m_super, ms = s - nt * hp.m_super;
+      const bool valid = ms * kMI + i < p.m_tiles;
+      uint32_t d_tmem = 0;
+      if (valid) {
+        const long long tw0 = p.prof ? clock64() : 0;
+        mbar_wait(&acc_empty[i * p.acc_stages + acc], acc_phase ^ 1);
+        if (p.prof) w_acc += clock64() - tw0;
+        tc_fence_after();
+        d_tmem = tmem_base + (i * p.acc_stages + acc) * p.BN;
+      }
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        uint64_t ad0 = 0;
+        if (valid) {
+          const long long tw0 = p.prof ? clock64() : 0;
+          mbar_wait(&a_full[i * hp.sa + as], aph);
+          if (p.prof) w_af += clock64() - tw0;
+          tc_fence_after();
+          ad0 = umma_desc_sw128_sbo(smem_u32(sA + (i * hp.sa + as) * hp.a_stage_bytes), kMPitch * 128);
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int r = tap / 3, sx = tap - r * 3;
+          uint32_t b_addr;
+          if (hp.b_resident) {
+            b_addr = sB_u32 + (kc * 9 + tap) * b_tile_bytes;
+          } else {
+            const long long tw0 = p.prof ? clock64() : 0;
+            mbar_wait(&b_full[bs], bph);
+            if (p.prof) w_bf += clock64() - tw0;
+            tc_fence_after();
+            b_addr = sB_u32 + bs * b_tile_bytes;
+          }
+          if (valid) {
+            // tap (r, sx): the A rows start (r*10 + sx) halo pixels (128 B each) into the stage
+            const uint64_t ad = ad0 + (uint64_t)((r * kMPitch + sx) * 8);
+            const uint64_t bd = umma_desc_sw128(b_addr);
+            const uint32_t first = (kc | tap) != 0 ? 1u : 0u;
+            if (elect_one_sync()) {
+              umma_bf16(d_tmem, ad, bd, idesc, first);
+              umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+              umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+              umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+              if (!hp.b_resident) umma_commit(&b_empty[bs]);
+            }
+            __syncwarp();
+          } else if (!hp.b_resident) {
+            // a tile-less issuer (odd tile count, last round) still has to hand the slot back
+            if (elect_one_sync()) mbar_arrive(&b_empty[bs]);
+            __syncwarp();
+          }
+          if (!hp.b_resident) {
+            if (++bs == hp.sb) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+        if (valid) {
+          if (elect_one_sync()) umma_commit(&a_empty[i * hp.sa + as]);
+          __syncwarp();
+          if (++as == hp.sa) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+      }
+      if (valid) {
+        if (elect_one_sync()) umma_commit(&acc_full[i * p.acc_stages + acc]);
+        __syncwarp();
+        if (++acc == p.acc_stages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 16 + 4 + i * 4 + 0] = w_af;
+      p.prof[blockIdx.x * 16 + 4 + i * 4 + 1] = w_bf;
+      p.prof[blockIdx.x * 16 + 4 + i * 4 + 2] = w_acc;
+      p.prof[blockIdx.x * 16 + 4 + i * 4 + 3] = clock64() - t_start;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps per issuer)
+    const int i = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int etid = threadIdx.x - 128 - i * 128;
+    const int tx = row & 7;
+    const int ty = row >> 3;
+    const bool row_in_tile = ty < hp.TH;
+    uint8_t* sOi = sO + i * p.obufs * obuf_bytes;
+    int acc = 0, obuf = 0;
+    uint32_t acc_phase = 0;
+    long long e_wacc = 0, e_wobuf = 0, e_tiles = 0;
+    const long long e_start = clock64();
+
+    for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+      const int nt = s / hp.m_super, ms = s - nt * hp.m_super;
+      const int mt = ms * kMI + i;
+      if (mt >= p.m_tiles) continue;
+      ++e_tiles;
+      const int x0 = (mt % p.tiles_x) * 8;
+      const int y0 = ((mt / p.tiles_x) % p.tiles_y) * hp.TH;
+      const int n = mt / (p.tiles_x * p.tiles_y);
+      const int ncol0 = nt * p.BN;
+      const int x = x0 + tx, y = y0 + ty;
+      const bool valid = row_in_tile && (x < p.W) && (y < p.H);
+      const long long pix = (long long)y * p.W + x;
+      const __nv_bfloat16* add_row =
+          reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)n * p.add_bstride + pix * p.add_cstride + ncol0;
+      const float* gate_row = p.gate + (long long)n * p.N + ncol0;
+      long long tw0 = p.prof ? clock64() : 0;
+      mbar_wait(&acc_full[i * p.acc_stages + acc], acc_phase);
+      if (p.prof) e_wacc += clock64() - tw0;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (i * p.acc_stages + acc) * p.BN;
+      float dot = 0.0f;
+      const int ncols = min(p.BN, p.N - ncol0);
+
+      uint32_t v[16];
+      __syncwarp();
+      if (hp.debug & 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      } else {
+        tmem_ld16(taddr, v);
+      }
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        const bool sub_start = (c0 & 63) == 0;
+        if (p.tma_store && sub_start) {
+          // staging buffer `obuf` must no longer be read by the TMA store issued obufs sub-tiles ago
+          tw0 = p.prof ? clock64() : 0;
+          if (etid == 0) {
+            if (p.obufs == 2) bulk_wait_group_read<1>();
+            else bulk_wait_group_read<0>();
+          }
+          named_bar_sync(1 + i, 128);
+          if (p.prof) e_wobuf += clock64() - tw0;
+        }
+        tmem_ld_wait();
+        float f[16];
+        epi_math16<kAct>(v, f, sScale, sBias, ncol0 + c0);
+        __syncwarp();
+        if (c0 + 16 < ncols && !(hp.debug & 1)) tmem_ld16(taddr + c0 + 16, v);
+        if (p.mode == UG_EPI_OUTC) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dot += f[j] * __ldg(p.outc_w + ncol0 + c0 + j);
+          continue;
+        }
+        const int groups = (c0 + 16 <= ncols) ? 2 : 1;
+        if ((p.mode == UG_EPI_ADD || p.mode == UG_EPI_GATE) && valid) {
+          for (int g = 0; g < groups; ++g) epi_add_gate8(p, f + g * 8, add_row + c0 + g * 8, gate_row + c0 + g * 8);
+        }
+        uint8_t* so_row = sOi + obuf * obuf_bytes + row * 128;
+        for (int g = 0; g < groups; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+          o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+          o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+          o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+          const int chunk = ((c0 & 63) >> 3) + g;
+          if (!(hp.debug & 2)) *reinterpret_cast<uint4*>(so_row + ((chunk ^ (row & 7)) << 4)) = o;
+        }
+        const bool sub_end = ((c0 + 16) & 63) == 0 || c0 + 16 >= ncols;
+        if (sub_end) {
+          if (c0 + 16 >= ncols) {  // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + i, 128);
+          if (etid == 0 && !(hp.debug & 2)) {
+            tma_store_4d(&tmO, sOi + obuf * obuf_bytes, ncol0 + (c0 & ~63), x0, y0, n);
+            bulk_commit_group();
+          }
+          if (p.obufs == 2) obuf ^= 1;
+        }
+      }
+      if (p.mode == UG_EPI_OUTC) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
+        if (valid) {
+          const float logit = dot + p.outc_b;
+          const long long o = ((long long)n * p.H + y) * p.W + x;
+          p.logits[o] = logit;
+          const float sg = 1.0f / (1.0f + expf(-logit));  // torch.sigmoid(seg_out) > 0.5 in fp32
+          p.mask[o] = sg > 0.5f ? 1 : 0;
+        }
+      }
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (p.tma_store && etid == 0) bulk_wait_group_all();
+    if (p.prof && etid == 0 && i == 0) {
+      p.prof[blockIdx.x * 16 + 12] = e_wacc;
+      p.prof[blockIdx.x * 16 + 13] = e_wobuf;
+      p.prof[blockIdx.x * 16 + 14] = clock64() - e_start;
+      p.prof[blockIdx.x * 16 + 15] = e_tiles;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+
+static inline int cdiv_m(int a, int b) { return (a + b - 1) / b; }
+
+// Fills L for the multi-issuer kernel.  Returns UG_EUNSUPPORTED when the shape does not fit it.
+int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* L) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return set_error(h, UG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (d->R != 3 || d->S != 3 || d->pad != 1 || d->up == 2)
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): 3x3 pad-1 stride-1 convolutions only");
+  if (BN > 128) return set_error(h, UG_EUNSUPPORTED, "conv(multi): BN <= 128");
+  const int TH = cdiv_m(d->H, cdiv_m(d->H, 16));  // <= 16 rows per tile, no wasted tile rows
+  const int cin_pad = cdiv_m(d->Cin, 64) * 64;
+  const int kchunks = cin_pad / 64;
+  const int n_tiles = cdiv_m(d->N, BN);
+  const int npad = n_tiles * BN;
+  const long long ktot = 9LL * cin_pad;
+  const int tma_store = d->mode != UG_EPI_OUTC;
+  const int obuf_bytes = tma_store ? kABytesPerStage : 0;
+  const int acc_stages = std::max(1, std::min(4, 512 / (kMI * BN)));
+  const int a_stage = ((kMPitch * (TH + 2) * 128 + 1023) / 1024) * 1024;
+  const int b_tile = BN * 128;
+
+  MultiParams hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.TH = TH;
+  hp.a_stage_bytes = a_stage;
+  const int fixed = 1024 + 8 * (2 * kMI * 4 + 2 * 12 + 2 * kMI * 4) + 16 + 2 * npad * (int)sizeof(float);
+  const long long budget = 227LL * 1024 - fixed;
+  int obufs = tma_store ? 2 : 0;
+  const long long resB = 9LL * kchunks * b_tile;
+  if (n_tiles == 1 && resB + kMI * 2LL * a_stage + (tma_store ? kMI * obuf_bytes : 0) <= budget) {
+    hp.b_resident = 1;
+    hp.sb = 1;
+    if (resB + kMI * 2LL * a_stage + kMI * obufs * obuf_bytes > budget) obufs = 1;
+    hp.sa = (int)std::min<long long>(4, (budget - resB - kMI * obufs * obuf_bytes) / (kMI * a_stage));
+  } else {
+    hp.b_resident = 0;
+    hp.sa = 2;
+    long long rest = budget - kMI * 2LL * a_stage - kMI * obufs * obuf_bytes;
+    if (rest < 6LL * b_tile && obufs == 2) {  // prefer a deeper weight ring over double-buffered staging
+      obufs = 1;
+      rest = budget - kMI * 2LL * a_stage - kMI * obuf_bytes;
+    }
+    hp.sb = (int)std::min<long long>(12, rest / b_tile);
+    if (hp.sb < 3) return set_error(h, UG_EUNSUPPORTED, "conv(multi): tile does not fit in shared memory");
+    if (hp.sb >= 10 && rest - 9LL * b_tile >= kMI * a_stage) {  // room for a third activation stage
+      hp.sa = 3;
+      hp.sb = (int)std::min<long long>(12, (rest - kMI * a_stage) / b_tile);
+    }
+  }
+
+  ConvKParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  p.H = d->H; p.W = d->W; p.B = d->B;
+  p.TW = 8; p.TH = TH; p.TN = 1;
+  p.tiles_x = cdiv_m(d->W, 8);
+  p.tiles_y = cdiv_m(d->H, TH);
+  p.R = 3; p.S = 3; p.pad = 1;
+  p.kchunks = kchunks; p.num_k = 9 * kchunks;
+  p.N = d->N; p.BN = BN; p.stages = hp.sa;
+  int tcols = 32;
+  while (tcols < kMI * acc_stages * BN) tcols <<= 1;
+  p.tmem_cols = tcols;
+  p.scale = d->scale; p.bias = d->bias;
+  p.act = d->act; p.mode = d->mode;
+  p.out = d->out; p.out_cstride = d->out_cstride;
+  p.up = 1; p.OH = d->H; p.OW = d->W;
+  p.add = d->add; p.add_bstride = d->add_bstride; p.add_cstride = d->add_cstride;
+  p.gate = d->gate; p.outc_w = d->outc_w; p.outc_b = d->outc_b;
+  p.logits = d->logits; p.mask = d->mask;
+  p.m_tiles = p.tiles_x * p.tiles_y * d->B; p.n_tiles = n_tiles; p.acc_stages = acc_stages;
+  p.tma_store = tma_store; p.obufs = obufs; p.npad = npad;
+  hp.m_super = cdiv_m(p.m_tiles, kMI);
+  L->variant = 5;
+  L->halo_mode = 1;
+  L->halo_TH = TH; L->halo_a_stage = a_stage; L->halo_copy = hp.m_super;
+  L->halo_sa = hp.sa; L->halo_sb = hp.sb; L->halo_bres = hp.b_resident;
+  L->halo_debug = d->stages >= 100 ? d->stages - 100 : 0;  // profiling ablations (scripts/conv_prof.py)
+
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)d->W * d->in_cstride * 2,
+                             (cuuint64_t)d->H * d->W * d->in_cstride * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)kMPitch, (cuuint32_t)(TH + 2), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&L->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->in), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv(multi): activation tensor map encode failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)npad};
+    cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv(multi): weight tensor map encode failed (%d)", (int)r);
+  }
+  if (tma_store) {
+    cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->out_cstride * 2, (cuuint64_t)d->W * d->out_cstride * 2,
+                             (cuuint64_t)d->H * d->W * d->out_cstride * 2};
+    cuuint32_t box[4] = {64, 8, (cuuint32_t)TH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&L->tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv(multi): output tensor map encode failed (%d)", (int)r);
+  } else {
+    memset(&L->tmO, 0, sizeof(L->tmO));
+  }
+  const long long total_super = (long long)hp.m_super * n_tiles;
+  L->grid = dim3((unsigned)std::min<long long>(total_super, (long long)h->num_sms), 1, 1);
+  const int nb_tiles = hp.b_resident ? 9 * kchunks : hp.sb;
+  L->smem = 1024 + (size_t)kMI * hp.sa * a_stage + (size_t)nb_tiles * b_tile + (size_t)kMI * obufs * obuf_bytes +
+            8 * (2 * kMI * hp.sa + 2 * hp.sb + 2 * kMI * acc_stages) + 16 + 2 * (size_t)npad * sizeof(float);
+  if (L->smem > (size_t)227 * 1024)
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): shared memory request %zu too large", L->smem);
+  return UG_OK;
+}
+
+int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaSuccess;
+    const void* fns[] = {(const void*)conv3x3_multi_kernel<UG_ACT_NONE>, (const void*)conv3x3_multi_kernel<UG_ACT_RELU>,
+                         (const void*)conv3x3_multi_kernel<UG_ACT_GELU>};
+    for (const void* f : fns)
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv3x3_multi_kernel)");
+    attr_set = true;
+  }
+  MultiParams hp;
+  hp.TH = L->halo_TH; hp.a_stage_bytes = L->halo_a_stage;
+  hp.sa = L->halo_sa; hp.sb = L->halo_sb; hp.b_resident = L->halo_bres; hp.m_super = L->halo_copy;
+  hp.debug = L->halo_debug;
+  const int act = L->p.act;
+  if (act == UG_ACT_RELU)
+    conv3x3_multi_kernel<UG_ACT_RELU><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p, hp);
+  else if (act == UG_ACT_GELU)
+    conv3x3_multi_kernel<UG_ACT_GELU><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p, hp);
+  else
+    conv3x3_multi_kernel<UG_ACT_NONE><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p, hp);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "conv3x3_multi_kernel launch");
+}
+
+}  // namespace ug

@@ -568,6 +568,14 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   }
 
   if (d->variant == 3 || d->variant == 4) return conv_halo_prepare(h, d, BN, d->variant == 3 ? 2 : 1, L);
+  if (d->variant == 5) return conv_multi_prepare(h, d, std::min(BN, 128), L);
+  if (d->variant == 0 && d->R == 3 && up == 1 && d->H * d->W >= 784) {
+    // maps of at least 28x28: one CTA per SM, two MMA issuers sharing resident / streamed weights
+    // (conv3x3_multi.cu); measured against the other variants in profiles/r01_conv_sweep.txt
+    const int rc = conv_multi_prepare(h, d, std::min(BN, 128), L);
+    if (rc == UG_OK) return rc;
+    if (rc != UG_EUNSUPPORTED) return rc;
+  }
   if (d->variant == 0 && d->R == 3 && up == 1) {
     // measured choice (profiles/r01_conv_sweep.txt): halo kernel with two CTAs per SM for BN <= 128 on maps of
     // at least 28x28, halo kernel with one CTA per SM for BN = 256 on maps of at least 56x56
@@ -716,6 +724,7 @@ int conv_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
     attr_set = true;
   }
   if (L->variant == 3) return conv_halo_launch(h, L, s);
+  if (L->variant == 5) return conv_multi_launch(h, L, s);
   const int act = L->p.act;
   if (L->variant == 1) {
     if (act == UG_ACT_RELU) conv_gemm_kernel<UG_ACT_RELU><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->p);

@@ -49,8 +49,8 @@ struct ConvLaunch {
   ConvKParams p;
   dim3 grid;
   size_t smem;
-  int variant;  // 0 = persistent, 1 = one tile per CTA, 3 = 3x3 halo kernel
-  int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres;
+  int variant;  // 0 = persistent, 1 = one tile per CTA, 3 = 3x3 halo kernel, 5 = 3x3 multi-issuer kernel
+  int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres, halo_debug;
 };
 
 // Stem convolution (csrc/stem_conv.cu): kernel parameters and a prepared launch.
@@ -79,6 +79,8 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
 int conv_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 int conv_halo_prepare(ug_engine* h, const ug_conv_desc* d, int BN, int mode, ConvLaunch* out);
 int conv_halo_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
+int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* out);
+int conv_multi_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 
 int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* out);
 int stem_launch(ug_engine* h, const StemLaunch* l, cudaStream_t s);

@@ -55,20 +55,22 @@ __global__ void __launch_bounds__(128) mma_bench_kernel(int N, int n_acc, int it
 // Second form: `issuers` warps of ONE CTA each issue their own dependent MMA chain(s) (n_acc accumulators per
 // issuer, private A tile, shared B tile).  Answers whether several issuing threads of one CTA overlap the way
 // co-resident CTAs do.  The smem footprint is small (issuers*16 KB + N*128 B) so up to 4 CTAs fit per SM.
-__global__ void __launch_bounds__(128) mma_bench2_kernel(int N, int n_acc, int issuers, int iters, long long* out) {
+__global__ void __launch_bounds__(128) mma_bench2_kernel(int N, int n_acc, int issuers, int iters, int a_off,
+                                                         int a_sbo, int acc_stride, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar[4];
   __shared__ uint32_t tmem_ptr;
-  for (int i = threadIdx.x; i < (issuers * 16384 + N * 128) / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (issuers * 24576 + N * 128) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
     fence_mbar_init();
   }
   int cols = 32;
-  while (cols < issuers * n_acc * N) cols <<= 1;
+  const int acc_step = acc_stride > 0 ? acc_stride : n_acc * N;  // TMEM columns between the issuers' accumulators
+  while (cols < (issuers - 1) * acc_step + n_acc * N) cols <<= 1;
   if (warp == 0) {
     tmem_alloc(&tmem_ptr, cols);
     tmem_relinquish();
@@ -80,9 +82,12 @@ __global__ void __launch_bounds__(128) mma_bench2_kernel(int N, int n_acc, int i
   const uint32_t tmem_base = tmem_ptr;
   if (warp < issuers && lane == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, N);
-    const uint64_t ad = umma_desc_sw128(smem_u32(smem + warp * 16384));
-    const uint64_t bd = umma_desc_sw128(smem_u32(smem + issuers * 16384));
-    const uint32_t d0 = tmem_base + warp * n_acc * N;
+    // A: start address shifted by a_off bytes (multiple of 128) and 8-row groups a_sbo bytes apart, as in the
+    // halo layout of the 3x3 kernels (a_off = 0, a_sbo = 1024 is the plain tile)
+    uint64_t ad = umma_desc_sw128(smem_u32(smem + warp * 24576 + a_off));
+    ad = (ad & ~(0x3FFFULL << 32)) | (static_cast<uint64_t>(a_sbo >> 4) << 32);
+    const uint64_t bd = umma_desc_sw128(smem_u32(smem + issuers * 24576));
+    const uint32_t d0 = tmem_base + warp * acc_step;
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -137,23 +142,25 @@ extern "C" int ug_mma_microbench(ug_handle h, int N, int n_acc, int iters, int c
 }
 
 extern "C" int ug_mma_microbench2(ug_handle h, int N, int n_acc, int issuers, int iters, int ctas_per_sm,
-                                  double* out2) {
+                                  int a_off, int a_sbo, int acc_stride, double* out2) {
   if (!h || !out2 || N % 16 || N < 16 || N > 256 || n_acc < 1 || issuers < 1 || issuers > 4 ||
-      issuers * n_acc * N * ctas_per_sm > 512)
+      issuers * n_acc * N * ctas_per_sm > 512 || a_off % 128 || a_off < 0 || a_off > 3072 || a_sbo % 128 ||
+      a_sbo < 1024 || a_sbo > 1280 || acc_stride < 0 || (acc_stride > 0 && acc_stride < n_acc * N) ||
+      ((issuers - 1) * acc_stride + n_acc * N) * ctas_per_sm > 512)
     return UG_EINVAL;
   using namespace ug;
   const int ctas = h->num_sms * ctas_per_sm;
   long long* dev = nullptr;
   if (cudaMalloc(&dev, sizeof(long long) * ctas) != cudaSuccess) return UG_ENOMEM;
-  const size_t smem = 1024 + (size_t)issuers * 16384 + (size_t)N * 128;
+  const size_t smem = 1024 + (size_t)issuers * 24576 + (size_t)N * 128;
   cudaFuncSetAttribute(mma_bench2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaMemset(dev, 0, sizeof(long long) * ctas);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  mma_bench2_kernel<<<ctas, 128, smem>>>(N, n_acc, issuers, 10, dev);
+  mma_bench2_kernel<<<ctas, 128, smem>>>(N, n_acc, issuers, 10, a_off, a_sbo, acc_stride, dev);
   cudaEventRecord(e0);
-  mma_bench2_kernel<<<ctas, 128, smem>>>(N, n_acc, issuers, iters, dev);
+  mma_bench2_kernel<<<ctas, 128, smem>>>(N, n_acc, issuers, iters, a_off, a_sbo, acc_stride, dev);
   cudaEventRecord(e1);
   int rc = check_cuda(h, cudaGetLastError(), "mma_bench2 launch");
   if (rc == UG_OK) rc = check_cuda(h, cudaDeviceSynchronize(), "mma_bench2");

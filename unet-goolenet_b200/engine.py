@@ -107,7 +107,7 @@ _SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_INC_IM2COL: "ug_inc_im2col", OP_POOL: "u
 EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
                     "ug_program_destroy", "ug_program_run_host", "ug_program_run_timed", "ug_conv_profile", "ug_mma_microbench",
-                    "ug_mma_microbench2"]
+                    "ug_mma_microbench2", "ug_conv_profile16"]
 
 _lib = None
 
@@ -131,7 +131,8 @@ def load_library():
     for name in _SINGLE_ENTRY.values():
         getattr(lib, name).argtypes = [_vp, _vp, _vp]
     lib.ug_mma_microbench.argtypes = [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]
-    lib.ug_mma_microbench2.argtypes = [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]
+    lib.ug_mma_microbench2.argtypes = [_vp, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]
+    lib.ug_conv_profile16.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_double)]
     lib.ug_conv_profile.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_double)]
     lib.ug_program_create.argtypes = [_vp, _vp, _i, C.POINTER(_vp)]
     lib.ug_program_run.argtypes = [_vp, _vp, _vp]
@@ -237,6 +238,16 @@ class Engine:
         self._check(self.lib.ug_conv_profile(self.handle, C.byref(desc), s, out))
         keys = ["prod_wait_empty", "prod_total", "mma_wait_full", "mma_wait_acc", "epi_wait_acc", "epi_wait_obuf",
                 "epi_math", "epi_store", "ctas", "tiles_per_cta"]
+        return dict(zip(keys, list(out)))
+
+    def conv_profile16(self, desc, stream=None):
+        """Per-role cycle counters of the multi-issuer 3x3 kernel for one op (see ug_conv_profile16)."""
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        out = (C.c_double * 16)()
+        self._check(self.lib.ug_conv_profile16(self.handle, C.byref(desc), s, out))
+        keys = ["prod_wait_a", "prod_wait_b", "prod_cycles", "prod_ns", "i0_wait_a", "i0_wait_b", "i0_wait_acc",
+                "i0_cycles", "i1_wait_a", "i1_wait_b", "i1_wait_acc", "i1_cycles", "epi_wait_acc", "epi_wait_obuf",
+                "epi_cycles", "epi_tiles"]
         return dict(zip(keys, list(out)))
 
     def program(self, descs, keepalive=()):
