@@ -71,10 +71,10 @@ typedef struct ug_conv_desc {
   unsigned char* mask;
   int TW, TH, TN, BN, stages; /* tiling; 0 = engine chooses */
   int variant;                /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel (TMEM multi-buffered
-                                 accumulators, TMA-store epilogue); 3 / 4 = 3x3 halo kernel with 2 / 1
-                                 CTAs per SM (activation tile fetched once per 64-channel chunk for all
-                                 nine taps; see csrc/conv3x3_halo.cu); 5 = 3x3 multi-issuer kernel (one CTA per
-                                 SM, two MMA issuers sharing resident or streamed weights, conv3x3_multi.cu) */
+                                 accumulators, TMA-store epilogue); 5 = 3x3 multi-issuer kernel (one CTA per
+                                 SM, two MMA-issuing warps sharing resident or streamed weights, activation
+                                 halo tile fetched once per 64-channel chunk for all nine taps; see
+                                 csrc/conv3x3_multi.cu) */
 } ug_conv_desc;
 
 /* x: fp32 NCHW [B,3,H,W] -> out: bf16 [B*H*W][64], column (r*3+s)*3+c = x[n,c,y+r-1,x+s-1] (0 outside),

@@ -47,19 +47,23 @@ def timeit(d, n=5):
 
 SHAPES = [(64, 224, 224, 64, 64, 3), (64, 224, 224, 128, 64, 3), (64, 112, 112, 64, 128, 3), (64, 112, 112, 128, 128, 3),
           (64, 112, 112, 256, 64, 3), (64, 56, 56, 256, 256, 3), (64, 56, 56, 512, 128, 3), (64, 28, 28, 512, 512, 3),
-          (64, 28, 28, 1024, 256, 3), (64, 14, 14, 512, 512, 3), (256, 56, 56, 64, 192, 3), (256, 28, 28, 128, 192, 3)]
+          (64, 28, 28, 1024, 256, 3), (64, 14, 14, 512, 512, 3), (256, 56, 56, 64, 192, 3), (256, 28, 28, 128, 192, 3),
+          (256, 28, 28, 16, 32, 3), (256, 14, 14, 96, 208, 3), (256, 14, 14, 160, 320, 3), (256, 14, 14, 24, 64, 3),
+          (256, 7, 7, 160, 320, 3), (256, 7, 7, 192, 384, 3), (256, 7, 7, 48, 128, 3),
+          (1, 1, 12544, 512, 1536, 1), (1, 1, 12544, 512, 512, 1), (1, 1, 12544, 2048, 512, 1),
+          (1, 1, 200704, 192, 64, 1), (1, 1, 200704, 256, 128, 1), (1, 1, 50176, 512, 160, 1), (1, 1, 12544, 832, 384, 1)]
 if len(sys.argv) > 1:
     SHAPES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
 if __name__ != "__main__":
     SHAPES = []
-CONFIGS = [dict(variant=2, bn=256), dict(variant=3), dict(variant=4, bn=256), dict(variant=5), dict(variant=5, mode=2)]
+CONFIGS = [dict(variant=1), dict(variant=2), dict(variant=2, bn=256), dict(variant=5), dict(variant=5, mode=2)]
 if os.environ.get("UG_ABLATE"):
     CONFIGS = [dict(variant=5)] + [dict(variant=5, stages=100 + f) for f in (1, 2, 3, 4, 7)]
 for shp in SHAPES:
     B, H, W, Cin, N, R = shp
     fl = 2.0 * B * H * W * N * Cin * R * R
     for cfg in CONFIGS:
-        if cfg.get("bn", 0) > N:
+        if cfg.get("bn", 0) > N or (cfg.get("variant") == 5 and R != 3) or (cfg.get("mode") == 2 and H * W < 784):
             continue
         try:
             d, keep = make(*shp, **cfg)

@@ -1,19 +1,26 @@
-// 3x3 convolution, one persistent CTA per SM with TWO MMA-issuing warps that share the weight tiles.
+// 3x3 convolution (stride 1, pad 1), one persistent CTA per SM with TWO MMA-issuing warps sharing the weights.
 //
-// Why: a single thread's chain of M=128 tcgen05.mma instructions retires one MMA per ~110 cycles for N <= 128
-// (profiles/r01_mma_multi_issuer.txt); two issuing warps of ONE CTA interleave exactly like two co-resident CTAs
-// (N=64: 63 cycles per MMA per SM, N=128: 73), but unlike two CTAs they can share one copy of the weights:
-//   * weights that fit (9*Cin_pad*BN*2 bytes, e.g. 72 KB for 64->64) stay RESIDENT in shared memory for the
-//     whole launch - the two-CTA halo kernel re-streamed 72 KB of weights per 16 KB output tile and was bound by
-//     the chip-wide L2->SM bandwidth (~42 B/clk/SM);
+// Activation tiles: an 8 x TH block of output pixels (TH <= 16, 128 MMA rows) plus a one-pixel border is fetched
+// ONCE per 64-channel chunk as a TMA box {64 ch, 10 px, TH+2 rows} (out-of-bounds coordinates are zero-filled =
+// the conv padding); halo pixel (hy, hx) sits at smem row hy*10 + hx (128 B per row, SWIZZLE_128B).  For filter tap
+// (r, s) the MMA row group g (= output row g of the tile) starts at ((g + r)*10 + s) * 128 B: stride-byte-offset
+// 1280 and a start address that is only 128-byte aligned.  The 128B swizzle of tcgen05 operands is a function of
+// the absolute shared-memory address (profiles/r01_halo_descriptor_probe.txt), so descriptors keep base_offset 0.
+//
+// Why two issuers: one thread's chain of M=128 tcgen05.mma instructions retires one MMA per ~110 cycles for any
+// N <= 128; two issuing warps of ONE CTA interleave exactly like two co-resident CTAs (N=64: 63 cycles per MMA per
+// SM, N=128: 72; profiles/r01_mma_multi_issuer.txt) but can share one copy of the weights:
+//   * weights that fit (9*Cin_pad*BN*2 bytes, e.g. 72 KB for 64->64) stay RESIDENT in shared memory for the launch;
 //   * otherwise every streamed weight tile is consumed by both issuers (each for its own pixel tile) before its
 //     slot is released, which halves the weight traffic per FLOP (an effective 256 x BN CTA tile).
+// The issue loops are warp-uniform with the asynchronous instructions under elect_one_sync() (see common.cuh):
+// with `if (lane == 0)` loops the issuing thread needed ~16 SASS instructions per MMA and bounded every N <= 128
+// layer (224x224 64->64: 0.375 ms before, 0.236 ms after; profiles/r01_conv_sweep_multi_issuer.txt).
 //
-// Each issuer i owns a pixel-tile stream (8 x TH output pixels, activation halo tile {64 ch, 10 px, TH+2 rows}
-// fetched once per 64-channel chunk and read by all nine taps through shifted UMMA descriptors, see
-// conv3x3_halo.cu), a ring of activation stages, TMEM accumulators and a warpgroup of four epilogue warps.
-// Warp roles (384 threads): warp 0 TMA producer, warps 1-2 MMA issuers, warp 3 TMEM allocator,
-// warps 4-7 epilogue of issuer 0, warps 8-11 epilogue of issuer 1.
+// Each issuer i owns a pixel-tile stream, a ring of activation stages, TMEM accumulators and a warpgroup of four
+// epilogue warps (folded BN/bias + activation, residual / CoordAtt3 combine / outc epilogues, bf16 tile staged in
+// swizzled smem and written with TMA stores).  Warp roles (384 threads): warp 0 TMA producer, warps 1-2 MMA
+// issuers, warp 3 TMEM allocator, warps 4-7 epilogue of issuer 0, warps 8-11 epilogue of issuer 1.
 #include <cstring>
 #include "conv_common.cuh"
 
@@ -102,71 +109,77 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      if (hp.b_resident) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
+    if (hp.b_resident) {
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&b_full[0], (uint32_t)(9 * p.kchunks * b_tile_bytes));
         for (int kc = 0; kc < p.kchunks; ++kc)
           for (int tap = 0; tap < 9; ++tap)
             tma_load_2d(sB + (kc * 9 + tap) * b_tile_bytes, &tmB, &b_full[0], (tap * p.kchunks + kc) * 64, 0);
       }
-      int as[kMI] = {0, 0}, bs = 0;
-      uint32_t aph[kMI] = {0, 0}, bph = 0;
-      const uint32_t a_tx = (uint32_t)(kMPitch * (hp.TH + 2) * 128);
-      long long w_a = 0, w_b = 0;
-      const long long t_start = clock64();
-      unsigned long long ns0 = 0;
-      if (p.prof) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns0));
-      for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
-        const int nt = s / hp.m_super, ms = s - nt * hp.m_super;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+      __syncwarp();
+    }
+    int as[kMI] = {0, 0}, bs = 0;
+    uint32_t aph[kMI] = {0, 0}, bph = 0;
+    const uint32_t a_tx = (uint32_t)(kMPitch * (hp.TH + 2) * 128);
+    long long w_a = 0, w_b = 0;
+    const long long t_start = clock64();
+    unsigned long long ns0 = 0;
+    if (p.prof) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns0));
+    for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+      const int nt = s / hp.m_super, ms = s - nt * hp.m_super;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
 #pragma unroll
-          for (int i = 0; i < kMI; ++i) {
-            const int mt = ms * kMI + i;
-            if (mt >= p.m_tiles) continue;
-            const int x0 = (mt % p.tiles_x) * 8;
-            const int y0 = ((mt / p.tiles_x) % p.tiles_y) * hp.TH;
-            const int n = mt / (p.tiles_x * p.tiles_y);
-            const int slot = i * hp.sa + as[i];
-            const long long tw0 = p.prof ? clock64() : 0;
-            mbar_wait(&a_empty[slot], aph[i] ^ 1);
-            if (p.prof) w_a += clock64() - tw0;
+        for (int i = 0; i < kMI; ++i) {
+          const int mt = ms * kMI + i;
+          if (mt >= p.m_tiles) continue;
+          const int x0 = (mt % p.tiles_x) * 8;
+          const int y0 = ((mt / p.tiles_x) % p.tiles_y) * hp.TH;
+          const int n = mt / (p.tiles_x * p.tiles_y);
+          const int slot = i * hp.sa + as[i];
+          const long long tw0 = p.prof ? clock64() : 0;
+          mbar_wait(&a_empty[slot], aph[i] ^ 1);
+          if (p.prof) w_a += clock64() - tw0;
+          if (elect_one_sync()) {
             if ((hp.debug & 4) && s >= (int)gridDim.x * 2) {
               mbar_arrive(&a_full[slot]);
             } else {
               mbar_arrive_expect_tx(&a_full[slot], a_tx);
               tma_load_4d(sA + slot * hp.a_stage_bytes, &tmA, &a_full[slot], kc * 64, x0 - 1, y0 - 1, n);
             }
-            if (++as[i] == hp.sa) {
-              as[i] = 0;
-              aph[i] ^= 1;
-            }
           }
-          if (!hp.b_resident) {
-            for (int tap = 0; tap < 9; ++tap) {
-              const long long tw0 = p.prof ? clock64() : 0;
-              mbar_wait(&b_empty[bs], bph ^ 1);
-              if (p.prof) w_b += clock64() - tw0;
+          __syncwarp();
+          if (++as[i] == hp.sa) {
+            as[i] = 0;
+            aph[i] ^= 1;
+          }
+        }
+        if (!hp.b_resident) {
+          for (int tap = 0; tap < 9; ++tap) {
+            const long long tw0 = p.prof ? clock64() : 0;
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (p.prof) w_b += clock64() - tw0;
+            if (elect_one_sync()) {
               mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_tile_bytes);
               tma_load_2d(sB + bs * b_tile_bytes, &tmB, &b_full[bs], (tap * p.kchunks + kc) * 64, nt * p.BN);
-              if (++bs == hp.sb) {
-                bs = 0;
-                bph ^= 1;
-              }
+            }
+            __syncwarp();
+            if (++bs == hp.sb) {
+              bs = 0;
+              bph ^= 1;
             }
           }
         }
       }
-      if (p.prof) {
-        unsigned long long ns1;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1));
-        p.prof[blockIdx.x * 16 + 0] = w_a;
-        p.prof[blockIdx.x * 16 + 1] = w_b;
-        p.prof[blockIdx.x * 16 + 2] = clock64() - t_start;
-        p.prof[blockIdx.x * 16 + 3] = (long long)(ns1 - ns0);
-      }
     }
-    __syncwarp();
+    if (p.prof && lane == 0) {
+      unsigned long long ns1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1));
+      p.prof[blockIdx.x * 16 + 0] = w_a;
+      p.prof[blockIdx.x * 16 + 1] = w_b;
+      p.prof[blockIdx.x * 16 + 2] = clock64() - t_start;
+      p.prof[blockIdx.x * 16 + 3] = (long long)(ns1 - ns0);
+    }
   } else if (warp == 1 || warp == 2) {
     // ------------------------------------------------------------------ MMA issuers (whole warp, one elected lane issues)
     const int i = warp - 1;

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);
   float* sBias = sScale + p.BN;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   // tile coordinates
@@ -74,52 +74,53 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
-      int it = 0;
-      for (int tap = 0; tap < p.R * p.S; ++tap) {
-        const int r = tap / p.S, s = tap % p.S;
-        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
+    int it = 0;
+    for (int tap = 0; tap < p.R * p.S; ++tap) {
+      const int r = tap / p.S, s = tap % p.S;
+      for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full[stage], tx_bytes);
           tma_load_4d(sA + stage * kABytesPerStage, &tmA, &full[stage], kc * 64, x0 + s - p.pad, y0 + r - p.pad, n0);
           tma_load_2d(sB + stage * b_stage_bytes, &tmB, &full[stage], it * 64, ncol0);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < p.num_k; ++it) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytesPerStage));
-        const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * b_stage_bytes));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // +32 bytes (= 16 bf16) along K inside the 128B swizzle atom: +2 in the encoded start address
-          umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+        __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(tmem_full);  // accumulator complete
     }
-    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < p.num_k; ++it) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytesPerStage));
+      const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * b_stage_bytes));
+      const uint32_t acc = it != 0 ? 1u : 0u;
+      if (elect_one_sync()) {
+        // +32 bytes (= 16 bf16) along K inside the 128B swizzle atom: +2 in the encoded start address
+        umma_bf16(tmem_base, ad, bd, idesc, acc);
+        umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+        umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+        umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
+        umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+        if (it == p.num_k - 1) umma_commit(tmem_full);  // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps, 1 pixel / thread)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
   float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);
   float* sBias = sScale + p.npad;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
@@ -256,81 +257,84 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
-      long long w_empty = 0;
-      const long long t_start = clock64();
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int mt = t % p.m_tiles, nt = t / p.m_tiles;
-        const int x0 = (mt % p.tiles_x) * p.TW;
-        const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.TH;
-        const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.TN;
-        int it = 0;
-        for (int tap = 0; tap < p.R * p.S; ++tap) {
-          const int r = tap / p.S, s = tap % p.S;
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-            const long long tw0 = p.prof ? clock64() : 0;
-            mbar_wait(&empty[stage], phase ^ 1);
-            if (p.prof) w_empty += clock64() - tw0;
+    // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
+    long long w_empty = 0;
+    const long long t_start = clock64();
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+      const int x0 = (mt % p.tiles_x) * p.TW;
+      const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.TH;
+      const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.TN;
+      int it = 0;
+      for (int tap = 0; tap < p.R * p.S; ++tap) {
+        const int r = tap / p.S, s = tap % p.S;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+          const long long tw0 = p.prof ? clock64() : 0;
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (p.prof) w_empty += clock64() - tw0;
+          if (elect_one_sync()) {
             mbar_arrive_expect_tx(&full[stage], tx_bytes);
             tma_load_4d(sA + stage * kABytesPerStage, &tmA, &full[stage], kc * 64, x0 + s - p.pad, y0 + r - p.pad, n0);
             tma_load_2d(sB + stage * b_stage_bytes, &tmB, &full[stage], it * 64, nt * p.BN);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1;
-            }
           }
-        }
-      }
-      if (p.prof) {
-        p.prof[blockIdx.x * 8 + 0] = w_empty;
-        p.prof[blockIdx.x * 8 + 1] = clock64() - t_start;
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      long long w_full = 0, w_acc = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        long long tw0 = p.prof ? clock64() : 0;
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
-        if (p.prof) w_acc += clock64() - tw0;
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * p.BN;
-        for (int it = 0; it < p.num_k; ++it) {
-          tw0 = p.prof ? clock64() : 0;
-          mbar_wait(&full[stage], phase);
-          if (p.prof) w_full += clock64() - tw0;
-          tc_fence_after();
-          const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytesPerStage));
-          const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * b_stage_bytes));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&acc_full[acc]);
-        if (++acc == p.acc_stages) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
-      }
-      if (p.prof) {
-        p.prof[blockIdx.x * 8 + 2] = w_full;
-        p.prof[blockIdx.x * 8 + 3] = w_acc;
       }
     }
-    __syncwarp();
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 8 + 0] = w_empty;
+      p.prof[blockIdx.x * 8 + 1] = clock64() - t_start;
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    long long w_full = 0, w_acc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      long long tw0 = p.prof ? clock64() : 0;
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      if (p.prof) w_acc += clock64() - tw0;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * p.BN;
+      for (int it = 0; it < p.num_k; ++it) {
+        tw0 = p.prof ? clock64() : 0;
+        mbar_wait(&full[stage], phase);
+        if (p.prof) w_full += clock64() - tw0;
+        tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytesPerStage));
+        const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * b_stage_bytes));
+        const uint32_t accum = it != 0 ? 1u : 0u;
+        if (elect_one_sync()) {
+          umma_bf16(d_tmem, ad, bd, idesc, accum);
+          umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+          umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+          umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+          umma_commit(&empty[stage]);
+          if (it == p.num_k - 1) umma_commit(&acc_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 8 + 2] = w_full;
+      p.prof[blockIdx.x * 8 + 3] = w_acc;
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps, 1 pixel / thread)
     const int q = warp & 3;
@@ -567,21 +571,11 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
     if (d->mode == UG_EPI_GATE && !d->gate) return set_error(h, UG_EINVAL, "conv: GATE epilogue needs gate");
   }
 
-  if (d->variant == 3 || d->variant == 4) return conv_halo_prepare(h, d, BN, d->variant == 3 ? 2 : 1, L);
   if (d->variant == 5) return conv_multi_prepare(h, d, std::min(BN, 128), L);
-  if (d->variant == 0 && d->R == 3 && up == 1 && d->H * d->W >= 784) {
-    // maps of at least 28x28: one CTA per SM, two MMA issuers sharing resident / streamed weights
-    // (conv3x3_multi.cu); measured against the other variants in profiles/r01_conv_sweep.txt
+  if (d->variant == 0 && d->R == 3 && up == 1 && d->H * d->W >= 196) {
+    // maps of at least 14x14: one CTA per SM, two MMA issuers sharing resident / streamed weights
+    // (conv3x3_multi.cu); measured against the other variants in profiles/r01_conv_sweep_multi_issuer.txt
     const int rc = conv_multi_prepare(h, d, std::min(BN, 128), L);
-    if (rc == UG_OK) return rc;
-    if (rc != UG_EUNSUPPORTED) return rc;
-  }
-  if (d->variant == 0 && d->R == 3 && up == 1) {
-    // measured choice (profiles/r01_conv_sweep.txt): halo kernel with two CTAs per SM for BN <= 128 on maps of
-    // at least 28x28, halo kernel with one CTA per SM for BN = 256 on maps of at least 56x56
-    int rc = UG_EUNSUPPORTED;
-    if (BN <= 128 && d->H * d->W >= 784) rc = conv_halo_prepare(h, d, BN, 2, L);
-    else if (BN == 256 && d->H * d->W >= 3136) rc = conv_halo_prepare(h, d, BN, 1, L);
     if (rc == UG_OK) return rc;
     if (rc != UG_EUNSUPPORTED) return rc;
   }
@@ -723,7 +717,6 @@ int conv_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_gemm kernels)");
     attr_set = true;
   }
-  if (L->variant == 3) return conv_halo_launch(h, L, s);
   if (L->variant == 5) return conv_multi_launch(h, L, s);
   const int act = L->p.act;
   if (L->variant == 1) {

@@ -49,7 +49,7 @@ struct ConvLaunch {
   ConvKParams p;
   dim3 grid;
   size_t smem;
-  int variant;  // 0 = persistent, 1 = one tile per CTA, 3 = 3x3 halo kernel, 5 = 3x3 multi-issuer kernel
+  int variant;  // 0 = persistent, 1 = one tile per CTA, 5 = 3x3 multi-issuer kernel
   int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres, halo_debug;
 };
 
@@ -77,8 +77,6 @@ int check_cuda(ug_engine* h, cudaError_t e, const char* what);
 
 int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
 int conv_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
-int conv_halo_prepare(ug_engine* h, const ug_conv_desc* d, int BN, int mode, ConvLaunch* out);
-int conv_halo_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* out);
 int conv_multi_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 
