@@ -56,22 +56,23 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
                                                                          const __grid_constant__ CUtensorMap tmO,
                                                                          const ConvKParams p, const MultiParams hp) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   const int b_tile_bytes = p.BN * 128;
   const int obuf_bytes = p.tma_store ? kABytesPerStage : 0;  // one 64-channel sub-tile per staging buffer
   const int nb_tiles = hp.b_resident ? 9 * p.kchunks : hp.sb;
   uint8_t* sA = smem;                                        // [kMI][sa] activation stages
   uint8_t* sB = sA + kMI * hp.sa * hp.a_stage_bytes;
   uint8_t* sO = sB + nb_tiles * b_tile_bytes;                // [kMI][obufs] output staging
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sO + kMI * p.obufs * obuf_bytes);  // [kMI][sa]
+  float* sScale = reinterpret_cast<float*>(sO + kMI * p.obufs * obuf_bytes);  // 16-byte aligned: read as float4
+  float* sBias = sScale + p.npad;
+  float* sGate = sBias + p.npad;                              // [kMI][128]: 1 + gate of the tile's image (GATE epilogue)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sGate + kMI * 128);          // [kMI][sa]
   uint64_t* a_empty = a_full + kMI * hp.sa;
   uint64_t* b_full = a_empty + kMI * hp.sa;                  // [sb] (entry 0 only when resident)
   uint64_t* b_empty = b_full + hp.sb;
   uint64_t* acc_full = b_empty + hp.sb;                      // [kMI][acc_stages]
   uint64_t* acc_empty = acc_full + kMI * p.acc_stages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + kMI * p.acc_stages);
-  float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);
-  float* sBias = sScale + p.npad;
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -305,13 +306,24 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
       const __nv_bfloat16* add_row =
           reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)n * p.add_bstride + pix * p.add_cstride + ncol0;
       const float* gate_row = p.gate + (long long)n * p.N + ncol0;
+      const int ncols = min(p.BN, p.N - ncol0);
+      const bool has_add = p.mode == UG_EPI_ADD || p.mode == UG_EPI_GATE;
+      // residual row of the first 64-channel sub-tile: issued before the accumulator wait so that the loads are
+      // in flight while the MMAs of this tile finish (16-byte pieces of this thread's own pixel row)
+      uint4 addv[8];
+      if (has_add) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          addv[g] = (valid && g * 8 < ncols) ? __ldg(reinterpret_cast<const uint4*>(add_row + g * 8))
+                                             : make_uint4(0, 0, 0, 0);
+        if (p.mode == UG_EPI_GATE && etid < ncols) sGate[i * 128 + etid] = 1.0f + __ldg(gate_row + etid);
+      }
       long long tw0 = p.prof ? clock64() : 0;
       mbar_wait(&acc_full[i * p.acc_stages + acc], acc_phase);
       if (p.prof) e_wacc += clock64() - tw0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (i * p.acc_stages + acc) * p.BN;
       float dot = 0.0f;
-      const int ncols = min(p.BN, p.N - ncol0);
 
       uint32_t v[16];
       __syncwarp();
@@ -321,10 +333,17 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
       } else {
         tmem_ld16(taddr, v);
       }
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
-        const bool sub_start = (c0 & 63) == 0;
-        if (p.tma_store && sub_start) {
+      for (int sub = 0; sub * 64 < ncols; ++sub) {
+        if (p.tma_store) {
+          if (has_add && sub != 0) {  // second sub-tile (BN = 128): its residual row is fetched here
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              addv[g] = (valid && sub * 64 + g * 8 < ncols)
+                            ? __ldg(reinterpret_cast<const uint4*>(add_row + sub * 64 + g * 8))
+                            : make_uint4(0, 0, 0, 0);
+          }
           // staging buffer `obuf` must no longer be read by the TMA store issued obufs sub-tiles ago
+          // (the barrier also publishes sGate of this tile)
           tw0 = p.prof ? clock64() : 0;
           if (etid == 0) {
             if (p.obufs == 2) bulk_wait_group_read<1>();
@@ -333,45 +352,62 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
           named_bar_sync(1 + i, 128);
           if (p.prof) e_wobuf += clock64() - tw0;
         }
-        tmem_ld_wait();
-        float f[16];
-        epi_math16<kAct>(v, f, sScale, sBias, ncol0 + c0);
-        __syncwarp();
-        if (c0 + 16 < ncols && !(hp.debug & 1)) tmem_ld16(taddr + c0 + 16, v);
-        if (p.mode == UG_EPI_OUTC) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) dot += f[j] * __ldg(p.outc_w + ncol0 + c0 + j);
-          continue;
-        }
-        const int groups = (c0 + 16 <= ncols) ? 2 : 1;
-        if ((p.mode == UG_EPI_ADD || p.mode == UG_EPI_GATE) && valid) {
-          for (int g = 0; g < groups; ++g) epi_add_gate8(p, f + g * 8, add_row + c0 + g * 8, gate_row + c0 + g * 8);
-        }
         uint8_t* so_row = sOi + obuf * obuf_bytes + row * 128;
-        for (int g = 0; g < groups; ++g) {
-          uint4 o;
-          o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-          o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-          o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-          o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-          const int chunk = ((c0 & 63) >> 3) + g;
-          if (!(hp.debug & 2)) *reinterpret_cast<uint4*>(so_row + ((chunk ^ (row & 7)) << 4)) = o;
-        }
-        const bool sub_end = ((c0 + 16) & 63) == 0 || c0 + 16 >= ncols;
-        if (sub_end) {
-          if (c0 + 16 >= ncols) {  // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c0 = sub * 64 + cc * 16;
+          if (c0 >= ncols) break;
+          tmem_ld_wait();
+          float f[16];
+          epi_math16<kAct>(v, f, sScale, sBias, ncol0 + c0);
+          __syncwarp();
+          if (c0 + 16 < ncols && !(hp.debug & 1)) tmem_ld16(taddr + c0 + 16, v);
+          if (p.mode == UG_EPI_OUTC) {
+            const float4* ow = reinterpret_cast<const float4*>(p.outc_w + ncol0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 w4 = __ldg(ow + j);
+              dot += f[4 * j] * w4.x + f[4 * j + 1] * w4.y + f[4 * j + 2] * w4.z + f[4 * j + 3] * w4.w;
+            }
+            continue;
           }
-          fence_proxy_async_smem();
-          named_bar_sync(1 + i, 128);
-          if (etid == 0 && !(hp.debug & 2)) {
-            tma_store_4d(&tmO, sOi + obuf * obuf_bytes, ncol0 + (c0 & ~63), x0, y0, n);
-            bulk_commit_group();
+          const int groups = (c0 + 16 <= ncols) ? 2 : 1;
+          if (has_add) {
+            if (p.mode == UG_EPI_GATE) {
+              const float4* gp = reinterpret_cast<const float4*>(sGate + i * 128 + c0);
+              epi_gate8(f, addv[2 * cc], gp[0], gp[1]);
+              if (groups == 2) epi_gate8(f + 8, addv[2 * cc + 1], gp[2], gp[3]);
+            } else {
+              epi_add8(f, addv[2 * cc]);
+              if (groups == 2) epi_add8(f + 8, addv[2 * cc + 1]);
+            }
           }
-          if (p.obufs == 2) obuf ^= 1;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (g < groups) {
+              uint4 o;
+              o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+              o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+              o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+              o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+              const int chunk = cc * 2 + g;
+              if (!(hp.debug & 2)) *reinterpret_cast<uint4*>(so_row + ((chunk ^ (row & 7)) << 4)) = o;
+            }
+          }
         }
+        if (p.mode == UG_EPI_OUTC) continue;
+        if ((sub + 1) * 64 >= ncols) {  // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + i, 128);
+        if (etid == 0 && !(hp.debug & 2)) {
+          tma_store_4d(&tmO, sOi + obuf * obuf_bytes, ncol0 + sub * 64, x0, y0, n);
+          bulk_commit_group();
+        }
+        if (p.obufs == 2) obuf ^= 1;
       }
       if (p.mode == UG_EPI_OUTC) {
         tc_fence_before();
@@ -435,7 +471,8 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   memset(&hp, 0, sizeof(hp));
   hp.TH = TH;
   hp.a_stage_bytes = a_stage;
-  const int fixed = 1024 + 8 * (2 * kMI * 4 + 2 * 12 + 2 * kMI * 4) + 16 + 2 * npad * (int)sizeof(float);
+  const int fixed = 1024 + 8 * (2 * kMI * 4 + 2 * 12 + 2 * kMI * 4) + 16 + 2 * npad * (int)sizeof(float) +
+                    kMI * 128 * (int)sizeof(float);
   const long long budget = 227LL * 1024 - fixed;
   int obufs = tma_store ? 2 : 0;
   const long long resB = 9LL * kchunks * b_tile;
@@ -526,7 +563,8 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   L->grid = dim3((unsigned)std::min<long long>(total_super, (long long)h->num_sms), 1, 1);
   const int nb_tiles = hp.b_resident ? 9 * kchunks : hp.sb;
   L->smem = 1024 + (size_t)kMI * hp.sa * a_stage + (size_t)nb_tiles * b_tile + (size_t)kMI * obufs * obuf_bytes +
-            8 * (2 * kMI * hp.sa + 2 * hp.sb + 2 * kMI * acc_stages) + 16 + 2 * (size_t)npad * sizeof(float);
+            8 * (2 * kMI * hp.sa + 2 * hp.sb + 2 * kMI * acc_stages) + 16 + 2 * (size_t)npad * sizeof(float) +
+            kMI * 128 * sizeof(float);
   if (L->smem > (size_t)227 * 1024)
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): shared memory request %zu too large", L->smem);
   return UG_OK;

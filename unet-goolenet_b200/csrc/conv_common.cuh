@@ -18,11 +18,41 @@ __device__ __forceinline__ float apply_act(float t) {
   else return t;
 }
 
+// folded BN / bias + activation of 16 consecutive channels starting at `col` (a multiple of 16); scale and bias
+// live in shared memory and are read as float4
 template <int kAct>
 __device__ __forceinline__ void epi_math16(const uint32_t (&v)[16], float (&f)[16], const float* sScale,
                                            const float* sBias, int col) {
+  const float4* s4 = reinterpret_cast<const float4*>(sScale + col);
+  const float4* b4 = reinterpret_cast<const float4*>(sBias + col);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) f[j] = apply_act<kAct>(__uint_as_float(v[j]) * sScale[col + j] + sBias[col + j]);
+  for (int j = 0; j < 4; ++j) {
+    const float4 sc = s4[j], bi = b4[j];
+    f[4 * j + 0] = apply_act<kAct>(__uint_as_float(v[4 * j + 0]) * sc.x + bi.x);
+    f[4 * j + 1] = apply_act<kAct>(__uint_as_float(v[4 * j + 1]) * sc.y + bi.y);
+    f[4 * j + 2] = apply_act<kAct>(__uint_as_float(v[4 * j + 2]) * sc.z + bi.z);
+    f[4 * j + 3] = apply_act<kAct>(__uint_as_float(v[4 * j + 3]) * sc.w + bi.w);
+  }
+}
+
+// residual add of 8 bf16 values held in a register quad
+__device__ __forceinline__ void epi_add8(float* f, const uint4& a) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] += bf16_lo(aw[j]);
+    f[2 * j + 1] += bf16_hi(aw[j]);
+  }
+}
+// CoordAtt3 combine e1 + d*(1+g) (basicUnet.py:229) with g1 = 1 + g of 8 channels
+__device__ __forceinline__ void epi_gate8(float* f, const uint4& a, const float4& g1a, const float4& g1b) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+  const float g1[8] = {g1a.x, g1a.y, g1a.z, g1a.w, g1b.x, g1b.y, g1b.z, g1b.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = bf16_lo(aw[j]) + f[2 * j] * g1[2 * j];
+    f[2 * j + 1] = bf16_hi(aw[j]) + f[2 * j + 1] * g1[2 * j + 1];
+  }
 }
 
 __device__ __forceinline__ void epi_add_gate8(const ConvKParams& p, float* f, const __nv_bfloat16* add_ptr,

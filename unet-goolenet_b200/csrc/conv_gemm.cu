@@ -26,16 +26,16 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   const int b_stage_bytes = p.BN * 128;
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.stages * kABytesPerStage;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + p.stages * b_stage_bytes);
+  float* sScale = reinterpret_cast<float*>(sB + p.stages * b_stage_bytes);  // 16-byte aligned: read as float4
+  float* sBias = sScale + p.BN;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sBias + p.BN);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);
-  float* sBias = sScale + p.BN;
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -159,10 +159,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
       tmem_ld16(taddr + c0, v);
       tmem_ld_wait();
       float f[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        f[j] = apply_act<kAct>(__uint_as_float(v[j]) * sScale[c0 + j] + sBias[c0 + j]);
-      }
+      epi_math16<kAct>(v, f, sScale, sBias, c0);
       if (p.mode == UG_EPI_OUTC) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) dot += f[j] * __ldg(p.outc_w + ncol0 + c0 + j);
@@ -210,20 +207,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
                                                                            const __grid_constant__ CUtensorMap tmO,
                                                                            const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   const int b_stage_bytes = p.BN * 128;
   const int n_sub = (p.BN + 63) / 64;
   const int obuf_bytes = (p.tma_store || p.stage_copy) ? n_sub * kABytesPerStage : 0;
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.stages * kABytesPerStage;
   uint8_t* sO = sB + p.stages * b_stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sO + p.obufs * obuf_bytes);
+  float* sScale = reinterpret_cast<float*>(sO + p.obufs * obuf_bytes);  // 16-byte aligned: read as float4
+  float* sBias = sScale + p.npad;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sBias + p.npad);
   uint64_t* empty = full + p.stages;
   uint64_t* acc_full = empty + p.stages;
   uint64_t* acc_empty = acc_full + p.acc_stages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + p.acc_stages);
-  float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);
-  float* sBias = sScale + p.npad;
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;

@@ -7,7 +7,7 @@ namespace ug {
 
 __global__ void __launch_bounds__(128) mma_bench_kernel(int N, int n_acc, int iters, int distinct_ab, long long* out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_ptr;
   // A: 4 tiles x 16 KB, B: 4 tiles x N*128 B (zero-filled: values are irrelevant for timing)
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) mma_bench_kernel(int N, int n_acc, int it
 __global__ void __launch_bounds__(128) mma_bench2_kernel(int N, int n_acc, int issuers, int iters, int a_off,
                                                          int a_sbo, int acc_stride, long long* out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   __shared__ uint64_t bar[4];
   __shared__ uint32_t tmem_ptr;
   for (int i = threadIdx.x; i < (issuers * 24576 + N * 128) / 16; i += blockDim.x)

@@ -12,7 +12,7 @@
 // N = 64 output channels.  Per tile: (kind 1: stage the transformed bf16 source patch in smem) -> every thread
 // writes its im2col row into the 128B-swizzled K-major A tile -> one thread issues the MMAs -> all threads read
 // their accumulator row from TMEM, apply folded BN + ReLU, stage the bf16 tile in swizzled smem -> TMA store.
-// The phases of one CTA are serial; several co-resident CTAs per SM (5 for inc, 2 for conv1) overlap them.
+// The phases of one CTA are serial; several co-resident CTAs per SM (7 for inc, 2 for conv1) overlap them.
 // Both layers are bound by the 64-channel output write (128 B per pixel), not by the tensor pipe.
 #include <cstring>
 #include "conv_common.cuh"
@@ -22,6 +22,9 @@ namespace ug {
 static constexpr int kStemTW = 16, kStemTH = 8;          // output tile
 static constexpr int kG1PatchW = 2 * kStemTW + 5;        // 37 source pixels
 static constexpr int kG1PatchH = 2 * kStemTH + 5;        // 21 source rows
+static constexpr int kIncPatchH = kStemTH + 2, kIncPatchW = kStemTW + 2;   // 10 x 18 source pixels per channel
+static constexpr int kIncPatchPitch = 48;                // floats per patch row: the two tile rows of a warp (ty, ty+1)
+                                                         // then read banks [tx+s, ..] and [16+tx+s, ..]: no conflicts
 static constexpr int kG1PatchPitch = 112;                // bf16 elements per patch row (111 used); 56 words keeps
                                                          // the 4-byte run copies of a warp on distinct banks
 
@@ -31,17 +34,20 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
   constexpr int kAtoms = kKind == 0 ? 1 : 3;             // 64-column swizzle atoms of the A / B tiles
   constexpr int kKSteps = kKind == 0 ? 2 : 10;           // K=16 MMAs per tile
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
+  constexpr int kPatchBytes = kKind == 0 ? 3 * kIncPatchH * kIncPatchPitch * 4 : kG1PatchH * kG1PatchPitch * 2;
   uint8_t* sA = smem;                                    // kAtoms x [128 rows][128 B]
+  uint8_t* sO = sA;                                      // output staging [128 rows][128 B] reuses the first A atom:
+                                                         // the A tile is dead once the MMAs of the tile completed
   uint8_t* sB = sA + kAtoms * kABytesPerStage;           // kAtoms x [64 rows][128 B]
-  uint8_t* sO = sB + kAtoms * 64 * 128;                  // [128 rows][128 B] output staging
-  __nv_bfloat16* sPatch = reinterpret_cast<__nv_bfloat16*>(sO + kABytesPerStage);
-  uint8_t* tail = reinterpret_cast<uint8_t*>(sPatch) + (kKind == 1 ? kG1PatchH * kG1PatchPitch * 2 : 0);
-  uint64_t* b_full = reinterpret_cast<uint64_t*>(tail);
+  __nv_bfloat16* sPatch = reinterpret_cast<__nv_bfloat16*>(sB + kAtoms * 64 * 128);   // kind 1: bf16 patch
+  float* sPatchF = reinterpret_cast<float*>(sPatch);                                  // kind 0: fp32 patch
+  uint8_t* tail = reinterpret_cast<uint8_t*>(sPatch) + kPatchBytes;
+  float* sScale = reinterpret_cast<float*>(tail);       // 16-byte aligned: read as float4
+  float* sBias = sScale + 64;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(sBias + 64);
   uint64_t* acc_full = b_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
-  float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);
-  float* sBias = sScale + 64;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -55,6 +61,9 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
   if (warp == 0) {
     tmem_alloc(tmem_ptr, 64);
     tmem_relinquish();
+  }
+  if constexpr (kKind == 1) {  // element 111 of every patch row is read (times a zero weight) but never staged
+    if (tid < kG1PatchH) sPatch[tid * kG1PatchPitch + kG1PatchPitch - 1] = __float2bfloat16_rn(0.0f);
   }
   if (tid < 64) {
     sScale[tid] = p.scale ? p.scale[tid] : 1.0f;
@@ -84,24 +93,41 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
     const int n = t / (p.tiles_x * p.tiles_y);
 
     if constexpr (kKind == 0) {
-      // ---- inc: 27 taps straight from the fp32 NCHW image (neighbouring threads share lines through L1)
+      // ---- inc: stage the 3 x 10 x 18 fp32 source patch (zero outside the image) with coalesced loads, then every
+      // thread gathers its 27 taps from shared memory
       const float* xn = p.in_f32 + (long long)n * 3 * p.H * p.W;
-      const int px = x0 + tx, py = y0 + ty;
+      constexpr int kElems = 3 * kIncPatchH * kIncPatchW;  // 540
+      constexpr int kSteps = (kElems + 127) / 128;
+      float raw[kSteps];
+#pragma unroll
+      for (int k = 0; k < kSteps; ++k) {
+        const int idx = tid + k * 128;
+        const int c = idx / (kIncPatchH * kIncPatchW), rem = idx - c * (kIncPatchH * kIncPatchW);
+        const int r = rem / kIncPatchW, xx = rem - r * kIncPatchW;
+        const int iy = y0 - 1 + r, ix = x0 - 1 + xx;
+        const bool inb = idx < kElems && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        raw[k] = inb ? __ldg(xn + ((long long)c * p.H + iy) * p.W + ix) : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < kSteps; ++k) {
+        const int idx = tid + k * 128;
+        const int c = idx / (kIncPatchH * kIncPatchW), rem = idx - c * (kIncPatchH * kIncPatchW);
+        const int r = rem / kIncPatchW, xx = rem - r * kIncPatchW;
+        if (idx < kElems) sPatchF[(c * kIncPatchH + r) * kIncPatchPitch + xx] = raw[k];
+      }
+      if (tid == 0) bulk_wait_group_read<0>();  // previous tile's TMA store has finished reading sO (= sA)
+      __syncthreads();
+      const float* pt = sPatchF + ty * kIncPatchPitch + tx;
       float v[32];
 #pragma unroll
       for (int i = 27; i < 32; ++i) v[i] = 0.0f;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int iy = py + r - 1;
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int ix = px + s - 1;
-          const bool in = (iy >= 0) && (iy < p.H) && (ix >= 0) && (ix < p.W);
+        for (int sx = 0; sx < 3; ++sx)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            v[(r * 3 + s) * 3 + c] = in ? __ldg(xn + ((long long)c * p.H + iy) * p.W + ix) : 0.0f;
-        }
-      }
+            v[(r * 3 + sx) * 3 + c] = pt[(c * kIncPatchH + r) * kIncPatchPitch + sx];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint4 o;
@@ -116,18 +142,40 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
       const float sc[3] = {0.229f / 0.5f, 0.224f / 0.5f, 0.225f / 0.5f};
       const float sh[3] = {(0.485f - 0.5f) / 0.5f, (0.456f - 0.5f) / 0.5f, (0.406f - 0.5f) / 0.5f};
       const int iy0 = 2 * y0 - 3, ix0 = 2 * x0 - 3;
-      for (int i = tid; i < kG1PatchH * kG1PatchPitch; i += 128) {
-        const int r = i / kG1PatchPitch, e = i - r * kG1PatchPitch;
-        const int px = e / 3, c = e - px * 3;
+      // one source pixel (3 channels) per thread and step; all loads of a tile are issued before any is used
+      constexpr int kPix = kG1PatchW * kG1PatchH;
+      constexpr int kSteps = (kPix + 127) / 128;
+      float raw[kSteps][3];
+      unsigned inb_mask = 0;
+#pragma unroll
+      for (int k = 0; k < kSteps; ++k) {
+        const int idx = tid + k * 128;
+        const int r = idx / kG1PatchW, px = idx - r * kG1PatchW;
         const int iy = iy0 + r, ix = ix0 + px;
-        float val = 0.0f;
-        if (px < kG1PatchW && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-          const float f = p.in_f32 ? __ldg(p.in_f32 + (((long long)n * 3 + c) * p.H + iy) * p.W + ix)
-                                   : (float)p.in_u8[(((long long)n * p.H + iy) * p.W + ix) * 3 + c] / 255.0f;
-          val = f * sc[c] + sh[c];
+        const bool inb = idx < kPix && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        inb_mask |= (inb ? 1u : 0u) << k;
+        if (p.in_f32) {
+          const float* src = p.in_f32 + ((long long)n * 3 * p.H + iy) * p.W + ix;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) raw[k][c] = inb ? __ldg(src + (long long)c * p.H * p.W) : 0.0f;
+        } else {
+          const unsigned char* src = p.in_u8 + (((long long)n * p.H + iy) * p.W + ix) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) raw[k][c] = inb ? (float)__ldg(src + c) / 255.0f : 0.0f;
         }
-        sPatch[i] = __float2bfloat16_rn(val);
       }
+#pragma unroll
+      for (int k = 0; k < kSteps; ++k) {
+        const int idx = tid + k * 128;
+        const int r = idx / kG1PatchW, px = idx - r * kG1PatchW;
+        if (idx < kPix) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)  // zero padding is applied after the affine: out-of-image taps are exactly 0
+            sPatch[r * kG1PatchPitch + px * 3 + c] =
+                __float2bfloat16_rn(((inb_mask >> k) & 1u) ? raw[k][c] * sc[c] + sh[c] : 0.0f);
+        }
+      }
+      if (tid == 0) bulk_wait_group_read<0>();  // previous tile's TMA store has finished reading sO (= sA)
       __syncthreads();
       uint32_t w[80];
 #pragma unroll
@@ -144,8 +192,6 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
         *reinterpret_cast<uint4*>(a_row + (j >> 3) * kABytesPerStage + (((j & 7) ^ sw) << 4)) = o;
       }
     }
-    // the TMA store of the previous tile must have finished reading the staging buffer before it is rewritten
-    if (tid == 0) bulk_wait_group_read<0>();
     fence_proxy_async_smem();  // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -247,10 +293,11 @@ int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* L) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "stem: output tensor map encode failed (%d)", (int)r);
   }
-  const int ctas_per_sm = d->kind == 0 ? 5 : 2;
+  const int ctas_per_sm = d->kind == 0 ? 7 : 2;  // 31 KB / 79 KB of shared memory and 64 TMEM columns per CTA
   L->grid = (unsigned)std::min<long long>(p.total_tiles, (long long)h->num_sms * ctas_per_sm);
-  L->smem = 1024 + (size_t)katoms * kABytesPerStage + (size_t)katoms * 64 * 128 + kABytesPerStage +
-            (d->kind == 1 ? kG1PatchH * kG1PatchPitch * 2 : 0) + 16 + 8 + 2 * 64 * sizeof(float);
+  L->smem = 1024 + (size_t)katoms * kABytesPerStage + (size_t)katoms * 64 * 128 +
+            (d->kind == 1 ? kG1PatchH * kG1PatchPitch * 2 : 3 * kIncPatchH * kIncPatchPitch * 4) + 16 + 8 +
+            2 * 64 * sizeof(float);
   return UG_OK;
 }
 
