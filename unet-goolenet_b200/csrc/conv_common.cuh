@@ -5,7 +5,12 @@
 
 namespace ug {
 
-static constexpr int kThreads = 192;               // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+// Warp roles of the 192-thread GEMM kernels: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer,
+// warp 5 TMEM allocator + MMA issuer.  The scheduler prefers the highest eligible warp id, so the latency-critical
+// issue warps sit above the epilogue warps (see conv3x3_multi.cu).
+static constexpr int kThreads = 192;
+static constexpr int kProducerWarp = 4;
+static constexpr int kMmaWarp = 5;
 static constexpr int kABytesPerStage = 128 * 128;  // 128 rows x 64 bf16
 
 // kAct is a template parameter on purpose: with a run-time activation switch the compiler if-converts the erf

@@ -10,7 +10,7 @@
 // * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator; four epilogue warps
 //   read it back with tcgen05.ld (one output pixel per thread) and apply folded BN / bias, activation and the
 //   fused epilogue (residual add, CoordAtt3 gate combine, ConvTranspose pixel shuffle, outc+sigmoid+threshold).
-// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// * Warp roles: warps 0..3 = epilogue, warp 4 = TMA producer, warp 5 = TMEM allocator + MMA issuer.
 //
 // Reference ops this kernel replaces are listed on ug_conv_desc in include/ugnet.h.
 #include <cstdarg>
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.TN;
   const int ncol0 = blockIdx.y * p.BN;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int i = 0; i < p.stages; ++i) {
@@ -57,12 +57,12 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     mbar_init(tmem_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_ptr, p.tmem_cols);
     tmem_relinquish();
   }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < p.BN; i += 128) {
+  if (warp < 4) {
+    for (int i = threadIdx.x; i < p.BN; i += 128) {
       const int n = ncol0 + i;
       sScale[i] = (n < p.N) ? (p.scale ? p.scale[n] : 1.0f) : 0.0f;
       sBias[i] = (n < p.N && p.bias) ? p.bias[n] : 0.0f;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
     int stage = 0;
     uint32_t phase = 0;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
     const uint32_t idesc = umma_idesc_bf16(128, p.BN);
     int stage = 0;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     if (p.tma_store) prefetch_tmap(&tmO);
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_ptr, p.tmem_cols);
     tmem_relinquish();
   }
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
     int stage = 0;
     uint32_t phase = 0;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
       p.prof[blockIdx.x * 8 + 0] = w_empty;
       p.prof[blockIdx.x * 8 + 1] = clock64() - t_start;
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
     const uint32_t idesc = umma_idesc_bf16(128, p.BN);
     int stage = 0, acc = 0;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
     // ------------------------------------------------------------------ epilogue (4 warps, 1 pixel / thread)
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int etid = threadIdx.x - 64;  // 0..127
+    const int etid = threadIdx.x;  // 0..127
     long long w_accfull = 0, w_obuf = 0, t_proc = 0, t_store = 0;
     const int tx = row % p.TW;
     const int trest = row / p.TW;
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ host side
