@@ -9,8 +9,10 @@ shape = tuple(int(v) for v in args[0].split(","))
 cfg = dict(variant=int(args[1]))
 if len(args) > 2:
     cfg["mode"] = int(args[2])
-if len(args) > 3:
+if len(args) > 3 and int(args[3]):
     cfg["bn"] = int(args[3])
+if len(args) > 4:
+    cfg["up"] = int(args[4])
 d, keep = cp.make(*shape, **cfg)
 for _ in range(3):
     cp.eng.run_op(d)

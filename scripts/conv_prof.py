@@ -11,18 +11,20 @@ eng = E.Engine.get(0)
 g = torch.Generator(device="cuda").manual_seed(0)
 
 
-def make(B, H, W, Cin, N, R, mode=0, bn=None, stages=0, variant=0, tile=None):
+def make(B, H, W, Cin, N, R, mode=0, bn=None, stages=0, variant=0, tile=None, up=1):
     x = torch.randn((B, H, W, Cin), generator=g, device="cuda").to(torch.bfloat16)
     wt = torch.randn((N, Cin, R, R), generator=g, device="cuda") * (Cin * R * R) ** -0.5
-    BN = bn or pack.choose_bn(N)
+    BN = bn or (pack.choose_bn(N, N // 4) if up == 2 else pack.choose_bn(N))
     wp = pack.pack_conv_weight(wt, BN)
-    out = torch.empty((B, H, W, N), device="cuda", dtype=torch.bfloat16)
+    out = torch.empty((B, H * up, W * up, N // (up * up)), device="cuda", dtype=torch.bfloat16)
     scale = torch.ones(N, device="cuda"); bias = torch.zeros(N, device="cuda")
     d = E.ConvDesc()
     d.inp = x.data_ptr(); d.in_cstride = Cin; d.Cin = Cin; d.B, d.H, d.W = B, H, W
     d.R = d.S = R; d.pad = (R - 1) // 2; d.w = wp.data_ptr(); d.N = N
     d.scale = scale.data_ptr(); d.bias = bias.data_ptr(); d.act = 1; d.mode = mode
-    d.out = out.data_ptr(); d.out_cstride = N; d.up = 1; d.BN = BN; d.stages = stages; d.variant = variant
+    d.out = out.data_ptr(); d.out_cstride = N // (up * up); d.up = up; d.BN = BN; d.stages = stages; d.variant = variant
+    if up == 2:
+        d.convt_cout = N // 4; d.act = 0
     if tile: d.TW, d.TH, d.TN = tile
     keep = [x, wp, out, scale, bias]
     if mode == 2:
@@ -51,20 +53,29 @@ SHAPES = [(64, 224, 224, 64, 64, 3), (64, 224, 224, 128, 64, 3), (64, 112, 112, 
           (256, 28, 28, 16, 32, 3), (256, 14, 14, 96, 208, 3), (256, 14, 14, 160, 320, 3), (256, 14, 14, 24, 64, 3),
           (256, 7, 7, 160, 320, 3), (256, 7, 7, 192, 384, 3), (256, 7, 7, 48, 128, 3),
           (1, 1, 12544, 512, 1536, 1), (1, 1, 12544, 512, 512, 1), (1, 1, 12544, 2048, 512, 1),
-          (1, 1, 200704, 192, 64, 1), (1, 1, 200704, 256, 128, 1), (1, 1, 50176, 512, 160, 1), (1, 1, 12544, 832, 384, 1)]
+          (1, 1, 200704, 192, 64, 1), (1, 1, 200704, 256, 128, 1), (1, 1, 50176, 512, 160, 1), (1, 1, 12544, 832, 384, 1),
+          (64, 14, 14, 512, 2048, 0), (64, 28, 28, 256, 1024, 0), (64, 56, 56, 128, 512, 0), (64, 112, 112, 64, 256, 0)]
 if len(sys.argv) > 1:
     SHAPES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
 if __name__ != "__main__":
     SHAPES = []
-CONFIGS = [dict(variant=1), dict(variant=2), dict(variant=2, bn=256), dict(variant=5), dict(variant=5, mode=2)]
+CONFIGS = [dict(variant=1), dict(variant=2), dict(variant=2, bn=256), dict(variant=5), dict(variant=5, mode=2),
+           dict(variant=5, bn=256)]
 if os.environ.get("UG_ABLATE"):
     CONFIGS = [dict(variant=5)] + [dict(variant=5, stages=100 + f) for f in (1, 2, 3, 4, 7)]
 for shp in SHAPES:
     B, H, W, Cin, N, R = shp
-    fl = 2.0 * B * H * W * N * Cin * R * R
+    fl = 2.0 * B * H * W * N * Cin * max(R, 1) ** 2
     for cfg in CONFIGS:
-        if cfg.get("bn", 0) > N or (cfg.get("variant") == 5 and R != 3) or (cfg.get("mode") == 2 and H * W < 784):
+        if cfg.get("bn", 0) > N or (cfg.get("mode") == 2 and (H * W < 784 or R != 3)):
             continue
+        if cfg.get("variant") == 5 and cfg.get("bn") == 256 and R == 3:
+            continue
+        if R == 0:   # ConvTranspose 2x2 s2 shapes are written with R = 0
+            shp = (B, H, W, Cin, N, 1)
+            cfg = dict(cfg, up=2)
+            if cfg.get("bn", 0) > N // 4 and cfg.get("variant") != 5:
+                continue
         try:
             d, keep = make(*shp, **cfg)
             ms = timeit(d)

@@ -146,6 +146,17 @@ CASES = [
     dict(B=5, H=7, W=7, Cin=160, N=320, R=3, variant=5),           # GoogLeNet 5a-like, tiny map
     dict(B=2, H=16, W=16, Cin=64, N=64, R=3, mode=1, variant=5),   # residual add, resident weights
     dict(B=70, H=32, W=32, Cin=64, N=128, R=3, variant=5),        # several rounds per CTA
+    # multi-issuer kernel on 1x1 convolutions / linear layers / ConvTranspose (plain pixel tiles)
+    dict(B=1, H=1, W=256, Cin=64, N=64, R=1, variant=5),                      # resident weights, one round
+    dict(B=1, H=1, W=1000, Cin=512, N=1536, R=1, act=0, variant=5),           # qkv-shaped GEMM, ragged M
+    dict(B=1, H=1, W=392, Cin=512, N=2048, R=1, act=2, variant=5),            # FFN up-projection with GELU
+    dict(B=1, H=1, W=392, Cin=512, N=512, R=1, mode=1, act=0, variant=5),     # linear + residual
+    dict(B=5, H=7, W=7, Cin=832, N=48, R=1, variant=5),                       # TN > 1, BN = 48
+    dict(B=2, H=28, W=28, Cin=192, N=96, R=1, out_extra=160, out_off=64, variant=5),  # concat-offset store, N = 96
+    dict(B=2, H=14, W=14, Cin=512, N=2048, R=1, up=2, act=0, variant=5),      # ConvTranspose 2x2 s2 (512 -> 512)
+    dict(B=1, H=112, W=112, Cin=64, N=256, R=1, up=2, act=0, out_extra=64, variant=5),  # ConvT into a concat buffer
+    dict(B=3, H=28, W=28, Cin=256, N=1024, R=1, up=2, act=0, out_extra=256, variant=5),  # ConvT, odd tile count
+    dict(B=70, H=14, W=14, Cin=480, N=192, R=1, variant=5),                   # several rounds, ragged channel chunk
     # legacy one-tile-per-CTA variant stays covered
     dict(B=2, H=16, W=16, Cin=64, N=64, R=3, variant=1),
     dict(B=2, H=56, W=56, Cin=256, N=128, R=3, variant=1),

@@ -505,7 +505,7 @@ EncodeTiledFn get_encode_fn() {
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // Pick the pixel-tile rectangle with the best fill of the 128 MMA rows.
-static void choose_tile(int B, int H, int W, int* TW, int* TH, int* TN) {
+void choose_tile(int B, int H, int W, int* TW, int* TH, int* TN) {
   double best = -1.0;
   int bw = 1, bh = 1, bn = 1;
   for (int tw = 1; tw <= W && tw <= 128; ++tw) {
@@ -551,7 +551,7 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   }
   if (BN % 16 || BN < 16 || BN > 256) return set_error(h, UG_EINVAL, "conv: BN must be a multiple of 16 in [16,256]");
   if (up == 2) {
-    if (d->convt_cout <= 0 || d->N != 4 * d->convt_cout || d->convt_cout % BN)
+    if (d->convt_cout <= 0 || d->N != 4 * d->convt_cout || (d->convt_cout % BN && d->variant != 5))
       return set_error(h, UG_EINVAL, "conv: ConvTranspose mode needs N == 4*cout and BN | cout");
     if (d->R != 1) return set_error(h, UG_EINVAL, "conv: ConvTranspose mode is a 1x1 GEMM");
   }
@@ -568,7 +568,14 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
     if (d->mode == UG_EPI_GATE && !d->gate) return set_error(h, UG_EINVAL, "conv: GATE epilogue needs gate");
   }
 
-  if (d->variant == 5) return conv_multi_prepare(h, d, std::min(BN, 128), L);
+  if (d->variant == 5) return conv_multi_prepare(h, d, d->R == 3 ? std::min(BN, 128) : BN, L);
+  if (d->variant == 0 && up == 2 && d->H * d->W >= 784 && d->convt_cout % 64 == 0) {
+    // ConvTranspose 2x2 s2 on maps of at least 28x28: multi-issuer kernel (two epilogue warpgroups, pixel shuffle as
+    // four strided TMA-store views); one 256-wide n-tile when that covers all four quadrants
+    const int rc = conv_multi_prepare(h, d, d->N == 256 ? 256 : 128, L);
+    if (rc == UG_OK) return rc;
+    if (rc != UG_EUNSUPPORTED) return rc;
+  }
   if (d->variant == 0 && d->R == 3 && up == 1 && d->H * d->W >= 196) {
     // maps of at least 14x14: one CTA per SM, two MMA issuers sharing resident / streamed weights
     // (conv3x3_multi.cu); measured against the other variants in profiles/r01_conv_sweep_multi_issuer.txt

@@ -48,26 +48,49 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
   return d;
 }
 
+// Division by a launch-time constant as multiply + shift (exact for n < 2^24): the role loops decode a tile index
+// into (image, tile row, tile column) once per tile, and on the short K=64 / N=64 tiles that decode (four integer
+// divisions, ~25 instructions each) was a third of the epilogue time.
+struct FastDiv {
+  unsigned mul, shift;
+  __device__ __forceinline__ int div(int n) const {
+    return (int)(((unsigned long long)(unsigned)n * mul) >> shift);
+  }
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  int s = 0;
+  while ((1 << s) < d) ++s;
+  f.shift = 24 + s;
+  f.mul = (unsigned)(((1ULL << f.shift) + d - 1) / d);
+  return f;
+}
+
 struct MultiParams {
   int TH;             // output rows per tile (tile = 8 x TH pixels)
   int a_stage_bytes;  // bytes of one activation stage
   int sa, sb;         // activation stages per issuer / shared weight stages
   int b_resident;     // whole weight matrix kept in smem (requires n_tiles == 1)
   int m_super;        // ceil(m_tiles / kMI): pixel tiles are handed out in groups of kMI
+  FastDiv d_msuper, d_tx, d_ty;   // dividers by m_super, tiles_x, tiles_y
   int debug;          // ablation switches for profiling (results are wrong when set): 1 = no TMEM loads,
                       // 2 = no staging stores / TMA store, 4 = activation TMA loads only for the first stages
 };
 
-template <int kAct>
-__global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                         const __grid_constant__ CUtensorMap tmB,
-                                                                         const __grid_constant__ CUtensorMap tmO,
-                                                                         const ConvKParams p, const MultiParams hp) {
+struct StoreMaps {  // output maps: [0] for plain stores, [q] = quadrant (dy,dx) of a ConvTranspose 2x2 s2 scatter
+  CUtensorMap m[4];
+};
+
+template <int kAct, int kTaps>
+__global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                      const __grid_constant__ CUtensorMap tmB,
+                                                                      const __grid_constant__ StoreMaps tmO,
+                                                                      const ConvKParams p, const MultiParams hp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   const int b_tile_bytes = p.BN * 128;
   const int obuf_bytes = p.tma_store ? kABytesPerStage : 0;  // one 64-channel sub-tile per staging buffer
-  const int nb_tiles = hp.b_resident ? 9 * p.kchunks : hp.sb;
+  const int nb_tiles = hp.b_resident ? kTaps * p.kchunks : hp.sb;
   uint8_t* sA = smem;                                        // [kMI][sa] activation stages
   uint8_t* sB = sA + kMI * hp.sa * hp.a_stage_bytes;
   uint8_t* sO = sB + nb_tiles * b_tile_bytes;                // [kMI][obufs] output staging
@@ -89,7 +112,14 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
   if (warp == kMProducerWarp && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    if (p.tma_store) prefetch_tmap(&tmO);
+    if (p.tma_store) {
+      prefetch_tmap(&tmO.m[0]);
+      if (p.up == 2) {
+        prefetch_tmap(&tmO.m[1]);
+        prefetch_tmap(&tmO.m[2]);
+        prefetch_tmap(&tmO.m[3]);
+      }
+    }
     for (int i = 0; i < kMI * hp.sa; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
@@ -121,30 +151,37 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
     // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
     if (hp.b_resident) {
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&b_full[0], (uint32_t)(9 * p.kchunks * b_tile_bytes));
+        mbar_arrive_expect_tx(&b_full[0], (uint32_t)(kTaps * p.kchunks * b_tile_bytes));
         for (int kc = 0; kc < p.kchunks; ++kc)
-          for (int tap = 0; tap < 9; ++tap)
-            tma_load_2d(sB + (kc * 9 + tap) * b_tile_bytes, &tmB, &b_full[0], (tap * p.kchunks + kc) * 64, 0);
+          for (int tap = 0; tap < kTaps; ++tap)
+            tma_load_2d(sB + (kc * kTaps + tap) * b_tile_bytes, &tmB, &b_full[0], (tap * p.kchunks + kc) * 64, 0);
       }
       __syncwarp();
     }
     int as[kMI] = {0, 0}, bs = 0;
     uint32_t aph[kMI] = {0, 0}, bph = 0;
-    const uint32_t a_tx = (uint32_t)(kMPitch * (hp.TH + 2) * 128);
+    const uint32_t a_tx = kTaps == 9 ? (uint32_t)(kMPitch * (hp.TH + 2) * 128) : p.a_bytes;
     long long w_a = 0, w_b = 0;
     const long long t_start = clock64();
     unsigned long long ns0 = 0;
     if (p.prof) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns0));
     for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
-      const int nt = s / hp.m_super, ms = s - nt * hp.m_super;
+      const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
+      int cx[kMI], cy[kMI], cn[kMI];
+#pragma unroll
+      for (int i = 0; i < kMI; ++i) {
+        const int mt = ms * kMI + i;
+        const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
+        cx[i] = (mt - t1 * p.tiles_x) * p.TW;
+        cy[i] = (t1 - t2 * p.tiles_y) * p.TH;
+        cn[i] = t2 * p.TN;
+      }
       for (int kc = 0; kc < p.kchunks; ++kc) {
 #pragma unroll
         for (int i = 0; i < kMI; ++i) {
           const int mt = ms * kMI + i;
           if (mt >= p.m_tiles) continue;
-          const int x0 = (mt % p.tiles_x) * 8;
-          const int y0 = ((mt / p.tiles_x) % p.tiles_y) * hp.TH;
-          const int n = mt / (p.tiles_x * p.tiles_y);
+          const int x0 = cx[i], y0 = cy[i], n = cn[i];
           const int slot = i * hp.sa + as[i];
           const long long tw0 = p.prof ? clock64() : 0;
           mbar_wait(&a_empty[slot], aph[i] ^ 1);
@@ -154,7 +191,8 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
               mbar_arrive(&a_full[slot]);
             } else {
               mbar_arrive_expect_tx(&a_full[slot], a_tx);
-              tma_load_4d(sA + slot * hp.a_stage_bytes, &tmA, &a_full[slot], kc * 64, x0 - 1, y0 - 1, n);
+              if (kTaps == 9) tma_load_4d(sA + slot * hp.a_stage_bytes, &tmA, &a_full[slot], kc * 64, x0 - 1, y0 - 1, n);
+              else tma_load_4d(sA + slot * hp.a_stage_bytes, &tmA, &a_full[slot], kc * 64, x0, y0, n);
             }
           }
           __syncwarp();
@@ -164,7 +202,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
           }
         }
         if (!hp.b_resident) {
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < kTaps; ++tap) {
             const long long tw0 = p.prof ? clock64() : 0;
             mbar_wait(&b_empty[bs], bph ^ 1);
             if (p.prof) w_b += clock64() - tw0;
@@ -203,7 +241,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
     }
     const uint32_t sB_u32 = smem_u32(sB);
     for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
-      const int nt = s / hp.m_super, ms = s - nt * hp.m_super;
+      const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
       const bool valid = ms * kMI + i < p.m_tiles;
       uint32_t d_tmem = 0;
       if (valid) {
@@ -220,15 +258,16 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
           mbar_wait(&a_full[i * hp.sa + as], aph);
           if (p.prof) w_af += clock64() - tw0;
           tc_fence_after();
-          ad0 = umma_desc_sw128_sbo(smem_u32(sA + (i * hp.sa + as) * hp.a_stage_bytes), kMPitch * 128);
+          ad0 = kTaps == 9 ? umma_desc_sw128_sbo(smem_u32(sA + (i * hp.sa + as) * hp.a_stage_bytes), kMPitch * 128)
+                           : umma_desc_sw128(smem_u32(sA + (i * hp.sa + as) * hp.a_stage_bytes));
         }
         // (tap loop unrolled by one filter row only: keeps the issue loop inside the L0 instruction cache)
 #pragma unroll 3
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < kTaps; ++tap) {
           const int r = tap / 3, sx = tap - r * 3;
           uint32_t b_addr;
           if (hp.b_resident) {
-            b_addr = sB_u32 + (kc * 9 + tap) * b_tile_bytes;
+            b_addr = sB_u32 + (kc * kTaps + tap) * b_tile_bytes;
           } else {
             const long long tw0 = p.prof ? clock64() : 0;
             mbar_wait(&b_full[bs], bph);
@@ -291,9 +330,10 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int etid = threadIdx.x - i * 128;
-    const int tx = row & 7;
-    const int ty = row >> 3;
-    const bool row_in_tile = ty < hp.TH;
+    const int tx = kTaps == 9 ? (row & 7) : row % p.TW;
+    const int ty = kTaps == 9 ? (row >> 3) : (row / p.TW) % p.TH;
+    const int tn = kTaps == 9 ? 0 : row / (p.TW * p.TH);
+    const bool row_in_tile = kTaps == 9 ? (ty < hp.TH) : (row < p.TW * p.TH * p.TN);
     uint8_t* sOi = sO + i * p.obufs * obuf_bytes;
     int acc = 0, obuf = 0;
     uint32_t acc_phase = 0;
@@ -301,16 +341,18 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
     const long long e_start = clock64();
 
     for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
-      const int nt = s / hp.m_super, ms = s - nt * hp.m_super;
+      const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
       const int mt = ms * kMI + i;
       if (mt >= p.m_tiles) continue;
       ++e_tiles;
-      const int x0 = (mt % p.tiles_x) * 8;
-      const int y0 = ((mt / p.tiles_x) % p.tiles_y) * hp.TH;
-      const int n = mt / (p.tiles_x * p.tiles_y);
+      const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
+      const int x0 = (mt - t1 * p.tiles_x) * p.TW;
+      const int y0 = (t1 - t2 * p.tiles_y) * p.TH;
+      const int n0 = t2 * p.TN;
+      const int n = n0 + tn;
       const int ncol0 = nt * p.BN;
       const int x = x0 + tx, y = y0 + ty;
-      const bool valid = row_in_tile && (x < p.W) && (y < p.H);
+      const bool valid = row_in_tile && (x < p.W) && (y < p.H) && (n < p.B);
       const long long pix = (long long)y * p.W + x;
       const __nv_bfloat16* add_row =
           reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)n * p.add_bstride + pix * p.add_cstride + ncol0;
@@ -422,7 +464,13 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv3x3_multi_kernel(const _
         fence_proxy_async_smem();
         named_bar_sync(1 + i, 128);
         if (etid == 0 && !(hp.debug & 2)) {
-          tma_store_4d(&tmO, sOi + obuf * obuf_bytes, ncol0 + sub * 64, x0, y0, n);
+          const int col = ncol0 + sub * 64;
+          if (p.up == 2) {  // ConvTranspose 2x2 s2: column block -> quadrant (dy,dx) map, channel inside the quadrant
+            const int qd = col / p.convt_cout;
+            tma_store_4d(&tmO.m[qd], sOi + obuf * obuf_bytes, col - qd * p.convt_cout, x0, y0, n0);
+          } else {
+            tma_store_4d(&tmO.m[0], sOi + obuf * obuf_bytes, col, x0, y0, n0);
+          }
           bulk_commit_group();
         }
         if (p.obufs == 2) obuf ^= 1;
@@ -466,23 +514,47 @@ EncodeTiledFn get_encode_fn();
 
 static inline int cdiv_m(int a, int b) { return (a + b - 1) / b; }
 
-// Fills L for the multi-issuer kernel.  Returns UG_EUNSUPPORTED when the shape does not fit it.
+void choose_tile(int B, int H, int W, int* TW, int* TH, int* TN);  // conv_gemm.cu
+
+static int encode_map(EncodeTiledFn encode, CUtensorMap* m, void* base, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapL2promotion promo) {
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return (int)encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+// Fills L for the multi-issuer kernel: 3x3 pad-1 convolutions (halo tiles) and 1x1 convolutions / linear layers /
+// ConvTranspose 2x2 s2 (plain pixel tiles).  Returns UG_EUNSUPPORTED when the shape does not fit it.
 int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* L) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return set_error(h, UG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  if (d->R != 3 || d->S != 3 || d->pad != 1 || d->up == 2)
-    return set_error(h, UG_EUNSUPPORTED, "conv(multi): 3x3 pad-1 stride-1 convolutions only");
-  if (BN > 128) return set_error(h, UG_EUNSUPPORTED, "conv(multi): BN <= 128");
-  const int TH = cdiv_m(d->H, cdiv_m(d->H, 16));  // <= 16 rows per tile, no wasted tile rows
+  const int up = d->up == 2 ? 2 : 1;
+  const int taps = d->R == 3 ? 9 : 1;
+  if (!((d->R == 3 && d->S == 3 && d->pad == 1 && up == 1) || (d->R == 1 && d->S == 1 && d->pad == 0)))
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): 3x3 pad-1 or 1x1 stride-1 convolutions only");
+  if (BN > (taps == 9 ? 128 : 256)) return set_error(h, UG_EUNSUPPORTED, "conv(multi): BN <= 128 (3x3) / 256 (1x1)");
+  if (up == 2 && (d->convt_cout % 64 || BN % 64))  // every 64-column store block lies inside one quadrant
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): ConvTranspose needs cout %% 64 == 0 and BN %% 64 == 0");
+  if (taps == 1 && d->mode == UG_EPI_OUTC) return set_error(h, UG_EUNSUPPORTED, "conv(multi): OUTC is a 3x3 epilogue");
+  int TW, TH, TN;
+  if (taps == 9) {
+    TW = 8;
+    TH = cdiv_m(d->H, cdiv_m(d->H, 16));  // <= 16 rows per tile, no wasted tile rows
+    TN = 1;
+  } else {
+    choose_tile(d->B, d->H, d->W, &TW, &TH, &TN);
+    if (TW > 256 || TH > 256 || TN > 256) return set_error(h, UG_EUNSUPPORTED, "conv(multi): tile exceeds the TMA box limits");
+  }
   const int cin_pad = cdiv_m(d->Cin, 64) * 64;
   const int kchunks = cin_pad / 64;
   const int n_tiles = cdiv_m(d->N, BN);
   const int npad = n_tiles * BN;
-  const long long ktot = 9LL * cin_pad;
+  const long long ktot = (long long)taps * cin_pad;
   const int tma_store = d->mode != UG_EPI_OUTC;
   const int obuf_bytes = tma_store ? kABytesPerStage : 0;
   const int acc_stages = std::max(1, std::min(4, 512 / (kMI * BN)));
-  const int a_stage = ((kMPitch * (TH + 2) * 128 + 1023) / 1024) * 1024;
+  const int a_bytes = taps == 9 ? kMPitch * (TH + 2) * 128 : TW * TH * TN * 128;
+  const int a_stage = ((a_bytes + 1023) / 1024) * 1024;
   const int b_tile = BN * 128;
 
   MultiParams hp;
@@ -493,7 +565,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
                     kMI * 128 * (int)sizeof(float);
   const long long budget = 227LL * 1024 - fixed;
   int obufs = tma_store ? 2 : 0;
-  const long long resB = 9LL * kchunks * b_tile;
+  const long long resB = (long long)taps * kchunks * b_tile;
   if (n_tiles == 1 && resB + kMI * 2LL * a_stage + (tma_store ? kMI * obuf_bytes : 0) <= budget) {
     hp.b_resident = 1;
     hp.sb = 1;
@@ -518,27 +590,29 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   ConvKParams& p = L->p;
   memset(&p, 0, sizeof(p));
   p.H = d->H; p.W = d->W; p.B = d->B;
-  p.TW = 8; p.TH = TH; p.TN = 1;
-  p.tiles_x = cdiv_m(d->W, 8);
+  p.TW = TW; p.TH = TH; p.TN = TN;
+  p.tiles_x = cdiv_m(d->W, TW);
   p.tiles_y = cdiv_m(d->H, TH);
-  p.R = 3; p.S = 3; p.pad = 1;
-  p.kchunks = kchunks; p.num_k = 9 * kchunks;
+  p.R = d->R; p.S = d->S; p.pad = d->pad;
+  p.kchunks = kchunks; p.num_k = taps * kchunks;
   p.N = d->N; p.BN = BN; p.stages = hp.sa;
   int tcols = 32;
   while (tcols < kMI * acc_stages * BN) tcols <<= 1;
   p.tmem_cols = tcols;
+  p.a_bytes = (unsigned)a_bytes; p.b_bytes = (unsigned)b_tile;
   p.scale = d->scale; p.bias = d->bias;
   p.act = d->act; p.mode = d->mode;
   p.out = d->out; p.out_cstride = d->out_cstride;
-  p.up = 1; p.OH = d->H; p.OW = d->W;
+  p.up = up; p.convt_cout = d->convt_cout;
+  p.OH = d->H * up; p.OW = d->W * up;
   p.add = d->add; p.add_bstride = d->add_bstride; p.add_cstride = d->add_cstride;
   p.gate = d->gate; p.outc_w = d->outc_w; p.outc_b = d->outc_b;
   p.logits = d->logits; p.mask = d->mask;
-  p.m_tiles = p.tiles_x * p.tiles_y * d->B; p.n_tiles = n_tiles; p.acc_stages = acc_stages;
+  p.m_tiles = p.tiles_x * p.tiles_y * cdiv_m(d->B, TN); p.n_tiles = n_tiles; p.acc_stages = acc_stages;
   p.tma_store = tma_store; p.obufs = obufs; p.npad = npad;
   hp.m_super = cdiv_m(p.m_tiles, kMI);
   L->variant = 5;
-  L->halo_mode = 1;
+  L->halo_mode = taps;
   L->halo_TH = TH; L->halo_a_stage = a_stage; L->halo_copy = hp.m_super;
   L->halo_sa = hp.sa; L->halo_sb = hp.sb; L->halo_bres = hp.b_resident;
   L->halo_debug = d->stages >= 100 ? d->stages - 100 : 0;  // profiling ablations (scripts/conv_prof.py)
@@ -547,39 +621,49 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)d->W * d->in_cstride * 2,
                              (cuuint64_t)d->H * d->W * d->in_cstride * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)kMPitch, (cuuint32_t)(TH + 2), 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = encode(&L->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->in), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv(multi): activation tensor map encode failed (%d)", (int)r);
+    cuuint32_t box9[4] = {64, (cuuint32_t)kMPitch, (cuuint32_t)(TH + 2), 1};
+    cuuint32_t box1[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    const int r = encode_map(encode, &L->tmA, const_cast<void*>(d->in), 4, dims, strides, taps == 9 ? box9 : box1,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (r) return set_error(h, UG_ECUDA, "conv(multi): activation tensor map encode failed (%d)", r);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)npad};
+    // rows beyond N are zero-filled by TMA (the packed matrix is only guaranteed to hold N rows rounded up to the
+    // packer's own tile, which may differ from BN)
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d->N};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)BN};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = encode(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv(multi): weight tensor map encode failed (%d)", (int)r);
+    const int r = encode_map(encode, &L->tmB, const_cast<void*>(d->w), 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (r) return set_error(h, UG_ECUDA, "conv(multi): weight tensor map encode failed (%d)", r);
   }
+  memset(L->tmQ, 0, sizeof(L->tmQ));
+  memset(&L->tmO, 0, sizeof(L->tmO));
   if (tma_store) {
-    cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
-    cuuint64_t strides[3] = {(cuuint64_t)d->out_cstride * 2, (cuuint64_t)d->W * d->out_cstride * 2,
-                             (cuuint64_t)d->H * d->W * d->out_cstride * 2};
-    cuuint32_t box[4] = {64, 8, (cuuint32_t)TH, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = encode(&L->tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out, dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv(multi): output tensor map encode failed (%d)", (int)r);
-  } else {
-    memset(&L->tmO, 0, sizeof(L->tmO));
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    if (up == 1) {
+      cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+      cuuint64_t strides[3] = {(cuuint64_t)d->out_cstride * 2, (cuuint64_t)d->W * d->out_cstride * 2,
+                               (cuuint64_t)d->H * d->W * d->out_cstride * 2};
+      const int r = encode_map(encode, &L->tmO, d->out, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+      if (r) return set_error(h, UG_ECUDA, "conv(multi): output tensor map encode failed (%d)", r);
+    } else {
+      // ConvTranspose 2x2 s2: quadrant (dy,dx) of input pixel (y,x) is output pixel (2y+dy, 2x+dx); one strided view
+      // of the output per quadrant turns the pixel shuffle into plain TMA tile stores
+      const long long cs = d->out_cstride, OW = 2LL * d->W, OH = 2LL * d->H;
+      for (int q = 0; q < 4; ++q) {
+        const int dy = q >> 1, dx = q & 1;
+        void* base = static_cast<char*>(d->out) + ((long long)dy * OW + dx) * cs * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)d->convt_cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)(2 * cs * 2), (cuuint64_t)(2 * OW * cs * 2), (cuuint64_t)(OH * OW * cs * 2)};
+        CUtensorMap* m = q == 0 ? &L->tmO : &L->tmQ[q - 1];
+        const int r = encode_map(encode, m, base, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+        if (r) return set_error(h, UG_ECUDA, "conv(multi): ConvTranspose output tensor map encode failed (%d)", r);
+      }
+    }
   }
   const long long total_super = (long long)hp.m_super * n_tiles;
   L->grid = dim3((unsigned)std::min<long long>(total_super, (long long)h->num_sms), 1, 1);
-  const int nb_tiles = hp.b_resident ? 9 * kchunks : hp.sb;
+  const int nb_tiles = hp.b_resident ? taps * kchunks : hp.sb;
   L->smem = 1024 + (size_t)kMI * hp.sa * a_stage + (size_t)nb_tiles * b_tile + (size_t)kMI * obufs * obuf_bytes +
             8 * (2 * kMI * hp.sa + 2 * hp.sb + 2 * kMI * acc_stages) + 16 + 2 * (size_t)npad * sizeof(float) +
             kMI * 128 * sizeof(float);
@@ -588,30 +672,46 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   return UG_OK;
 }
 
+template <int kTaps>
+static void launch_multi(const ConvLaunch* L, const StoreMaps& maps, const MultiParams& hp, cudaStream_t s) {
+  const int act = L->p.act;
+  if (act == UG_ACT_RELU)
+    conv_multi_kernel<UG_ACT_RELU, kTaps><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, maps, L->p, hp);
+  else if (act == UG_ACT_GELU)
+    conv_multi_kernel<UG_ACT_GELU, kTaps><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, maps, L->p, hp);
+  else
+    conv_multi_kernel<UG_ACT_NONE, kTaps><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, maps, L->p, hp);
+}
+
 int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaSuccess;
-    const void* fns[] = {(const void*)conv3x3_multi_kernel<UG_ACT_NONE>, (const void*)conv3x3_multi_kernel<UG_ACT_RELU>,
-                         (const void*)conv3x3_multi_kernel<UG_ACT_GELU>};
+    const void* fns[] = {(const void*)conv_multi_kernel<UG_ACT_NONE, 9>, (const void*)conv_multi_kernel<UG_ACT_RELU, 9>,
+                         (const void*)conv_multi_kernel<UG_ACT_GELU, 9>, (const void*)conv_multi_kernel<UG_ACT_NONE, 1>,
+                         (const void*)conv_multi_kernel<UG_ACT_RELU, 1>, (const void*)conv_multi_kernel<UG_ACT_GELU, 1>};
     for (const void* f : fns)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv3x3_multi_kernel)");
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_multi_kernel)");
     attr_set = true;
   }
   MultiParams hp;
+  memset(&hp, 0, sizeof(hp));
   hp.TH = L->halo_TH; hp.a_stage_bytes = L->halo_a_stage;
   hp.sa = L->halo_sa; hp.sb = L->halo_sb; hp.b_resident = L->halo_bres; hp.m_super = L->halo_copy;
   hp.debug = L->halo_debug;
-  const int act = L->p.act;
-  if (act == UG_ACT_RELU)
-    conv3x3_multi_kernel<UG_ACT_RELU><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p, hp);
-  else if (act == UG_ACT_GELU)
-    conv3x3_multi_kernel<UG_ACT_GELU><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p, hp);
-  else
-    conv3x3_multi_kernel<UG_ACT_NONE><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p, hp);
+  hp.d_msuper = make_fastdiv(hp.m_super);
+  hp.d_tx = make_fastdiv(L->p.tiles_x);
+  hp.d_ty = make_fastdiv(L->p.tiles_y);
+  StoreMaps maps;
+  maps.m[0] = L->tmO;
+  maps.m[1] = L->tmQ[0];
+  maps.m[2] = L->tmQ[1];
+  maps.m[3] = L->tmQ[2];
+  if (L->halo_mode == 9) launch_multi<9>(L, maps, hp, s);
+  else launch_multi<1>(L, maps, hp, s);
   h->launches++;
-  return check_cuda(h, cudaGetLastError(), "conv3x3_multi_kernel launch");
+  return check_cuda(h, cudaGetLastError(), "conv_multi_kernel launch");
 }
 
 }  // namespace ug

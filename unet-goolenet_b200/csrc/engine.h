@@ -45,11 +45,12 @@ struct ConvKParams {
 struct ConvLaunch {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
-  alignas(64) CUtensorMap tmO;  // output map for the TMA-store epilogue (persistent variant)
+  alignas(64) CUtensorMap tmO;  // output map for the TMA-store epilogues
+  alignas(64) CUtensorMap tmQ[3];  // multi-issuer kernel, ConvTranspose: output views of quadrants 1..3 (tmO = quadrant 0)
   ConvKParams p;
   dim3 grid;
   size_t smem;
-  int variant;  // 0 = persistent, 1 = one tile per CTA, 5 = 3x3 multi-issuer kernel
+  int variant;  // 0 = persistent, 1 = one tile per CTA, 5 = multi-issuer kernel (halo_mode = taps: 9 or 1)
   int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres, halo_debug;
 };
 
