@@ -5,7 +5,7 @@
   python bench.py --impl reference ...                      (the reference's CPU arithmetic: the oracle port)
 
 A step is one pass of the whole path over this rank's batch of synthetic 224x224 images (default 256 per GPU,
-run as micro-batches of 64 — BASELINE.json config 4/5: 512 images on 2 GPUs, 2048 on 8), followed for N>1 by
+run as micro-batches of 128 — BASELINE.json config 4/5: 512 images on 2 GPUs, 2048 on 8), followed for N>1 by
 the path's only collective: an NCCL all-gather of masks and class logits.  Weak scaling: per-GPU work is fixed.
 
   value     device-timed whole-job images/s, inputs already resident in HBM (staging buffer of the program)
@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=64)
+    ap.add_argument("--micro-batch", type=int, default=128, help="UNet micro-batch (images sharing one workspace)")
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -20,7 +20,7 @@
 // Each issuer i owns a pixel-tile stream, a ring of activation stages, TMEM accumulators and a warpgroup of four
 // epilogue warps (folded BN/bias + activation, residual / CoordAtt3 combine / outc epilogues, bf16 tile staged in
 // swizzled smem and written with TMA stores).  Warp roles (384 threads): warps 0-3 / 4-7 epilogue of issuer 0 / 1,
-// warp 8 TMEM allocator, warp 9 TMA producer, warps 10-11 MMA issuers.
+// warp 8 TMEM allocator + weight producer, warp 9 activation producer, warps 10-11 MMA issuers.
 #include <cstring>
 #include "conv_common.cuh"
 
@@ -34,8 +34,8 @@ static constexpr int kMPitch = 10;      // halo tile pitch: 8 output pixels + on
 // TMA producer; the epilogue warps (which have plenty of slack but dense instruction streams) get the lowest.
 // Measured on the 224x224 64->64 layer: issuers at warps 1-2 below a tightened epilogue: 0.29 ms, here: see
 // profiles/r01_conv_sweep_multi_issuer.txt.
-static constexpr int kMAllocWarp = 4 * kMI;          // 8: TMEM allocator (idle otherwise)
-static constexpr int kMProducerWarp = 4 * kMI + 1;   // 9
+static constexpr int kMAllocWarp = 4 * kMI;          // 8: TMEM allocator + weight (B) producer
+static constexpr int kMProducerWarp = 4 * kMI + 1;   // 9: activation (A) producer
 static constexpr int kMIssuerWarp0 = 4 * kMI + 2;    // 10, 11
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
@@ -148,20 +148,11 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == kMProducerWarp) {
-    // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
-    if (hp.b_resident) {
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&b_full[0], (uint32_t)(kTaps * p.kchunks * b_tile_bytes));
-        for (int kc = 0; kc < p.kchunks; ++kc)
-          for (int tap = 0; tap < kTaps; ++tap)
-            tma_load_2d(sB + (kc * kTaps + tap) * b_tile_bytes, &tmB, &b_full[0], (tap * p.kchunks + kc) * 64, 0);
-      }
-      __syncwarp();
-    }
-    int as[kMI] = {0, 0}, bs = 0;
-    uint32_t aph[kMI] = {0, 0}, bph = 0;
+    // ------------------------------------------------------------------ activation producer (whole warp, elected lane issues)
+    int as[kMI] = {0, 0};
+    uint32_t aph[kMI] = {0, 0};
     const uint32_t a_tx = kTaps == 9 ? (uint32_t)(kMPitch * (hp.TH + 2) * 128) : p.a_bytes;
-    long long w_a = 0, w_b = 0;
+    long long w_a = 0;
     const long long t_start = clock64();
     unsigned long long ns0 = 0;
     if (p.prof) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns0));
@@ -201,7 +192,33 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
             aph[i] ^= 1;
           }
         }
-        if (!hp.b_resident) {
+      }
+    }
+    if (p.prof && lane == 0) {
+      unsigned long long ns1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1));
+      p.prof[blockIdx.x * 16 + 0] = w_a;
+      p.prof[blockIdx.x * 16 + 2] = clock64() - t_start;
+      p.prof[blockIdx.x * 16 + 3] = (long long)(ns1 - ns0);
+    }
+  } else if (warp == kMAllocWarp) {
+    // ------------------------------------------------------------------ weight producer (its own warp: a full weight
+    // ring must not delay the activation loads of the next chunk, and vice versa)
+    long long w_b = 0;
+    if (hp.b_resident) {
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&b_full[0], (uint32_t)(kTaps * p.kchunks * b_tile_bytes));
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int tap = 0; tap < kTaps; ++tap)
+            tma_load_2d(sB + (kc * kTaps + tap) * b_tile_bytes, &tmB, &b_full[0], (tap * p.kchunks + kc) * 64, 0);
+      }
+      __syncwarp();
+    } else {
+      int bs = 0;
+      uint32_t bph = 0;
+      for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+        const int nt = hp.d_msuper.div(s);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int tap = 0; tap < kTaps; ++tap) {
             const long long tw0 = p.prof ? clock64() : 0;
             mbar_wait(&b_empty[bs], bph ^ 1);
@@ -219,14 +236,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
         }
       }
     }
-    if (p.prof && lane == 0) {
-      unsigned long long ns1;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1));
-      p.prof[blockIdx.x * 16 + 0] = w_a;
-      p.prof[blockIdx.x * 16 + 1] = w_b;
-      p.prof[blockIdx.x * 16 + 2] = clock64() - t_start;
-      p.prof[blockIdx.x * 16 + 3] = (long long)(ns1 - ns0);
-    }
+    if (p.prof && lane == 0) p.prof[blockIdx.x * 16 + 1] = w_b;
   } else if (warp >= kMIssuerWarp0) {
     // ------------------------------------------------------------------ MMA issuers (whole warp, one elected lane issues)
     const int i = warp - kMIssuerWarp0;

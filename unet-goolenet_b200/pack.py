@@ -17,6 +17,8 @@ def choose_bn(n_out, convt_cout=None, r=1):
         return min(128, convt_cout)
     if r == 3 and n_out % 256 == 0:
         return 256
+    if r == 1 and n_out >= 1024 and n_out % 256 == 0:
+        return 256        # wide linear layers (qkv, FFN): persistent kernel with 256-wide n-tiles (measured)
     return 128 if n_out >= 128 else round_up(n_out, 16)
 
 
