@@ -571,7 +571,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   memset(&hp, 0, sizeof(hp));
   hp.TH = TH;
   hp.a_stage_bytes = a_stage;
-  const int fixed = 1024 + 8 * (2 * kMI * 4 + 2 * 12 + 2 * kMI * 4) + 16 + 2 * npad * (int)sizeof(float) +
+  const int fixed = 1024 + 8 * (2 * kMI * 4 + 2 * 16 + 2 * kMI * 4) + 16 + 2 * npad * (int)sizeof(float) +
                     kMI * 128 * (int)sizeof(float);
   const long long budget = 227LL * 1024 - fixed;
   int obufs = tma_store ? 2 : 0;
@@ -582,18 +582,18 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     if (resB + kMI * 2LL * a_stage + kMI * obufs * obuf_bytes > budget) obufs = 1;
     hp.sa = (int)std::min<long long>(4, (budget - resB - kMI * obufs * obuf_bytes) / (kMI * a_stage));
   } else {
+    // streamed weights: the MMA time per tile is long, so one staging buffer per epilogue group is enough and the
+    // shared memory goes to a deep weight ring instead (a slot is only handed back when the MMAs that read it have
+    // COMPLETED, so several slots are always "in flight"; with 8 slots the issuers waited on weights 18 % of the time)
     hp.b_resident = 0;
     hp.sa = 2;
+    if (obufs == 2) obufs = 1;
     long long rest = budget - kMI * 2LL * a_stage - kMI * obufs * obuf_bytes;
-    if (rest < 6LL * b_tile && obufs == 2) {  // prefer a deeper weight ring over double-buffered staging
-      obufs = 1;
-      rest = budget - kMI * 2LL * a_stage - kMI * obuf_bytes;
-    }
-    hp.sb = (int)std::min<long long>(12, rest / b_tile);
+    hp.sb = (int)std::min<long long>(16, rest / b_tile);
     if (hp.sb < 3) return set_error(h, UG_EUNSUPPORTED, "conv(multi): tile does not fit in shared memory");
-    if (hp.sb >= 10 && rest - 9LL * b_tile >= kMI * a_stage) {  // room for a third activation stage
+    if (hp.sb >= 12 && rest - 10LL * b_tile >= kMI * a_stage) {  // room for a third activation stage
       hp.sa = 3;
-      hp.sb = (int)std::min<long long>(12, (rest - kMI * a_stage) / b_tile);
+      hp.sb = (int)std::min<long long>(16, (rest - kMI * a_stage) / b_tile);
     }
   }
 
