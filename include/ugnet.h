@@ -189,6 +189,19 @@ typedef struct ug_stem_desc {
   int B, H, W;
 } ug_stem_desc;
 
+/* Device front-end: the reference's CDDataAugmentation.transform live lines
+ * (分类/util/data_utils.py:146-147, 分割/util/data_utils.py): F.resize(PIL image, (S,S), BILINEAR) + F.to_tensor.
+ * src: uint8 HWC [B][Hs][Ws][3] of any size up to 8*S per side (e.g. the 512x512 sources of BASELINE config 5);
+ * Pillow's antialiased resample is restated bit-exactly (support = max(in/out, 1), horizontal pass then vertical
+ * pass, 22-bit fixed point, uint8 intermediate).  out_f32: fp32 NCHW [B][3][S][S] = value / 255 (the UNet input);
+ * out_u8 (optional): the resized uint8 HWC image [B][S][S][3].  Either output may be NULL, not both. */
+typedef struct ug_resize_desc {
+  const unsigned char* src;
+  float* out_f32;
+  unsigned char* out_u8;
+  int B, Hs, Ws, S;
+} ug_resize_desc;
+
 /* AdaptiveAvgPool2d(1) + Linear(C, ncls): in NHWC bf16 [B][HW][C], w fp32 [ncls][C], logits fp32 [B][ncls]. */
 typedef struct ug_head_desc {
   const void* in;
@@ -210,7 +223,8 @@ enum {
   UG_OP_CROPRESIZE = 9,
   UG_OP_G1_IM2COL = 10,
   UG_OP_HEAD = 11,
-  UG_OP_STEM = 12
+  UG_OP_STEM = 12,
+  UG_OP_RESIZE = 13
 };
 
 typedef struct ug_op {
@@ -229,6 +243,7 @@ typedef struct ug_op {
     ug_g1_im2col_desc g1;
     ug_head_desc head;
     ug_stem_desc stem;
+    ug_resize_desc resize;
   } u;
 } ug_op;
 
@@ -273,6 +288,7 @@ int ug_cropresize(ug_handle h, const ug_cropresize_desc* d, void* stream);
 int ug_g1_im2col(ug_handle h, const ug_g1_im2col_desc* d, void* stream);
 int ug_head(ug_handle h, const ug_head_desc* d, void* stream);
 int ug_stem(ug_handle h, const ug_stem_desc* d, void* stream);
+int ug_resize_u8(ug_handle h, const ug_resize_desc* d, void* stream);
 
 /* Programs: a validated op list with tensor maps and launch geometry prepared once; run = launches only. */
 int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out);

@@ -19,6 +19,15 @@ def test_resize_matches_pil_bit_exact(h, w):
     assert np.array_equal(roi_ref.pil_resize_bilinear_u8(img, 224), ref)
 
 
+@pytest.mark.parametrize("h,w", [(512, 512), (300, 400), (1000, 700), (225, 223), (1792, 448)])
+def test_downscale_matches_pil_bit_exact(h, w):
+    """The front-end case: Pillow's antialiased resample, support = in/out > 1."""
+    rng = np.random.default_rng(h * 1000 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((224, 224), Image.BILINEAR))
+    assert np.array_equal(roi_ref.pil_resize_bilinear_u8(img, 224), ref)
+
+
 def test_bbox_edge_cases():
     H = W = 224
     m = np.zeros((H, W), np.uint8)

@@ -51,6 +51,7 @@ static int run_simple(ug_engine* h, const ug_op* op, cudaStream_t s) {
     case UG_OP_CROPRESIZE: return launch_cropresize(h, &op->u.crop, s);
     case UG_OP_G1_IM2COL: return launch_g1_im2col(h, &op->u.g1, s);
     case UG_OP_HEAD: return launch_head(h, &op->u.head, s);
+    case UG_OP_RESIZE: return launch_resize_u8(h, &op->u.resize, s);
     default: return set_error(h, UG_EINVAL, "unknown op kind %d", op->kind);
   }
 }
@@ -177,6 +178,7 @@ UG_SIMPLE_ENTRY(ug_bbox, ug_bbox_desc, launch_bbox)
 UG_SIMPLE_ENTRY(ug_cropresize, ug_cropresize_desc, launch_cropresize)
 UG_SIMPLE_ENTRY(ug_g1_im2col, ug_g1_im2col_desc, launch_g1_im2col)
 UG_SIMPLE_ENTRY(ug_head, ug_head_desc, launch_head)
+UG_SIMPLE_ENTRY(ug_resize_u8, ug_resize_desc, launch_resize_u8)
 
 int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out) {
   if (!h || !ops || n_ops <= 0 || !out) return UG_EINVAL;
@@ -204,7 +206,7 @@ int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out)
         delete p;
         return rc;
       }
-    } else if (po.kind < UG_OP_CONV || po.kind > UG_OP_STEM) {
+    } else if (po.kind < UG_OP_CONV || po.kind > UG_OP_RESIZE) {
       delete p;
       return set_error(h, UG_EINVAL, "op %d: unknown kind %d", i, po.kind);
     }

@@ -2,6 +2,8 @@
 // input im2col packs, max pooling, LayerNorm, attention, CoordAtt3 statistics + gate, mask -> bbox,
 // PIL-exact crop/resize and the GoogLeNet head.  Reference lines are cited on the descriptors in ugnet.h.
 #include <cfloat>
+#include <cmath>
+#include <algorithm>
 #include "common.cuh"
 #include "engine.h"
 
@@ -712,6 +714,132 @@ int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s)
   cropresize_kernel<<<dim3(cdiv(d->S, rows), d->B), 256, 0, s>>>(*d, rows);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "cropresize launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device front-end: PIL-exact bilinear resize of uint8 HWC source images of ANY size to SxS (the reference's
+// CDDataAugmentation.transform: F.resize(..., BILINEAR) on a PIL image + to_tensor; Pillow's antialiased
+// resample: support = max(in/out, 1), up to 2*ceil(support)+1 taps per axis), written as fp32 NCHW / 255.
+// One block per (group of R output rows, image): the horizontal pass of the source rows those output rows need is
+// kept in shared memory as uint8 (exactly Pillow's intermediate image), the vertical pass reads it from there.
+static constexpr int kRsMaxTaps = 17;   // support <= 8: source side up to 8 * S
+static constexpr int kRsRows = 8;       // output rows per block
+
+struct RsCoef {
+  int xmin, n;
+  int kk[kRsMaxTaps];
+};
+
+__device__ void pil_coef_general(int in_size, int out_size, int xx, RsCoef* c) {
+  const double scale = __ddiv_rn((double)in_size, (double)out_size);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = filterscale;  // bilinear: support 1.0 * filterscale
+  const double ss = __ddiv_rn(1.0, filterscale);
+  const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), scale);
+  int xmin = (int)__dadd_rn(__dadd_rn(center, -support), 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+  if (xmax > in_size) xmax = in_size;
+  int n = xmax - xmin;
+  if (n > kRsMaxTaps) n = kRsMaxTaps;
+  double k[kRsMaxTaps];
+  double ww = 0.0;
+  for (int x = 0; x < n; ++x) {
+    double a = __dmul_rn(__dadd_rn(__dadd_rn((double)(x + xmin), -center), 0.5), ss);
+    if (a < 0.0) a = -a;
+    const double w = a < 1.0 ? __dadd_rn(1.0, -a) : 0.0;
+    k[x] = w;
+    ww = __dadd_rn(ww, w);
+  }
+  c->xmin = xmin;
+  c->n = n;
+  for (int x = 0; x < n; ++x) {
+    double kv = k[x];
+    if (ww != 0.0) kv = __ddiv_rn(kv, ww);
+    const double scaled = __dmul_rn(kv, (double)(1 << kPrecBits));
+    c->kk[x] = kv < 0.0 ? (int)__dadd_rn(-0.5, scaled) : (int)__dadd_rn(0.5, scaled);
+  }
+}
+
+__global__ void __launch_bounds__(256) resize_u8_kernel(ug_resize_desc d, int max_src_rows) {
+  extern __shared__ unsigned char rs_smem[];
+  RsCoef* s_h = reinterpret_cast<RsCoef*>(rs_smem);                   // [S] horizontal coefficients
+  RsCoef* s_v = s_h + d.S;                                             // [kRsRows] vertical coefficients
+  unsigned char* s_tmp = reinterpret_cast<unsigned char*>(s_v + kRsRows);  // [max_src_rows][S*3] after the h-pass
+  const int n = blockIdx.y;
+  const int oy0 = blockIdx.x * kRsRows;
+  const int rows = min(kRsRows, d.S - oy0);
+  for (int i = threadIdx.x; i < d.S; i += blockDim.x) pil_coef_general(d.Ws, d.S, i, &s_h[i]);
+  if (threadIdx.x < rows) pil_coef_general(d.Hs, d.S, oy0 + threadIdx.x, &s_v[threadIdx.x]);
+  __syncthreads();
+  const int sy0 = s_v[0].xmin;                                          // first / one-past-last source row needed
+  const int sy1 = s_v[rows - 1].xmin + s_v[rows - 1].n;
+  const unsigned char* src = d.src + (long long)n * d.Hs * d.Ws * 3;
+  const int row_elems = d.S * 3;
+  for (int t = threadIdx.x; t < (sy1 - sy0) * d.S; t += blockDim.x) {   // horizontal pass (one output pixel, 3 ch)
+    const int r = t / d.S, ox = t - r * d.S;
+    const RsCoef& hc = s_h[ox];
+    const unsigned char* sp = src + ((long long)(sy0 + r) * d.Ws + hc.xmin) * 3;
+    int a0 = 1 << (kPrecBits - 1), a1 = a0, a2 = a0;
+    for (int i = 0; i < hc.n; ++i) {
+      const int k = hc.kk[i];
+      a0 += (int)__ldg(sp + 3 * i) * k;
+      a1 += (int)__ldg(sp + 3 * i + 1) * k;
+      a2 += (int)__ldg(sp + 3 * i + 2) * k;
+    }
+    unsigned char* tp = s_tmp + r * row_elems + ox * 3;
+    tp[0] = (unsigned char)clip8(a0);
+    tp[1] = (unsigned char)clip8(a1);
+    tp[2] = (unsigned char)clip8(a2);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < rows * d.S; t += blockDim.x) {          // vertical pass + to_tensor
+    const int ry = t / d.S, ox = t - ry * d.S;
+    const RsCoef& vc = s_v[ry];
+    const unsigned char* tp = s_tmp + (vc.xmin - sy0) * row_elems + ox * 3;
+    int a0 = 1 << (kPrecBits - 1), a1 = a0, a2 = a0;
+    for (int j = 0; j < vc.n; ++j) {
+      const int k = vc.kk[j];
+      a0 += (int)tp[j * row_elems] * k;
+      a1 += (int)tp[j * row_elems + 1] * k;
+      a2 += (int)tp[j * row_elems + 2] * k;
+    }
+    const int v[3] = {clip8(a0), clip8(a1), clip8(a2)};
+    const int oy = oy0 + ry;
+    if (d.out_u8) {
+      unsigned char* o = d.out_u8 + (((long long)n * d.S + oy) * d.S + ox) * 3;
+      o[0] = (unsigned char)v[0];
+      o[1] = (unsigned char)v[1];
+      o[2] = (unsigned char)v[2];
+    }
+    if (d.out_f32) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)  // F.to_tensor: uint8 -> float32, divided by 255
+        d.out_f32[(((long long)n * 3 + c) * d.S + oy) * d.S + ox] = (float)v[c] / 255.0f;
+    }
+  }
+}
+
+int launch_resize_u8(ug_engine* h, const ug_resize_desc* d, cudaStream_t s) {
+  if (!d->src || (!d->out_f32 && !d->out_u8) || d->B <= 0 || d->Hs <= 0 || d->Ws <= 0 || d->S <= 0 || d->S > 512)
+    return set_error(h, UG_EINVAL, "resize: bad args (S <= 512)");
+  const double sc = std::max((double)d->Hs / d->S, (double)d->Ws / d->S);
+  if (2 * (int)ceil(std::max(sc, 1.0)) + 1 > kRsMaxTaps)
+    return set_error(h, UG_EUNSUPPORTED, "resize: source more than 8x larger than the output");
+  // source rows needed by kRsRows output rows: (kRsRows - 1) * scale + 2 * support + 2
+  const double scy = std::max((double)d->Hs / d->S, 1.0);
+  const int max_rows = std::min(d->Hs, (int)ceil((kRsRows - 1) * ((double)d->Hs / d->S) + 2.0 * scy + 3.0));
+  const size_t smem = (size_t)(d->S + kRsRows) * sizeof(RsCoef) + (size_t)max_rows * d->S * 3;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    if (smem > 200 * 1024) return set_error(h, UG_EUNSUPPORTED, "resize: shared memory request %zu too large", smem);
+    cudaError_t e = cudaFuncSetAttribute((const void*)resize_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(resize_u8_kernel)");
+    attr_smem = smem;
+  }
+  resize_u8_kernel<<<dim3(cdiv(d->S, kRsRows), d->B), 256, smem, s>>>(*d, max_rows);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "resize_u8 launch");
 }
 
 // ------------------------------------------------------------------------------------------------

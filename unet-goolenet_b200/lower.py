@@ -478,9 +478,12 @@ class PipelineRunner:
         self.plans = {}
         self._pools = {}
 
-    def plan(self, B):
-        """Program for a batch of B images; B must be <= micro_batch or a multiple of it."""
-        if B not in self.plans:
+    def plan(self, B, source=None):
+        """Program for a batch of B images; B must be <= micro_batch or a multiple of it.  With `source` =
+        (Hs, Ws) the program starts with the device front-end (PIL-exact resize of uint8 HWC sources + to_tensor,
+        util/data_utils.py) writing the UNet input, and `ws["src_u8"]` is the program's input buffer."""
+        key = B if source is None else (B,) + tuple(source)
+        if key not in self.plans:
             mb = min(B, self.micro_batch)
             assert B % mb == 0
             dev = self.dev
@@ -490,6 +493,10 @@ class PipelineRunner:
                       boxes=torch.empty((B, 4), device=dev, dtype=torch.int32),
                       u8=torch.empty((B, IMG, IMG, 3), device=dev, dtype=torch.uint8))
             ops = []
+            if source is not None:
+                ws["src_u8"] = torch.empty((B, source[0], source[1], 3), device=dev, dtype=torch.uint8)
+                ops.append(E.ResizeDesc(ws["src_u8"].data_ptr(), ws["x_in"].data_ptr(), None, B, source[0], source[1],
+                                        IMG))
             pool = self._pools.setdefault(mb, [])
             for s in range(0, B, mb):
                 sl = slice(s, s + mb)
@@ -503,8 +510,8 @@ class PipelineRunner:
                 ws.setdefault("sub", []).append(sub)
             self.gnet._emit_googlenet(B, ws, ops, u8=ws["u8"])
             ws["program"] = self.engine.program(ops)
-            self.plans[B] = ws
-        return self.plans[B]
+            self.plans[key] = ws
+        return self.plans[key]
 
     def _chunks(self, n):
         """Split n images into plan-able chunks: multiples of micro_batch up to cls_batch, then the remainder."""
@@ -519,11 +526,20 @@ class PipelineRunner:
 
     @torch.no_grad()
     def __call__(self, imgs, return_logits=False):
-        """imgs: float [B,3,224,224] CUDA -> (masks u8 [B,224,224], boxes i32 [B,4], cls_logits f32 [B,6])."""
+        """imgs: float [B,3,224,224] CUDA, or uint8 [B,Hs,Ws,3] CUDA source images of any size (resized on the
+        device exactly as the reference's PIL transform does) ->
+        (masks u8 [B,224,224], boxes i32 [B,4], cls_logits f32 [B,6])."""
         masks, boxes, cls, seg = [], [], [], []
+        from_u8 = imgs.dtype == torch.uint8
+        if from_u8 and (imgs.dim() != 4 or imgs.shape[3] != 3):
+            raise ValueError(f"uint8 input must be HWC [B,H,W,3], got {tuple(imgs.shape)}")
         for s, c in self._chunks(imgs.shape[0]):
-            ws = self.plan(c)
-            ws["x_in"].copy_(imgs[s:s + c])
+            if from_u8:
+                ws = self.plan(c, source=(imgs.shape[1], imgs.shape[2]))
+                ws["src_u8"].copy_(imgs[s:s + c])
+            else:
+                ws = self.plan(c)
+                ws["x_in"].copy_(imgs[s:s + c])
             ws["program"].run()
             masks.append(ws["mask"].clone())
             boxes.append(ws["boxes"].clone())
