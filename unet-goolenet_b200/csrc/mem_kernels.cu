@@ -97,11 +97,61 @@ __global__ void __launch_bounds__(256) pool_kernel(const __nv_bfloat16* __restri
   *reinterpret_cast<uint4*>(out + (((long long)n * d.OH + oy) * d.OW + ox) * d.out_cstride + g * 8) = m;
 }
 
+// 3x3 stride-1 pad-1 max pooling (the Inception branch4 pools): one thread per (image, output row, 8-channel group)
+// slides along the row keeping the last three column maxima, so every input pixel is loaded three times instead of
+// nine (these maps are L2 resident and the generic kernel was bound by the 9x re-read).
+__global__ void __launch_bounds__(256) pool3x3s1_kernel(const __nv_bfloat16* __restrict__ in,
+                                                        __nv_bfloat16* __restrict__ out, ug_pool_desc d) {
+  const int cg = d.C / 8;
+  const long long total = (long long)d.B * d.H * cg;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int g = (int)(t % cg);
+  const long long pp = t / cg;
+  const int oy = (int)(pp % d.H);
+  const int n = (int)(pp / d.H);
+  const uint32_t ninf = 0xFF80FF80u;  // (-inf, -inf) in bf16
+  const uint4 vinf = make_uint4(ninf, ninf, ninf, ninf);
+  const int r0 = oy > 0 ? oy - 1 : oy, r1 = oy + 1 < d.H ? oy + 1 : oy;   // valid input rows r0..r1
+  const __nv_bfloat16* base = in + ((long long)n * d.H * d.W) * d.in_cstride + g * 8;
+  auto colmax = [&](int x) {
+    uint4 m = vinf;
+    for (int r = r0; r <= r1; ++r) {
+      const uint4 v = *reinterpret_cast<const uint4*>(base + ((long long)r * d.W + x) * d.in_cstride);
+      m.x = bf16x2_max(m.x, v.x);
+      m.y = bf16x2_max(m.y, v.y);
+      m.z = bf16x2_max(m.z, v.z);
+      m.w = bf16x2_max(m.w, v.w);
+    }
+    return m;
+  };
+  uint4 a = vinf, b = colmax(0);  // column maxima at x-1 and x
+  __nv_bfloat16* orow = out + (((long long)n * d.H + oy) * d.W) * d.out_cstride + g * 8;
+  for (int x = 0; x < d.W; ++x) {
+    const uint4 c = x + 1 < d.W ? colmax(x + 1) : vinf;
+    uint4 m;
+    m.x = bf16x2_max(bf16x2_max(a.x, b.x), c.x);
+    m.y = bf16x2_max(bf16x2_max(a.y, b.y), c.y);
+    m.z = bf16x2_max(bf16x2_max(a.z, b.z), c.z);
+    m.w = bf16x2_max(bf16x2_max(a.w, b.w), c.w);
+    *reinterpret_cast<uint4*>(orow + (long long)x * d.out_cstride) = m;
+    a = b;
+    b = c;
+  }
+}
+
 int launch_pool(ug_engine* h, const ug_pool_desc* d, cudaStream_t s) {
   if (!d->in || !d->out || d->C % 8 || d->in_cstride % 8 || d->out_cstride % 8 || d->k <= 0 || d->stride <= 0)
     return set_error(h, UG_EINVAL, "pool: bad args (C and strides must be multiples of 8)");
   if ((d->OH - 1) * d->stride - d->pad >= d->H || (d->OW - 1) * d->stride - d->pad >= d->W)
     return set_error(h, UG_EINVAL, "pool: last window starts outside the input");
+  if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->OH == d->H && d->OW == d->W) {
+    const long long total = (long long)d->B * d->H * (d->C / 8);
+    pool3x3s1_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d->in),
+                                                      reinterpret_cast<__nv_bfloat16*>(d->out), *d);
+    h->launches++;
+    return check_cuda(h, cudaGetLastError(), "pool3x3s1 launch");
+  }
   const long long total = (long long)d->B * d->OH * d->OW * (d->C / 8);
   pool_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d->in),
                                                reinterpret_cast<__nv_bfloat16*>(d->out), *d);
@@ -623,97 +673,9 @@ int launch_bbox(ug_engine* h, const ug_bbox_desc* d, cudaStream_t s) {
 //   22-bit fixed point; horizontal pass first (uint8 result), vertical pass second.
 static constexpr int kPrecBits = 22;  // 32 - 8 - 2
 
-struct AxisCoef {
-  int xmin;
-  int n;
-  int kk[3];
-};
-
-__device__ void pil_coef(int in_size, int out_size, int xx, AxisCoef* c) {
-  // Pillow: scale = in/out; filterscale = max(scale, 1); support = 1.0 * filterscale (bilinear)
-  const double scale = __ddiv_rn((double)in_size, (double)out_size);
-  const double filterscale = scale < 1.0 ? 1.0 : scale;
-  const double support = filterscale;  // bilinear support 1.0
-  const double ss = __ddiv_rn(1.0, filterscale);
-  const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), scale);
-  int xmin = (int)__dadd_rn(__dadd_rn(center, -support), 0.5);
-  if (xmin < 0) xmin = 0;
-  int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
-  if (xmax > in_size) xmax = in_size;
-  const int n = xmax - xmin;  // <= 3 when up-sampling (support == 1)
-  double k[3] = {0.0, 0.0, 0.0};
-  double ww = 0.0;
-  for (int x = 0; x < n && x < 3; ++x) {
-    double a = __dmul_rn(__dadd_rn(__dadd_rn((double)(x + xmin), -center), 0.5), ss);
-    if (a < 0.0) a = -a;
-    const double w = a < 1.0 ? __dadd_rn(1.0, -a) : 0.0;
-    k[x] = w;
-    ww = __dadd_rn(ww, w);
-  }
-  c->xmin = xmin;
-  c->n = n < 3 ? n : 3;
-  for (int x = 0; x < 3; ++x) {
-    double kv = k[x];
-    if (x < n && ww != 0.0) kv = __ddiv_rn(kv, ww);
-    const double scaled = __dmul_rn(kv, (double)(1 << kPrecBits));
-    c->kk[x] = kv < 0.0 ? (int)__dadd_rn(-0.5, scaled) : (int)__dadd_rn(0.5, scaled);
-  }
-}
-
 __device__ __forceinline__ int clip8(int v) {
   v >>= kPrecBits;
   return v < 0 ? 0 : (v > 255 ? 255 : v);
-}
-
-// grid (S / rows_per_block, B); each block produces rows_per_block output rows of one image.
-__global__ void __launch_bounds__(256) cropresize_kernel(ug_cropresize_desc d, int rows_per_block) {
-  __shared__ AxisCoef s_h[256];
-  __shared__ AxisCoef s_v[32];
-  const int n = blockIdx.y;
-  const int oy0 = blockIdx.x * rows_per_block;
-  const int x0 = d.boxes[n * 4 + 0], y0 = d.boxes[n * 4 + 1];
-  const int cw = d.boxes[n * 4 + 2] - x0, ch = d.boxes[n * 4 + 3] - y0;
-  for (int i = threadIdx.x; i < d.S; i += blockDim.x) pil_coef(cw, d.S, i, &s_h[i]);
-  if (threadIdx.x < rows_per_block && oy0 + threadIdx.x < d.S) pil_coef(ch, d.S, oy0 + threadIdx.x, &s_v[threadIdx.x]);
-  __syncthreads();
-  const float* img = d.img + (long long)n * 3 * d.H * d.W;
-  const int total = rows_per_block * d.S;
-  for (int t = threadIdx.x; t < total; t += blockDim.x) {
-    const int ry = t / d.S, ox = t - ry * d.S;
-    const int oy = oy0 + ry;
-    if (oy >= d.S) break;
-    const AxisCoef hc = s_h[ox];
-    const AxisCoef vc = s_v[ry];
-    unsigned char res[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* plane = img + (long long)(2 - c) * d.H * d.W;  // cv2.COLOR_BGR2RGB: channel flip
-      int acc_v = 1 << (kPrecBits - 1);
-      for (int j = 0; j < vc.n; ++j) {
-        const float* srow = plane + (long long)(y0 + vc.xmin + j) * d.W + x0 + hc.xmin;
-        int acc_h = 1 << (kPrecBits - 1);
-        for (int i = 0; i < hc.n; ++i) {
-          const int u8 = ((int)__fmul_rn(__ldg(srow + i), 255.0f)) & 255;  // (roi*255).astype(uint8): fp32 mul, truncate
-          acc_h += u8 * hc.kk[i];
-        }
-        acc_v += clip8(acc_h) * vc.kk[j];
-      }
-      res[c] = (unsigned char)clip8(acc_v);
-    }
-    unsigned char* o = d.out_u8 + (((long long)n * d.S + oy) * d.S + ox) * 3;
-    o[0] = res[0];
-    o[1] = res[1];
-    o[2] = res[2];
-  }
-}
-
-int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s) {
-  if (!d->img || !d->boxes || !d->out_u8 || d->S <= 0 || d->S > 256 || d->B <= 0)
-    return set_error(h, UG_EINVAL, "cropresize: bad args (S <= 256)");
-  const int rows = 8;
-  cropresize_kernel<<<dim3(cdiv(d->S, rows), d->B), 256, 0, s>>>(*d, rows);
-  h->launches++;
-  return check_cuda(h, cudaGetLastError(), "cropresize launch");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -761,7 +723,12 @@ __device__ void pil_coef_general(int in_size, int out_size, int xx, RsCoef* c) {
   }
 }
 
-__global__ void __launch_bounds__(256) resize_u8_kernel(ug_resize_desc d, int max_src_rows) {
+// kCrop = false: source = uint8 HWC images (ug_resize_desc).  kCrop = true: source = the box (x0,y0,x1,y1) of an fp32
+// NCHW image in [0,1], quantised as (x*255).astype(uint8) with the channel order reversed (roi.py:39-44), i.e. the
+// ROI stage (ug_cropresize_desc); d.src is unused, `img` / `boxes` / `IH` / `IW` describe the float image.
+template <bool kCrop>
+__global__ void __launch_bounds__(256) resize_u8_kernel(ug_resize_desc d, int max_src_rows, const float* __restrict__ img,
+                                                        const int* __restrict__ boxes, int IH, int IW) {
   extern __shared__ unsigned char rs_smem[];
   RsCoef* s_h = reinterpret_cast<RsCoef*>(rs_smem);                   // [S] horizontal coefficients
   RsCoef* s_v = s_h + d.S;                                             // [kRsRows] vertical coefficients
@@ -769,23 +736,43 @@ __global__ void __launch_bounds__(256) resize_u8_kernel(ug_resize_desc d, int ma
   const int n = blockIdx.y;
   const int oy0 = blockIdx.x * kRsRows;
   const int rows = min(kRsRows, d.S - oy0);
+  int bx0 = 0, by0 = 0;
+  if (kCrop) {
+    bx0 = boxes[n * 4 + 0];
+    by0 = boxes[n * 4 + 1];
+    d.Ws = boxes[n * 4 + 2] - bx0;
+    d.Hs = boxes[n * 4 + 3] - by0;
+  }
   for (int i = threadIdx.x; i < d.S; i += blockDim.x) pil_coef_general(d.Ws, d.S, i, &s_h[i]);
   if (threadIdx.x < rows) pil_coef_general(d.Hs, d.S, oy0 + threadIdx.x, &s_v[threadIdx.x]);
   __syncthreads();
   const int sy0 = s_v[0].xmin;                                          // first / one-past-last source row needed
   const int sy1 = s_v[rows - 1].xmin + s_v[rows - 1].n;
-  const unsigned char* src = d.src + (long long)n * d.Hs * d.Ws * 3;
+  const unsigned char* src = kCrop ? nullptr : d.src + (long long)n * d.Hs * d.Ws * 3;
+  const float* fimg = kCrop ? img + (long long)n * 3 * IH * IW : nullptr;
   const int row_elems = d.S * 3;
   for (int t = threadIdx.x; t < (sy1 - sy0) * d.S; t += blockDim.x) {   // horizontal pass (one output pixel, 3 ch)
     const int r = t / d.S, ox = t - r * d.S;
     const RsCoef& hc = s_h[ox];
-    const unsigned char* sp = src + ((long long)(sy0 + r) * d.Ws + hc.xmin) * 3;
     int a0 = 1 << (kPrecBits - 1), a1 = a0, a2 = a0;
-    for (int i = 0; i < hc.n; ++i) {
-      const int k = hc.kk[i];
-      a0 += (int)__ldg(sp + 3 * i) * k;
-      a1 += (int)__ldg(sp + 3 * i + 1) * k;
-      a2 += (int)__ldg(sp + 3 * i + 2) * k;
+    if (kCrop) {
+      // (roi*255).astype(uint8): fp32 multiply, truncate; output channel c reads plane 2-c (cv2.COLOR_BGR2RGB)
+      const float* p0 = fimg + ((long long)(by0 + sy0 + r)) * IW + bx0 + hc.xmin;
+      const long long plane = (long long)IH * IW;
+      for (int i = 0; i < hc.n; ++i) {
+        const int k = hc.kk[i];
+        a0 += (((int)__fmul_rn(__ldg(p0 + 2 * plane + i), 255.0f)) & 255) * k;
+        a1 += (((int)__fmul_rn(__ldg(p0 + plane + i), 255.0f)) & 255) * k;
+        a2 += (((int)__fmul_rn(__ldg(p0 + i), 255.0f)) & 255) * k;
+      }
+    } else {
+      const unsigned char* sp = src + ((long long)(sy0 + r) * d.Ws + hc.xmin) * 3;
+      for (int i = 0; i < hc.n; ++i) {
+        const int k = hc.kk[i];
+        a0 += (int)__ldg(sp + 3 * i) * k;
+        a1 += (int)__ldg(sp + 3 * i + 1) * k;
+        a2 += (int)__ldg(sp + 3 * i + 2) * k;
+      }
     }
     unsigned char* tp = s_tmp + r * row_elems + ox * 3;
     tp[0] = (unsigned char)clip8(a0);
@@ -833,13 +820,37 @@ int launch_resize_u8(ug_engine* h, const ug_resize_desc* d, cudaStream_t s) {
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     if (smem > 200 * 1024) return set_error(h, UG_EUNSUPPORTED, "resize: shared memory request %zu too large", smem);
-    cudaError_t e = cudaFuncSetAttribute((const void*)resize_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute((const void*)resize_u8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(resize_u8_kernel)");
     attr_smem = smem;
   }
-  resize_u8_kernel<<<dim3(cdiv(d->S, kRsRows), d->B), 256, smem, s>>>(*d, max_rows);
+  resize_u8_kernel<false><<<dim3(cdiv(d->S, kRsRows), d->B), 256, smem, s>>>(*d, max_rows, nullptr, nullptr, 0, 0);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "resize_u8 launch");
+}
+
+// ROI stage (roi.py:39-44 + data_utils.py:102,146-147): the same two-pass kernel reading the box of the float image.
+// Crops are at most HxW with S >= both sides in the pipeline (224 -> 224: up-sampling, <= 3 taps), but any ratio up
+// to 8x is handled.
+int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s) {
+  if (!d->img || !d->boxes || !d->out_u8 || d->S <= 0 || d->S > 512 || d->B <= 0 || d->H <= 0 || d->W <= 0)
+    return set_error(h, UG_EINVAL, "cropresize: bad args (S <= 512)");
+  const double sc = std::max(std::max((double)d->H / d->S, (double)d->W / d->S), 1.0);
+  if (2 * (int)ceil(sc) + 1 > kRsMaxTaps) return set_error(h, UG_EUNSUPPORTED, "cropresize: image more than 8x the output");
+  const int max_rows = std::min(d->H, (int)ceil((kRsRows - 1) * sc + 2.0 * sc + 3.0));
+  const size_t smem = (size_t)(d->S + kRsRows) * sizeof(RsCoef) + (size_t)max_rows * d->S * 3;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    if (smem > 200 * 1024) return set_error(h, UG_EUNSUPPORTED, "cropresize: shared memory request %zu too large", smem);
+    cudaError_t e = cudaFuncSetAttribute((const void*)resize_u8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(resize_u8_kernel<crop>)");
+    attr_smem = smem;
+  }
+  ug_resize_desc r;
+  r.src = nullptr; r.out_f32 = nullptr; r.out_u8 = d->out_u8; r.B = d->B; r.Hs = d->H; r.Ws = d->W; r.S = d->S;
+  resize_u8_kernel<true><<<dim3(cdiv(d->S, kRsRows), d->B), 256, smem, s>>>(r, max_rows, d->img, d->boxes, d->H, d->W);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "cropresize launch");
 }
 
 // ------------------------------------------------------------------------------------------------
