@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -314,10 +314,17 @@ def main():
     conv_ms = sum(t for t, d in zip(per_op_ms, prog.descs) if isinstance(d, tc_kinds))
     n_conv = sum(isinstance(d, tc_kinds) for d in prog.descs)
     achieved = total_flop / (conv_ms / 1e3) / 1e12
+    traffic, traffic_src = None, None
+    try:                                                      # DRAM bytes per launch from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None,
-                "kernel": "tcgen05 implicit-GEMM conv family (conv3x3_halo_kernel, conv_gemm_kernel, "
-                          "conv_gemm_persistent_kernel, stem_conv_kernel)", "launches_per_step": n_conv,
+                "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "tcgen05 implicit-GEMM conv family (conv_multi_kernel, conv_gemm_persistent_kernel, "
+                          "conv_gemm_kernel, stem_conv_kernel)", "launches_per_step": n_conv,
                 "avg_launch_ms": conv_ms / n_conv, "share_of_step": conv_ms / sum(per_op_ms),
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"}
 
