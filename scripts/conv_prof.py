@@ -62,7 +62,7 @@ if __name__ != "__main__":
 CONFIGS = [dict(variant=1), dict(variant=2), dict(variant=2, bn=256), dict(variant=5), dict(variant=5, mode=2),
            dict(variant=5, bn=256)]
 if os.environ.get("UG_ABLATE"):
-    CONFIGS = [dict(variant=5)] + [dict(variant=5, stages=100 + f) for f in (1, 2, 3, 4, 7)]
+    CONFIGS = [dict(variant=5, stages=108), dict(variant=5, stages=108, mode=2)]
 for shp in SHAPES:
     B, H, W, Cin, N, R = shp
     fl = 2.0 * B * H * W * N * Cin * max(R, 1) ** 2

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
         }
       }
     }
-    if (p.prof && lane == 0) {
+    if (p.prof && lane == 0 && !((hp.debug & 8) && i == 1)) {
       p.prof[blockIdx.x * 16 + 4 + i * 4 + 0] = w_af;
       p.prof[blockIdx.x * 16 + 4 + i * 4 + 1] = w_bf;
       p.prof[blockIdx.x * 16 + 4 + i * 4 + 2] = w_acc;
@@ -347,8 +347,32 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
     uint8_t* sOi = sO + i * p.obufs * obuf_bytes;
     int acc = 0, obuf = 0;
     uint32_t acc_phase = 0;
-    long long e_wacc = 0, e_wobuf = 0, e_tiles = 0;
+    long long e_wacc = 0, e_wobuf = 0, e_tiles = 0, e_loop = 0, e_tail = 0;
     const long long e_start = clock64();
+
+    // Residual (ADD / GATE) rows: 16-byte pieces of this thread's own pixel row, prefetched into registers ONE
+    // SUB-TILE AHEAD (right after the chunk loop of the previous sub-tile, whose residual registers are dead by
+    // then): with the loads issued at the start of the same tile the HBM latency was exposed in the first chunk of
+    // every tile of the epilogue-bound 64-channel layers (chunk loop 1000 cycles per chunk instead of 400).
+    const bool has_add = p.mode == UG_EPI_ADD || p.mode == UG_EPI_GATE;
+    uint4 addv[8];
+    auto prefetch_add = [&](int s2, int sub2) {
+      const int nt2 = hp.d_msuper.div(s2), mt2 = (s2 - nt2 * hp.m_super) * kMI + i;
+      const int u1 = hp.d_tx.div(mt2), u2 = hp.d_ty.div(u1);
+      const int x2 = (mt2 - u1 * p.tiles_x) * p.TW + tx, y2 = (u1 - u2 * p.tiles_y) * p.TH + ty, n2 = u2 * p.TN + tn;
+      const bool v2 = row_in_tile && (x2 < p.W) && (y2 < p.H) && (n2 < p.B);
+      const int col2 = nt2 * p.BN + sub2 * 64;
+      const __nv_bfloat16* ar = reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)n2 * p.add_bstride +
+                                ((long long)y2 * p.W + x2) * p.add_cstride + col2;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        addv[g] = (v2 && col2 + g * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(ar + g * 8)) : make_uint4(0, 0, 0, 0);
+    };
+    if (has_add) {
+      int s0 = blockIdx.x;
+      while (s0 < total_super && ((s0 - hp.d_msuper.div(s0) * hp.m_super) * kMI + i) >= p.m_tiles) s0 += gridDim.x;
+      if (s0 < total_super) prefetch_add(s0, 0);
+    }
 
     for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
       const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
@@ -363,22 +387,9 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
       const int ncol0 = nt * p.BN;
       const int x = x0 + tx, y = y0 + ty;
       const bool valid = row_in_tile && (x < p.W) && (y < p.H) && (n < p.B);
-      const long long pix = (long long)y * p.W + x;
-      const __nv_bfloat16* add_row =
-          reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)n * p.add_bstride + pix * p.add_cstride + ncol0;
       const float* gate_row = p.gate + (long long)n * p.N + ncol0;
       const int ncols = min(p.BN, p.N - ncol0);
-      const bool has_add = p.mode == UG_EPI_ADD || p.mode == UG_EPI_GATE;
-      // residual row of the first 64-channel sub-tile: issued before the accumulator wait so that the loads are
-      // in flight while the MMAs of this tile finish (16-byte pieces of this thread's own pixel row)
-      uint4 addv[8];
-      if (has_add) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          addv[g] = (valid && g * 8 < ncols) ? __ldg(reinterpret_cast<const uint4*>(add_row + g * 8))
-                                             : make_uint4(0, 0, 0, 0);
-        if (p.mode == UG_EPI_GATE && etid < ncols) sGate[i * 128 + etid] = 1.0f + __ldg(gate_row + etid);
-      }
+      if (has_add && p.mode == UG_EPI_GATE && etid < ncols) sGate[i * 128 + etid] = 1.0f + __ldg(gate_row + etid);
       long long tw0 = p.prof ? clock64() : 0;
       mbar_wait(&acc_full[i * p.acc_stages + acc], acc_phase);
       if (p.prof) e_wacc += clock64() - tw0;
@@ -396,13 +407,6 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
       }
       for (int sub = 0; sub * 64 < ncols; ++sub) {
         if (p.tma_store) {
-          if (has_add && sub != 0) {  // second sub-tile (BN = 128): its residual row is fetched here
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              addv[g] = (valid && sub * 64 + g * 8 < ncols)
-                            ? __ldg(reinterpret_cast<const uint4*>(add_row + sub * 64 + g * 8))
-                            : make_uint4(0, 0, 0, 0);
-          }
           // staging buffer `obuf` must no longer be read by the TMA store issued obufs sub-tiles ago
           // (the barrier also publishes sGate of this tile)
           tw0 = p.prof ? clock64() : 0;
@@ -416,6 +420,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
         uint8_t* so_row = sOi + obuf * obuf_bytes + row * 128;
         // not unrolled on purpose: the four epilogue warps of an SMSP share its 6 KB L0 instruction cache with an
         // MMA issuer / producer warp, and a 4x larger loop body measurably slowed the MMA issue (0.24 -> 0.29 ms)
+        const long long tl0 = p.prof ? clock64() : 0;
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const int c0 = sub * 64 + cc * 16;
@@ -465,6 +470,8 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
             }
           }
         }
+        const long long tl1 = p.prof ? clock64() : 0;
+        if (p.prof) e_loop += tl1 - tl0;
         if (p.mode == UG_EPI_OUTC) continue;
         if ((sub + 1) * 64 >= ncols) {  // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
           tc_fence_before();
@@ -472,6 +479,15 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
           if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
         }
         fence_proxy_async_smem();
+        // (issued after the proxy fence: the fence waits for outstanding loads, which would expose their latency here)
+        if (has_add) {  // residual of the next sub-tile of this group (same tile, or the group's next tile)
+          if ((sub + 1) * 64 < ncols) {
+            prefetch_add(s, sub + 1);
+          } else {
+            const int s2 = s + gridDim.x;
+            if (s2 < total_super && ((s2 - hp.d_msuper.div(s2) * hp.m_super) * kMI + i) < p.m_tiles) prefetch_add(s2, 0);
+          }
+        }
         named_bar_sync(1 + i, 128);
         if (etid == 0 && !(hp.debug & 2)) {
           const int col = ncol0 + sub * 64;
@@ -483,6 +499,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
           }
           bulk_commit_group();
         }
+        if (p.prof) e_tail += clock64() - tl1;
         if (p.obufs == 2) obuf ^= 1;
       }
       if (p.mode == UG_EPI_OUTC) {
@@ -508,6 +525,10 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
       p.prof[blockIdx.x * 16 + 13] = e_wobuf;
       p.prof[blockIdx.x * 16 + 14] = clock64() - e_start;
       p.prof[blockIdx.x * 16 + 15] = e_tiles;
+      if (hp.debug & 8) {  // finer epilogue split in the slots of issuer 1 (profiling runs only)
+        p.prof[blockIdx.x * 16 + 9] = e_loop;
+        p.prof[blockIdx.x * 16 + 10] = e_tail;
+      }
     }
   }
 

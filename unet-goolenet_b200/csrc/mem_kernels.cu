@@ -160,7 +160,9 @@ int launch_pool(ug_engine* h, const ug_pool_desc* d, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per token, C in {256, 512, 768, 1024}; two-pass statistics in registers.
+// LayerNorm: one warp per token, C = 256 * kNV in {256, 512, 768, 1024}; two-pass statistics in registers (kNV is a
+// template parameter so that the row stays in registers: with a run-time trip count it lived in local memory).
+template <int kNV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ in,
                                                         __nv_bfloat16* __restrict__ out,
                                                         const float* __restrict__ gamma,
@@ -168,10 +170,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
-  const int nv = C / 256;  // 16-byte vectors per lane
+  constexpr int nv = kNV;  // 16-byte vectors per lane
   const __nv_bfloat16* row = in + (long long)warp * C;
-  float v[32];
+  float v[kNV * 8];
   float sum = 0.0f;
+#pragma unroll
   for (int i = 0; i < nv; ++i) {
     const uint4 u = *reinterpret_cast<const uint4*>(row + (i * 32 + lane) * 8);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -186,6 +189,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / C;
   float sq = 0.0f;
+#pragma unroll
   for (int i = 0; i < nv * 8; ++i) {
     const float dlt = v[i] - mean;
     sq += dlt * dlt;
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / C + eps);
   __nv_bfloat16* orow = out + (long long)warp * C;
+#pragma unroll
   for (int i = 0; i < nv; ++i) {
     const int c0 = (i * 32 + lane) * 8;
     float r[8];
@@ -211,9 +216,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 int launch_layernorm(ug_engine* h, const ug_layernorm_desc* d, cudaStream_t s) {
   if (!d->in || !d->out || !d->gamma || !d->beta || d->M <= 0 || d->C % 256 || d->C > 1024 || d->C <= 0)
     return set_error(h, UG_EINVAL, "layernorm: C must be a multiple of 256 up to 1024");
-  layernorm_kernel<<<cdiv((long long)d->M * 32, 256), 256, 0, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d->in), reinterpret_cast<__nv_bfloat16*>(d->out), d->gamma, d->beta, d->M,
-      d->C, d->eps);
+  const dim3 grid(cdiv((long long)d->M * 32, 256));
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d->in);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  switch (d->C / 256) {
+    case 1: layernorm_kernel<1><<<grid, 256, 0, s>>>(in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
+    case 2: layernorm_kernel<2><<<grid, 256, 0, s>>>(in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
+    case 3: layernorm_kernel<3><<<grid, 256, 0, s>>>(in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
+    default: layernorm_kernel<4><<<grid, 256, 0, s>>>(in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
+  }
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "layernorm launch");
 }
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(ug_attn_desc d)
 // of O = P V (accumulator layout of the first MMA == A-fragment layout of the second).
 static constexpr int kAttnSP = 208;           // padded sequence length (multiple of 16)
 static constexpr int kAttnKPitch = 72;        // bf16 elements per sK row  (144 B: conflict-free fragment loads)
-static constexpr int kAttnVPitch = kAttnSP + 8;  // bf16 elements per sVt row (432 B)
+static constexpr int kAttnVPitch = 72;        // bf16 elements per sV row (row-major [key][dim]; fragments via ldmatrix.trans)
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -337,7 +348,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 __global__ void __launch_bounds__(128) attention_mma_kernel(ug_attn_desc d) {
   extern __shared__ uint4 attn_smem[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(attn_smem);   // [kAttnSP][kAttnKPitch]
-  __nv_bfloat16* sVt = sK + kAttnSP * kAttnKPitch;                    // [64][kAttnVPitch]
+  __nv_bfloat16* sV = sK + kAttnSP * kAttnKPitch;                     // [kAttnSP][kAttnVPitch]
   const int b = blockIdx.x / d.heads;
   const int hd = blockIdx.x % d.heads;
   const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(d.q);
@@ -352,9 +363,7 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(ug_attn_desc d) {
       vv = *reinterpret_cast<const uint4*>(v + tok * d.v_stride + hd * 64 + part * 8);
     }
     *reinterpret_cast<uint4*>(sK + row * kAttnKPitch + part * 8) = kv;
-    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) sVt[(part * 8 + e) * kAttnVPitch + row] = ve[e];
+    *reinterpret_cast<uint4*>(sV + row * kAttnVPitch + part * 8) = vv;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -423,10 +432,18 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(ug_attn_desc d) {
       pa[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
       pa[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
       pa[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+      // B fragments of V[16 keys][8 dims] blocks: V is row-major in smem (key-major), the mma wants it key-contiguous
+      // per dim, i.e. transposed: ldmatrix.trans (lanes 0-15 address the 16 key rows, lanes 16-31 those of the next
+      // 8-dim block).  The element-wise transposed staging this replaces cost 12.5k conflicted 2-byte stores per block.
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const __nv_bfloat16* vrow = sVt + (nt * 8 + g) * kAttnVPitch + kk * 16 + 2 * t;
-        mma_bf16_16816(o[nt], pa, *reinterpret_cast<const uint32_t*>(vrow), *reinterpret_cast<const uint32_t*>(vrow + 8));
+      for (int nt = 0; nt < 8; nt += 2) {
+        const __nv_bfloat16* vp = sV + (kk * 16 + (lane & 15)) * kAttnVPitch + (nt + (lane >> 4)) * 8;
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(smem_u32(vp)));
+        mma_bf16_16816(o[nt], pa, b0, b1);
+        mma_bf16_16816(o[nt + 1], pa, b2, b3);
       }
     }
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
@@ -454,7 +471,7 @@ int launch_attention(ug_engine* h, const ug_attn_desc* d, cudaStream_t s) {
     attr_set = true;
   }
   if (d->S <= kAttnSP && d->variant == 0) {
-    const size_t smem = (size_t)(kAttnSP * kAttnKPitch + 64 * kAttnVPitch) * sizeof(__nv_bfloat16);
+    const size_t smem = (size_t)(kAttnSP * kAttnKPitch + kAttnSP * kAttnVPitch) * sizeof(__nv_bfloat16);
     attention_mma_kernel<<<d->B * d->heads, 128, smem, s>>>(*d);
   } else {  // generic fp32 CUDA-core path (S up to 256)
     const size_t smem = (size_t)d->S * 8 * sizeof(uint4) * 2;
