@@ -339,6 +339,7 @@ def main():
                                     "(BASELINE.json configs[4]), random-init weights"),
                        "images_per_gpu_per_step": PB, "micro_batch": MB, "global_batch": world * PB,
                        "collective": "nccl all_gather(masks u8, logits f32)" if world > 1 else "none",
+                       "autotuned_conv_ops": ws.get("tuned_ops"),
                        "l2": f"per-step inputs ({h2d / 1e6:.0f} MB) and activations (GBs) exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},

@@ -294,6 +294,10 @@ int ug_resize_u8(ug_handle h, const ug_resize_desc* d, void* stream);
 int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out);
 int ug_program_run(ug_handle h, ug_program p, void* stream);
 int ug_program_num_launches(ug_program p);
+/* Measured kernel-variant choice for every conv op created with variant 0 (auto): each kernel structure that accepts
+ * the op is timed on the op's own buffers (which are overwritten; call before the first real run) and the fastest
+ * is kept.  Synchronizes the stream.  n_changed (optional) receives the number of switched ops. */
+int ug_program_autotune(ug_handle h, ug_program p, void* stream, int* n_changed);
 /* Profiling aid: run with a CUDA event pair around every op, synchronize, and return the device time of each
  * op in milliseconds (ms_per_op has ug_program_num_launches(p) entries). */
 int ug_program_run_timed(ug_handle h, ug_program p, void* stream, float* ms_per_op);

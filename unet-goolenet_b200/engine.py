@@ -113,7 +113,7 @@ _SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_INC_IM2COL: "ug_inc_im2col", OP_POOL: "u
 
 EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
-                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_timed", "ug_conv_profile", "ug_mma_microbench",
+                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_timed", "ug_program_autotune", "ug_conv_profile", "ug_mma_microbench",
                     "ug_mma_microbench2", "ug_conv_profile16"]
 
 _lib = None
@@ -145,6 +145,7 @@ def load_library():
     lib.ug_program_run.argtypes = [_vp, _vp, _vp]
     lib.ug_program_num_launches.argtypes = [_vp]
     lib.ug_program_run_timed.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_float)]
+    lib.ug_program_autotune.argtypes = [_vp, _vp, _vp, C.POINTER(_i)]
     lib.ug_program_destroy.argtypes = [_vp, _vp]
     lib.ug_program_run_host.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _vp]
     _lib = lib
@@ -176,6 +177,14 @@ class Program:
     def run(self, stream=None):
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         self.engine._check(self.engine.lib.ug_program_run(self.engine.handle, self.handle, s))
+
+    def autotune(self, stream=None):
+        """Time every auto-variant conv op with each kernel structure and keep the fastest (ug_program_autotune).
+        Overwrites the ops' output buffers; call before the first real run.  Returns the number of switched ops."""
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        n = _i(0)
+        self.engine._check(self.engine.lib.ug_program_autotune(self.engine.handle, self.handle, s, C.byref(n)))
+        return n.value
 
     def run_timed(self, stream=None):
         """Per-op device times in ms (event pair around every op; profiling aid, not the benchmark path)."""

@@ -11,12 +11,25 @@ lays out the NHWC bf16 activation workspace in HBM and emits the op descriptors 
 Dead compute of the reference forward is skipped: the `x` output of the bottleneck (attention1, the first
 cross_attention_cl call, x_mlp_norm, x_feed) feeds only a discarded result (basicUnet.py:418).
 """
+import os
+
 import torch
 
 from . import engine as E
 from . import pack
 
 IMG = 224
+# UG_AUTOTUNE=1: measured kernel-variant choice at plan time (ug_program_autotune).  Off by default: on the B200 it
+# switched 52 of 133 conv ops but the step time stayed within run-to-run noise (9.69k vs 9.70k img/s), and the static
+# choice keeps results bit-identical from one process to the next.
+AUTOTUNE = os.environ.get("UG_AUTOTUNE", "0") == "1"
+
+
+def _finish(engine, ops, ws):
+    ws["program"] = engine.program(ops)
+    if AUTOTUNE:
+        ws["tuned_ops"] = ws["program"].autotune()
+    return ws
 
 
 class View:
@@ -305,7 +318,7 @@ class UNetRunner(_Builder):
             ws, ops = {}, []
             self._emit_unet(B, ws, ops)
             self._emit_bbox(B, ws, ops, padding)
-            ws["program"] = self.engine.program(ops)
+            _finish(self.engine, ops, ws)
             self.plans[key] = ws
         return self.plans[key]
 
@@ -429,7 +442,7 @@ class GoogLeNetRunner(_Builder):
             else:
                 ws["in"] = self.buf(B, 3, IMG, IMG, dtype=torch.float32)
                 self._emit_googlenet(B, ws, ops, f32=ws["in"])
-            ws["program"] = self.engine.program(ops)
+            _finish(self.engine, ops, ws)
             self.plans[key] = ws
         return self.plans[key]
 
@@ -509,7 +522,7 @@ class PipelineRunner:
                                             ws["u8"][sl].data_ptr(), mb, IMG, IMG, IMG))
                 ws.setdefault("sub", []).append(sub)
             self.gnet._emit_googlenet(B, ws, ops, u8=ws["u8"])
-            ws["program"] = self.engine.program(ops)
+            _finish(self.engine, ops, ws)
             self.plans[key] = ws
         return self.plans[key]
 
