@@ -202,6 +202,19 @@ typedef struct ug_resize_desc {
   int B, Hs, Ws, S;
 } ug_resize_desc;
 
+/* `wavelet_enhance` (分类/test.py:17-63): grayscale uint8 [B][H][W] -> pseudo-RGB uint8 HWC [B][H][W][3]:
+ * R = normalize(image), G = normalize(resize(cA)), B = normalize(resize(sqrt(cH^2+cV^2+cD^2))) with the single-level
+ * Haar transform of PyWavelets (float32, 'symmetric' extension), cv2.resize INTER_LINEAR back to HxW and
+ * normalize(x) = ((x - min) / max(x - min) * 255).astype(uint8) per image.  workspace: device scratch of at least
+ * ug_wavelet_workspace_bytes(B, H, W) bytes.  Five small launches on the stream. */
+typedef struct ug_wavelet_desc {
+  const unsigned char* gray;
+  unsigned char* out_u8;
+  void* workspace;
+  size_t workspace_bytes;
+  int B, H, W;
+} ug_wavelet_desc;
+
 /* AdaptiveAvgPool2d(1) + Linear(C, ncls): in NHWC bf16 [B][HW][C], w fp32 [ncls][C], logits fp32 [B][ncls]. */
 typedef struct ug_head_desc {
   const void* in;
@@ -224,7 +237,8 @@ enum {
   UG_OP_G1_IM2COL = 10,
   UG_OP_HEAD = 11,
   UG_OP_STEM = 12,
-  UG_OP_RESIZE = 13
+  UG_OP_RESIZE = 13,
+  UG_OP_WAVELET = 14
 };
 
 typedef struct ug_op {
@@ -244,6 +258,7 @@ typedef struct ug_op {
     ug_head_desc head;
     ug_stem_desc stem;
     ug_resize_desc resize;
+    ug_wavelet_desc wavelet;
   } u;
 } ug_op;
 
@@ -289,6 +304,8 @@ int ug_g1_im2col(ug_handle h, const ug_g1_im2col_desc* d, void* stream);
 int ug_head(ug_handle h, const ug_head_desc* d, void* stream);
 int ug_stem(ug_handle h, const ug_stem_desc* d, void* stream);
 int ug_resize_u8(ug_handle h, const ug_resize_desc* d, void* stream);
+int ug_wavelet(ug_handle h, const ug_wavelet_desc* d, void* stream);
+size_t ug_wavelet_workspace_bytes(int B, int H, int W);
 
 /* Programs: a validated op list with tensor maps and launch geometry prepared once; run = launches only. */
 int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out);

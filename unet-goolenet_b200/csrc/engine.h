@@ -95,5 +95,6 @@ int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s)
 int launch_g1_im2col(ug_engine* h, const ug_g1_im2col_desc* d, cudaStream_t s);
 int launch_head(ug_engine* h, const ug_head_desc* d, cudaStream_t s);
 int launch_resize_u8(ug_engine* h, const ug_resize_desc* d, cudaStream_t s);
+int launch_wavelet(ug_engine* h, const ug_wavelet_desc* d, cudaStream_t s);
 
 }  // namespace ug

@@ -15,7 +15,7 @@ UG_OK = 0
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 EPI_STORE, EPI_ADD, EPI_GATE, EPI_OUTC = 0, 1, 2, 3
 (OP_CONV, OP_INC_IM2COL, OP_POOL, OP_LAYERNORM, OP_ATTN, OP_CHANSTATS, OP_GATE, OP_BBOX, OP_CROPRESIZE,
- OP_G1_IM2COL, OP_HEAD, OP_STEM, OP_RESIZE) = range(1, 14)
+ OP_G1_IM2COL, OP_HEAD, OP_STEM, OP_RESIZE, OP_WAVELET) = range(1, 15)
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
@@ -83,11 +83,16 @@ class ResizeDesc(C.Structure):
     _fields_ = [("src", _vp), ("out_f32", _vp), ("out_u8", _vp), ("B", _i), ("Hs", _i), ("Ws", _i), ("S", _i)]
 
 
+class WaveletDesc(C.Structure):
+    _fields_ = [("gray", _vp), ("out_u8", _vp), ("workspace", _vp), ("workspace_bytes", C.c_size_t), ("B", _i),
+                ("H", _i), ("W", _i)]
+
+
 class _OpUnion(C.Union):
     _fields_ = [("conv", ConvDesc), ("inc", IncIm2colDesc), ("pool", PoolDesc), ("ln", LayerNormDesc),
                 ("attn", AttnDesc), ("stats", ChanStatsDesc), ("gate", GateDesc), ("bbox", BBoxDesc),
                 ("crop", CropResizeDesc), ("g1", G1Im2colDesc), ("head", HeadDesc), ("stem", StemDesc),
-                ("resize", ResizeDesc)]
+                ("resize", ResizeDesc), ("wavelet", WaveletDesc)]
 
 
 class Op(C.Structure):
@@ -100,21 +105,22 @@ class Copy(C.Structure):
 
 _KIND_FIELD = {OP_CONV: "conv", OP_INC_IM2COL: "inc", OP_POOL: "pool", OP_LAYERNORM: "ln", OP_ATTN: "attn",
                OP_CHANSTATS: "stats", OP_GATE: "gate", OP_BBOX: "bbox", OP_CROPRESIZE: "crop",
-               OP_G1_IM2COL: "g1", OP_HEAD: "head", OP_STEM: "stem", OP_RESIZE: "resize"}
+               OP_G1_IM2COL: "g1", OP_HEAD: "head", OP_STEM: "stem", OP_RESIZE: "resize",
+               OP_WAVELET: "wavelet"}
 _DESC_KIND = {ConvDesc: OP_CONV, IncIm2colDesc: OP_INC_IM2COL, PoolDesc: OP_POOL, LayerNormDesc: OP_LAYERNORM,
               AttnDesc: OP_ATTN, ChanStatsDesc: OP_CHANSTATS, GateDesc: OP_GATE, BBoxDesc: OP_BBOX,
               CropResizeDesc: OP_CROPRESIZE, G1Im2colDesc: OP_G1_IM2COL, HeadDesc: OP_HEAD, StemDesc: OP_STEM,
-              ResizeDesc: OP_RESIZE}
+              ResizeDesc: OP_RESIZE, WaveletDesc: OP_WAVELET}
 _SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_INC_IM2COL: "ug_inc_im2col", OP_POOL: "ug_pool",
                  OP_LAYERNORM: "ug_layernorm", OP_ATTN: "ug_attention", OP_CHANSTATS: "ug_chanstats",
                  OP_GATE: "ug_gate", OP_BBOX: "ug_bbox", OP_CROPRESIZE: "ug_cropresize",
                  OP_G1_IM2COL: "ug_g1_im2col", OP_HEAD: "ug_head", OP_STEM: "ug_stem",
-                 OP_RESIZE: "ug_resize_u8"}
+                 OP_RESIZE: "ug_resize_u8", OP_WAVELET: "ug_wavelet"}
 
 EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
                     "ug_program_destroy", "ug_program_run_host", "ug_program_run_timed", "ug_program_autotune", "ug_conv_profile", "ug_mma_microbench",
-                    "ug_mma_microbench2", "ug_conv_profile16"]
+                    "ug_mma_microbench2", "ug_conv_profile16", "ug_wavelet_workspace_bytes"]
 
 _lib = None
 
@@ -145,6 +151,8 @@ def load_library():
     lib.ug_program_run.argtypes = [_vp, _vp, _vp]
     lib.ug_program_num_launches.argtypes = [_vp]
     lib.ug_program_run_timed.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_float)]
+    lib.ug_wavelet_workspace_bytes.argtypes = [_i, _i, _i]
+    lib.ug_wavelet_workspace_bytes.restype = C.c_size_t
     lib.ug_program_autotune.argtypes = [_vp, _vp, _vp, C.POINTER(_i)]
     lib.ug_program_destroy.argtypes = [_vp, _vp]
     lib.ug_program_run_host.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _vp]
