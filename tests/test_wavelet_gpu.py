@@ -55,3 +55,23 @@ def test_wavelet_feeds_the_pipeline(engine):
     masks, boxes, cls = pipe(rgb)
     assert masks.shape == (2, 224, 224) and boxes.shape == (2, 4) and cls.shape == (2, 6)
     assert torch.isfinite(cls).all()
+
+
+def test_grade_images_end_to_end(engine, tmp_path):
+    """infer.grade_images == composing the device stages by hand; records sorted by numeric file name."""
+    from oracle import fixtures
+    from ugnet_b200.infer import grade_images
+    from ugnet_b200.lower import PipelineRunner
+    from ugnet_b200.util.data_utils import resize_to_tensor
+    from ugnet_b200.util.wavelet import wavelet_enhance_batch
+    usd = fixtures.procedural_state(fixtures.unet_template(), seed=7)
+    gsd = fixtures.procedural_state(fixtures.googlenet_template(), seed=11)
+    pipe = PipelineRunner(usd, gsd, "cuda:0", micro_batch=4)
+    gray = _images(11, 5, 256, 320)
+    names = ["10.png", "9.png", "2.png", "33.png", "1.png"]
+    recs = grade_images(pipe, gray, names, save_dir=str(tmp_path), batch_size=4)
+    x = resize_to_tensor(wavelet_enhance_batch(torch.from_numpy(gray).cuda()), 224)
+    ref = torch.argmax(pipe(x)[2], dim=1).cpu().numpy()
+    want = sorted((f"{n.replace('.png', '')} {int(c)}" for n, c in zip(names, ref)), key=lambda r: int(r.split()[0]))
+    assert recs == want
+    assert (tmp_path / "result.txt").read_text().splitlines() == want

@@ -50,4 +50,30 @@ def inference_all_seg(model, test_loader, device, save_dir=None):
     return out
 
 
+@torch.no_grad()
+def grade_images(pipeline, gray_images, filenames, save_dir=None, batch_size=256):
+    """The whole of 分类/test.py:122-134 + :74-96 on the device for a list of grayscale images of one size:
+    cv2.imread(path, 0) output (uint8 [H, W]) -> wavelet_enhance -> resize 224 + to_tensor -> UNet -> mask -> bbox ->
+    ROI crop/resize -> GoogLeNet -> argmax; returns the sorted "<name> <class>" records (and writes result.txt).
+
+    pipeline: pipeline.TwoStagePipeline (or lower.PipelineRunner); gray_images: uint8 array / tensor [N, H, W]."""
+    from .util.wavelet import wavelet_enhance_batch
+    runner = getattr(pipeline, "runner", pipeline)
+    g = torch.as_tensor(np.ascontiguousarray(gray_images) if isinstance(gray_images, np.ndarray) else gray_images)
+    records = []
+    for s in range(0, g.shape[0], batch_size):
+        rgb = wavelet_enhance_batch(g[s:s + batch_size].to(runner.dev))      # [B,H,W,3] uint8, test.py:128-129
+        _, _, cls = runner(rgb)                                              # test.py:130-131 and :82-84
+        pred = torch.argmax(torch.softmax(cls, dim=1), dim=1).cpu().numpy()  # test.py:86
+        for i, name in enumerate(filenames[s:s + batch_size]):
+            records.append(f"{name.replace('.png', '')} {int(pred[i])}")
+    records.sort(key=lambda x: int(x.split()[0].replace(".jpg", "").replace(".png", "")))
+    if save_dir is not None:
+        os.makedirs(save_dir, exist_ok=True)
+        with open(os.path.join(save_dir, "result.txt"), "w") as f:
+            for line in records:
+                f.write(line + "\n")
+    return records
+
+
 inference_all = inference_all_cls
