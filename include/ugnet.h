@@ -69,6 +69,10 @@ typedef struct ug_conv_desc {
   float outc_b;
   float* logits;
   unsigned char* mask;
+  void* pool_out;             /* optional (3x3 multi-issuer kernel, STORE epilogue, H and W even): also write
+                                 nn.MaxPool2d(2) of the output (basicUnet.py:47 DownBlock) to
+                                 pool_out[((n*H/2+y)*W/2+x)*pool_cstride + c], fused into the epilogue */
+  int pool_cstride;
   int TW, TH, TN, BN, stages; /* tiling; 0 = engine chooses */
   int variant;                /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel (TMEM multi-buffered
                                  accumulators, TMA-store epilogue); 5 = 3x3 multi-issuer kernel (one CTA per
@@ -187,6 +191,9 @@ typedef struct ug_stem_desc {
   void* out;
   int out_cstride;
   int B, H, W;
+  void* pool_out;   /* optional (kind 0, H and W even): also write nn.MaxPool2d(2) of the output (DownBlock,
+                       basicUnet.py:47) to bf16 NHWC [B,H/2,W/2,pool_cstride], fused into the epilogue */
+  int pool_cstride;
 } ug_stem_desc;
 
 /* Device front-end: the reference's CDDataAugmentation.transform live lines

@@ -13,7 +13,7 @@ def _mk(shape, gen, scale=1.0):
 
 
 def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_extra=0, in_off=0, out_off=0,
-             seed=0, tile=None, bn=None, stages=0, add_broadcast=False, variant=0):
+             seed=0, tile=None, bn=None, stages=0, add_broadcast=False, variant=0, pool=False):
     from ugnet_b200 import engine as E
     from ugnet_b200 import pack
     g = torch.Generator(device="cuda").manual_seed(seed)
@@ -50,6 +50,10 @@ def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_ex
     d.BN = BN; d.stages = stages; d.variant = variant
     if tile:
         d.TW, d.TH, d.TN = tile
+    pbuf = None
+    if pool:    # fused nn.MaxPool2d(2) side output into a channel slice of a wider buffer
+        pbuf = torch.full((B, H // 2, W // 2, cout + 24), 3.0, device="cuda", dtype=torch.bfloat16)
+        d.pool_out = pbuf.data_ptr() + 2 * 8; d.pool_cstride = cout + 24
     addt = gate = outw = logits = mask = None
     if mode in (E.EPI_ADD, E.EPI_GATE):
         ab = 1 if add_broadcast else B
@@ -96,6 +100,10 @@ def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_ex
     bad = (got - y).abs() > tol
     assert not bad.any(), (f"{bad.sum().item()} / {bad.numel()} mismatches, max err "
                            f"{(got - y).abs().max().item():.4f}, first at {bad.nonzero()[0].tolist()}")
+    if pool:   # exactly the max-pool of what was stored (rounding is monotonic), neighbouring channels untouched
+        want = F.max_pool2d(obuf[..., out_off:out_off + cout].float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+        assert torch.equal(pbuf[..., 8:8 + cout].float(), want)
+        assert (pbuf[..., :8] == 3.0).all() and (pbuf[..., 8 + cout:] == 3.0).all()
     # channels outside the written slice must be untouched
     if out_extra:
         keep = torch.ones(out_cs, dtype=torch.bool, device="cuda")
@@ -146,6 +154,11 @@ CASES = [
     dict(B=5, H=7, W=7, Cin=160, N=320, R=3, variant=5),           # GoogLeNet 5a-like, tiny map
     dict(B=2, H=16, W=16, Cin=64, N=64, R=3, mode=1, variant=5),   # residual add, resident weights
     dict(B=70, H=32, W=32, Cin=64, N=128, R=3, variant=5),        # several rounds per CTA
+    # fused 2x2 max-pool side output (DownBlock): exact tiles, ragged width (28 = 3.5 tiles), streamed and resident weights
+    dict(B=2, H=112, W=112, Cin=128, N=128, R=3, pool=True),
+    dict(B=3, H=28, W=28, Cin=256, N=512, R=3, pool=True, out_extra=64, out_off=32),
+    dict(B=2, H=56, W=56, Cin=64, N=64, R=3, pool=True),
+    dict(B=5, H=20, W=12, Cin=64, N=96, R=3, pool=True),
     # multi-issuer kernel on 1x1 convolutions / linear layers / ConvTranspose (plain pixel tiles)
     dict(B=1, H=1, W=256, Cin=64, N=64, R=1, variant=5),                      # resident weights, one round
     dict(B=1, H=1, W=1000, Cin=512, N=1536, R=1, act=0, variant=5),           # qkv-shaped GEMM, ragged M

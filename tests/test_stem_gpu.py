@@ -18,8 +18,9 @@ def _check(got, ref):
                            f"{(got - ref).abs().max().item():.4f}, first at {bad.nonzero()[0].tolist()}")
 
 
+@pytest.mark.parametrize("pool", [False, True])
 @pytest.mark.parametrize("B,H,W,extra", [(1, 224, 224, 0), (3, 224, 224, 64), (2, 40, 56, 0), (70, 32, 48, 0)])
-def test_stem_inc(engine, B, H, W, extra):
+def test_stem_inc(engine, B, H, W, extra, pool):
     from ugnet_b200 import engine as E
     from ugnet_b200 import pack
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + H)
@@ -30,9 +31,13 @@ def test_stem_inc(engine, B, H, W, extra):
     wp = pack.pack_linear_weight(wt.permute(0, 2, 3, 1).reshape(64, 27), 64)
     cs = 64 + extra
     out = torch.full((B, H, W, cs), 7.0, device="cuda", dtype=torch.bfloat16)
+    pbuf = torch.full((B, H // 2, W // 2, 80), 3.0, device="cuda", dtype=torch.bfloat16) if pool else None
     engine.run_op(E.StemDesc(0, x.data_ptr(), None, wp.data_ptr(), scale.data_ptr(), bias.data_ptr(),
-                             out.data_ptr(), cs, B, H, W))
+                             out.data_ptr(), cs, B, H, W, E.ptr(pbuf), 80))
     torch.cuda.synchronize()
+    if pool:   # fused nn.MaxPool2d(2) of the stored output, exactly
+        want = F.max_pool2d(out[..., :64].float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+        assert torch.equal(pbuf[..., :64].float(), want) and (pbuf[..., 64:] == 3.0).all()
     xq, wq = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
     ref = torch.relu(F.conv2d(xq, wq, padding=1) * scale[None, :, None, None] + bias[None, :, None, None])
     _check(out[..., :64].float(), ref.permute(0, 2, 3, 1))

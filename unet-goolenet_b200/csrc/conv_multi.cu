@@ -77,6 +77,12 @@ struct MultiParams {
                       // 2 = no staging stores / TMA store, 4 = activation TMA loads only for the first stages
 };
 
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+static constexpr int kPoolBytes = 4096;   // pooled sub-tile staging: 4 x TH/2 <= 32 pixels x 64 channels bf16
+
 struct StoreMaps {  // output maps: [0] for plain stores, [q] = quadrant (dy,dx) of a ConvTranspose 2x2 s2 scatter
   CUtensorMap m[4];
 };
@@ -94,7 +100,8 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
   uint8_t* sA = smem;                                        // [kMI][sa] activation stages
   uint8_t* sB = sA + kMI * hp.sa * hp.a_stage_bytes;
   uint8_t* sO = sB + nb_tiles * b_tile_bytes;                // [kMI][obufs] output staging
-  float* sScale = reinterpret_cast<float*>(sO + kMI * p.obufs * obuf_bytes);  // 16-byte aligned: read as float4
+  uint8_t* sP = sO + kMI * p.obufs * obuf_bytes;              // [kMI][obufs] pooled staging (4 KB each) when p.pool
+  float* sScale = reinterpret_cast<float*>(sP + (p.pool ? kMI * p.obufs * kPoolBytes : 0));  // 16-byte aligned
   float* sBias = sScale + p.npad;
   float* sGate = sBias + p.npad;                              // [kMI][128]: 1 + gate of the tile's image (GATE epilogue)
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sGate + kMI * 128);          // [kMI][sa]
@@ -114,6 +121,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
     prefetch_tmap(&tmB);
     if (p.tma_store) {
       prefetch_tmap(&tmO.m[0]);
+      if (p.pool) prefetch_tmap(&tmO.m[1]);
       if (p.up == 2) {
         prefetch_tmap(&tmO.m[1]);
         prefetch_tmap(&tmO.m[2]);
@@ -467,6 +475,23 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
               o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
               const int chunk = cc * 2 + g;
               if (!(hp.debug & 2)) *reinterpret_cast<uint4*>(so_row + ((chunk ^ (row & 7)) << 4)) = o;
+              if (p.pool) {
+                // fused nn.MaxPool2d(2): the 2x2 window of pixel (tx, ty) lives in lanes ^1 (x) and ^8 (y) of this
+                // warp (row = ty*8 + tx); max of the rounded bf16 values == rounded max (rounding is monotonic)
+                uint4 m = o;
+                m.x = bf16x2_max(m.x, __shfl_xor_sync(0xffffffffu, m.x, 1));
+                m.y = bf16x2_max(m.y, __shfl_xor_sync(0xffffffffu, m.y, 1));
+                m.z = bf16x2_max(m.z, __shfl_xor_sync(0xffffffffu, m.z, 1));
+                m.w = bf16x2_max(m.w, __shfl_xor_sync(0xffffffffu, m.w, 1));
+                m.x = bf16x2_max(m.x, __shfl_xor_sync(0xffffffffu, m.x, 8));
+                m.y = bf16x2_max(m.y, __shfl_xor_sync(0xffffffffu, m.y, 8));
+                m.z = bf16x2_max(m.z, __shfl_xor_sync(0xffffffffu, m.z, 8));
+                m.w = bf16x2_max(m.w, __shfl_xor_sync(0xffffffffu, m.w, 8));
+                if (((tx | ty) & 1) == 0) {
+                  const int pr = (ty >> 1) * 4 + (tx >> 1);  // pooled pixel row of the 4 x TH/2 tile
+                  *reinterpret_cast<uint4*>(sP + (i * p.obufs + obuf) * kPoolBytes + pr * 128 + ((chunk ^ (pr & 7)) << 4)) = m;
+                }
+              }
             }
           }
         }
@@ -496,6 +521,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
             tma_store_4d(&tmO.m[qd], sOi + obuf * obuf_bytes, col - qd * p.convt_cout, x0, y0, n0);
           } else {
             tma_store_4d(&tmO.m[0], sOi + obuf * obuf_bytes, col, x0, y0, n0);
+            if (p.pool) tma_store_4d(&tmO.m[1], sP + (i * p.obufs + obuf) * kPoolBytes, col, x0 >> 1, y0 >> 1, n0);
           }
           bulk_commit_group();
         }
@@ -582,7 +608,11 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   const int npad = n_tiles * BN;
   const long long ktot = (long long)taps * cin_pad;
   const int tma_store = d->mode != UG_EPI_OUTC;
-  const int obuf_bytes = tma_store ? kABytesPerStage : 0;
+  const int pool = d->pool_out != nullptr;
+  if (pool && (taps != 9 || d->mode != UG_EPI_STORE || (d->H & 1) || (d->W & 1) || (TH & 1) || d->pool_cstride % 8 ||
+               (reinterpret_cast<uintptr_t>(d->pool_out) & 15)))
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): fused max-pool needs a 3x3 STORE conv on an even map");
+  const int obuf_bytes = tma_store ? kABytesPerStage + (pool ? kPoolBytes : 0) : 0;  // per staging buffer, for sizing
   const int acc_stages = std::max(1, std::min(4, 512 / (kMI * BN)));
   const int a_bytes = taps == 9 ? kMPitch * (TH + 2) * 128 : TW * TH * TN * 128;
   const int a_stage = ((a_bytes + 1023) / 1024) * 1024;
@@ -640,7 +670,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   p.gate = d->gate; p.outc_w = d->outc_w; p.outc_b = d->outc_b;
   p.logits = d->logits; p.mask = d->mask;
   p.m_tiles = p.tiles_x * p.tiles_y * cdiv_m(d->B, TN); p.n_tiles = n_tiles; p.acc_stages = acc_stages;
-  p.tma_store = tma_store; p.obufs = obufs; p.npad = npad;
+  p.tma_store = tma_store; p.obufs = obufs; p.npad = npad; p.pool = pool;
   hp.m_super = cdiv_m(p.m_tiles, kMI);
   L->variant = 5;
   L->halo_mode = taps;
@@ -677,6 +707,15 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
                                (cuuint64_t)d->H * d->W * d->out_cstride * 2};
       const int r = encode_map(encode, &L->tmO, d->out, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
       if (r) return set_error(h, UG_ECUDA, "conv(multi): output tensor map encode failed (%d)", r);
+      if (pool) {  // fused nn.MaxPool2d(2): pooled tile = 4 x TH/2 pixels of the half-resolution map
+        const long long pcs = d->pool_cstride;
+        cuuint64_t pdims[4] = {(cuuint64_t)d->N, (cuuint64_t)(d->W / 2), (cuuint64_t)(d->H / 2), (cuuint64_t)d->B};
+        cuuint64_t pstrides[3] = {(cuuint64_t)(pcs * 2), (cuuint64_t)((d->W / 2) * pcs * 2),
+                                  (cuuint64_t)((long long)(d->H / 2) * (d->W / 2) * pcs * 2)};
+        cuuint32_t pbox[4] = {64, 4, (cuuint32_t)(TH / 2), 1};
+        const int rp = encode_map(encode, &L->tmQ[0], d->pool_out, 4, pdims, pstrides, pbox, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+        if (rp) return set_error(h, UG_ECUDA, "conv(multi): pooled output tensor map encode failed (%d)", rp);
+      }
     } else {
       // ConvTranspose 2x2 s2: quadrant (dy,dx) of input pixel (y,x) is output pixel (2y+dy, 2x+dx); one strided view
       // of the output per quadrant turns the pixel shuffle into plain TMA tile stores

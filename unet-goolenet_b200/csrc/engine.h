@@ -37,6 +37,7 @@ struct ConvKParams {
   unsigned char* mask;
   // persistent variant
   int m_tiles, n_tiles, acc_stages, tma_store, obufs, npad;
+  int pool;        // multi-issuer 3x3 kernel: fused 2x2 max-pool side output (second TMA store per sub-tile)
   int stage_copy;  // ConvTranspose scatter: stage the tile in smem, then coalesced cooperative copy-out
   long long* prof;  // optional per-CTA cycle counters [grid][8] (debug / profiling builds of the plan)
 };
@@ -63,10 +64,12 @@ struct StemParams {
   int B, H, W;  // source image
   int OH, OW;   // output map
   int tiles_x, tiles_y, total_tiles;
+  int pool;     // fused 2x2 max-pool side output
 };
 struct StemLaunch {
   alignas(64) CUtensorMap tmB;
   alignas(64) CUtensorMap tmO;
+  alignas(64) CUtensorMap tmP;  // pooled output (kind 0 with pool_out)
   StemParams p;
   int kind;
   unsigned grid;

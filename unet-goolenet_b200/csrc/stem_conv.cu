@@ -28,9 +28,16 @@ static constexpr int kIncPatchPitch = 48;                // floats per patch row
 static constexpr int kG1PatchPitch = 112;                // bf16 elements per patch row (111 used); 56 words keeps
                                                          // the 4-byte run copies of a warp on distinct banks
 
+__device__ __forceinline__ uint32_t stem_bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+static constexpr int kStemPoolBytes = 4096;  // pooled tile staging: 8 x 4 pixels x 64 channels bf16
+
 template <int kKind>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ CUtensorMap tmB,
-                                                        const __grid_constant__ CUtensorMap tmO, const StemParams p) {
+                                                        const __grid_constant__ CUtensorMap tmO,
+                                                        const __grid_constant__ CUtensorMap tmP, const StemParams p) {
   constexpr int kAtoms = kKind == 0 ? 1 : 3;             // 64-column swizzle atoms of the A / B tiles
   constexpr int kKSteps = kKind == 0 ? 2 : 10;           // K=16 MMAs per tile
   extern __shared__ uint8_t smem_raw[];
@@ -40,7 +47,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
   uint8_t* sO = sA;                                      // output staging [128 rows][128 B] reuses the first A atom:
                                                          // the A tile is dead once the MMAs of the tile completed
   uint8_t* sB = sA + kAtoms * kABytesPerStage;           // kAtoms x [64 rows][128 B]
-  __nv_bfloat16* sPatch = reinterpret_cast<__nv_bfloat16*>(sB + kAtoms * 64 * 128);   // kind 1: bf16 patch
+  uint8_t* sPool = sB + kAtoms * 64 * 128;               // pooled tile staging (4 KB, 1024-aligned) when p.pool
+  __nv_bfloat16* sPatch = reinterpret_cast<__nv_bfloat16*>(sPool + (p.pool ? kStemPoolBytes : 0));   // kind 1: bf16 patch
   float* sPatchF = reinterpret_cast<float*>(sPatch);                                  // kind 0: fp32 patch
   uint8_t* tail = reinterpret_cast<uint8_t*>(sPatch) + kPatchBytes;
   float* sScale = reinterpret_cast<float*>(tail);       // 16-byte aligned: read as float4
@@ -54,6 +62,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
   if (tid == 0) {
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmO);
+    if (p.pool) prefetch_tmap(&tmP);
     mbar_init(b_full, 1);
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -229,6 +238,22 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
         o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
         o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
         *reinterpret_cast<uint4*>(o_row + ((((c0 >> 3) + g) ^ sw) << 4)) = o;
+        if (p.pool) {
+          // fused nn.MaxPool2d(2): pixel (tx, ty) = row ty*16 + tx; its 2x2 window lives in lanes ^1 (x) and ^16 (y)
+          uint4 m = o;
+          m.x = stem_bf16x2_max(m.x, __shfl_xor_sync(0xffffffffu, m.x, 1));
+          m.y = stem_bf16x2_max(m.y, __shfl_xor_sync(0xffffffffu, m.y, 1));
+          m.z = stem_bf16x2_max(m.z, __shfl_xor_sync(0xffffffffu, m.z, 1));
+          m.w = stem_bf16x2_max(m.w, __shfl_xor_sync(0xffffffffu, m.w, 1));
+          m.x = stem_bf16x2_max(m.x, __shfl_xor_sync(0xffffffffu, m.x, 16));
+          m.y = stem_bf16x2_max(m.y, __shfl_xor_sync(0xffffffffu, m.y, 16));
+          m.z = stem_bf16x2_max(m.z, __shfl_xor_sync(0xffffffffu, m.z, 16));
+          m.w = stem_bf16x2_max(m.w, __shfl_xor_sync(0xffffffffu, m.w, 16));
+          if (((tx | ty) & 1) == 0) {
+            const int pr = (ty >> 1) * 8 + (tx >> 1);  // pooled pixel row of the 8 x 4 tile
+            *reinterpret_cast<uint4*>(sPool + pr * 128 + ((((c0 >> 3) + g) ^ (pr & 7)) << 4)) = m;
+          }
+        }
       }
     }
     fence_proxy_async_smem();
@@ -236,6 +261,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
     __syncthreads();  // staging complete; every TMEM read of this accumulator is done
     if (tid == 0) {
       tma_store_4d(&tmO, sO, 0, x0, y0, n);
+      if (p.pool) tma_store_4d(&tmP, sPool, 0, x0 >> 1, y0 >> 1, n);
       bulk_commit_group();
     }
   }
@@ -272,6 +298,10 @@ int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* L) {
   p.tiles_x = (OW + kStemTW - 1) / kStemTW;
   p.tiles_y = (OH + kStemTH - 1) / kStemTH;
   p.total_tiles = p.tiles_x * p.tiles_y * d->B;
+  p.pool = d->pool_out != nullptr;
+  if (p.pool && (d->kind != 0 || (d->H & 1) || (d->W & 1) || d->pool_cstride % 8 || d->pool_cstride < 64 ||
+                 (reinterpret_cast<uintptr_t>(d->pool_out) & 15)))
+    return set_error(h, UG_EINVAL, "stem: fused max-pool needs kind 0 on an even image, 16B-aligned pooled output");
   {
     cuuint64_t dims[2] = {(cuuint64_t)katoms * 64, 64};
     cuuint64_t strides[1] = {(cuuint64_t)katoms * 64 * 2};
@@ -293,11 +323,23 @@ int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* L) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "stem: output tensor map encode failed (%d)", (int)r);
   }
+  if (p.pool) {
+    const long long pcs = d->pool_cstride;
+    cuuint64_t dims[4] = {64, (cuuint64_t)(OW / 2), (cuuint64_t)(OH / 2), (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)(pcs * 2), (cuuint64_t)((OW / 2) * pcs * 2),
+                             (cuuint64_t)((long long)(OH / 2) * (OW / 2) * pcs * 2)};
+    cuuint32_t box[4] = {64, (cuuint32_t)(kStemTW / 2), (cuuint32_t)(kStemTH / 2), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&L->tmP, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->pool_out, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "stem: pooled output tensor map encode failed (%d)", (int)r);
+  }
   const int ctas_per_sm = d->kind == 0 ? 7 : 2;  // 31 KB / 79 KB of shared memory and 64 TMEM columns per CTA
   L->grid = (unsigned)std::min<long long>(p.total_tiles, (long long)h->num_sms * ctas_per_sm);
   L->smem = 1024 + (size_t)katoms * kABytesPerStage + (size_t)katoms * 64 * 128 +
-            (d->kind == 1 ? kG1PatchH * kG1PatchPitch * 2 : 3 * kIncPatchH * kIncPatchPitch * 4) + 16 + 8 +
-            2 * 64 * sizeof(float);
+            (d->kind == 1 ? kG1PatchH * kG1PatchPitch * 2 : 3 * kIncPatchH * kIncPatchPitch * 4) +
+            (p.pool ? kStemPoolBytes : 0) + 16 + 8 + 2 * 64 * sizeof(float);
   return UG_OK;
 }
 
@@ -312,8 +354,8 @@ int stem_launch(ug_engine* h, const StemLaunch* L, cudaStream_t s) {
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(stem_conv_kernel)");
     attr_set = true;
   }
-  if (L->kind == 0) stem_conv_kernel<0><<<L->grid, 128, L->smem, s>>>(L->tmB, L->tmO, L->p);
-  else stem_conv_kernel<1><<<L->grid, 128, L->smem, s>>>(L->tmB, L->tmO, L->p);
+  if (L->kind == 0) stem_conv_kernel<0><<<L->grid, 128, L->smem, s>>>(L->tmB, L->tmO, L->tmP, L->p);
+  else stem_conv_kernel<1><<<L->grid, 128, L->smem, s>>>(L->tmB, L->tmO, L->tmP, L->p);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "stem_conv_kernel launch");
 }

@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
                 ("R", _i), ("S", _i), ("pad", _i), ("w", _vp), ("N", _i), ("scale", _vp), ("bias", _vp),
                 ("act", _i), ("mode", _i), ("out", _vp), ("out_cstride", _i), ("up", _i), ("convt_cout", _i),
                 ("add", _vp), ("add_bstride", _ll), ("add_cstride", _i), ("gate", _vp), ("outc_w", _vp),
-                ("outc_b", _f), ("logits", _vp), ("mask", _vp),
+                ("outc_b", _f), ("logits", _vp), ("mask", _vp), ("pool_out", _vp), ("pool_cstride", _i),
                 ("TW", _i), ("TH", _i), ("TN", _i), ("BN", _i), ("stages", _i), ("variant", _i)]
 
 
@@ -76,7 +76,8 @@ class HeadDesc(C.Structure):
 
 class StemDesc(C.Structure):
     _fields_ = [("kind", _i), ("in_f32", _vp), ("in_u8", _vp), ("w", _vp), ("scale", _vp), ("bias", _vp),
-                ("out", _vp), ("out_cstride", _i), ("B", _i), ("H", _i), ("W", _i)]
+                ("out", _vp), ("out_cstride", _i), ("B", _i), ("H", _i), ("W", _i), ("pool_out", _vp),
+                ("pool_cstride", _i)]
 
 
 class ResizeDesc(C.Structure):

@@ -23,6 +23,8 @@ IMG = 224
 # switched 52 of 133 conv ops but the step time stayed within run-to-run noise (9.69k vs 9.70k img/s), and the static
 # choice keeps results bit-identical from one process to the next.
 AUTOTUNE = os.environ.get("UG_AUTOTUNE", "0") == "1"
+# UG_FUSE_POOL=0 falls back to separate max-pool launches after the encoder convolutions (A/B measurements).
+FUSE_POOL = os.environ.get("UG_FUSE_POOL", "1") != "0"
 
 
 def _finish(engine, ops, ws):
@@ -91,7 +93,7 @@ class _Builder:
 
     # ---- ops -----------------------------------------------------------------------------------
     def conv(self, ops, wd, x, geom, out=None, act=E.ACT_RELU, mode=E.EPI_STORE, up=1, add=None, add_bstride=0,
-             gate=None, outc=None):
+             gate=None, outc=None, pool_out=None):
         B, H, W = geom
         d = E.ConvDesc()
         d.algo_k = wd.get("algo_k", wd["Cin"] * wd["R"] * wd["R"])   # true reduction length (for FLOP accounting)
@@ -112,6 +114,8 @@ class _Builder:
             d.add, d.add_cstride, d.add_bstride = add.ptr, add.cstride, add_bstride
         if gate is not None:
             d.gate = gate.data_ptr()
+        if pool_out is not None:                                     # fused nn.MaxPool2d(2) side output
+            d.pool_out, d.pool_cstride = pool_out.data_ptr(), pool_out.shape[-1]
         if outc is not None:
             d.outc_w, d.outc_b = outc["w"].data_ptr(), outc["b"]
             d.logits, d.mask = outc["logits"].data_ptr(), outc["mask"].data_ptr()
@@ -216,21 +220,30 @@ class UNetRunner(_Builder):
         ws["logits"] = io["logits"] if "logits" in io else torch.empty((B, 1, IMG, IMG), device=self.dev)
         ws["mask"] = io["mask"] if "mask" in io else torch.empty((B, IMG, IMG), device=self.dev, dtype=torch.uint8)
         # ---- encoder (basicUnet.py:409-416)
+        # nn.MaxPool2d(2) of every DownBlock (basicUnet.py:47) is fused into the epilogue of the conv that produces its
+        # input: that conv writes the full-resolution skip tensor AND the pooled tensor of the next level
         x1 = buf(B, IMG, IMG, 64)                                    # inc: im2col built in smem (stem_conv.cu)
+        pooled = buf(B, IMG // 2, IMG // 2, 64)
         wi = self.w["inc"]
         ops.append(E.StemDesc(0, ws["x_in"].data_ptr(), None, wi["w"].data_ptr(), wi["scale"].data_ptr(),
-                              wi["bias"].data_ptr(), x1.data_ptr(), 64, B, IMG, IMG))
+                              wi["bias"].data_ptr(), x1.data_ptr(), 64, B, IMG, IMG,
+                              pooled.data_ptr() if FUSE_POOL else None, 64))
+        if not FUSE_POOL:
+            ops.append(E.PoolDesc(x1.data_ptr(), 64, pooled.data_ptr(), 64, 64, B, IMG, IMG, IMG // 2, IMG // 2, 2, 2, 0))
         skips = [x1]
-        cur, size, cin = x1, IMG, 64
+        size = IMG
         for blk, cout in (("down1", 128), ("down2", 256), ("down3", 512), ("down4", 512)):
             half = size // 2
-            p = buf(B, half, half, cin)
-            ops.append(E.PoolDesc(cur.data_ptr(), cin, p.data_ptr(), cin, cin, B, size, size, half, half, 2, 2, 0))
             t0 = buf(B, half, half, cout)
-            self.conv(ops, self.w[blk + ".0"], View(p), (B, half, half), View(t0))
+            self.conv(ops, self.w[blk + ".0"], View(pooled), (B, half, half), View(t0))
             t1 = buf(B, half, half, cout)
-            self.conv(ops, self.w[blk + ".1"], View(t0), (B, half, half), View(t1))
-            cur, size, cin = t1, half, cout
+            nxt = buf(B, half // 2, half // 2, cout) if blk != "down4" else None
+            self.conv(ops, self.w[blk + ".1"], View(t0), (B, half, half), View(t1), pool_out=nxt if FUSE_POOL else None)
+            if nxt is not None and not FUSE_POOL:
+                ops.append(E.PoolDesc(t1.data_ptr(), cout, nxt.data_ptr(), cout, cout, B, half, half, half // 2,
+                                      half // 2, 2, 2, 0))
+            ws.setdefault("keep", []).append(pooled)
+            pooled, size = nxt, half
             skips.append(t1)
             ws[blk] = t1
         ws["x1"] = x1
