@@ -73,6 +73,11 @@ typedef struct ug_conv_desc {
                                  nn.MaxPool2d(2) of the output (basicUnet.py:47 DownBlock) to
                                  pool_out[((n*H/2+y)*W/2+x)*pool_cstride + c], fused into the epilogue */
   int pool_cstride;
+  float* stats_sum;           /* optional (3x3 multi-issuer kernel, STORE epilogue): per-tile partial channel sums and */
+  float* stats_max;           /* maxima of the stored output, [B][stats_tiles][N] fp32 — stage 1 of CoordAtt3's
+                                 AdaptiveAvg/MaxPool2d(1) (basicUnet.py:217-218) fused into the epilogue; fold with
+                                 ug_gate (splits = stats_tiles).  Deterministic (no atomics). */
+  int stats_tiles;            /* must equal ceil(W/8) * ceil(H/16) (pixel tiles per image); checked */
   int TW, TH, TN, BN, stages; /* tiling; 0 = engine chooses */
   int variant;                /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel (TMEM multi-buffered
                                  accumulators, TMA-store epilogue); 5 = 3x3 multi-issuer kernel (one CTA per

@@ -185,6 +185,39 @@ def test_conv_parity(engine, case):
     run_conv(engine, **case)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,N", [(2, 56, 56, 64, 64), (3, 28, 28, 128, 256), (2, 112, 112, 64, 128), (2, 20, 36, 64, 96)])
+def test_conv_fused_channel_stats(engine, B, H, W, Cin, N):
+    """CoordAtt3 statistics fused into the conv epilogue: per-tile partials fold to the sum / max of the stored tensor."""
+    from ugnet_b200 import engine as E
+    from ugnet_b200 import pack
+    g = torch.Generator(device="cuda").manual_seed(H + N)
+    x = _mk((B, H, W, Cin), g).to(torch.bfloat16)
+    wt = _mk((N, Cin, 3, 3), g, (1.0 / (Cin * 9)) ** 0.5)
+    BN = pack.choose_bn(N)
+    wp = pack.pack_conv_weight(wt, BN)
+    scale = torch.rand((N,), generator=g, device="cuda") + 0.5
+    bias = _mk((N,), g)
+    out = torch.empty((B, H, W, N), device="cuda", dtype=torch.bfloat16)
+    th = -(-H // -(-H // 16))
+    S = -(-W // 8) * -(-H // th)
+    psum = torch.full((B, S, N), 7.0, device="cuda")
+    pmax = torch.full((B, S, N), 7.0, device="cuda")
+    d = E.ConvDesc()
+    d.inp = x.data_ptr(); d.in_cstride = Cin; d.Cin = Cin; d.B, d.H, d.W = B, H, W
+    d.R = d.S = 3; d.pad = 1; d.w = wp.data_ptr(); d.N = N
+    d.scale = scale.data_ptr(); d.bias = bias.data_ptr(); d.act = 1; d.mode = 0
+    d.out = out.data_ptr(); d.out_cstride = N; d.up = 1; d.BN = BN
+    d.stats_sum, d.stats_max, d.stats_tiles = psum.data_ptr(), pmax.data_ptr(), S
+    engine.run_op(d)
+    torch.cuda.synchronize()
+    of = out.float()
+    assert torch.allclose(psum.sum(1), of.sum((1, 2)), rtol=1e-4, atol=1e-2)
+    assert torch.equal(pmax.amax(1), of.amax((1, 2)))
+    d.stats_tiles = S + 1
+    with pytest.raises(RuntimeError):
+        engine.run_op(d)
+
+
 def test_conv_rejects_bad_args(engine):
     from ugnet_b200 import engine as E
     d = E.ConvDesc()

@@ -584,7 +584,8 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
     if (rc != UG_EUNSUPPORTED) return rc;
   }
 
-  if (d->pool_out) return set_error(h, UG_EUNSUPPORTED, "conv: the fused max-pool output needs the 3x3 multi-issuer kernel");
+  if (d->pool_out || d->stats_sum)
+    return set_error(h, UG_EUNSUPPORTED, "conv: fused max-pool / channel statistics need the 3x3 multi-issuer kernel");
   int TW = d->TW, TH = d->TH, TN = d->TN;
   if (TW <= 0 || TH <= 0 || TN <= 0) choose_tile(d->B, d->H, d->W, &TW, &TH, &TN);
   if (TW * TH * TN > 128 || TW > 256 || TH > 256 || TN > 256)

@@ -21,6 +21,7 @@
 // epilogue warps (folded BN/bias + activation, residual / CoordAtt3 combine / outc epilogues, bf16 tile staged in
 // swizzled smem and written with TMA stores).  Warp roles (384 threads): warps 0-3 / 4-7 epilogue of issuer 0 / 1,
 // warp 8 TMEM allocator + weight producer, warp 9 activation producer, warps 10-11 MMA issuers.
+#include <cfloat>
 #include <cstring>
 #include "conv_common.cuh"
 
@@ -104,7 +105,8 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
   float* sScale = reinterpret_cast<float*>(sP + (p.pool ? kMI * p.obufs * kPoolBytes : 0));  // 16-byte aligned
   float* sBias = sScale + p.npad;
   float* sGate = sBias + p.npad;                              // [kMI][128]: 1 + gate of the tile's image (GATE epilogue)
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sGate + kMI * 128);          // [kMI][sa]
+  float* sStat = sGate + kMI * 128;                           // [kMI][4 row quarters][64 ch][sum, max] (fused stats)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sStat + (p.stats_sum ? kMI * 512 : 0));   // [kMI][sa]
   uint64_t* a_empty = a_full + kMI * hp.sa;
   uint64_t* b_full = a_empty + kMI * hp.sa;                  // [sb] (entry 0 only when resident)
   uint64_t* b_empty = b_full + hp.sb;
@@ -525,6 +527,38 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
           }
           bulk_commit_group();
         }
+        if (p.stats_sum) {
+          // CoordAtt3 statistics, stage 1: per-channel sum / max of this staged sub-tile (the bf16 values just stored).
+          // Thread (channel pair cp, row quarter rq) folds 32 rows of two channels; the four quarters are combined in
+          // a fixed order through smem and written as one partial per (image, tile, channel).
+          const uint8_t* sbuf = sOi + obuf * obuf_bytes;
+          const int cp = etid & 31, rq = etid >> 5;
+          const int wvalid = min(8, p.W - x0);
+          float s0 = 0.0f, s1 = 0.0f, m0 = -FLT_MAX, m1 = -FLT_MAX;
+#pragma unroll 4
+          for (int k = 0; k < 32; ++k) {
+            const int r = rq * 32 + k;
+            if ((r >> 3) >= hp.TH || (r & 7) >= wvalid) continue;
+            const uint32_t wv = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + ((((cp >> 2) ^ (r & 7)) << 4) | ((cp & 3) << 2)));
+            const float a = bf16_lo(wv), b = bf16_hi(wv);
+            s0 += a;
+            s1 += b;
+            m0 = fmaxf(m0, a);
+            m1 = fmaxf(m1, b);
+          }
+          *reinterpret_cast<float4*>(sStat + i * 512 + rq * 128 + cp * 4) = make_float4(s0, m0, s1, m1);
+          named_bar_sync(1 + i, 128);
+          const int nsub = min(64, ncols - sub * 64);
+          if (etid < nsub) {
+            const float* q0 = sStat + i * 512 + (etid >> 1) * 4 + (etid & 1) * 2;
+            const float sum = ((q0[0] + q0[128]) + q0[256]) + q0[384];
+            const float mx = fmaxf(fmaxf(q0[1], q0[129]), fmaxf(q0[257], q0[385]));
+            const int tiles_pi = p.tiles_x * p.tiles_y;
+            const long long o = ((long long)n0 * tiles_pi + (mt - n0 * tiles_pi)) * p.N + ncol0 + sub * 64 + etid;
+            p.stats_sum[o] = sum;
+            p.stats_max[o] = mx;
+          }
+        }
         if (p.prof) e_tail += clock64() - tl1;
         if (p.obufs == 2) obuf ^= 1;
       }
@@ -612,6 +646,11 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   if (pool && (taps != 9 || d->mode != UG_EPI_STORE || (d->H & 1) || (d->W & 1) || (TH & 1) || d->pool_cstride % 8 ||
                (reinterpret_cast<uintptr_t>(d->pool_out) & 15)))
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): fused max-pool needs a 3x3 STORE conv on an even map");
+  const int stats = d->stats_sum != nullptr;
+  if (stats && (taps != 9 || d->mode != UG_EPI_STORE || !d->stats_max ||
+                d->stats_tiles != cdiv_m(d->W, 8) * cdiv_m(d->H, TH)))
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): fused channel statistics need a 3x3 STORE conv and stats_tiles == %d",
+                     cdiv_m(d->W, 8) * cdiv_m(d->H, TH));
   const int obuf_bytes = tma_store ? kABytesPerStage + (pool ? kPoolBytes : 0) : 0;  // per staging buffer, for sizing
   const int acc_stages = std::max(1, std::min(4, 512 / (kMI * BN)));
   const int a_bytes = taps == 9 ? kMPitch * (TH + 2) * 128 : TW * TH * TN * 128;
@@ -623,7 +662,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   hp.TH = TH;
   hp.a_stage_bytes = a_stage;
   const int fixed = 1024 + 8 * (2 * kMI * 4 + 2 * 16 + 2 * kMI * 4) + 16 + 2 * npad * (int)sizeof(float) +
-                    kMI * 128 * (int)sizeof(float);
+                    kMI * 128 * (int)sizeof(float) + (stats ? kMI * 512 * (int)sizeof(float) : 0);
   const long long budget = 227LL * 1024 - fixed;
   int obufs = tma_store ? 2 : 0;
   const long long resB = (long long)taps * kchunks * b_tile;
@@ -671,6 +710,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   p.logits = d->logits; p.mask = d->mask;
   p.m_tiles = p.tiles_x * p.tiles_y * cdiv_m(d->B, TN); p.n_tiles = n_tiles; p.acc_stages = acc_stages;
   p.tma_store = tma_store; p.obufs = obufs; p.npad = npad; p.pool = pool;
+  p.stats_sum = d->stats_sum; p.stats_max = d->stats_max;
   hp.m_super = cdiv_m(p.m_tiles, kMI);
   L->variant = 5;
   L->halo_mode = taps;
@@ -736,7 +776,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   const int nb_tiles = hp.b_resident ? taps * kchunks : hp.sb;
   L->smem = 1024 + (size_t)kMI * hp.sa * a_stage + (size_t)nb_tiles * b_tile + (size_t)kMI * obufs * obuf_bytes +
             8 * (2 * kMI * hp.sa + 2 * hp.sb + 2 * kMI * acc_stages) + 16 + 2 * (size_t)npad * sizeof(float) +
-            kMI * 128 * sizeof(float);
+            kMI * 128 * sizeof(float) + (stats ? kMI * 512 * sizeof(float) : 0);
   if (L->smem > (size_t)227 * 1024)
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): shared memory request %zu too large", L->smem);
   return UG_OK;

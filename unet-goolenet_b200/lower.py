@@ -25,6 +25,10 @@ IMG = 224
 AUTOTUNE = os.environ.get("UG_AUTOTUNE", "0") == "1"
 # UG_FUSE_POOL=0 falls back to separate max-pool launches after the encoder convolutions (A/B measurements).
 FUSE_POOL = os.environ.get("UG_FUSE_POOL", "1") != "0"
+# UG_FUSE_STATS=<side>: fuse CoordAtt3's channel statistics into the conv1_e epilogue on maps up to <side> pixels.
+# Off by default: the extra epilogue work costs what the separate pass over e1 saves (same-box A/B: all maps fused
+# 10.01k vs 10.09k img/s, maps <= 56 fused 9.82k vs 9.88k).
+FUSE_STATS = int(os.environ.get("UG_FUSE_STATS", "0"))
 
 
 def _finish(engine, ops, ws):
@@ -93,7 +97,7 @@ class _Builder:
 
     # ---- ops -----------------------------------------------------------------------------------
     def conv(self, ops, wd, x, geom, out=None, act=E.ACT_RELU, mode=E.EPI_STORE, up=1, add=None, add_bstride=0,
-             gate=None, outc=None, pool_out=None):
+             gate=None, outc=None, pool_out=None, stats=None):
         B, H, W = geom
         d = E.ConvDesc()
         d.algo_k = wd.get("algo_k", wd["Cin"] * wd["R"] * wd["R"])   # true reduction length (for FLOP accounting)
@@ -116,6 +120,8 @@ class _Builder:
             d.gate = gate.data_ptr()
         if pool_out is not None:                                     # fused nn.MaxPool2d(2) side output
             d.pool_out, d.pool_cstride = pool_out.data_ptr(), pool_out.shape[-1]
+        if stats is not None:                                        # fused per-tile channel sums / maxima
+            d.stats_sum, d.stats_max, d.stats_tiles = stats[0].data_ptr(), stats[1].data_ptr(), stats[2]
         if outc is not None:
             d.outc_w, d.outc_b = outc["w"].data_ptr(), outc["b"]
             d.logits, d.mask = outc["logits"].data_ptr(), outc["mask"].data_ptr()
@@ -295,10 +301,17 @@ class UNetRunner(_Builder):
             self.conv(ops, self.w[blk + ".up"], View(prev), (B, psize, psize), View(cat, C, 0), act=E.ACT_NONE,
                       up=2)
             e1 = buf(B, size, size, C)
-            self.conv(ops, self.w[blk + ".conv1_e"], View(skip), geom, View(e1))
-            S = self.STATS_SPLITS
-            psum, pmax = buf(B, S, C, dtype=torch.float32), buf(B, S, C, dtype=torch.float32)
-            ops.append(E.ChanStatsDesc(e1.data_ptr(), C, C, B, size * size, S, psum.data_ptr(), pmax.data_ptr()))
+            if size <= FUSE_STATS:
+                # AdaptiveAvg/MaxPool2d(1) of e1 (basicUnet.py:217-218), stage 1 fused into the conv epilogue: one
+                # partial per pixel tile (8 x TH pixels, TH = the conv kernel's tile height); ug_gate folds them
+                S = -(-size // 8) * -(-size // (-(-size // -(-size // 16))))
+                psum, pmax = buf(B, S, C, dtype=torch.float32), buf(B, S, C, dtype=torch.float32)
+                self.conv(ops, self.w[blk + ".conv1_e"], View(skip), geom, View(e1), stats=(psum, pmax, S))
+            else:
+                S = self.STATS_SPLITS
+                psum, pmax = buf(B, S, C, dtype=torch.float32), buf(B, S, C, dtype=torch.float32)
+                self.conv(ops, self.w[blk + ".conv1_e"], View(skip), geom, View(e1))
+                ops.append(E.ChanStatsDesc(e1.data_ptr(), C, C, B, size * size, S, psum.data_ptr(), pmax.data_ptr()))
             gw = self.w[blk + ".gate"]
             g, hid = buf(B, C, dtype=torch.float32), buf(B, C // 2, dtype=torch.float32)
             ops.append(E.GateDesc(psum.data_ptr(), pmax.data_ptr(), gw["w1"].data_ptr(), gw["b1"].data_ptr(),
