@@ -341,6 +341,13 @@ typedef struct ug_copy {
 } ug_copy;
 int ug_program_run_host(ug_handle h, ug_program p, const ug_copy* h2d, int n_h2d, const ug_copy* d2h, int n_d2h,
                         void* stream);
+/* Double-buffered form for back-to-back steps (a serving loop): the H2D copies of this call go to device staging
+ * buffers (stage0[i] / stage1[i], alternating per call, each at least h2d[i].bytes, caller-owned) on an engine-owned
+ * copy stream, so the copy of step i+1 overlaps the kernels of step i; the compute stream then moves the staged
+ * input into h2d[i].dst (device to device), runs the program and enqueues the D2H copies.  Does NOT synchronize:
+ * results are valid after the caller synchronizes `stream`. */
+int ug_program_run_host_pipelined(ug_handle h, ug_program p, const ug_copy* h2d, void* const* stage0,
+                                  void* const* stage1, int n_h2d, const ug_copy* d2h, int n_d2h, void* stream);
 
 #ifdef __cplusplus
 }

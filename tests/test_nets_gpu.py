@@ -188,3 +188,25 @@ def test_pipeline_parity(engine, unet_sd, gnet_sd, images, oracle_unet):
     m2, b2, c2 = pipe(x)
     assert torch.equal(m2, masks) and torch.equal(b2, boxes) and torch.equal(c2, cls)
     print(f"pipeline: cls rel err (same-box images) {rel[sel].max():.5f}")
+
+
+def test_run_host_pipelined_matches_serial(engine, unet_sd, gnet_sd, images):
+    """ug_program_run_host_pipelined (double-buffered H2D on the copy stream) == ug_program_run_host, step by step."""
+    from ugnet_b200.lower import PipelineRunner
+    pipe = PipelineRunner(unet_sd, gnet_sd, "cuda:0", micro_batch=4)
+    B = 4
+    ws = pipe.plan(B)
+    prog = ws["program"]
+    steps = [torch.from_numpy(images[0][i:i + B].copy()).pin_memory() for i in (0, 2, 4, 1, 3)]
+    serial = []
+    for h_in in steps:
+        hm = torch.empty((B, 224, 224), dtype=torch.uint8).pin_memory()
+        hc = torch.empty((B, 6), dtype=torch.float32).pin_memory()
+        prog.run_host([(ws["x_in"], h_in)], [(hm, ws["mask"]), (hc, ws["cls_logits"])])
+        serial.append((hm.clone(), hc.clone()))
+    outs = [(torch.empty((B, 224, 224), dtype=torch.uint8).pin_memory(), torch.empty((B, 6)).pin_memory()) for _ in steps]
+    for h_in, (hm, hc) in zip(steps, outs):
+        prog.run_host_pipelined([(ws["x_in"], h_in)], [(hm, ws["mask"]), (hc, ws["cls_logits"])])
+    torch.cuda.synchronize()
+    for (m0, c0), (m1, c1) in zip(serial, outs):
+        assert torch.equal(m0, m1) and torch.equal(c0, c1)

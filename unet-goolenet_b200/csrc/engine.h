@@ -11,6 +11,11 @@ struct ug_engine {
   int num_sms = 148;
   std::string last_error;
   long long launches = 0;
+  // double-buffered host feeding (ug_program_run_host_pipelined): engine-owned copy stream and slot events
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr};   // staging slot filled (recorded on the copy stream)
+  cudaEvent_t ev_free[2] = {nullptr, nullptr};  // staging slot consumed (recorded on the compute stream)
+  long long pipelined_steps = 0;
 };
 
 namespace ug {

@@ -121,7 +121,7 @@ _SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_INC_IM2COL: "ug_inc_im2col", OP_POOL: "u
 
 EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
-                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_timed", "ug_program_autotune", "ug_conv_profile", "ug_mma_microbench",
+                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_host_pipelined", "ug_program_run_timed", "ug_program_autotune", "ug_conv_profile", "ug_mma_microbench",
                     "ug_mma_microbench2", "ug_conv_profile16", "ug_wavelet_workspace_bytes"]
 
 _lib = None
@@ -158,6 +158,7 @@ def load_library():
     lib.ug_program_autotune.argtypes = [_vp, _vp, _vp, C.POINTER(_i)]
     lib.ug_program_destroy.argtypes = [_vp, _vp]
     lib.ug_program_run_host.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _vp]
+    lib.ug_program_run_host_pipelined.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]
     _lib = lib
     return lib
 
@@ -214,6 +215,24 @@ class Program:
             b[i] = Copy(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size())
         self.engine._check(self.engine.lib.ug_program_run_host(self.engine.handle, self.handle, C.byref(a), len(h2d),
                                                                C.byref(b), len(d2h), s))
+
+    def run_host_pipelined(self, h2d, d2h, stream=None):
+        """Like run_host but double-buffered and NOT synchronizing: the H2D copies of this call run on the engine's
+        copy stream into device staging buffers and overlap the kernels of the previous call (ug_program_run_host_
+        pipelined).  Results are valid after the caller synchronizes the stream."""
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        if not hasattr(self, "_stage"):
+            self._stage = [[torch.empty_like(dst) for dst, _ in h2d] for _ in range(2)]
+        a = (Copy * max(1, len(h2d)))()
+        st = [(_vp * max(1, len(h2d)))(), (_vp * max(1, len(h2d)))()]
+        for i, (dst, src) in enumerate(h2d):
+            a[i] = Copy(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size())
+            st[0][i], st[1][i] = self._stage[0][i].data_ptr(), self._stage[1][i].data_ptr()
+        b = (Copy * max(1, len(d2h)))()
+        for i, (dst, src) in enumerate(d2h):
+            b[i] = Copy(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size())
+        self.engine._check(self.engine.lib.ug_program_run_host_pipelined(
+            self.engine.handle, self.handle, C.byref(a), st[0], st[1], len(h2d), C.byref(b), len(d2h), s))
 
     def __del__(self):
         try:
