@@ -187,6 +187,48 @@ def cpu_baseline(sample, budget_s=20.0):
                       f"restatement of the reference path), {dt:.1f} s"}
 
 
+def run_stage_alone(args, dev, rank):
+    """BASELINE configs[1] (UNet forward, batch 64) / configs[2] (GoogLeNet forward on ROI crops, batch 256) on one GPU:
+    device-resident inputs, CUDA-event timing, one JSON line (same keys as the headline line where they apply)."""
+    import torch
+    from ugnet_b200 import engine as E
+    from ugnet_b200.googlenet import GoogLeNetClassifier
+    from ugnet_b200.lower import GoogLeNetRunner, UNetRunner
+    from ugnet_b200.nets import UNetTaskAligWeight
+    torch.manual_seed(1234)
+    B = args.batch if args.batch != 256 or args.workload == "googlenet" else 64
+    if args.workload == "unet":
+        runner = UNetRunner(UNetTaskAligWeight(3, 1).state_dict(), dev, max_batch=B)
+        ws = runner.plan(B)
+        ws["x_in"].copy_(synth_batch(B, 1234, dev))
+        name, flop_img = f"UNet forward + mask + bbox, batch {B} (BASELINE.json configs[1])", 78.54e9
+    else:
+        runner = GoogLeNetRunner(GoogLeNetClassifier(6).state_dict(), dev, max_batch=B)
+        ws = runner.plan(B, "u8")
+        ws["in"].copy_((synth_batch(B, 1234, dev) * 255).to(torch.uint8).permute(0, 2, 3, 1))
+        name, flop_img = f"GoogLeNet forward on uint8 ROI crops, batch {B} (BASELINE.json configs[2])", 2.995e9
+    prog = ws["program"]
+    W = max(3, args.warmup)
+    for _ in range(W):
+        prog.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = runner.engine.launch_count
+    e0.record()
+    for _ in range(args.steps):
+        prog.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    v = B * args.steps / (ms / 1e3)
+    if rank == 0:
+        print(json.dumps({"metric": f"{args.workload} images/sec (stage alone)", "value": v, "unit": UNIT, "n_gpus": 1,
+                          "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                          "dtype": "bf16", "data": "synthetic", "config": {"workload": name, "batch": B},
+                          "gpu_launches": runner.engine.launch_count - l0,
+                          "model_tflops": v * flop_img / 1e12}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -198,6 +240,10 @@ def main():
     ap.add_argument("--source-size", type=int, default=0,
                     help="N > 0: inputs are uint8 HWC NxN source images resized on the device by the front-end op "
                          "(BASELINE.json configs[4]: 512); 0: float 224x224 inputs (configs[3])")
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "unet", "googlenet"],
+                    help="pipeline: the headline two-stage path (BASELINE configs[3]/[4]); unet: segmentation stage "
+                         "alone at --batch images (configs[1]: 64); googlenet: classification stage alone on uint8 "
+                         "ROI crops (configs[2]: 256).  The stage-alone lines are parity/throughput cases, not the headline")
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -220,6 +266,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.workload != "pipeline":
+        return run_stage_alone(args, dev, rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)

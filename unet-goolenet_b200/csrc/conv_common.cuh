@@ -40,6 +40,28 @@ __device__ __forceinline__ void epi_math16(const uint32_t (&v)[16], float (&f)[1
   }
 }
 
+// Deferred ReLU: kernels instantiated for ReLU compute only scale*acc + bias in epi_math16_linear and apply the
+// max(.,0) where the value is consumed — folded into the bf16 conversion for plain stores (pack_bf16x2_relu),
+// explicitly before a residual add / gate / outc dot.
+template <int kAct>
+__device__ __forceinline__ void epi_math16_linear(const uint32_t (&v)[16], float (&f)[16], const float* sScale,
+                                                  const float* sBias, int col) {
+  if constexpr (kAct == UG_ACT_RELU) epi_math16<UG_ACT_NONE>(v, f, sScale, sBias, col);
+  else epi_math16<kAct>(v, f, sScale, sBias, col);
+}
+template <int kAct>
+__device__ __forceinline__ void epi_relu16(float (&f)[16]) {
+  if constexpr (kAct == UG_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+  }
+}
+template <int kAct>
+__device__ __forceinline__ uint32_t epi_pack2(float lo, float hi) {
+  if constexpr (kAct == UG_ACT_RELU) return pack_bf16x2_relu(lo, hi);
+  else return pack_bf16x2(lo, hi);
+}
+
 // residual add of 8 bf16 values held in a register quad
 __device__ __forceinline__ void epi_add8(float* f, const uint4& a) {
   const uint32_t aw[4] = {a.x, a.y, a.z, a.w};

@@ -437,9 +437,10 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
           if (c0 >= ncols) break;
           tmem_ld_wait();
           float f[16];
-          epi_math16<kAct>(v, f, sScale, sBias, ncol0 + c0);
+          epi_math16_linear<kAct>(v, f, sScale, sBias, ncol0 + c0);   // ReLU deferred (see conv_common.cuh)
           __syncwarp();
           if (c0 + 16 < ncols && !(hp.debug & 1)) tmem_ld16(taddr + c0 + 16, v);
+          if (p.mode != UG_EPI_STORE) epi_relu16<kAct>(f);  // stores fold the ReLU into the bf16 conversion below
           if (p.mode == UG_EPI_OUTC) {
             const float4* ow = reinterpret_cast<const float4*>(p.outc_w + ncol0 + c0);
 #pragma unroll
@@ -471,10 +472,20 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
           for (int g = 0; g < 2; ++g) {
             if (g < groups) {
               uint4 o;
-              o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-              o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-              o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-              o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+              // (after a residual add / gate the values may be negative again: only the STORE epilogue's ReLU is
+              // folded here; for the other modes f is already activated and the relu conversion is an identity on
+              // the activation but NOT on the sum, so they use the plain conversion)
+              if (p.mode == UG_EPI_STORE) {
+                o.x = epi_pack2<kAct>(f[g * 8 + 0], f[g * 8 + 1]);
+                o.y = epi_pack2<kAct>(f[g * 8 + 2], f[g * 8 + 3]);
+                o.z = epi_pack2<kAct>(f[g * 8 + 4], f[g * 8 + 5]);
+                o.w = epi_pack2<kAct>(f[g * 8 + 6], f[g * 8 + 7]);
+              } else {
+                o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+                o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+                o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+                o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+              }
               const int chunk = cc * 2 + g;
               if (!(hp.debug & 2)) *reinterpret_cast<uint4*>(so_row + ((chunk ^ (row & 7)) << 4)) = o;
               if (p.pool) {

@@ -229,14 +229,14 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
       tmem_ld16(taddr + c0, v);
       tmem_ld_wait();
       float f[16];
-      epi_math16<UG_ACT_RELU>(v, f, sScale, sBias, c0);
+      epi_math16<UG_ACT_NONE>(v, f, sScale, sBias, c0);   // ReLU folded into the bf16 conversion
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         uint4 o;
-        o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-        o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-        o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-        o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+        o.x = pack_bf16x2_relu(f[g * 8 + 0], f[g * 8 + 1]);
+        o.y = pack_bf16x2_relu(f[g * 8 + 2], f[g * 8 + 3]);
+        o.z = pack_bf16x2_relu(f[g * 8 + 4], f[g * 8 + 5]);
+        o.w = pack_bf16x2_relu(f[g * 8 + 6], f[g * 8 + 7]);
         *reinterpret_cast<uint4*>(o_row + ((((c0 >> 3) + g) ^ sw) << 4)) = o;
         if (p.pool) {
           // fused nn.MaxPool2d(2): pixel (tx, ty) = row ty*16 + tx; its 2x2 window lives in lanes ^1 (x) and ^16 (y)
