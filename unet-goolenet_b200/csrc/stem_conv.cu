@@ -96,6 +96,56 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
   uint32_t acc_phase = 0;
   bool b_ready = false;
 
+  // inc: the fp32 source patch (3 x 10 x 18, zero outside the image) of a tile is fetched with coalesced loads ONE TILE
+  // AHEAD into registers: fetched in the same iteration, every tile exposed one HBM latency (20 % of the samples)
+  constexpr int kIncElems = 3 * kIncPatchH * kIncPatchW;  // 540
+  constexpr int kIncSteps = (kIncElems + 127) / 128;
+  float inc_raw[kIncSteps];
+  auto load_inc_patch = [&](int t2) {
+    const int px0 = (t2 % p.tiles_x) * kStemTW, py0 = ((t2 / p.tiles_x) % p.tiles_y) * kStemTH;
+    const float* xn = p.in_f32 + (long long)(t2 / (p.tiles_x * p.tiles_y)) * 3 * p.H * p.W;
+#pragma unroll
+    for (int k = 0; k < kIncSteps; ++k) {
+      const int idx = tid + k * 128;
+      const int c = idx / (kIncPatchH * kIncPatchW), rem = idx - c * (kIncPatchH * kIncPatchW);
+      const int r = rem / kIncPatchW, xx = rem - r * kIncPatchW;
+      const int iy = py0 - 1 + r, ix = px0 - 1 + xx;
+      const bool inb = idx < kIncElems && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      inc_raw[k] = inb ? __ldg(xn + ((long long)c * p.H + iy) * p.W + ix) : 0.0f;
+    }
+  };
+  // conv1: one source pixel (3 channels) per thread and step, fetched one tile ahead like the inc patch
+  constexpr int kG1Pix = kG1PatchW * kG1PatchH;
+  constexpr int kG1Steps = (kG1Pix + 127) / 128;
+  float g1_raw[kG1Steps][3];
+  unsigned g1_mask = 0;
+  auto load_g1_patch = [&](int t2) {
+    const int qx0 = 2 * ((t2 % p.tiles_x) * kStemTW) - 3, qy0 = 2 * (((t2 / p.tiles_x) % p.tiles_y) * kStemTH) - 3;
+    const int n2 = t2 / (p.tiles_x * p.tiles_y);
+    g1_mask = 0;
+#pragma unroll
+    for (int k = 0; k < kG1Steps; ++k) {
+      const int idx = tid + k * 128;
+      const int r = idx / kG1PatchW, px = idx - r * kG1PatchW;
+      const int iy = qy0 + r, ix = qx0 + px;
+      const bool inb = idx < kG1Pix && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      g1_mask |= (inb ? 1u : 0u) << k;
+      if (p.in_f32) {
+        const float* src = p.in_f32 + ((long long)n2 * 3 * p.H + iy) * p.W + ix;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g1_raw[k][c] = inb ? __ldg(src + (long long)c * p.H * p.W) : 0.0f;
+      } else {
+        const unsigned char* src = p.in_u8 + (((long long)n2 * p.H + iy) * p.W + ix) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g1_raw[k][c] = inb ? (float)__ldg(src + c) / 255.0f : 0.0f;
+      }
+    }
+  };
+  if ((int)blockIdx.x < p.total_tiles) {
+    if constexpr (kKind == 0) load_inc_patch(blockIdx.x);
+    else load_g1_patch(blockIdx.x);
+  }
+
   for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
     const int x0 = (t % p.tiles_x) * kStemTW;
     const int y0 = ((t / p.tiles_x) % p.tiles_y) * kStemTH;
@@ -104,28 +154,18 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
     if constexpr (kKind == 0) {
       // ---- inc: stage the 3 x 10 x 18 fp32 source patch (zero outside the image) with coalesced loads, then every
       // thread gathers its 27 taps from shared memory
-      const float* xn = p.in_f32 + (long long)n * 3 * p.H * p.W;
-      constexpr int kElems = 3 * kIncPatchH * kIncPatchW;  // 540
-      constexpr int kSteps = (kElems + 127) / 128;
-      float raw[kSteps];
+      // (the patch values of THIS tile were fetched into inc_raw one tile ahead, see load_inc_patch below)
 #pragma unroll
-      for (int k = 0; k < kSteps; ++k) {
+      for (int k = 0; k < kIncSteps; ++k) {
         const int idx = tid + k * 128;
         const int c = idx / (kIncPatchH * kIncPatchW), rem = idx - c * (kIncPatchH * kIncPatchW);
         const int r = rem / kIncPatchW, xx = rem - r * kIncPatchW;
-        const int iy = y0 - 1 + r, ix = x0 - 1 + xx;
-        const bool inb = idx < kElems && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        raw[k] = inb ? __ldg(xn + ((long long)c * p.H + iy) * p.W + ix) : 0.0f;
-      }
-#pragma unroll
-      for (int k = 0; k < kSteps; ++k) {
-        const int idx = tid + k * 128;
-        const int c = idx / (kIncPatchH * kIncPatchW), rem = idx - c * (kIncPatchH * kIncPatchW);
-        const int r = rem / kIncPatchW, xx = rem - r * kIncPatchW;
-        if (idx < kElems) sPatchF[(c * kIncPatchH + r) * kIncPatchPitch + xx] = raw[k];
+        if (idx < kIncElems) sPatchF[(c * kIncPatchH + r) * kIncPatchPitch + xx] = inc_raw[k];
       }
       if (tid == 0) bulk_wait_group_read<0>();  // previous tile's TMA store has finished reading sO (= sA)
       __syncthreads();
+      if (t + (int)gridDim.x < p.total_tiles) load_inc_patch(t + gridDim.x);  // next tile's patch: in flight during
+                                                                              // the gather, the MMA and the epilogue
       const float* pt = sPatchF + ty * kIncPatchPitch + tx;
       float v[32];
 #pragma unroll
@@ -150,29 +190,9 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
       // ---- conv1: stage the transformed source patch (zero outside the image), then copy seven 22-element runs
       const float sc[3] = {0.229f / 0.5f, 0.224f / 0.5f, 0.225f / 0.5f};
       const float sh[3] = {(0.485f - 0.5f) / 0.5f, (0.456f - 0.5f) / 0.5f, (0.406f - 0.5f) / 0.5f};
-      const int iy0 = 2 * y0 - 3, ix0 = 2 * x0 - 3;
       // one source pixel (3 channels) per thread and step; all loads of a tile are issued before any is used
       constexpr int kPix = kG1PatchW * kG1PatchH;
-      constexpr int kSteps = (kPix + 127) / 128;
-      float raw[kSteps][3];
-      unsigned inb_mask = 0;
-#pragma unroll
-      for (int k = 0; k < kSteps; ++k) {
-        const int idx = tid + k * 128;
-        const int r = idx / kG1PatchW, px = idx - r * kG1PatchW;
-        const int iy = iy0 + r, ix = ix0 + px;
-        const bool inb = idx < kPix && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        inb_mask |= (inb ? 1u : 0u) << k;
-        if (p.in_f32) {
-          const float* src = p.in_f32 + ((long long)n * 3 * p.H + iy) * p.W + ix;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) raw[k][c] = inb ? __ldg(src + (long long)c * p.H * p.W) : 0.0f;
-        } else {
-          const unsigned char* src = p.in_u8 + (((long long)n * p.H + iy) * p.W + ix) * 3;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) raw[k][c] = inb ? (float)__ldg(src + c) / 255.0f : 0.0f;
-        }
-      }
+      constexpr int kSteps = kG1Steps;   // source pixels of THIS tile were fetched one tile ahead (load_g1_patch)
 #pragma unroll
       for (int k = 0; k < kSteps; ++k) {
         const int idx = tid + k * 128;
@@ -181,11 +201,12 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
 #pragma unroll
           for (int c = 0; c < 3; ++c)  // zero padding is applied after the affine: out-of-image taps are exactly 0
             sPatch[r * kG1PatchPitch + px * 3 + c] =
-                __float2bfloat16_rn(((inb_mask >> k) & 1u) ? raw[k][c] * sc[c] + sh[c] : 0.0f);
+                __float2bfloat16_rn(((g1_mask >> k) & 1u) ? g1_raw[k][c] * sc[c] + sh[c] : 0.0f);
         }
       }
       if (tid == 0) bulk_wait_group_read<0>();  // previous tile's TMA store has finished reading sO (= sA)
       __syncthreads();
+      if (t + (int)gridDim.x < p.total_tiles) load_g1_patch(t + gridDim.x);  // next tile's source pixels in flight
       uint32_t w[80];
 #pragma unroll
       for (int r = 0; r < 7; ++r) {
