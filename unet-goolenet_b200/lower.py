@@ -29,6 +29,8 @@ FUSE_POOL = os.environ.get("UG_FUSE_POOL", "1") != "0"
 # Off by default: the extra epilogue work costs what the separate pass over e1 saves (same-box A/B: all maps fused
 # 10.01k vs 10.09k img/s, maps <= 56 fused 9.82k vs 9.88k).
 FUSE_STATS = int(os.environ.get("UG_FUSE_STATS", "0"))
+# UG_FUSE_REDUCE=0: run the two Inception reduce convolutions (branch2.0 / branch3.0, same input) as separate launches.
+FUSE_REDUCE = os.environ.get("UG_FUSE_REDUCE", "1") != "0"
 
 
 def _finish(engine, ops, ws):
@@ -408,6 +410,14 @@ class GoogLeNetRunner(_Builder):
         for name in _INCEPTION_CFG:
             for br in ("branch1", "branch2.0", "branch2.1", "branch3.0", "branch3.1", "branch4.1"):
                 self.conv_bn(f"{name}.{br}", f"{name}.{br}.conv", f"{name}.{br}.bn", self.EPS)
+            # the two 1x1 reduce convolutions read the same tensor: one GEMM with the output channels concatenated
+            # ([3x3-reduce | 5x5-reduce]); the 3x3 / 5x5 branches then read channel slices of its output
+            a, b = self.w[f"{name}.branch2.0"], self.w[f"{name}.branch3.0"]
+            wt = torch.cat([_f32(sd[f"{name}.branch2.0.conv.weight"], dev), _f32(sd[f"{name}.branch3.0.conv.weight"], dev)], 0)
+            bn_tile = pack.choose_bn(wt.shape[0])
+            self.w[f"{name}.reduce"] = dict(w=pack.pack_conv_weight(wt, bn_tile), scale=torch.cat([a["scale"], b["scale"]]),
+                                            bias=torch.cat([a["bias"], b["bias"]]), N=wt.shape[0], Cin=wt.shape[1], R=1,
+                                            BN=bn_tile)
         self.w["fc"] = (_f32(sd["fc.weight"], dev), _f32(sd["fc.bias"], dev))
         self.ncls = self.w["fc"][0].shape[0]
 
@@ -441,16 +451,23 @@ class GoogLeNetRunner(_Builder):
             geom = (B, sp, sp)
             xin = View(cur)
             self.conv(ops, self.w[name + ".branch1"], xin, flat, View(out, c1x1, 0))
-            r2 = buf(B, sp, sp, c3r)
-            self.conv(ops, self.w[name + ".branch2.0"], xin, flat, View(r2))
-            self.conv(ops, self.w[name + ".branch2.1"], View(r2), geom, View(out, c3x3, c1x1))
-            r3 = buf(B, sp, sp, c5r)
-            self.conv(ops, self.w[name + ".branch3.0"], xin, flat, View(r3))
-            self.conv(ops, self.w[name + ".branch3.1"], View(r3), geom, View(out, c5x5, c1x1 + c3x3))
+            if FUSE_REDUCE:
+                r23 = buf(B, sp, sp, c3r + c5r)
+                self.conv(ops, self.w[name + ".reduce"], xin, flat, View(r23))
+                r2, r3 = View(r23, c3r, 0), View(r23, c5r, c3r)
+                keep.append(r23)
+            else:
+                t2, t3 = buf(B, sp, sp, c3r), buf(B, sp, sp, c5r)
+                self.conv(ops, self.w[name + ".branch2.0"], xin, flat, View(t2))
+                self.conv(ops, self.w[name + ".branch3.0"], xin, flat, View(t3))
+                r2, r3 = View(t2), View(t3)
+                keep += [t2, t3]
+            self.conv(ops, self.w[name + ".branch2.1"], r2, geom, View(out, c3x3, c1x1))
+            self.conv(ops, self.w[name + ".branch3.1"], r3, geom, View(out, c5x5, c1x1 + c3x3))
             pl = buf(B, sp, sp, cin)
             ops.append(E.PoolDesc(cur.data_ptr(), cin, pl.data_ptr(), cin, cin, B, sp, sp, sp, sp, 3, 1, 1))
             self.conv(ops, self.w[name + ".branch4.1"], View(pl), flat, View(out, pp, c1x1 + c3x3 + c5x5))
-            keep += [out, r2, r3, pl]
+            keep += [out, pl]
             ws[name] = out
             cur = out
         ws["cls_logits"] = buf(B, self.ncls, dtype=torch.float32)
