@@ -12,6 +12,9 @@ def _mk(shape, gen, scale=1.0):
     return (torch.randn(shape, generator=gen, device="cuda") * scale)
 
 
+from guard import guarded
+
+
 def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_extra=0, in_off=0, out_off=0,
              seed=0, tile=None, bn=None, stages=0, add_broadcast=False, variant=0, pool=False):
     from ugnet_b200 import engine as E
@@ -37,7 +40,7 @@ def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_ex
         bias = _mk((N,), g)
     OH, OW = H * up, W * up
     out_cs = cout + out_extra
-    obuf = torch.full((B, OH, OW, out_cs), 7.0, device="cuda", dtype=torch.bfloat16)
+    obuf, o_intact = guarded((B, OH, OW, out_cs), 7.0, torch.bfloat16)
     d = E.ConvDesc()
     d.inp = x.data_ptr(); d.in_cstride = in_cs; d.Cin = Cin
     d.B, d.H, d.W = B, H, W
@@ -52,7 +55,7 @@ def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_ex
         d.TW, d.TH, d.TN = tile
     pbuf = None
     if pool:    # fused nn.MaxPool2d(2) side output into a channel slice of a wider buffer
-        pbuf = torch.full((B, H // 2, W // 2, cout + 24), 3.0, device="cuda", dtype=torch.bfloat16)
+        pbuf, p_intact = guarded((B, H // 2, W // 2, cout + 24), 3.0, torch.bfloat16)
         d.pool_out = pbuf.data_ptr() + 2 * 8; d.pool_cstride = cout + 24
     addt = gate = outw = logits = mask = None
     if mode in (E.EPI_ADD, E.EPI_GATE):
@@ -71,6 +74,9 @@ def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_ex
         d.logits = logits.data_ptr(); d.mask = mask.data_ptr()
     engine.run_op(d)
     torch.cuda.synchronize()
+    o_intact()
+    if pool:
+        p_intact()
 
     # ---- reference in fp32 on the same bf16-rounded operands
     xf = x.float().permute(0, 3, 1, 2)

@@ -5,6 +5,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from guard import guarded
+
 pytestmark = pytest.mark.gpu
 
 
@@ -36,9 +38,10 @@ def test_pool(engine, k, stride, pad, H, W):
     xb = torch.randn((B, H, W, cs_in), generator=g, device="cuda").to(torch.bfloat16)
     ref = F.max_pool2d(xb[..., 8:8 + C].float().permute(0, 3, 1, 2), k, stride, pad, ceil_mode=True)
     OH, OW = ref.shape[2], ref.shape[3]
-    ob = torch.zeros((B, OH, OW, cs_out), device="cuda", dtype=torch.bfloat16)
+    ob, intact = guarded((B, OH, OW, cs_out), 0.0, torch.bfloat16)
     d = E.PoolDesc(xb.data_ptr() + 16, cs_in, ob.data_ptr(), cs_out, C, B, H, W, OH, OW, k, stride, pad)
     engine.run_op(d)
+    intact()
     assert torch.equal(ob[..., :C].float(), ref.permute(0, 2, 3, 1))
     assert (ob[..., C:] == 0).all()
 
@@ -50,8 +53,9 @@ def test_layernorm(engine):
     x = (torch.randn((M, Cn), generator=g, device="cuda") * 3 + 1).to(torch.bfloat16)
     gamma = torch.rand((Cn,), generator=g, device="cuda") + 0.5
     beta = torch.randn((Cn,), generator=g, device="cuda")
-    out = torch.empty_like(x)
+    out, intact = guarded((M, Cn), 9.0, torch.bfloat16)
     engine.run_op(E.LayerNormDesc(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), M, Cn, 1e-5))
+    intact()
     ref = F.layer_norm(x.float(), (Cn,), gamma, beta, 1e-5)
     # one bf16 rounding of the result: 2^-8 relative + small absolute
     assert ((out.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-3).all()
@@ -63,11 +67,12 @@ def test_attention(engine, S, variant):
     g = _gen(4)
     B, heads = 3, 8
     qkv = torch.randn((B * S, 1536), generator=g, device="cuda").to(torch.bfloat16)
-    out = torch.empty((B * S, 512), device="cuda", dtype=torch.bfloat16)
+    out, intact = guarded((B * S, 512), 9.0, torch.bfloat16)
     scale = 512 ** -0.5
     d = E.AttnDesc(qkv.data_ptr(), qkv.data_ptr() + 2 * 512, qkv.data_ptr() + 2 * 1024, 1536, 1536, 1536,
                    out.data_ptr(), 512, B, S, heads, scale, variant)
     engine.run_op(d)
+    intact()
     q, k, v = [t.float().reshape(B, S, heads, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1)]
     att = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
     ref = (att @ v).permute(0, 2, 1, 3).reshape(B * S, 512)
@@ -144,8 +149,9 @@ def test_cropresize_bit_exact_vs_oracle_and_pil(engine):
     img[0, :, :5, :5] = 1.0   # exact 1.0 -> 255
     img[1, :, 60:70, 60:70] = 0.0
     boxes = torch.from_numpy(boxes_np).cuda()
-    out = torch.zeros((B, 224, 224, 3), dtype=torch.uint8, device="cuda")
+    out, intact = guarded((B, 224, 224, 3), 0, torch.uint8)
     engine.run_op(E.CropResizeDesc(img.data_ptr(), boxes.data_ptr(), out.data_ptr(), B, 224, 224, 224))
+    intact()
     got = out.cpu().numpy()
     imgs = img.cpu().numpy()
     for i in range(B):

@@ -5,6 +5,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from guard import guarded
+
 pytestmark = pytest.mark.gpu
 
 _SC = torch.tensor([0.229 / 0.5, 0.224 / 0.5, 0.225 / 0.5])
@@ -30,11 +32,12 @@ def test_stem_inc(engine, B, H, W, extra, pool):
     bias = torch.randn((64,), generator=g, device="cuda")
     wp = pack.pack_linear_weight(wt.permute(0, 2, 3, 1).reshape(64, 27), 64)
     cs = 64 + extra
-    out = torch.full((B, H, W, cs), 7.0, device="cuda", dtype=torch.bfloat16)
-    pbuf = torch.full((B, H // 2, W // 2, 80), 3.0, device="cuda", dtype=torch.bfloat16) if pool else None
+    out, o_intact = guarded((B, H, W, cs), 7.0, torch.bfloat16)
+    pbuf, p_intact = guarded((B, H // 2, W // 2, 80), 3.0, torch.bfloat16) if pool else (None, lambda: None)
     engine.run_op(E.StemDesc(0, x.data_ptr(), None, wp.data_ptr(), scale.data_ptr(), bias.data_ptr(),
                              out.data_ptr(), cs, B, H, W, E.ptr(pbuf), 80))
     torch.cuda.synchronize()
+    o_intact(); p_intact()
     if pool:   # fused nn.MaxPool2d(2) of the stored output, exactly
         want = F.max_pool2d(out[..., :64].float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
         assert torch.equal(pbuf[..., :64].float(), want) and (pbuf[..., 64:] == 3.0).all()
@@ -60,7 +63,7 @@ def test_stem_conv1(engine, B, S, src):
     scale = torch.rand((64,), generator=g, device="cuda") + 0.5
     bias = torch.randn((64,), generator=g, device="cuda")
     wp = _pack_conv1(wt)
-    out = torch.full((B, S // 2, S // 2, 64), 7.0, device="cuda", dtype=torch.bfloat16)
+    out, o_intact = guarded((B, S // 2, S // 2, 64), 7.0, torch.bfloat16)
     if src == "u8":
         u8 = torch.randint(0, 256, (B, S, S, 3), generator=g, device="cuda", dtype=torch.uint8)
         xf = (u8.float() / 255.0).permute(0, 3, 1, 2)
@@ -72,6 +75,7 @@ def test_stem_conv1(engine, B, S, src):
                        B, S, S)
     engine.run_op(d)
     torch.cuda.synchronize()
+    o_intact()
     xt = xf * _SC.cuda()[None, :, None, None] + _SH.cuda()[None, :, None, None]   # GoogLeNet._transform_input
     xq, wq = xt.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
     ref = torch.relu(F.conv2d(xq, wq, stride=2, padding=3) * scale[None, :, None, None] + bias[None, :, None, None])

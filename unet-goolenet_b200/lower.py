@@ -30,6 +30,7 @@ FUSE_POOL = os.environ.get("UG_FUSE_POOL", "1") != "0"
 # 10.01k vs 10.09k img/s, maps <= 56 fused 9.82k vs 9.88k).
 FUSE_STATS = int(os.environ.get("UG_FUSE_STATS", "0"))
 # UG_FUSE_REDUCE=0: run the two Inception reduce convolutions (branch2.0 / branch3.0, same input) as separate launches.
+# Same-box A/B: 9756 / 9721 img/s fused vs 9732 / 9742 separate (neutral); kept on, it removes 9 launches per batch.
 FUSE_REDUCE = os.environ.get("UG_FUSE_REDUCE", "1") != "0"
 
 
