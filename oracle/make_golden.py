@@ -4,6 +4,7 @@ committed with the vectors it made).  Run from the repo root:  python -m oracle.
   unet_golden.npz       reference UNetTaskAligWeight(3,1) logits for 2 synthetic images with the seeded
                         procedural weights (oracle.fixtures.procedural_state, seed 7) + the reference's
                         state_dict key list and shapes
+  unet_cls_golden.npz   the classifier-head UNetTaskAligWeight of 分类/nets/basicUnet.py on the same weights and images
   googlenet_golden.npz  torchvision GoogLeNet (built as 分类/test.py:64-73 builds it) logits for 4 crops with
                         procedural weights (seed 11)
   roi_golden.npz        reference process_and_augment_roi outputs (roi tensor as uint8, box) for hand-made
@@ -54,6 +55,16 @@ def main():
     with open(os.path.join(OUT, "unet_state_keys.json"), "w") as f:
         json.dump({k: list(v.shape) for k, v in ref_sd.items()}, f, indent=0)
     print("unet golden", logits.shape, float(np.abs(logits).mean()))
+
+    # ---- classifier-head variant (分类/nets/basicUnet.py:369-436): same state_dict, forward -> cl_out [B,1]
+    RefCls = ref_import.reference_unet_cls_class()
+    refc = RefCls(n_channels=3, n_classes=1).eval()
+    assert list(refc.state_dict().keys()) == list(ref_sd.keys()), "classifier-head variant has a different state_dict"
+    refc.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        cl = refc(torch.from_numpy(imgs)).numpy()
+    np.savez_compressed(os.path.join(OUT, "unet_cls_golden.npz"), cl_out=cl.astype(np.float32))
+    print("unet cls-head golden", cl.ravel())
 
     # ---- GoogLeNet (torchvision, as the reference constructs it minus the download)
     import torchvision

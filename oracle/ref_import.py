@@ -61,6 +61,12 @@ def reference_unet_class():
     return m.UNetTaskAligWeight
 
 
+def reference_unet_cls_class():
+    """-> the classifier-head UNetTaskAligWeight of 分类/nets/basicUnet.py:369-436 (forward returns cl_out [B,1])."""
+    (m,) = _import_from(CLS_DIR, ["nets.basicUnet"])
+    return m.UNetTaskAligWeight
+
+
 def reference_roi():
     """-> (process_and_augment_roi, CDDataAugmentation) from 分类/util."""
     roi, du = _import_from(CLS_DIR, ["util.roi", "util.data_utils"])

@@ -106,6 +106,39 @@ def test_unet_shell_is_drop_in(engine, unet_sd, images, oracle_unet):
         model(torch.zeros(1, 3, 512, 512, device="cuda"))
 
 
+def test_unet_cls_head_variant(engine, unet_sd, images):
+    """分类/nets/basicUnet.py:369-436 (classifier-head UNetTaskAligWeight): same state_dict, forward ->
+    cl_out [B,1].  Checked against the golden cl_out of the IMPORTED reference class (procedural weights, seed 7) and
+    against the fp32 oracle on the trained fixture.  Tolerance: 3e-2 of the output scale (bf16 activations through
+    10 conv layers + the transformer block, then a mean over 196 tokens and a 512-term dot product)."""
+    import os
+    from oracle import fixtures, unet_ref
+    from ugnet_b200.nets.basicUnet_cls import UNetTaskAligWeight
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_cls_golden.npz"))["cl_out"]
+    sd = fixtures.procedural_state(fixtures.unet_template(), seed=7)
+    imgs, _, _ = fixtures.synth_images(2, seed=99)
+    model = UNetTaskAligWeight(n_channels=3, n_classes=1)
+    model.load_state_dict(sd, strict=True)
+    model = model.to("cuda").eval()
+    with torch.no_grad():
+        out = model(torch.from_numpy(imgs).cuda())
+    assert out.shape == (2, 1) and out.dtype == torch.float32
+    err = np.abs(out.cpu().numpy() - gold).max()
+    print(f"cls-head golden: engine {out.cpu().numpy().ravel()} reference {gold.ravel()} err {err:.4f}")
+    assert err <= 3e-2 * max(1.0, np.abs(gold).max())
+    # trained encoder weights, 8 images, live oracle
+    model.load_state_dict(unet_sd)
+    x = torch.from_numpy(images[0])
+    with torch.no_grad():
+        ref = unet_ref.unet_cls_forward({k: v.cpu() for k, v in unet_sd.items()}, x).numpy()
+        got = model(x.cuda()).cpu().numpy()
+    err = np.abs(got - ref).max()
+    print(f"cls-head trained fixture: err {err:.4f} of scale {np.abs(ref).max():.3f}")
+    assert err <= 3e-2 * max(1.0, np.abs(ref).max())
+    with pytest.raises(RuntimeError):
+        model.forward_mask_boxes(x.cuda())
+
+
 def test_roi_drop_in_matches_oracle(engine, unet_sd, images):
     """process_and_augment_roi (roi.py:12-51): crop pixels bit-exact given the engine's own mask."""
     from oracle import roi_ref

@@ -48,6 +48,17 @@ def test_unet_oracle_matches_reference_golden():
     assert np.abs(out - gold).max() <= 2e-5 * scale, np.abs(out - gold).max() / scale
 
 
+def test_unet_cls_head_oracle_matches_reference_golden():
+    """分类/nets/basicUnet.py:369-436 (classifier-head variant, same state_dict): golden cl_out of the imported class."""
+    gold = np.load(os.path.join(GOLD, "unet_cls_golden.npz"))["cl_out"]
+    sd = fixtures.procedural_state(fixtures.unet_template(), seed=7)
+    imgs, _, _ = fixtures.synth_images(2, seed=99)
+    with torch.no_grad():
+        out = unet_ref.unet_cls_forward(sd, torch.from_numpy(imgs)).numpy()
+    assert out.shape == gold.shape == (2, 1)
+    assert np.abs(out - gold).max() <= 2e-5 * np.abs(gold).max()
+
+
 def test_googlenet_oracle_matches_torchvision_and_golden():
     import torchvision
     gold = np.load(os.path.join(GOLD, "googlenet_golden.npz"))["logits"]

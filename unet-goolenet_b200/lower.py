@@ -164,8 +164,10 @@ class UNetRunner(_Builder):
     EPS = 1e-5
     STATS_SPLITS = 16
 
-    def __init__(self, sd, dev, max_batch=64):
+    def __init__(self, sd, dev, max_batch=64, head="seg"):
         super().__init__(sd, torch.device(dev))
+        assert head in ("seg", "cls")
+        self.head = head          # "seg": basicUnet.py forward (logits map); "cls": 分类/nets/basicUnet.py forward
         self.max_batch = max_batch
         self.plans = {}
         self._pack()
@@ -189,11 +191,13 @@ class UNetRunner(_Builder):
             pos = _f32(sd[f"task2.pos_embedding_decoder_{name[5:]}"], dev)[0]       # [512,14,14]
             self.w[f"pos_{name}"] = pos.permute(1, 2, 0).contiguous().to(torch.bfloat16)   # [14,14,512]
         L = "task2.layers.0."
-        self.linear("qkv2", [L + "attention2.to_qkv.weight"])
-        self.linear("out2", [L + "attention2.to_out.0.weight"], L + "attention2.to_out.0.bias")
         self.linear("cq", [L + "cross_attention_cl.to_q.weight"])
         self.linear("ckv", [L + "cross_attention_cl.to_k.weight", L + "cross_attention_cl.to_v.weight"])
         self.linear("cout", [L + "cross_attention_cl.to_out.0.weight"], L + "cross_attention_cl.to_out.0.bias")
+        if self.head == "cls":
+            return self._pack_cls_head()
+        self.linear("qkv2", [L + "attention2.to_qkv.weight"])
+        self.linear("out2", [L + "attention2.to_out.0.weight"], L + "attention2.to_out.0.bias")
         self.linear("ff1", [L + "m_feed.net.0.weight"], L + "m_feed.net.0.bias")
         self.linear("ff2", [L + "m_feed.net.3.weight"], L + "m_feed.net.3.bias")
         for n in ("x_att_norm", "m_att_norm", "m_mlp_norm"):
@@ -219,15 +223,29 @@ class UNetRunner(_Builder):
         self.w["outc"] = dict(w=_f32(sd["outc.weight"], dev).reshape(64).contiguous(),
                               b=float(sd["outc.bias"].float().item()))
 
+    def _pack_cls_head(self):
+        """Weights of the classifier-head variant (分类/nets/basicUnet.py:406-436): the `x` token stream of
+        Multi_Attention (attention1, cross_attention_cl(x, m), x_mlp_norm, x_feed) + avgpool2 + fc1 + fc2."""
+        sd, dev = self.sd, self.dev
+        L = "task2.layers.0."
+        self.linear("qkv1", [L + "attention1.to_qkv.weight"])
+        self.linear("out1", [L + "attention1.to_out.0.weight"], L + "attention1.to_out.0.bias")
+        self.linear("xff1", [L + "x_feed.net.0.weight"], L + "x_feed.net.0.bias")
+        self.linear("xff2", [L + "x_feed.net.3.weight"], L + "x_feed.net.3.bias")
+        for n in ("x_att_norm", "m_att_norm", "x_mlp_norm"):
+            self.w[n] = (_f32(sd[L + n + ".weight"], dev), _f32(sd[L + n + ".bias"], dev))
+        # fc2(fc1(.)) has no activation in between (:433-434), so the two Linear layers compose into one [1, 512]
+        # matrix (composed in float64, stored fp32); the mean over the 196 tokens is the head kernel's first step
+        w1, b1 = sd["fc1.weight"].detach().double().cpu(), sd["fc1.bias"].detach().double().cpu()
+        w2, b2 = sd["fc2.weight"].detach().double().cpu(), sd["fc2.bias"].detach().double().cpu()
+        self.w["cls_head"] = ((w2 @ w1).float().contiguous().to(dev), (w2 @ b1 + b2).float().contiguous().to(dev))
+
     # ---------------------------------------------------------------------------- program
-    def _emit_unet(self, B, ws, ops, io=None):
-        """Append the ops of one UNet forward at batch B; `ws` receives the workspace tensors.  `io` may supply
-        pre-allocated x_in / logits / mask tensors (slices of larger buffers)."""
+    def _emit_encoder(self, B, ws, ops, io=None):
+        """inc + down1..down4 (basicUnet.py:409-416); returns [x1, x2, x3, x4, out0] (NHWC bf16)."""
         buf = self.buf
         io = io or {}
         ws["x_in"] = io["x_in"] if "x_in" in io else torch.empty((B, 3, IMG, IMG), device=self.dev)
-        ws["logits"] = io["logits"] if "logits" in io else torch.empty((B, 1, IMG, IMG), device=self.dev)
-        ws["mask"] = io["mask"] if "mask" in io else torch.empty((B, IMG, IMG), device=self.dev, dtype=torch.uint8)
         # ---- encoder (basicUnet.py:409-416)
         # nn.MaxPool2d(2) of every DownBlock (basicUnet.py:47) is fused into the epilogue of the conv that produces its
         # input: that conv writes the full-resolution skip tensor AND the pooled tensor of the next level
@@ -256,8 +274,12 @@ class UNetRunner(_Builder):
             skips.append(t1)
             ws[blk] = t1
         ws["x1"] = x1
-        out0 = skips.pop()                                           # [B,14,14,512]
-        # ---- bottleneck (tasks.py:218-231, Multi_Attention :166-184), live `m` branch only
+        return skips
+
+    def _emit_tokens(self, B, ws, ops, out0):
+        """TransformerDecoder entry (tasks.py:218-225): conv_cl / conv_seg + positional embedding -> token matrices
+        X, M [B*196, 512] and their first LayerNorms (Multi_Attention :168-169)."""
+        buf = self.buf
         T = B * 196
         X, M = buf(T, 512), buf(T, 512)
         g14 = (B, 14, 14)
@@ -269,6 +291,21 @@ class UNetRunner(_Builder):
         for src, dst, n in ((X, xn, "x_att_norm"), (M, mn, "m_att_norm")):
             ops.append(E.LayerNormDesc(src.data_ptr(), dst.data_ptr(), self.w[n][0].data_ptr(),
                                        self.w[n][1].data_ptr(), T, 512, 1e-5))
+        ws.setdefault("keep", []).extend([X, M, xn, mn, out0])
+        return X, M, xn, mn
+
+    def _emit_unet(self, B, ws, ops, io=None):
+        """Append the ops of one UNet forward at batch B; `ws` receives the workspace tensors.  `io` may supply
+        pre-allocated x_in / logits / mask tensors (slices of larger buffers)."""
+        buf = self.buf
+        io = io or {}
+        ws["logits"] = io["logits"] if "logits" in io else torch.empty((B, 1, IMG, IMG), device=self.dev)
+        ws["mask"] = io["mask"] if "mask" in io else torch.empty((B, IMG, IMG), device=self.dev, dtype=torch.uint8)
+        skips = self._emit_encoder(B, ws, ops, io)
+        out0 = skips.pop()                                           # [B,14,14,512]
+        # ---- bottleneck (tasks.py:218-231, Multi_Attention :166-184), live `m` branch only
+        X, M, xn, mn = self._emit_tokens(B, ws, ops, out0)
+        T = B * 196
         flat = (1, 1, T)
         scale = 512 ** -0.5                                          # tasks.py:126 / :63 (dim ** -0.5)
         qkv = buf(T, 1536)
@@ -337,6 +374,44 @@ class UNetRunner(_Builder):
             ws.setdefault("keep", []).extend([cat, e1, psum, pmax, g, hid, n0])
         ws.setdefault("keep", []).extend([X, M, xn, mn, qkv, att, m1, cq, ckv, catt, m_in, mln, hid, out0])
 
+    def _emit_cls(self, B, ws, ops, io=None):
+        """Classifier-head forward (分类/nets/basicUnet.py:406-436): encoder, the `x` stream of the TransformerDecoder
+        (Multi_Attention tasks.py:166-184: x_att + x_cross + x, then x_feed), avgpool2 + fc1 + fc2 -> cl_out [B,1]."""
+        buf = self.buf
+        skips = self._emit_encoder(B, ws, ops, io)
+        out0 = skips.pop()
+        X, M, xn, mn = self._emit_tokens(B, ws, ops, out0)
+        T = B * 196
+        flat = (1, 1, T)
+        scale = 512 ** -0.5
+        qkv = buf(T, 1536)
+        self.conv(ops, self.w["qkv1"], View(xn), flat, View(qkv), act=E.ACT_NONE)
+        att = buf(T, 512)
+        ops.append(E.AttnDesc(qkv.data_ptr(), qkv.data_ptr() + 2 * 512, qkv.data_ptr() + 2 * 1024, 1536, 1536,
+                              1536, att.data_ptr(), 512, B, 196, 8, scale))
+        x1 = buf(T, 512)                                             # x + x_att
+        self.conv(ops, self.w["out1"], View(att), flat, View(x1), act=E.ACT_NONE, mode=E.EPI_ADD, add=View(X))
+        cq, ckv = buf(T, 512), buf(T, 1024)                          # cross_attention_cl(x_norm, m_norm): q <- x
+        self.conv(ops, self.w["cq"], View(xn), flat, View(cq), act=E.ACT_NONE)
+        self.conv(ops, self.w["ckv"], View(mn), flat, View(ckv), act=E.ACT_NONE)
+        catt = buf(T, 512)
+        ops.append(E.AttnDesc(cq.data_ptr(), ckv.data_ptr(), ckv.data_ptr() + 2 * 512, 512, 1024, 1024,
+                              catt.data_ptr(), 512, B, 196, 8, scale))
+        x_in = buf(T, 512)                                           # x_att + x_cross + x
+        self.conv(ops, self.w["cout"], View(catt), flat, View(x_in), act=E.ACT_NONE, mode=E.EPI_ADD, add=View(x1))
+        xln = buf(T, 512)
+        ops.append(E.LayerNormDesc(x_in.data_ptr(), xln.data_ptr(), self.w["x_mlp_norm"][0].data_ptr(),
+                                   self.w["x_mlp_norm"][1].data_ptr(), T, 512, 1e-5))
+        hid = buf(T, 2048)
+        self.conv(ops, self.w["xff1"], View(xln), flat, View(hid), act=E.ACT_GELU)
+        tok = buf(T, 512)                                            # x_mlp_in + x_feed
+        self.conv(ops, self.w["xff2"], View(hid), flat, View(tok), act=E.ACT_NONE, mode=E.EPI_ADD, add=View(x_in))
+        ws["cl_tokens"] = tok
+        ws["cl_out"] = io["cl_out"] if io and "cl_out" in io else torch.empty((B, 1), device=self.dev)
+        hw, hb = self.w["cls_head"]
+        ops.append(E.HeadDesc(tok.data_ptr(), hw.data_ptr(), hb.data_ptr(), ws["cl_out"].data_ptr(), B, 196, 512, 1))
+        ws.setdefault("keep", []).extend([qkv, att, x1, cq, ckv, catt, x_in, xln, hid] + skips)
+
     def _emit_bbox(self, B, ws, ops, padding=30, boxes=None):
         ws["boxes"] = boxes if boxes is not None else torch.empty((B, 4), device=self.dev, dtype=torch.int32)
         ops.append(E.BBoxDesc(ws["mask"].data_ptr(), ws["boxes"].data_ptr(), B, IMG, IMG, padding))
@@ -345,8 +420,11 @@ class UNetRunner(_Builder):
         key = (B, padding)
         if key not in self.plans:
             ws, ops = {}, []
-            self._emit_unet(B, ws, ops)
-            self._emit_bbox(B, ws, ops, padding)
+            if self.head == "cls":
+                self._emit_cls(B, ws, ops)
+            else:
+                self._emit_unet(B, ws, ops)
+                self._emit_bbox(B, ws, ops, padding)
             _finish(self.engine, ops, ws)
             self.plans[key] = ws
         return self.plans[key]
@@ -364,12 +442,17 @@ class UNetRunner(_Builder):
             ws = self.plan(xb.shape[0], padding)
             ws["x_in"].copy_(xb)                                     # also performs x.float() (:408)
             ws["program"].run()
+            if self.head == "cls":
+                outs[0].append(ws["cl_out"].clone())
+                continue
             outs[0].append(ws["logits"].clone())
             if with_mask_boxes:
                 outs[1].append(ws["mask"].clone())
                 outs[2].append(ws["boxes"].clone())
         logits = torch.cat(outs[0]) if len(outs[0]) > 1 else outs[0][0]
         if with_mask_boxes:
+            if self.head == "cls":
+                raise RuntimeError("the classifier-head variant produces no mask")
             return logits, torch.cat(outs[1]), torch.cat(outs[2])
         return logits
 
