@@ -187,6 +187,49 @@ def cpu_baseline(sample, budget_s=20.0):
                       f"restatement of the reference path), {dt:.1f} s"}
 
 
+def gpu_eager_yardstick(dev, iters=3):
+    """SURVEY §8(d) "stronger yardstick": the reference's network arithmetic (the oracle's torch restatement — a
+    checker, never the product path) run by PyTorch eager / cuDNN on the SAME B200, fp32 and bf16 autocast +
+    channels_last, UNet at B=64 and GoogLeNet at B=256, compute only (no mask -> bbox -> crop step, which the
+    reference does on the host).  images/s = 1 / (t_unet / 64 + t_googlenet / 256)."""
+    import torch
+    from oracle import fixtures, googlenet_ref, unet_ref
+    usd = {k: v.to(dev) for k, v in fixtures.procedural_state(fixtures.unet_template(), seed=7).items()}
+    gsd = {k: v.to(dev) for k, v in fixtures.procedural_state(fixtures.googlenet_template(), seed=11).items()}
+    xu = torch.rand((64, 3, 224, 224), device=dev)
+    xg = torch.rand((256, 3, 224, 224), device=dev)
+    out = {}
+    for name in ("fp32", "bf16_channels_last"):
+        if name == "fp32":
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            u, g, a, b = usd, gsd, xu, xg
+            ctx = torch.autocast("cuda", enabled=False)
+        else:
+            cl = lambda d: {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v)
+                            for k, v in d.items()}
+            u, g = cl(usd), cl(gsd)
+            a, b = xu.contiguous(memory_format=torch.channels_last), xg.contiguous(memory_format=torch.channels_last)
+            ctx = torch.autocast("cuda", dtype=torch.bfloat16)
+        ms = []
+        with torch.no_grad(), ctx:
+            for fn, sd, x in ((unet_ref.unet_forward, u, a), (googlenet_ref.googlenet_forward, g, b)):
+                fn(sd, x)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    fn(sd, x)
+                e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1) / iters)
+        out[name] = {"unet_ms_per_64": ms[0], "googlenet_ms_per_256": ms[1],
+                     "images_per_s": 1e3 / (ms[0] / 64 + ms[1] / 256)}
+    out["what"] = ("oracle restatement of the reference networks under PyTorch eager (cuDNN/cuBLAS) on this GPU, "
+                   "compute only; reported baseline, not the product path")
+    return out
+
+
 def run_stage_alone(args, dev, rank):
     """BASELINE configs[1] (UNet forward, batch 64) / configs[2] (GoogLeNet forward on ROI crops, batch 256) on one GPU:
     device-resident inputs, CUDA-event timing, one JSON line (same keys as the headline line where they apply)."""
@@ -246,6 +289,8 @@ def main():
                          "ROI crops (configs[2]: 256).  The stage-alone lines are parity/throughput cases, not the headline")
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--yardstick", action="store_true",
+                    help="also time the reference arithmetic under PyTorch eager on the GPU (fp32, bf16+channels_last)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -402,6 +447,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+        if world == 1 and args.yardstick:
+            line["gpu_eager_yardstick"] = gpu_eager_yardstick(dev)
         # per-op breakdown for profiles/ (not part of the contract line)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         kinds = {}
