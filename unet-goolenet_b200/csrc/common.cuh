@@ -18,6 +18,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // must assume divergence, keeps descriptors in vector registers and wraps every UTCHMMA / UTMALDG in an
 // ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall" (~16 instructions per MMA, measured: the issuing thread, not the
 // tensor pipe, then bounds N <= 128 tiles).  With warp-uniform control flow the operands live in uniform registers.
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident while its predecessor on the stream drains; pdl_wait() blocks until that predecessor has completed and its
+// writes are visible (a no-op for a normally launched kernel), so everything BEFORE it (barrier init, TMEM allocation,
+// descriptor prefetch, loads of constant weights) overlaps the predecessor's tail.  pdl_launch_dependents() is issued
+// AFTER the TMEM allocation: a dependent CTA that grabbed tensor memory first could starve this grid's allocation.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
   asm volatile(

@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                 // prologue above overlaps the previous kernel's tail (common.cuh)
+  pdl_launch_dependents();
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
@@ -252,6 +254,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                 // prologue above overlaps the previous kernel's tail (common.cuh)
+  pdl_launch_dependents();
 
   if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
@@ -725,20 +729,21 @@ int conv_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   }
   if (L->variant == 5) return conv_multi_launch(h, L, s);
   const int act = L->p.act;
+  cudaError_t le;
   if (L->variant == 1) {
-    if (act == UG_ACT_RELU) conv_gemm_kernel<UG_ACT_RELU><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->p);
-    else if (act == UG_ACT_GELU) conv_gemm_kernel<UG_ACT_GELU><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->p);
-    else conv_gemm_kernel<UG_ACT_NONE><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->p);
+    if (act == UG_ACT_RELU) le = launch_pdl(h, conv_gemm_kernel<UG_ACT_RELU>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->p);
+    else if (act == UG_ACT_GELU) le = launch_pdl(h, conv_gemm_kernel<UG_ACT_GELU>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->p);
+    else le = launch_pdl(h, conv_gemm_kernel<UG_ACT_NONE>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->p);
   } else {
     if (act == UG_ACT_RELU)
-      conv_gemm_persistent_kernel<UG_ACT_RELU><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p);
+      le = launch_pdl(h, conv_gemm_persistent_kernel<UG_ACT_RELU>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->tmO, L->p);
     else if (act == UG_ACT_GELU)
-      conv_gemm_persistent_kernel<UG_ACT_GELU><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p);
+      le = launch_pdl(h, conv_gemm_persistent_kernel<UG_ACT_GELU>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->tmO, L->p);
     else
-      conv_gemm_persistent_kernel<UG_ACT_NONE><<<L->grid, kThreads, L->smem, s>>>(L->tmA, L->tmB, L->tmO, L->p);
+      le = launch_pdl(h, conv_gemm_persistent_kernel<UG_ACT_NONE>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->tmO, L->p);
   }
   h->launches++;
-  return check_cuda(h, cudaGetLastError(), "conv_gemm kernel launch");
+  return check_cuda(h, le != cudaSuccess ? le : cudaGetLastError(), "conv_gemm kernel launch");
 }
 
 }  // namespace ug

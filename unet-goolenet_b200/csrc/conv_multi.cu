@@ -156,6 +156,11 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Everything above touched only kernel parameters and constant weights; from here on the roles read activations /
+  // write outputs, which must wait for the previous kernel of the stream.  The weight producer (kMAllocWarp) streams
+  // constants only and starts right away.
+  if (warp != kMAllocWarp) pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == kMProducerWarp) {
     // ------------------------------------------------------------------ activation producer (whole warp, elected lane issues)
@@ -794,14 +799,17 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
 }
 
 template <int kTaps>
-static void launch_multi(const ConvLaunch* L, const StoreMaps& maps, const MultiParams& hp, cudaStream_t s) {
+static cudaError_t launch_multi(const ug_engine* h, const ConvLaunch* L, const StoreMaps& maps, const MultiParams& hp,
+                                cudaStream_t s) {
   const int act = L->p.act;
+  cudaError_t e;
   if (act == UG_ACT_RELU)
-    conv_multi_kernel<UG_ACT_RELU, kTaps><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, maps, L->p, hp);
+    e = launch_pdl(h, conv_multi_kernel<UG_ACT_RELU, kTaps>, L->grid, kMultiThreads, L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
   else if (act == UG_ACT_GELU)
-    conv_multi_kernel<UG_ACT_GELU, kTaps><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, maps, L->p, hp);
+    e = launch_pdl(h, conv_multi_kernel<UG_ACT_GELU, kTaps>, L->grid, kMultiThreads, L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
   else
-    conv_multi_kernel<UG_ACT_NONE, kTaps><<<L->grid, kMultiThreads, L->smem, s>>>(L->tmA, L->tmB, maps, L->p, hp);
+    e = launch_pdl(h, conv_multi_kernel<UG_ACT_NONE, kTaps>, L->grid, kMultiThreads, L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
+  return e;
 }
 
 int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
@@ -829,10 +837,9 @@ int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   maps.m[1] = L->tmQ[0];
   maps.m[2] = L->tmQ[1];
   maps.m[3] = L->tmQ[2];
-  if (L->halo_mode == 9) launch_multi<9>(L, maps, hp, s);
-  else launch_multi<1>(L, maps, hp, s);
+  const cudaError_t e = L->halo_mode == 9 ? launch_multi<9>(h, L, maps, hp, s) : launch_multi<1>(h, L, maps, hp, s);
   h->launches++;
-  return check_cuda(h, cudaGetLastError(), "conv_multi_kernel launch");
+  return check_cuda(h, e != cudaSuccess ? e : cudaGetLastError(), "conv_multi_kernel launch");
 }
 
 }  // namespace ug

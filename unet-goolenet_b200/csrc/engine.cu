@@ -4,6 +4,7 @@
 #include <cstring>
 #include <new>
 #include "engine.h"
+#include <cstdlib>
 
 namespace ug {
 
@@ -80,6 +81,7 @@ int ug_create(int device, ug_handle* out) {
   if (!h) return UG_ENOMEM;
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("UG_PDL")) h->pdl = atoi(e) != 0;
   *out = h;
   return UG_OK;
 }

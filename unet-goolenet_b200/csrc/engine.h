@@ -16,6 +16,7 @@ struct ug_engine {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};   // staging slot filled (recorded on the copy stream)
   cudaEvent_t ev_free[2] = {nullptr, nullptr};  // staging slot consumed (recorded on the compute stream)
   long long pipelined_steps = 0;
+  int pdl = 1;  // launch kernels with programmatic stream serialization (UG_PDL=0 turns it off)
 };
 
 namespace ug {
@@ -85,6 +86,25 @@ struct StemLaunch {
 
 int set_error(ug_engine* h, int code, const char* fmt, ...);
 int check_cuda(ug_engine* h, cudaError_t e, const char* what);
+
+// Launch `kernel` on `s`; with h->pdl the launch carries the programmatic-stream-serialization attribute, so the kernel
+// may start its prologue while the previous kernel of the stream drains.  ONLY for kernels that execute pdl_wait()
+// (common.cuh) before their first access to memory written by earlier kernels.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(const ug_engine* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (h && h->pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
 int conv_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);

@@ -68,6 +68,8 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 
 __global__ void __launch_bounds__(256) pool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                    ug_pool_desc d) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   const int cg = d.C / 8;
   const long long total = (long long)d.B * d.OH * d.OW * cg;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(256) pool_kernel(const __nv_bfloat16* __restri
 // nine (these maps are L2 resident and the generic kernel was bound by the 9x re-read).
 __global__ void __launch_bounds__(256) pool3x3s1_kernel(const __nv_bfloat16* __restrict__ in,
                                                         __nv_bfloat16* __restrict__ out, ug_pool_desc d) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   const int cg = d.C / 8;
   const long long total = (long long)d.B * d.H * cg;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,13 +151,13 @@ int launch_pool(ug_engine* h, const ug_pool_desc* d, cudaStream_t s) {
     return set_error(h, UG_EINVAL, "pool: last window starts outside the input");
   if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->OH == d->H && d->OW == d->W) {
     const long long total = (long long)d->B * d->H * (d->C / 8);
-    pool3x3s1_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d->in),
+    launch_pdl(h, pool3x3s1_kernel, cdiv(total, 256), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(d->in),
                                                       reinterpret_cast<__nv_bfloat16*>(d->out), *d);
     h->launches++;
     return check_cuda(h, cudaGetLastError(), "pool3x3s1 launch");
   }
   const long long total = (long long)d->B * d->OH * d->OW * (d->C / 8);
-  pool_kernel<<<cdiv(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d->in),
+  launch_pdl(h, pool_kernel, cdiv(total, 256), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(d->in),
                                                reinterpret_cast<__nv_bfloat16*>(d->out), *d);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "pool launch");
@@ -167,6 +171,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
                                                         __nv_bfloat16* __restrict__ out,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int M, int C, float eps) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -220,10 +226,10 @@ int launch_layernorm(ug_engine* h, const ug_layernorm_desc* d, cudaStream_t s) {
   const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d->in);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d->out);
   switch (d->C / 256) {
-    case 1: layernorm_kernel<1><<<grid, 256, 0, s>>>(in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
-    case 2: layernorm_kernel<2><<<grid, 256, 0, s>>>(in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
-    case 3: layernorm_kernel<3><<<grid, 256, 0, s>>>(in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
-    default: layernorm_kernel<4><<<grid, 256, 0, s>>>(in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
+    case 1: launch_pdl(h, layernorm_kernel<1>, grid, 256, 0, s, in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
+    case 2: launch_pdl(h, layernorm_kernel<2>, grid, 256, 0, s, in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
+    case 3: launch_pdl(h, layernorm_kernel<3>, grid, 256, 0, s, in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
+    default: launch_pdl(h, layernorm_kernel<4>, grid, 256, 0, s, in, out, d->gamma, d->beta, d->M, d->C, d->eps); break;
   }
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "layernorm launch");
@@ -235,6 +241,8 @@ int launch_layernorm(ug_engine* h, const ug_layernorm_desc* d, cudaStream_t s) {
 static constexpr int kAttnThreads = 256;
 
 __global__ void __launch_bounds__(kAttnThreads) attention_kernel(ug_attn_desc d) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   extern __shared__ uint4 attn_smem[];
   uint4* sK = attn_smem;          // [S][8] uint4 (64 bf16 per row)
   uint4* sV = attn_smem + d.S * 8;
@@ -346,6 +354,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 }
 
 __global__ void __launch_bounds__(128) attention_mma_kernel(ug_attn_desc d) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   extern __shared__ uint4 attn_smem[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(attn_smem);   // [kAttnSP][kAttnKPitch]
   __nv_bfloat16* sV = sK + kAttnSP * kAttnKPitch;                     // [kAttnSP][kAttnVPitch]
@@ -477,10 +487,10 @@ int launch_attention(ug_engine* h, const ug_attn_desc* d, cudaStream_t s) {
   }
   if (d->S <= kAttnSP && d->variant == 0) {
     const size_t smem = (size_t)(kAttnSP * kAttnKPitch + kAttnSP * kAttnVPitch) * sizeof(__nv_bfloat16);
-    attention_mma_kernel<<<d->B * d->heads, 128, smem, s>>>(*d);
+    launch_pdl(h, attention_mma_kernel, d->B * d->heads, 128, smem, s, *d);
   } else {  // generic fp32 CUDA-core path (S up to 256)
     const size_t smem = (size_t)d->S * 8 * sizeof(uint4) * 2;
-    attention_kernel<<<d->B * d->heads, kAttnThreads, smem, s>>>(*d);
+    launch_pdl(h, attention_kernel, d->B * d->heads, kAttnThreads, smem, s, *d);
   }
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "attention launch");
@@ -490,6 +500,8 @@ int launch_attention(ug_engine* h, const ug_attn_desc* d, cudaStream_t s) {
 // CoordAtt3 statistics, stage 1: block (split, image) reduces its pixel range; threads are laid out as
 // (C/8 channel groups) x (256/(C/8) pixel lanes), partial results combined through shared memory.
 __global__ void __launch_bounds__(256) chanstats_kernel(ug_chanstats_desc d) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   __shared__ float s_sum[256 * 8];
   __shared__ float s_max[256 * 8];
   const int cg = d.C / 8;       // channel groups (<= 64)
@@ -543,7 +555,7 @@ int launch_chanstats(ug_engine* h, const ug_chanstats_desc* d, cudaStream_t s) {
   if (!d->in || !d->psum || !d->pmax || d->C % 8 || d->C > 512 || d->C < 8 || (256 % (d->C / 8)) || d->splits <= 0 ||
       d->in_cstride % 8)
     return set_error(h, UG_EINVAL, "chanstats: C must be 8*2^k <= 512");
-  chanstats_kernel<<<dim3(d->splits, d->B), 256, 0, s>>>(*d);
+  launch_pdl(h, chanstats_kernel, dim3(d->splits, d->B), 256, 0, s, *d);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "chanstats launch");
 }
@@ -554,6 +566,8 @@ int launch_chanstats(ug_engine* h, const ug_chanstats_desc* d, cudaStream_t s) {
 static constexpr int kGateSplit = 8;
 
 __global__ void __launch_bounds__(256) gate_hidden_kernel(ug_gate_desc d, float* __restrict__ hid_out) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   __shared__ float s_avg[512], s_max[512];
   const int n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -587,6 +601,8 @@ __global__ void __launch_bounds__(256) gate_hidden_kernel(ug_gate_desc d, float*
 }
 
 __global__ void __launch_bounds__(256) gate_out_kernel(ug_gate_desc d, const float* __restrict__ hid_in) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   __shared__ float s_hid[256];
   const int n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -608,8 +624,8 @@ int launch_gate(ug_engine* h, const ug_gate_desc* d, cudaStream_t s) {
   if (!d->psum || !d->pmax || !d->w1 || !d->w2 || !d->w3 || !d->b1 || !d->b2 || !d->b3 || !d->g || !d->hid ||
       d->C > 512 || d->C % 2 || d->HW <= 0 || d->splits <= 0)
     return set_error(h, UG_EINVAL, "gate: bad args (C <= 512, hid scratch required)");
-  gate_hidden_kernel<<<dim3(kGateSplit, d->B), 256, 0, s>>>(*d, d->hid);
-  gate_out_kernel<<<dim3(kGateSplit, d->B), 256, 0, s>>>(*d, d->hid);
+  launch_pdl(h, gate_hidden_kernel, dim3(kGateSplit, d->B), 256, 0, s, *d, d->hid);
+  launch_pdl(h, gate_out_kernel, dim3(kGateSplit, d->B), 256, 0, s, *d, d->hid);
   h->launches += 2;
   return check_cuda(h, cudaGetLastError(), "gate launch");
 }
@@ -618,6 +634,8 @@ int launch_gate(ug_engine* h, const ug_gate_desc* d, cudaStream_t s) {
 // mask -> bbox: one block per image; warp-shuffle min/max, then one thread applies roi.py:25-36.
 __global__ void __launch_bounds__(1024) bbox_kernel(const unsigned char* __restrict__ mask, int* __restrict__ boxes, int H,
                                                     int W, int padding) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   __shared__ int s_red[4][32];
   const int n = blockIdx.x;
   const unsigned char* m = mask + (long long)n * H * W;
@@ -684,7 +702,7 @@ __global__ void __launch_bounds__(1024) bbox_kernel(const unsigned char* __restr
 
 int launch_bbox(ug_engine* h, const ug_bbox_desc* d, cudaStream_t s) {
   if (!d->mask || !d->boxes || d->B <= 0 || d->H <= 0 || d->W <= 0) return set_error(h, UG_EINVAL, "bbox: bad args");
-  bbox_kernel<<<d->B, 1024, 0, s>>>(d->mask, d->boxes, d->H, d->W, d->padding);
+  launch_pdl(h, bbox_kernel, d->B, 1024, 0, s, d->mask, d->boxes, d->H, d->W, d->padding);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "bbox launch");
 }
@@ -751,6 +769,8 @@ __device__ void pil_coef_general(int in_size, int out_size, int xx, RsCoef* c) {
 template <bool kCrop>
 __global__ void __launch_bounds__(256) resize_u8_kernel(ug_resize_desc d, int max_src_rows, const float* __restrict__ img,
                                                         const int* __restrict__ boxes, int IH, int IW) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   extern __shared__ unsigned char rs_smem[];
   RsCoef* s_h = reinterpret_cast<RsCoef*>(rs_smem);                   // [S] horizontal coefficients
   RsCoef* s_v = s_h + d.S;                                             // [kRsRows] vertical coefficients
@@ -846,7 +866,7 @@ int launch_resize_u8(ug_engine* h, const ug_resize_desc* d, cudaStream_t s) {
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(resize_u8_kernel)");
     attr_smem = smem;
   }
-  resize_u8_kernel<false><<<dim3(cdiv(d->S, kRsRows), d->B), 256, smem, s>>>(*d, max_rows, nullptr, nullptr, 0, 0);
+  launch_pdl(h, resize_u8_kernel<false>, dim3(cdiv(d->S, kRsRows), d->B), 256, smem, s, *d, max_rows, nullptr, nullptr, 0, 0);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "resize_u8 launch");
 }
@@ -870,7 +890,7 @@ int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s)
   }
   ug_resize_desc r;
   r.src = nullptr; r.out_f32 = nullptr; r.out_u8 = d->out_u8; r.B = d->B; r.Hs = d->H; r.Ws = d->W; r.S = d->S;
-  resize_u8_kernel<true><<<dim3(cdiv(d->S, kRsRows), d->B), 256, smem, s>>>(r, max_rows, d->img, d->boxes, d->H, d->W);
+  launch_pdl(h, resize_u8_kernel<true>, dim3(cdiv(d->S, kRsRows), d->B), 256, smem, s, r, max_rows, d->img, d->boxes, d->H, d->W);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "cropresize launch");
 }
@@ -943,6 +963,8 @@ int launch_g1_im2col(ug_engine* h, const ug_g1_im2col_desc* d, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // GoogLeNet head: global average pool + fc, one block per image.
 __global__ void __launch_bounds__(256) head_kernel(ug_head_desc d) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
   __shared__ float s_avg[1024];
   const int n = blockIdx.x;
   const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d.in) + (long long)n * d.HW * d.C;
@@ -970,7 +992,7 @@ __global__ void __launch_bounds__(256) head_kernel(ug_head_desc d) {
 int launch_head(ug_engine* h, const ug_head_desc* d, cudaStream_t s) {
   if (!d->in || !d->w || !d->b || !d->logits || d->C > 1024 || d->C % 2 || d->HW <= 0 || d->ncls <= 0)
     return set_error(h, UG_EINVAL, "head: bad args (C <= 1024)");
-  head_kernel<<<d->B, 256, 0, s>>>(*d);
+  launch_pdl(h, head_kernel, d->B, 256, 0, s, *d);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "head launch");
 }

@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
     mbar_arrive_expect_tx(b_full, (uint32_t)(kAtoms * 64 * 128));
     for (int a = 0; a < kAtoms; ++a) tma_load_2d(sB + a * 64 * 128, &tmB, b_full, a * 64, 0);
   }
+  pdl_wait();                 // the prologue and the (constant) weight load overlap the previous kernel's tail
+  pdl_launch_dependents();
 
   const int tx = tid & (kStemTW - 1);
   const int ty = tid >> 4;
@@ -375,10 +377,10 @@ int stem_launch(ug_engine* h, const StemLaunch* L, cudaStream_t s) {
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(stem_conv_kernel)");
     attr_set = true;
   }
-  if (L->kind == 0) stem_conv_kernel<0><<<L->grid, 128, L->smem, s>>>(L->tmB, L->tmO, L->tmP, L->p);
-  else stem_conv_kernel<1><<<L->grid, 128, L->smem, s>>>(L->tmB, L->tmO, L->tmP, L->p);
+  const cudaError_t le = L->kind == 0 ? launch_pdl(h, stem_conv_kernel<0>, L->grid, 128, L->smem, s, L->tmB, L->tmO, L->tmP, L->p)
+                                      : launch_pdl(h, stem_conv_kernel<1>, L->grid, 128, L->smem, s, L->tmB, L->tmO, L->tmP, L->p);
   h->launches++;
-  return check_cuda(h, cudaGetLastError(), "stem_conv_kernel launch");
+  return check_cuda(h, le != cudaSuccess ? le : cudaGetLastError(), "stem_conv_kernel launch");
 }
 
 }  // namespace ug
