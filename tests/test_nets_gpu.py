@@ -223,6 +223,34 @@ def test_pipeline_parity(engine, unet_sd, gnet_sd, images, oracle_unet):
     print(f"pipeline: cls rel err (same-box images) {rel[sel].max():.5f}")
 
 
+def test_full_size_batch_invariance(engine, unet_sd, gnet_sd):
+    """BASELINE.json's per-GPU size (256 images, UNet micro-batch 128): size-independent properties instead of an
+    oracle run.  (1) every image's result is bit-identical to the one computed in a batch of 8 (images are independent
+    end to end; exercises the large-batch tile decode); (2) every box is exactly bbox(mask) of the oracle's integer
+    rule; (3) the run is deterministic."""
+    from oracle import fixtures, roi_ref
+    from ugnet_b200.pipeline import TwoStagePipeline
+    usd = {k: v.cuda() for k, v in unet_sd.items()}
+    gsd = {k: v.cuda() for k, v in gnet_sd.items()}
+    imgs, _, _ = fixtures.synth_images(256, seed=77)
+    x = torch.from_numpy(imgs).cuda()
+    big = TwoStagePipeline(usd, gsd, micro_batch=128)
+    masks, boxes, cls = big(x)
+    assert masks.shape == (256, 224, 224) and boxes.shape == (256, 4) and cls.shape == (256, 6)
+    m2, b2, c2 = big(x)
+    assert torch.equal(m2, masks) and torch.equal(b2, boxes) and torch.equal(c2, cls)
+    mh = masks.cpu().numpy()
+    for i in range(256):
+        assert tuple(boxes[i].tolist()) == roi_ref.bbox_from_mask(mh[i]), i
+    assert 0.01 < mh.mean() < 0.5, "fixture masks should be non-trivial"
+    small = TwoStagePipeline(usd, gsd, micro_batch=8)
+    for s0 in (0, 124, 248):      # first chunk, one straddling the micro-batch boundary, last chunk
+        ms, bs, cs = small(x[s0:s0 + 8])
+        assert torch.equal(ms, masks[s0:s0 + 8]), f"masks differ from the batch-8 run at {s0}"
+        assert torch.equal(bs, boxes[s0:s0 + 8])
+        assert torch.equal(cs, cls[s0:s0 + 8]), f"logits differ from the batch-8 run at {s0}"
+
+
 def test_run_host_pipelined_matches_serial(engine, unet_sd, gnet_sd, images):
     """ug_program_run_host_pipelined (double-buffered H2D on the copy stream) == ug_program_run_host, step by step."""
     from ugnet_b200.lower import PipelineRunner
