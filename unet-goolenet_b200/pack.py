@@ -3,7 +3,12 @@
 BN fold: scale = gamma / sqrt(var + eps); bias' = beta + (b_conv - mean) * scale.
 Packed conv weight: [Npad][R*S*Cin_pad] bf16, K index = (r*S + s)*Cin_pad + c (see ug_conv_desc).
 """
+import os
+
 import torch
+
+# UG_BN_FIT=0: always 128-wide n-tiles for N >= 128 (the last tile of N = 144 ... 320 layers is then mostly padding)
+BN_FIT = os.environ.get("UG_BN_FIT", "1") != "0"
 
 
 def round_up(x, m):
@@ -19,7 +24,23 @@ def choose_bn(n_out, convt_cout=None, r=1):
         return 256
     if r == 1 and n_out >= 1024 and n_out % 256 == 0:
         return 256        # wide linear layers (qkv, FFN): persistent kernel with 256-wide n-tiles (measured)
-    return 128 if n_out >= 128 else round_up(n_out, 16)
+    if n_out <= 128:
+        return round_up(n_out, 16)
+    if n_out % 128 == 0 or not BN_FIT or r != 1:
+        # (the 3x3 multi-issuer kernel stores 64-column boxes, so its n-tiles must be multiples of 64 when there are
+        # several of them: no better choice than 128 exists there)
+        return 128
+    # 1x1 layers whose width is not a multiple of 128 (GoogLeNet: 136 ... 240): pick the tile width that minimises
+    # n_tiles * (MMA issue interval of an M=128 x BN MMA); the single-issuer GEMM kernels issue one MMA per ~110 cycles
+    # up to N = 220, then N/2 (profiles/r01_mma_*.txt), BN <= 256.  Ties go to the least padding.
+    best, best_key = 128, None
+    for bn in range(16, 256 + 1, 16):
+        tiles = -(-n_out // bn)
+        cyc = max(110.0, 0.5 * bn)
+        key = (tiles * cyc, tiles * bn - n_out)
+        if best_key is None or key < best_key:
+            best, best_key = bn, key
+    return best
 
 
 def fold_bn(conv_bias, gamma, beta, mean, var, eps):
