@@ -16,7 +16,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_ref.log 
 CMD="python bench.py --steps 1 --warmup 3 --batch 128 --no-cpu-baseline"
 # launches per pass at batch 128: 57 (UNet) + 15 (tail ops) ... measured from the plain run's gpu_launches
 $CMD > $O/${TAG}_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 384 -c 128 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu1.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 357 -c 119 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu1.log 2>&1
 echo "ncu launches rc=$?"
 $CMD > $O/${TAG}_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:conv_multi -s 132 -c 44 -o $O/${TAG}_conv $CMD > $O/${TAG}_ncu2.log 2>&1
