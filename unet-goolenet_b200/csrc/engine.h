@@ -80,6 +80,7 @@ struct StemLaunch {
   alignas(64) CUtensorMap tmP;  // pooled output (kind 0 with pool_out)
   StemParams p;
   int kind;
+  int groups;   // warpgroups (independent tile pipelines) per CTA
   unsigned grid;
   size_t smem;
 };

@@ -8,12 +8,15 @@
 //           K index = r*22 + s*3 + c (each filter row is a run of 21 contiguous source values padded to 22 so
 //           that runs stay 4-byte aligned), 154 columns, ten K=16 MMAs.
 //
-// One CTA = 128 threads = one 16x8 tile of output pixels (thread t <-> pixel row t of the MMA <-> TMEM lane t),
-// N = 64 output channels.  Per tile: (kind 1: stage the transformed bf16 source patch in smem) -> every thread
+// One warpgroup (128 threads) = one 16x8 tile of output pixels (thread t <-> pixel row t of the MMA <-> TMEM lane t),
+// N = 64 output channels.  A CTA holds kGroups independent warpgroups (own A tile, patch, accumulator and named
+// barrier, one shared copy of the weights): conv1's 48 KB A tile + 24 KB weights allowed only two 128-thread CTAs per
+// SM (8 warps, latency-bound); three warpgroups in one CTA share the weights and fit.  Per tile: (kind 1: stage the transformed bf16 source patch in smem) -> every thread
 // writes its im2col row into the 128B-swizzled K-major A tile -> one thread issues the MMAs -> all threads read
 // their accumulator row from TMEM, apply folded BN + ReLU, stage the bf16 tile in swizzled smem -> TMA store.
-// The phases of one CTA are serial; several co-resident CTAs per SM (7 for inc, 2 for conv1) overlap them.
+// The phases of one warpgroup are serial; the co-resident warpgroups of an SM (6 for inc, 3 for conv1) overlap them.
 // Both layers are bound by the 64-channel output write (128 B per pixel), not by the tensor pipe.
+#include <cstdlib>
 #include <cstring>
 #include "conv_common.cuh"
 
@@ -34,8 +37,8 @@ __device__ __forceinline__ uint32_t stem_bf16x2_max(uint32_t a, uint32_t b) {
 }
 static constexpr int kStemPoolBytes = 4096;  // pooled tile staging: 8 x 4 pixels x 64 channels bf16
 
-template <int kKind>
-__global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ CUtensorMap tmB,
+template <int kKind, int kGroups>
+__global__ void __launch_bounds__(128 * kGroups) stem_conv_kernel(const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ CUtensorMap tmO,
                                                         const __grid_constant__ CUtensorMap tmP, const StemParams p) {
   constexpr int kAtoms = kKind == 0 ? 1 : 3;             // 64-column swizzle atoms of the A / B tiles
@@ -43,46 +46,55 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   constexpr int kPatchBytes = kKind == 0 ? 3 * kIncPatchH * kIncPatchPitch * 4 : kG1PatchH * kG1PatchPitch * 2;
-  uint8_t* sA = smem;                                    // kAtoms x [128 rows][128 B]
+  constexpr int kPatchAlloc = (kPatchBytes + 1023) / 1024 * 1024;
+  constexpr uint32_t kTmemCols = kGroups == 1 ? 64 : (kGroups == 2 ? 128 : (kGroups <= 4 ? 256 : 512));
+  const int grp = threadIdx.x >> 7;                      // warpgroup: an independent tile pipeline
+  const int tid = threadIdx.x & 127;                     // thread within the warpgroup = pixel row of the tile
+  const int warp = tid >> 5;                             // warp within the warpgroup = TMEM lane quarter
+  const int group_bytes = kAtoms * kABytesPerStage + (p.pool ? kStemPoolBytes : 0) + kPatchAlloc;
+  uint8_t* sB = smem;                                    // kAtoms x [64 rows][128 B], shared by the warpgroups
+  uint8_t* sA = sB + kAtoms * 64 * 128 + grp * group_bytes;   // kAtoms x [128 rows][128 B]
   uint8_t* sO = sA;                                      // output staging [128 rows][128 B] reuses the first A atom:
                                                          // the A tile is dead once the MMAs of the tile completed
-  uint8_t* sB = sA + kAtoms * kABytesPerStage;           // kAtoms x [64 rows][128 B]
-  uint8_t* sPool = sB + kAtoms * 64 * 128;               // pooled tile staging (4 KB, 1024-aligned) when p.pool
+  uint8_t* sPool = sA + kAtoms * kABytesPerStage;        // pooled tile staging (4 KB, 1024-aligned) when p.pool
   __nv_bfloat16* sPatch = reinterpret_cast<__nv_bfloat16*>(sPool + (p.pool ? kStemPoolBytes : 0));   // kind 1: bf16 patch
   float* sPatchF = reinterpret_cast<float*>(sPatch);                                  // kind 0: fp32 patch
-  uint8_t* tail = reinterpret_cast<uint8_t*>(sPatch) + kPatchBytes;
+  uint8_t* tail = sB + kAtoms * 64 * 128 + kGroups * group_bytes;
   float* sScale = reinterpret_cast<float*>(tail);       // 16-byte aligned: read as float4
   float* sBias = sScale + 64;
   uint64_t* b_full = reinterpret_cast<uint64_t*>(sBias + 64);
-  uint64_t* acc_full = b_full + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = b_full + 1 + grp;                 // one accumulator barrier per warpgroup
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1 + kGroups);
+  auto group_sync = [&]() {
+    if constexpr (kGroups == 1) __syncthreads();
+    else named_bar_sync(1 + grp, 128);
+  };
 
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmO);
     if (p.pool) prefetch_tmap(&tmP);
     mbar_init(b_full, 1);
-    mbar_init(acc_full, 1);
+    for (int g = 0; g < kGroups; ++g) mbar_init(b_full + 1 + g, 1);
     fence_mbar_init();
   }
-  if (warp == 0) {
-    tmem_alloc(tmem_ptr, 64);
+  if (threadIdx.x < 32) {
+    tmem_alloc(tmem_ptr, kTmemCols);
     tmem_relinquish();
   }
   if constexpr (kKind == 1) {  // element 111 of every patch row is read (times a zero weight) but never staged
     if (tid < kG1PatchH) sPatch[tid * kG1PatchPitch + kG1PatchPitch - 1] = __float2bfloat16_rn(0.0f);
   }
-  if (tid < 64) {
-    sScale[tid] = p.scale ? p.scale[tid] : 1.0f;
-    sBias[tid] = p.bias ? p.bias[tid] : 0.0f;
+  if (threadIdx.x < 64) {
+    sScale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.0f;
+    sBias[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.0f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  if (tid == 0) {  // the whole weight matrix, once per CTA
+  const uint32_t tmem_alloc_base = *tmem_ptr;
+  const uint32_t tmem_base = tmem_alloc_base + grp * 64;   // this warpgroup's 64 accumulator columns
+  if (threadIdx.x == 0) {  // the whole weight matrix, once per CTA
     mbar_arrive_expect_tx(b_full, (uint32_t)(kAtoms * 64 * 128));
     for (int a = 0; a < kAtoms; ++a) tma_load_2d(sB + a * 64 * 128, &tmB, b_full, a * 64, 0);
   }
@@ -143,12 +155,13 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
       }
     }
   };
-  if ((int)blockIdx.x < p.total_tiles) {
-    if constexpr (kKind == 0) load_inc_patch(blockIdx.x);
-    else load_g1_patch(blockIdx.x);
+  const int t_first = blockIdx.x * kGroups + grp, t_stride = gridDim.x * kGroups;
+  if (t_first < p.total_tiles) {
+    if constexpr (kKind == 0) load_inc_patch(t_first);
+    else load_g1_patch(t_first);
   }
 
-  for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+  for (int t = t_first; t < p.total_tiles; t += t_stride) {
     const int x0 = (t % p.tiles_x) * kStemTW;
     const int y0 = ((t / p.tiles_x) % p.tiles_y) * kStemTH;
     const int n = t / (p.tiles_x * p.tiles_y);
@@ -165,8 +178,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
         if (idx < kIncElems) sPatchF[(c * kIncPatchH + r) * kIncPatchPitch + xx] = inc_raw[k];
       }
       if (tid == 0) bulk_wait_group_read<0>();  // previous tile's TMA store has finished reading sO (= sA)
-      __syncthreads();
-      if (t + (int)gridDim.x < p.total_tiles) load_inc_patch(t + gridDim.x);  // next tile's patch: in flight during
+      group_sync();
+      if (t + t_stride < p.total_tiles) load_inc_patch(t + t_stride);         // next tile's patch: in flight during
                                                                               // the gather, the MMA and the epilogue
       const float* pt = sPatchF + ty * kIncPatchPitch + tx;
       float v[32];
@@ -207,8 +220,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
         }
       }
       if (tid == 0) bulk_wait_group_read<0>();  // previous tile's TMA store has finished reading sO (= sA)
-      __syncthreads();
-      if (t + (int)gridDim.x < p.total_tiles) load_g1_patch(t + gridDim.x);  // next tile's source pixels in flight
+      group_sync();
+      if (t + t_stride < p.total_tiles) load_g1_patch(t + t_stride);         // next tile's source pixels in flight
       uint32_t w[80];
 #pragma unroll
       for (int r = 0; r < 7; ++r) {
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
     }
     fence_proxy_async_smem();  // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
     tc_fence_before();
-    __syncthreads();
+    group_sync();
     if (tid == 0) {
       tc_fence_after();
       if (!b_ready) {
@@ -281,7 +294,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
     }
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();  // staging complete; every TMEM read of this accumulator is done
+    group_sync();     // staging complete; every TMEM read of this accumulator is done
     if (tid == 0) {
       tma_store_4d(&tmO, sO, 0, x0, y0, n);
       if (p.pool) tma_store_4d(&tmP, sPool, 0, x0 >> 1, y0 >> 1, n);
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
   if (tid == 0) bulk_wait_group_all();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 64);
+  if (threadIdx.x < 32) tmem_dealloc(tmem_alloc_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -358,27 +371,43 @@ int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* L) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "stem: pooled output tensor map encode failed (%d)", (int)r);
   }
-  const int ctas_per_sm = d->kind == 0 ? 7 : 2;  // 31 KB / 79 KB of shared memory and 64 TMEM columns per CTA
-  L->grid = (unsigned)std::min<long long>(p.total_tiles, (long long)h->num_sms * ctas_per_sm);
-  L->smem = 1024 + (size_t)katoms * kABytesPerStage + (size_t)katoms * 64 * 128 +
-            (d->kind == 1 ? kG1PatchH * kG1PatchPitch * 2 : 3 * kIncPatchH * kIncPatchPitch * 4) +
-            (p.pool ? kStemPoolBytes : 0) + 16 + 8 + 2 * 64 * sizeof(float);
+  // One CTA per SM holding several warpgroups that share the weights: conv1 three (48 KB A tile each; measured 0.557 ->
+  // 0.435 ms per 256 images against two single-warpgroup CTAs per SM), inc six at 80 registers per thread (0.296 ->
+  // 0.263 ms per 128 images against five single-warpgroup CTAs per SM).  UG_STEM_GROUPS=1 / UG_INC_GROUPS=1: former shape.
+  static const int g1_groups = [] { const char* e = getenv("UG_STEM_GROUPS"); return e && atoi(e) == 1 ? 1 : 3; }();
+  static const int inc_groups = [] { const char* e = getenv("UG_INC_GROUPS"); return e && atoi(e) == 1 ? 1 : 6; }();
+  L->groups = d->kind == 0 ? inc_groups : g1_groups;
+  const int ctas_per_sm = d->kind == 0 ? (L->groups == 1 ? 7 : 1) : (L->groups == 1 ? 2 : 1);
+  L->grid = (unsigned)std::min<long long>((p.total_tiles + L->groups - 1) / L->groups, (long long)h->num_sms * ctas_per_sm);
+  const size_t patch = d->kind == 1 ? kG1PatchH * kG1PatchPitch * 2 : 3 * kIncPatchH * kIncPatchPitch * 4;
+  L->smem = 1024 + (size_t)katoms * 64 * 128 +
+            L->groups * ((size_t)katoms * kABytesPerStage + (p.pool ? kStemPoolBytes : 0) + (patch + 1023) / 1024 * 1024) +
+            2 * 64 * sizeof(float) + 8 * (1 + L->groups) + 16;
   return UG_OK;
 }
 
 int stem_launch(ug_engine* h, const StemLaunch* L, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)stem_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute((const void*)stem_conv_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          100 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute((const void*)stem_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute((const void*)stem_conv_kernel<0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               210 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute((const void*)stem_conv_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                110 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute((const void*)stem_conv_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               210 * 1024);
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(stem_conv_kernel)");
     attr_set = true;
   }
-  const cudaError_t le = L->kind == 0 ? launch_pdl(h, stem_conv_kernel<0>, L->grid, 128, L->smem, s, L->tmB, L->tmO, L->tmP, L->p)
-                                      : launch_pdl(h, stem_conv_kernel<1>, L->grid, 128, L->smem, s, L->tmB, L->tmO, L->tmP, L->p);
+  cudaError_t le;
+  if (L->kind == 0 && L->groups == 6) le = launch_pdl(h, stem_conv_kernel<0, 6>, L->grid, 768, L->smem, s, L->tmB, L->tmO, L->tmP, L->p);
+  else if (L->kind == 0) le = launch_pdl(h, stem_conv_kernel<0, 1>, L->grid, 128, L->smem, s, L->tmB, L->tmO, L->tmP, L->p);
+  else if (L->groups == 1) le = launch_pdl(h, stem_conv_kernel<1, 1>, L->grid, 128, L->smem, s, L->tmB, L->tmO, L->tmP, L->p);
+  else le = launch_pdl(h, stem_conv_kernel<1, 3>, L->grid, 384, L->smem, s, L->tmB, L->tmO, L->tmP, L->p);
   h->launches++;
   return check_cuda(h, le != cudaSuccess ? le : cudaGetLastError(), "stem_conv_kernel launch");
 }
