@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "conv_common.cuh"
 
 namespace ug {
@@ -601,10 +602,24 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   const int n_tiles = ceil_div(d->N, BN);
   const long long ktot = (long long)d->R * d->S * cin_pad;
 
-  // variant: 0 = auto (persistent kernel for BN == 256, otherwise one tile per CTA, as measured in
-  // profiles/r01_conv_sweep.txt), 1 = one tile per CTA, 2 = persistent.
-  const int variant = d->variant == 1 ? 1 : (d->variant == 2 ? 0 : (BN == 256 ? 0 : 1));
+  // variant: 0 = auto, 1 = one tile per CTA, 2 = persistent.  Auto (measured, profiles/r01_conv_sweep.txt and
+  // profiles/r01_gemm_sweep_1x1.txt): persistent for BN == 256; for 1x1 layers with many pixel tiles the one-tile
+  // kernel (two CTAs per SM, 2-4 stages) is latency-bound: >= 1024 m-tiles -> multi-issuer kernel when K = 64
+  // (one chunk), persistent otherwise; >= 296 m-tiles with BN > 64 -> persistent; else one tile per CTA.
   const int m_tiles_total = ceil_div(d->W, TW) * ceil_div(d->H, TH) * ceil_div(d->B, TN);
+  static const int gemm_rule = [] { const char* e = getenv("UG_GEMM_RULE"); return e ? atoi(e) : 1; }();
+  int auto_persistent = BN == 256;
+  if (gemm_rule && d->variant == 0 && d->R == 1 && d->S == 1 && up == 1 && d->mode != UG_EPI_OUTC) {
+    if (m_tiles_total >= 1024 && kchunks == 1 && (n_tiles == 1 || BN % 64 == 0)) {
+      const int rc = conv_multi_prepare(h, d, BN, L);
+      if (rc == UG_OK) return rc;
+      if (rc != UG_EUNSUPPORTED) return rc;
+    }
+    // (the persistent kernel stores 64-column TMA boxes: several n-tiles must then be multiples of 64 wide)
+    const bool boxes_ok = n_tiles == 1 || BN % 64 == 0;
+    if (boxes_ok && (m_tiles_total >= 1024 || (m_tiles_total >= 296 && BN > 64))) auto_persistent = 1;
+  }
+  const int variant = d->variant == 1 ? 1 : (d->variant == 2 ? 0 : (auto_persistent ? 0 : 1));
   const int tma_store = (variant == 0 && up == 1 && d->mode != UG_EPI_OUTC) ? 1 : 0;
   const int stage_copy = (variant == 0 && up == 2) ? 1 : 0;
   const int n_sub = ceil_div(BN, 64);
