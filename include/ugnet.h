@@ -83,7 +83,7 @@ typedef struct ug_conv_desc {
                                  accumulators, TMA-store epilogue); 5 = 3x3 multi-issuer kernel (one CTA per
                                  SM, two MMA-issuing warps sharing resident or streamed weights, activation
                                  halo tile fetched once per 64-channel chunk for all nine taps; see
-                                 csrc/conv3x3_multi.cu) */
+                                 csrc/conv_multi.cu) */
 } ug_conv_desc;
 
 /* x: fp32 NCHW [B,3,H,W] -> out: bf16 [B*H*W][64], column (r*3+s)*3+c = x[n,c,y+r-1,x+s-1] (0 outside),

@@ -1,4 +1,4 @@
-// Device helpers shared by the implicit-GEMM kernels (conv_gemm.cu, conv3x3_halo.cu).
+// Device helpers shared by the implicit-GEMM kernels (conv_gemm.cu, conv_multi.cu, stem_conv.cu).
 #pragma once
 #include "common.cuh"
 #include "engine.h"
@@ -7,7 +7,7 @@ namespace ug {
 
 // Warp roles of the 192-thread GEMM kernels: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer,
 // warp 5 TMEM allocator + MMA issuer.  The scheduler prefers the highest eligible warp id, so the latency-critical
-// issue warps sit above the epilogue warps (see conv3x3_multi.cu).
+// issue warps sit above the epilogue warps (see conv_multi.cu).
 static constexpr int kThreads = 192;
 static constexpr int kProducerWarp = 4;
 static constexpr int kMmaWarp = 5;
