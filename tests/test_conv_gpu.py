@@ -147,6 +147,9 @@ CASES = [
     dict(B=1, H=1, W=392, Cin=512, N=2048, R=1, act=2, variant=2),  # persistent: GELU
     # 3x3 multi-issuer kernel (one CTA per SM, two MMA issuers sharing the weights)
     dict(B=1, H=224, W=224, Cin=64, N=64, R=3, variant=5),        # weights resident, 392 tiles over 148 CTAs
+    dict(B=3, H=28, W=28, Cin=128, N=192, R=3, bn=192, variant=5, out_extra=64, out_off=32),  # one 192-wide n-tile
+    dict(B=2, H=14, W=14, Cin=96, N=208, R=3, bn=208, variant=5),   # one 208-wide n-tile (last store box clipped at N)
+    dict(B=2, H=56, W=56, Cin=64, N=192, R=3, bn=192),              # auto -> multi-issuer with the fitted n-tile
     dict(B=3, H=16, W=8, Cin=64, N=64, R=3, variant=5),           # odd tile count: the second issuer idles once
     dict(B=2, H=28, W=28, Cin=128, N=256, R=3, variant=5),        # streamed weights, two n-tiles
     dict(B=1, H=24, W=8, Cin=128, N=256, R=3, variant=5),         # streamed weights + odd tile count

@@ -584,6 +584,11 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   if (d->variant == 0 && d->R == 3 && up == 1 && d->H * d->W >= 196) {
     // maps of at least 14x14: one CTA per SM, two MMA issuers sharing resident / streamed weights
     // (conv_multi.cu); measured against the other variants in profiles/r01_conv_sweep_multi_issuer.txt
+    if (BN > 128 && BN < 256) {  // a single fitted n-tile (pack.choose_bn: N = 192 ... 224)
+      const int rc = conv_multi_prepare(h, d, BN, L);
+      if (rc == UG_OK) return rc;
+      if (rc != UG_EUNSUPPORTED) return rc;
+    }
     const int rc = conv_multi_prepare(h, d, std::min(BN, 128), L);
     if (rc == UG_OK) return rc;
     if (rc != UG_EUNSUPPORTED) return rc;

@@ -639,7 +639,11 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   const int taps = d->R == 3 ? 9 : 1;
   if (!((d->R == 3 && d->S == 3 && d->pad == 1 && up == 1) || (d->R == 1 && d->S == 1 && d->pad == 0)))
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): 3x3 pad-1 or 1x1 stride-1 convolutions only");
-  if (BN > (taps == 9 ? 128 : 256)) return set_error(h, UG_EUNSUPPORTED, "conv(multi): BN <= 128 (3x3) / 256 (1x1)");
+  if (BN > 256) return set_error(h, UG_EUNSUPPORTED, "conv(multi): BN <= 256");
+  // 3x3 with one n-tile wider than 128 columns (GoogLeNet N = 192 ... 224): plain stores only (the gate / statistics
+  // staging is sized for 128 columns), one accumulator per issuer
+  if (taps == 9 && BN > 128 && (d->N > BN || d->mode != UG_EPI_STORE || d->pool_out || d->stats_sum))
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): 3x3 n-tiles wider than 128 need a single-tile STORE layer");
   if (up == 2 && (d->convt_cout % 64 || BN % 64))  // every 64-column store block lies inside one quadrant
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): ConvTranspose needs cout %% 64 == 0 and BN %% 64 == 0");
   if (taps == 1 && d->mode == UG_EPI_OUTC) return set_error(h, UG_EUNSUPPORTED, "conv(multi): OUTC is a 3x3 epilogue");
