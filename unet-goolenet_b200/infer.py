@@ -31,22 +31,26 @@ def inference_all_cls(model, test_loader, device, save_dir="test_results"):
 
 @torch.no_grad()
 def inference_all_seg(model, test_loader, device, save_dir=None):
-    """Returns {filename: uint8 mask [224,224]}; with save_dir, also paints each mask as the reference does
-    (red where mask == 1 on a black RGB canvas, predict.py:32-45) using a vectorised NumPy write."""
+    """Returns {filename: uint8 mask [224,224]}; with save_dir, also writes what predict.py:13-45 writes: one RGB PNG
+    per image under `save_dir/Segmentation_Results/`, named `filename.replace('.jpg', '') + '.png'`, red (255,0,0) where
+    mask == 1 on black (the reference's 50 176-iteration putpixel loop as one vectorised NumPy write)."""
     model.eval()
     out = {}
+    seg_dir = None
+    if save_dir is not None:
+        seg_dir = os.path.join(save_dir, "Segmentation_Results")
+        os.makedirs(seg_dir, exist_ok=True)
     for data in test_loader:
         imgs = data["image"].float().to(device)
         _, masks, _ = model.forward_mask_boxes(imgs)
         masks = masks.cpu().numpy()
-        for i, name in enumerate(data["filename"]):
-            out[name] = masks[i]
-            if save_dir is not None:
+        for i, filename in enumerate(data["filename"]):
+            out[filename] = masks[i]
+            if seg_dir is not None:
                 from PIL import Image
-                os.makedirs(save_dir, exist_ok=True)
                 canvas = np.zeros(masks[i].shape + (3,), np.uint8)
                 canvas[masks[i] == 1] = (255, 0, 0)
-                Image.fromarray(canvas).save(os.path.join(save_dir, name if name.endswith(".png") else name + ".png"))
+                Image.fromarray(canvas, "RGB").save(os.path.join(seg_dir, filename.replace(".jpg", "") + ".png"))
     return out
 
 
