@@ -58,3 +58,21 @@ def test_train_mode_is_rejected():
     from ugnet_b200.nets import UNetTaskAligWeight
     with pytest.raises(RuntimeError):
         UNetTaskAligWeight(3, 1).train()(torch.zeros(1, 3, 224, 224))
+
+
+def test_product_package_never_touches_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: nothing under the shipped package may import it, read /root/reference, or
+    fall back to a CPU / library implementation of the path (torch.nn.functional convolutions, cuDNN, Triton)."""
+    pkg = os.path.join(ROOT, "unet-goolenet_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if not fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                continue
+            src = open(os.path.join(dirpath, fn), encoding="utf-8").read()
+            rel = os.path.relpath(os.path.join(dirpath, fn), ROOT)
+            for pat in (r"^\s*(from|import)\s+oracle\b", r"/root/reference", r"\bimport\s+triton\b", r"torch\.compile\(",
+                        r"F\.conv2d\(", r"\bcudnn[A-Z]\w*\(", r"\bcublas[A-Z]\w*\("):
+                if re.search(pat, src, flags=re.M):
+                    bad.append((rel, pat))
+    assert not bad, bad
