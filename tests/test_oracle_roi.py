@@ -52,3 +52,48 @@ def test_roi_matches_reference_golden():
         roi, _ = roi_ref.roi_tensor(imgs[i], masks[i])
         got = np.round(roi * 255.0).astype(np.uint8)
         assert np.array_equal(got, rois[i]), f"case {i}"
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_import", fromlist=["x"]).available(),
+                    reason="reference tree only exists in the build container")
+def test_roi_oracle_matches_live_reference_on_random_masks():
+    """The reference's own process_and_augment_roi (分类/util/roi.py:12-51, through a stub segmentation model that
+    returns prescribed logits) against the restatement, on random blob / border / single-pixel / empty masks."""
+    import torch
+    from oracle import ref_import
+    proc, Aug = ref_import.reference_roi()
+    aug = Aug(img_size=224, ori_size=224, crop=None, p_hflip=0.0, p_vflip=0.0, color_jitter_params=None,
+              long_mask=True)                                     # as 分类/test.py:113-116 constructs it
+
+    class Stub(torch.nn.Module):
+        def __init__(self, mask):
+            super().__init__()
+            self.mask = mask
+
+        def forward(self, x):
+            return (torch.from_numpy(self.mask).float() * 8.0 - 4.0)[None, None]
+
+    rng = np.random.default_rng(123)
+    masks = [np.zeros((224, 224), np.uint8)]
+    for _ in range(9):
+        m = np.zeros((224, 224), np.uint8)
+        kind = rng.integers(0, 3)
+        if kind == 0:                                             # a rectangle anywhere, possibly touching the border
+            y0, x0 = rng.integers(0, 220, 2)
+            m[y0:y0 + rng.integers(1, 120), x0:x0 + rng.integers(1, 120)] = 1
+        elif kind == 1:                                           # a few isolated pixels
+            for _ in range(rng.integers(1, 4)):
+                m[rng.integers(0, 224), rng.integers(0, 224)] = 1
+        else:                                                     # an ellipse
+            yy, xx = np.mgrid[:224, :224]
+            cy, cx, a, b = rng.integers(40, 184), rng.integers(40, 184), rng.integers(5, 80), rng.integers(5, 80)
+            m[((yy - cy) / a) ** 2 + ((xx - cx) / b) ** 2 <= 1.0] = 1
+        masks.append(m)
+    imgs = rng.random((len(masks), 3, 224, 224), dtype=np.float32)
+    for i, m in enumerate(masks):
+        roi, se = proc(Stub(m), torch.from_numpy(imgs[i]), torch.device("cpu"), aug, f"{i}.png")
+        want, box = roi_ref.roi_tensor(imgs[i], m)
+        assert tuple(roi.shape) == (3, 224, 224)
+        assert np.array_equal(np.round(roi.numpy() * 255).astype(np.uint8), np.round(want * 255).astype(np.uint8)), \
+            f"case {i}, box {box}"
+        assert np.abs(roi.numpy() - want).max() < 1e-6
