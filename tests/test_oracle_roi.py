@@ -97,3 +97,22 @@ def test_roi_oracle_matches_live_reference_on_random_masks():
         assert np.array_equal(np.round(roi.numpy() * 255).astype(np.uint8), np.round(want * 255).astype(np.uint8)), \
             f"case {i}, box {box}"
         assert np.abs(roi.numpy() - want).max() < 1e-6
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_import", fromlist=["x"]).available(),
+                    reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("hs,ws", [(512, 512), (300, 400), (224, 224), (97, 131), (1000, 640)])
+def test_frontend_oracle_matches_live_reference_transform(hs, ws):
+    """the reference's CDDataAugmentation.transform in its inference configuration
+    (分类/util/data_utils.py:92-148; test.py:113-116) on a uint8 HWC source of any size == the oracle's Pillow
+    restatement followed by /255 (to_tensor), bit for bit."""
+    from oracle import ref_import
+    _, Aug = ref_import.reference_roi()
+    aug = Aug(img_size=224, ori_size=224, crop=None, p_hflip=0.0, p_vflip=0.0, color_jitter_params=None,
+              long_mask=True)
+    rng = np.random.default_rng(hs * 7 + ws)
+    src = rng.integers(0, 256, (hs, ws, 3), dtype=np.uint8)
+    ref = aug.transform(src).numpy()                                # float32 [3,224,224]
+    u8 = roi_ref.pil_resize_bilinear_u8(src, 224)                  # uint8 [224,224,3]
+    want = np.transpose(u8, (2, 0, 1)).astype(np.float32) / np.float32(255)
+    assert ref.shape == (3, 224, 224) and np.array_equal(ref, want)
