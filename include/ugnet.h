@@ -86,14 +86,6 @@ typedef struct ug_conv_desc {
                                  csrc/conv_multi.cu) */
 } ug_conv_desc;
 
-/* x: fp32 NCHW [B,3,H,W] -> out: bf16 [B*H*W][64], column (r*3+s)*3+c = x[n,c,y+r-1,x+s-1] (0 outside),
- * columns 27..63 zero.  Feeds `inc` (basicUnet.py:409) as a K=64 GEMM; also performs x.float() (:408). */
-typedef struct ug_inc_im2col_desc {
-  const float* x;
-  void* out;
-  int B, H, W;
-} ug_inc_im2col_desc;
-
 /* Max pooling on NHWC bf16 with -inf padding (nn.MaxPool2d(2), basicUnet.py:47; torchvision GoogLeNet
  * maxpool1-4 and Inception branch4 with ceil_mode=True: caller passes the ceil-mode OH/OW). */
 typedef struct ug_pool_desc {
@@ -125,7 +117,7 @@ typedef struct ug_attn_desc {
   int out_stride;
   int B, S, heads;
   float scale;
-  int variant; /* 0 = auto (mma.sync tensor-core kernel for S <= 208), 1 = fp32 CUDA-core kernel */
+  int variant; /* reserved, must be 0.  S <= 208 (the 14x14 bottleneck has S = 196); longer sequences are rejected */
 } ug_attn_desc;
 
 /* AdaptiveAvgPool2d(1)/AdaptiveMaxPool2d(1) of an NHWC bf16 map (basicUnet.py:217-218), stage 1: each of
@@ -166,17 +158,6 @@ typedef struct ug_cropresize_desc {
   unsigned char* out_u8;
   int B, H, W, S;
 } ug_cropresize_desc;
-
-/* u8 [B][S][S][3] -> bf16 [B*(S/2)^2][192] im2col of GoogLeNet conv1 (7x7, stride 2, pad 3) with
- * to_tensor (/255) and torchvision _transform_input applied per channel before zero padding;
- * column (r*7+s)*3+c, columns 147..191 zero.  If `f32` is non-NULL the source is instead a float NCHW
- * [B,3,S,S] image already in [0,1] (GoogLeNetClassifier.forward on an arbitrary float tensor). */
-typedef struct ug_g1_im2col_desc {
-  const unsigned char* u8;
-  void* out;
-  int B, S;
-  const float* f32;
-} ug_g1_im2col_desc;
 
 /* Stem convolution fused with its im2col (no im2col matrix in HBM), N = 64 output channels, folded BN + ReLU:
  *   kind 0: UNet inc (basicUnet.py:409; ConvBatchNorm :25-40): 3x3 s1 p1 on in_f32 = fp32 NCHW [B,3,H,W]
@@ -238,7 +219,7 @@ typedef struct ug_head_desc {
 
 enum {
   UG_OP_CONV = 1,
-  UG_OP_INC_IM2COL = 2,
+  /* 2 and 10 were the stand-alone im2col packs of round 1 (replaced by UG_OP_STEM); the numbers stay retired */
   UG_OP_POOL = 3,
   UG_OP_LAYERNORM = 4,
   UG_OP_ATTN = 5,
@@ -246,7 +227,6 @@ enum {
   UG_OP_GATE = 7,
   UG_OP_BBOX = 8,
   UG_OP_CROPRESIZE = 9,
-  UG_OP_G1_IM2COL = 10,
   UG_OP_HEAD = 11,
   UG_OP_STEM = 12,
   UG_OP_RESIZE = 13,
@@ -258,7 +238,6 @@ typedef struct ug_op {
   int reserved;
   union {
     ug_conv_desc conv;
-    ug_inc_im2col_desc inc;
     ug_pool_desc pool;
     ug_layernorm_desc ln;
     ug_attn_desc attn;
@@ -266,7 +245,6 @@ typedef struct ug_op {
     ug_gate_desc gate;
     ug_bbox_desc bbox;
     ug_cropresize_desc crop;
-    ug_g1_im2col_desc g1;
     ug_head_desc head;
     ug_stem_desc stem;
     ug_resize_desc resize;
@@ -281,30 +259,8 @@ const char* ug_last_error(ug_handle h);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 long long ug_launch_count(ug_handle h);
 
-/* Profiling aid for the persistent conv kernel: runs the op with per-role cycle counters enabled and returns,
- * averaged over CTAs, {producer wait-for-free-slot, producer total, MMA wait-for-data, MMA wait-for-accumulator,
- * epilogue wait-for-accumulator, epilogue wait-for-staging, epilogue math, epilogue store} in SM cycles,
- * plus out[8] = number of CTAs, out[9] = tiles per CTA (rounded up).  Synchronizes the stream. */
-int ug_conv_profile(ug_handle h, const ug_conv_desc* d, void* stream, double* out10);
-/* Same for the multi-issuer 3x3 kernel (variant 5), averages over CTAs: out[0..3] = producer {wait activation slot,
- * wait weight slot, total cycles, total ns (globaltimer)}; out[4..7] / out[8..11] = issuer 0 / 1 {wait activations,
- * wait weights, wait accumulator, total cycles}; out[12..15] = epilogue group 0 {wait accumulator, wait staging,
- * total cycles, tiles}. */
-int ug_conv_profile16(ug_handle h, const ug_conv_desc* d, void* stream, double* out16);
-
-/* Micro-benchmark (sizing aid, not on the product path): average SM cycles per tcgen05.mma (M=128, N, K=16)
- * with n_acc interleaved TMEM accumulators and ctas_per_sm co-resident CTAs. */
-int ug_mma_microbench(ug_handle h, int N, int n_acc, int iters, int ctas_per_sm, int distinct_ab,
-                      double* cycles_per_mma);
-/* Same, with `issuers` (1..4) warps of one CTA each issuing their own chain(s): out2[0] = cycles per MMA of one
- * issuer, out2[1] = launch wall time in ms.  The A descriptor starts a_off bytes (multiple of 128) into its tile
- * with 8-row groups a_sbo bytes apart (0 / 1024 = plain tile; 128..256 / 1280 = the 3x3 halo layout). */
-int ug_mma_microbench2(ug_handle h, int N, int n_acc, int issuers, int iters, int ctas_per_sm, int a_off, int a_sbo,
-                       int acc_stride /* TMEM columns between the issuers' accumulators, 0 = packed */, double* out2);
-
 /* Single ops (validated, tensor maps built per call) — used by the unit parity tests. */
 int ug_conv(ug_handle h, const ug_conv_desc* d, void* stream);
-int ug_inc_im2col(ug_handle h, const ug_inc_im2col_desc* d, void* stream);
 int ug_pool(ug_handle h, const ug_pool_desc* d, void* stream);
 int ug_layernorm(ug_handle h, const ug_layernorm_desc* d, void* stream);
 int ug_attention(ug_handle h, const ug_attn_desc* d, void* stream);
@@ -312,7 +268,6 @@ int ug_chanstats(ug_handle h, const ug_chanstats_desc* d, void* stream);
 int ug_gate(ug_handle h, const ug_gate_desc* d, void* stream);
 int ug_bbox(ug_handle h, const ug_bbox_desc* d, void* stream);
 int ug_cropresize(ug_handle h, const ug_cropresize_desc* d, void* stream);
-int ug_g1_im2col(ug_handle h, const ug_g1_im2col_desc* d, void* stream);
 int ug_head(ug_handle h, const ug_head_desc* d, void* stream);
 int ug_stem(ug_handle h, const ug_stem_desc* d, void* stream);
 int ug_resize_u8(ug_handle h, const ug_resize_desc* d, void* stream);

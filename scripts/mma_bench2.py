@@ -2,6 +2,7 @@
 descriptors, and the TMEM column distance between the accumulators of concurrent chains (csrc/microbench.cu)."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("UG_DEV_LIB", "1")   # profiling hooks live in libugnet_dev.so (include/ugnet_dev.h)
 import torch
 import ugnet_b200  # noqa
 from ugnet_b200 import engine as E

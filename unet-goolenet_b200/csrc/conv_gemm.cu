@@ -732,8 +732,7 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
 }
 
 int conv_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->attr_gemm) {
     cudaError_t e = cudaSuccess;
     const int kMax = 227 * 1024;
     const void* fns[] = {(const void*)conv_gemm_kernel<UG_ACT_NONE>,
@@ -745,7 +744,7 @@ int conv_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
     for (const void* f : fns)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_gemm kernels)");
-    attr_set = true;
+    h->attr_gemm = true;
   }
   if (L->variant == 5) return conv_multi_launch(h, L, s);
   const int act = L->p.act;

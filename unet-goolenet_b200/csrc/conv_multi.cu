@@ -817,8 +817,7 @@ static cudaError_t launch_multi(const ug_engine* h, const ConvLaunch* L, const S
 }
 
 int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->attr_multi) {
     cudaError_t e = cudaSuccess;
     const void* fns[] = {(const void*)conv_multi_kernel<UG_ACT_NONE, 9>, (const void*)conv_multi_kernel<UG_ACT_RELU, 9>,
                          (const void*)conv_multi_kernel<UG_ACT_GELU, 9>, (const void*)conv_multi_kernel<UG_ACT_NONE, 1>,
@@ -826,7 +825,7 @@ int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
     for (const void* f : fns)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_multi_kernel)");
-    attr_set = true;
+    h->attr_multi = true;
   }
   MultiParams hp;
   memset(&hp, 0, sizeof(hp));

@@ -42,7 +42,6 @@ struct ug_program_s {
 
 static int run_simple(ug_engine* h, const ug_op* op, cudaStream_t s) {
   switch (op->kind) {
-    case UG_OP_INC_IM2COL: return launch_inc_im2col(h, &op->u.inc, s);
     case UG_OP_POOL: return launch_pool(h, &op->u.pool, s);
     case UG_OP_LAYERNORM: return launch_layernorm(h, &op->u.ln, s);
     case UG_OP_ATTN: return launch_attention(h, &op->u.attn, s);
@@ -50,7 +49,6 @@ static int run_simple(ug_engine* h, const ug_op* op, cudaStream_t s) {
     case UG_OP_GATE: return launch_gate(h, &op->u.gate, s);
     case UG_OP_BBOX: return launch_bbox(h, &op->u.bbox, s);
     case UG_OP_CROPRESIZE: return launch_cropresize(h, &op->u.crop, s);
-    case UG_OP_G1_IM2COL: return launch_g1_im2col(h, &op->u.g1, s);
     case UG_OP_HEAD: return launch_head(h, &op->u.head, s);
     case UG_OP_RESIZE: return launch_resize_u8(h, &op->u.resize, s);
     case UG_OP_WAVELET: return launch_wavelet(h, &op->u.wavelet, s);
@@ -76,7 +74,6 @@ int ug_create(int device, ug_handle* out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return UG_ECUDA;
   if (prop.major != 10) return UG_EUNSUPPORTED;  // sm_100a only: there is no fallback path
-  if (cudaSetDevice(device) != cudaSuccess) return UG_ECUDA;
   ug_engine* h = new (std::nothrow) ug_engine();
   if (!h) return UG_ENOMEM;
   h->device = device;
@@ -88,6 +85,7 @@ int ug_create(int device, ug_handle* out) {
 
 int ug_destroy(ug_handle h) {
   if (h) {
+    DeviceGuard guard(h);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 2; ++i) {
       if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -103,6 +101,7 @@ long long ug_launch_count(ug_handle h) { return h ? h->launches : 0; }
 
 int ug_conv(ug_handle h, const ug_conv_desc* d, void* stream) {
   if (!h || !d) return UG_EINVAL;
+  DeviceGuard guard(h);
   ConvLaunch L;
   int rc = conv_prepare(h, d, &L);
   if (rc != UG_OK) return rc;
@@ -111,74 +110,19 @@ int ug_conv(ug_handle h, const ug_conv_desc* d, void* stream) {
 
 int ug_stem(ug_handle h, const ug_stem_desc* d, void* stream) {
   if (!h || !d) return UG_EINVAL;
+  DeviceGuard guard(h);
   StemLaunch L;
   int rc = stem_prepare(h, d, &L);
   if (rc != UG_OK) return rc;
   return stem_launch(h, &L, static_cast<cudaStream_t>(stream));
 }
 
-int ug_conv_profile(ug_handle h, const ug_conv_desc* d, void* stream, double* out10) {
-  if (!h || !d || !out10) return UG_EINVAL;
-  ConvLaunch L;
-  int rc = conv_prepare(h, d, &L);
-  if (rc != UG_OK) return rc;
-  if (L.variant != 0) return set_error(h, UG_EINVAL, "conv_profile: persistent variant only");
-  const int ctas = (int)L.grid.x;
-  long long* dev = nullptr;
-  rc = check_cuda(h, cudaMalloc(&dev, sizeof(long long) * 8 * ctas), "cudaMalloc(prof)");
-  if (rc != UG_OK) return rc;
-  cudaMemset(dev, 0, sizeof(long long) * 8 * ctas);
-  L.p.prof = dev;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  rc = conv_launch(h, &L, s);
-  if (rc == UG_OK) rc = check_cuda(h, cudaStreamSynchronize(s), "conv_profile sync");
-  std::vector<long long> host(8 * (size_t)ctas);
-  if (rc == UG_OK) rc = check_cuda(h, cudaMemcpy(host.data(), dev, host.size() * sizeof(long long), cudaMemcpyDeviceToHost), "prof copy");
-  cudaFree(dev);
-  if (rc != UG_OK) return rc;
-  for (int j = 0; j < 8; ++j) {
-    double a = 0;
-    for (int c = 0; c < ctas; ++c) a += (double)host[c * 8 + j];
-    out10[j] = a / ctas;
-  }
-  out10[8] = ctas;
-  out10[9] = (double)((L.p.m_tiles * (long long)L.p.n_tiles + ctas - 1) / ctas);
-  return UG_OK;
-}
-
-int ug_conv_profile16(ug_handle h, const ug_conv_desc* d, void* stream, double* out16) {
-  if (!h || !d || !out16) return UG_EINVAL;
-  ConvLaunch L;
-  int rc = conv_prepare(h, d, &L);
-  if (rc != UG_OK) return rc;
-  if (L.variant != 5) return set_error(h, UG_EINVAL, "conv_profile16: multi-issuer variant only");
-  const int ctas = (int)L.grid.x;
-  long long* dev = nullptr;
-  rc = check_cuda(h, cudaMalloc(&dev, sizeof(long long) * 16 * ctas), "cudaMalloc(prof)");
-  if (rc != UG_OK) return rc;
-  cudaMemset(dev, 0, sizeof(long long) * 16 * ctas);
-  L.p.prof = dev;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  rc = conv_launch(h, &L, s);
-  if (rc == UG_OK) rc = check_cuda(h, cudaStreamSynchronize(s), "conv_profile16 sync");
-  std::vector<long long> host(16 * (size_t)ctas);
-  if (rc == UG_OK) rc = check_cuda(h, cudaMemcpy(host.data(), dev, host.size() * sizeof(long long), cudaMemcpyDeviceToHost), "prof copy");
-  cudaFree(dev);
-  if (rc != UG_OK) return rc;
-  for (int j = 0; j < 16; ++j) {
-    double a = 0;
-    for (int c = 0; c < ctas; ++c) a += (double)host[c * 16 + j];
-    out16[j] = a / ctas;
-  }
-  return UG_OK;
-}
-
 #define UG_SIMPLE_ENTRY(name, type, fn)                         \
   int name(ug_handle h, const type* d, void* stream) {          \
     if (!h || !d) return UG_EINVAL;                             \
+    DeviceGuard guard(h);                                       \
     return fn(h, d, static_cast<cudaStream_t>(stream));         \
   }
-UG_SIMPLE_ENTRY(ug_inc_im2col, ug_inc_im2col_desc, launch_inc_im2col)
 UG_SIMPLE_ENTRY(ug_pool, ug_pool_desc, launch_pool)
 UG_SIMPLE_ENTRY(ug_layernorm, ug_layernorm_desc, launch_layernorm)
 UG_SIMPLE_ENTRY(ug_attention, ug_attn_desc, launch_attention)
@@ -186,7 +130,6 @@ UG_SIMPLE_ENTRY(ug_chanstats, ug_chanstats_desc, launch_chanstats)
 UG_SIMPLE_ENTRY(ug_gate, ug_gate_desc, launch_gate)
 UG_SIMPLE_ENTRY(ug_bbox, ug_bbox_desc, launch_bbox)
 UG_SIMPLE_ENTRY(ug_cropresize, ug_cropresize_desc, launch_cropresize)
-UG_SIMPLE_ENTRY(ug_g1_im2col, ug_g1_im2col_desc, launch_g1_im2col)
 UG_SIMPLE_ENTRY(ug_head, ug_head_desc, launch_head)
 UG_SIMPLE_ENTRY(ug_resize_u8, ug_resize_desc, launch_resize_u8)
 UG_SIMPLE_ENTRY(ug_wavelet, ug_wavelet_desc, launch_wavelet)
@@ -228,6 +171,7 @@ int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out)
 
 int ug_program_run(ug_handle h, ug_program p, void* stream) {
   if (!h || !p) return UG_EINVAL;
+  DeviceGuard guard(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (size_t i = 0; i < p->ops.size(); ++i) {
     const PreparedOp& po = p->ops[i];
@@ -242,6 +186,7 @@ int ug_program_run(ug_handle h, ug_program p, void* stream) {
 
 int ug_program_run_timed(ug_handle h, ug_program p, void* stream, float* ms_per_op) {
   if (!h || !p || !ms_per_op) return UG_EINVAL;
+  DeviceGuard guard(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t n = p->ops.size();
   std::vector<cudaEvent_t> ev(n + 1);
@@ -266,6 +211,7 @@ int ug_program_run_timed(ug_handle h, ug_program p, void* stream, float* ms_per_
 // pure functions of their inputs, so re-running them before the first real run is harmless.
 int ug_program_autotune(ug_handle h, ug_program p, void* stream, int* n_changed) {
   if (!h || !p) return UG_EINVAL;
+  DeviceGuard guard(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaEvent_t e0, e1;
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
@@ -322,6 +268,7 @@ int ug_program_destroy(ug_handle h, ug_program p) {
 int ug_program_run_host(ug_handle h, ug_program p, const ug_copy* h2d, int n_h2d, const ug_copy* d2h, int n_d2h,
                         void* stream) {
   if (!h || !p) return UG_EINVAL;
+  DeviceGuard guard(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (int i = 0; i < n_h2d; ++i) {
     int rc = check_cuda(h, cudaMemcpyAsync(h2d[i].dst, h2d[i].src, h2d[i].bytes, cudaMemcpyHostToDevice, s), "H2D copy");
@@ -339,6 +286,7 @@ int ug_program_run_host(ug_handle h, ug_program p, const ug_copy* h2d, int n_h2d
 int ug_program_run_host_pipelined(ug_handle h, ug_program p, const ug_copy* h2d, void* const* stage0,
                                   void* const* stage1, int n_h2d, const ug_copy* d2h, int n_d2h, void* stream) {
   if (!h || !p || (n_h2d > 0 && (!h2d || !stage0 || !stage1))) return UG_EINVAL;
+  DeviceGuard guard(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!h->copy_stream) {
     int rc = check_cuda(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking), "copy stream");

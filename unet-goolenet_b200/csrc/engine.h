@@ -17,7 +17,28 @@ struct ug_engine {
   cudaEvent_t ev_free[2] = {nullptr, nullptr};  // staging slot consumed (recorded on the compute stream)
   long long pipelined_steps = 0;
   int pdl = 1;  // launch kernels with programmatic stream serialization (UG_PDL=0 turns it off)
+  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the device that is current at the call, so the
+  // "already raised" flags are per handle (= per device), not process-wide
+  bool attr_gemm = false, attr_multi = false, attr_stem = false, attr_attn = false;
+  size_t attr_resize = 0, attr_crop = 0;
 };
+
+namespace ug {
+// Makes the handle's device current for the duration of an entry point and restores the caller's device afterwards
+// (PyTorch and other libraries in the host process own the "current device" state).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const ug_engine* h) {
+    if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = cudaSetDevice(h->device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+}  // namespace ug
 
 namespace ug {
 
@@ -115,7 +136,6 @@ int conv_multi_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* out);
 int stem_launch(ug_engine* h, const StemLaunch* l, cudaStream_t s);
 
-int launch_inc_im2col(ug_engine* h, const ug_inc_im2col_desc* d, cudaStream_t s);
 int launch_pool(ug_engine* h, const ug_pool_desc* d, cudaStream_t s);
 int launch_layernorm(ug_engine* h, const ug_layernorm_desc* d, cudaStream_t s);
 int launch_attention(ug_engine* h, const ug_attn_desc* d, cudaStream_t s);
@@ -123,7 +143,6 @@ int launch_chanstats(ug_engine* h, const ug_chanstats_desc* d, cudaStream_t s);
 int launch_gate(ug_engine* h, const ug_gate_desc* d, cudaStream_t s);
 int launch_bbox(ug_engine* h, const ug_bbox_desc* d, cudaStream_t s);
 int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s);
-int launch_g1_im2col(ug_engine* h, const ug_g1_im2col_desc* d, cudaStream_t s);
 int launch_head(ug_engine* h, const ug_head_desc* d, cudaStream_t s);
 int launch_resize_u8(ug_engine* h, const ug_resize_desc* d, cudaStream_t s);
 int launch_wavelet(ug_engine* h, const ug_wavelet_desc* d, cudaStream_t s);

@@ -1,5 +1,5 @@
 // Memory-bound kernels of the hot path (NHWC bf16 activations, 16-byte vector accesses, coalesced along C):
-// input im2col packs, max pooling, LayerNorm, attention, CoordAtt3 statistics + gate, mask -> bbox,
+// max pooling, LayerNorm, attention, CoordAtt3 statistics + gate, mask -> bbox,
 // PIL-exact crop/resize and the GoogLeNet head.  Reference lines are cited on the descriptors in ugnet.h.
 #include <cfloat>
 #include <cmath>
@@ -10,54 +10,6 @@
 namespace ug {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
-
-// ------------------------------------------------------------------------------------------------
-// inc im2col: fp32 NCHW [B,3,H,W] -> bf16 [B*H*W][64]; one thread per pixel writes one 128-byte row.
-__global__ void __launch_bounds__(256) inc_im2col_kernel(const float* __restrict__ x, uint4* __restrict__ out, int B,
-                                                         int H, int W) {
-  const long long total = (long long)B * H * W;
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total) return;
-  const int px = (int)(p % W);
-  const int py = (int)((p / W) % H);
-  const int n = (int)(p / ((long long)W * H));
-  const float* xn = x + (long long)n * 3 * H * W;
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int iy = py + r - 1;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int ix = px + s - 1;
-      const bool in = (iy >= 0) && (iy < H) && (ix >= 0) && (ix < W);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) v[(r * 3 + s) * 3 + c] = in ? __ldg(xn + ((long long)c * H + iy) * W + ix) : 0.0f;
-    }
-  }
-  uint4* row = out + p * 8;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint4 o;
-    o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-    o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-    o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-    o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-    row[g] = o;
-  }
-  const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-  for (int g = 4; g < 8; ++g) row[g] = z;
-}
-
-int launch_inc_im2col(ug_engine* h, const ug_inc_im2col_desc* d, cudaStream_t s) {
-  if (!d->x || !d->out || d->B <= 0 || d->H <= 0 || d->W <= 0) return set_error(h, UG_EINVAL, "inc_im2col: bad args");
-  const long long total = (long long)d->B * d->H * d->W;
-  inc_im2col_kernel<<<cdiv(total, 256), 256, 0, s>>>(d->x, reinterpret_cast<uint4*>(d->out), d->B, d->H, d->W);
-  h->launches++;
-  return check_cuda(h, cudaGetLastError(), "inc_im2col launch");
-}
 
 // ------------------------------------------------------------------------------------------------
 // max pooling: one thread per (output pixel, 8-channel group); channel groups vary fastest.
@@ -236,107 +188,6 @@ int launch_layernorm(ug_engine* h, const ug_layernorm_desc* d, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// attention: one block per (image, head); K and V of the head staged in shared memory as bf16, one query row
-// per thread, fp32 online softmax over key blocks of 4.  S <= 256, dim_head = 64.
-static constexpr int kAttnThreads = 256;
-
-__global__ void __launch_bounds__(kAttnThreads) attention_kernel(ug_attn_desc d) {
-  pdl_wait();  // programmatic dependent launch: see common.cuh
-  pdl_launch_dependents();
-  extern __shared__ uint4 attn_smem[];
-  uint4* sK = attn_smem;          // [S][8] uint4 (64 bf16 per row)
-  uint4* sV = attn_smem + d.S * 8;
-  const int b = blockIdx.x / d.heads;
-  const int hd = blockIdx.x % d.heads;
-  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(d.q);
-  const __nv_bfloat16* k = reinterpret_cast<const __nv_bfloat16*>(d.k);
-  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(d.v);
-  for (int i = threadIdx.x; i < d.S * 8; i += blockDim.x) {
-    const int row = i >> 3, part = i & 7;
-    const long long tok = (long long)b * d.S + row;
-    sK[i] = *reinterpret_cast<const uint4*>(k + tok * d.k_stride + hd * 64 + part * 8);
-    sV[i] = *reinterpret_cast<const uint4*>(v + tok * d.v_stride + hd * 64 + part * 8);
-  }
-  __syncthreads();
-  const int i = threadIdx.x;
-  if (i >= d.S) return;
-  const long long tok = (long long)b * d.S + i;
-  float qr[64], o[64];
-  const float qs = d.scale * 1.4426950408889634f;  // fold log2(e) so that exp2f can be used
-#pragma unroll
-  for (int p = 0; p < 8; ++p) {
-    const uint4 u = *reinterpret_cast<const uint4*>(q + tok * d.q_stride + hd * 64 + p * 8);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      qr[p * 8 + 2 * j] = bf16_lo(w[j]) * qs;
-      qr[p * 8 + 2 * j + 1] = bf16_hi(w[j]) * qs;
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < 64; ++c) o[c] = 0.0f;
-  float m = -FLT_MAX, l = 0.0f;
-  for (int j0 = 0; j0 < d.S; j0 += 4) {
-    float sc[4];
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = j0 + jj;
-      float acc = 0.0f;
-      if (j < d.S) {
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const uint4 u = sK[j * 8 + p];
-          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            acc += qr[p * 8 + 2 * t] * bf16_lo(w[t]);
-            acc += qr[p * 8 + 2 * t + 1] * bf16_hi(w[t]);
-          }
-        }
-      } else {
-        acc = -FLT_MAX;
-      }
-      sc[jj] = acc;
-    }
-    const float bm = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
-    if (bm > m) {
-      const float corr = exp2f(m - bm);
-      l *= corr;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) o[c] *= corr;
-      m = bm;
-    }
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = j0 + jj;
-      if (j >= d.S) break;
-      const float pj = exp2f(sc[jj] - m);
-      l += pj;
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const uint4 u = sV[j * 8 + p];
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          o[p * 8 + 2 * t] += pj * bf16_lo(w[t]);
-          o[p * 8 + 2 * t + 1] += pj * bf16_hi(w[t]);
-        }
-      }
-    }
-  }
-  const float inv = 1.0f / l;
-  __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(d.out) + tok * d.out_stride + hd * 64;
-#pragma unroll
-  for (int p = 0; p < 8; ++p) {
-    uint4 u;
-    u.x = pack_bf16x2(o[p * 8 + 0] * inv, o[p * 8 + 1] * inv);
-    u.y = pack_bf16x2(o[p * 8 + 2] * inv, o[p * 8 + 3] * inv);
-    u.z = pack_bf16x2(o[p * 8 + 4] * inv, o[p * 8 + 5] * inv);
-    u.w = pack_bf16x2(o[p * 8 + 6] * inv, o[p * 8 + 7] * inv);
-    *reinterpret_cast<uint4*>(orow + p * 8) = u;
-  }
-}
-
 // Tensor-core attention for S <= 208 tokens (the 14x14 bottleneck: S = 196), dim_head = 64.
 // One CTA (4 warps) per (image, head).  K (row-major, padded pitch) and V^T are staged in shared memory; each warp
 // owns 16-query slabs: S = Q K^T with mma.sync m16n8k16 (bf16 in, fp32 accumulate; the matrices are far too
@@ -473,25 +324,18 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(ug_attn_desc d) {
 }
 
 int launch_attention(ug_engine* h, const ug_attn_desc* d, cudaStream_t s) {
-  if (!d->q || !d->k || !d->v || !d->out || d->S <= 0 || d->S > kAttnThreads || d->heads <= 0 || d->B <= 0)
-    return set_error(h, UG_EINVAL, "attention: bad args (S <= 256)");
+  if (!d->q || !d->k || !d->v || !d->out || d->S <= 0 || d->heads <= 0 || d->B <= 0 || d->variant != 0)
+    return set_error(h, UG_EINVAL, "attention: bad args");
+  if (d->S > kAttnSP) return set_error(h, UG_EUNSUPPORTED, "attention: S <= %d tokens (the 14x14 bottleneck has 196)", kAttnSP);
   if (d->q_stride % 8 || d->k_stride % 8 || d->v_stride % 8 || d->out_stride % 8)
     return set_error(h, UG_EINVAL, "attention: row strides must be multiples of 8");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(attention kernels)");
-    attr_set = true;
+  if (!h->attr_attn) {
+    const cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(attention_mma_kernel)");
+    h->attr_attn = true;
   }
-  if (d->S <= kAttnSP && d->variant == 0) {
-    const size_t smem = (size_t)(kAttnSP * kAttnKPitch + kAttnSP * kAttnVPitch) * sizeof(__nv_bfloat16);
-    launch_pdl(h, attention_mma_kernel, d->B * d->heads, 128, smem, s, *d);
-  } else {  // generic fp32 CUDA-core path (S up to 256)
-    const size_t smem = (size_t)d->S * 8 * sizeof(uint4) * 2;
-    launch_pdl(h, attention_kernel, d->B * d->heads, kAttnThreads, smem, s, *d);
-  }
+  const size_t smem = (size_t)(kAttnSP * kAttnKPitch + kAttnSP * kAttnVPitch) * sizeof(__nv_bfloat16);
+  launch_pdl(h, attention_mma_kernel, d->B * d->heads, 128, smem, s, *d);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "attention launch");
 }
@@ -859,12 +703,11 @@ int launch_resize_u8(ug_engine* h, const ug_resize_desc* d, cudaStream_t s) {
   const double scy = std::max((double)d->Hs / d->S, 1.0);
   const int max_rows = std::min(d->Hs, (int)ceil((kRsRows - 1) * ((double)d->Hs / d->S) + 2.0 * scy + 3.0));
   const size_t smem = (size_t)(d->S + kRsRows) * sizeof(RsCoef) + (size_t)max_rows * d->S * 3;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
+  if (smem > h->attr_resize) {
     if (smem > 200 * 1024) return set_error(h, UG_EUNSUPPORTED, "resize: shared memory request %zu too large", smem);
     cudaError_t e = cudaFuncSetAttribute((const void*)resize_u8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(resize_u8_kernel)");
-    attr_smem = smem;
+    h->attr_resize = smem;
   }
   launch_pdl(h, resize_u8_kernel<false>, dim3(cdiv(d->S, kRsRows), d->B), 256, smem, s, *d, max_rows, nullptr, nullptr, 0, 0);
   h->launches++;
@@ -881,83 +724,17 @@ int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s)
   if (2 * (int)ceil(sc) + 1 > kRsMaxTaps) return set_error(h, UG_EUNSUPPORTED, "cropresize: image more than 8x the output");
   const int max_rows = std::min(d->H, (int)ceil((kRsRows - 1) * sc + 2.0 * sc + 3.0));
   const size_t smem = (size_t)(d->S + kRsRows) * sizeof(RsCoef) + (size_t)max_rows * d->S * 3;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
+  if (smem > h->attr_crop) {
     if (smem > 200 * 1024) return set_error(h, UG_EUNSUPPORTED, "cropresize: shared memory request %zu too large", smem);
     cudaError_t e = cudaFuncSetAttribute((const void*)resize_u8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(resize_u8_kernel<crop>)");
-    attr_smem = smem;
+    h->attr_crop = smem;
   }
   ug_resize_desc r;
   r.src = nullptr; r.out_f32 = nullptr; r.out_u8 = d->out_u8; r.B = d->B; r.Hs = d->H; r.Ws = d->W; r.S = d->S;
   launch_pdl(h, resize_u8_kernel<true>, dim3(cdiv(d->S, kRsRows), d->B), 256, smem, s, r, max_rows, d->img, d->boxes, d->H, d->W);
   h->launches++;
   return check_cuda(h, cudaGetLastError(), "cropresize launch");
-}
-
-// ------------------------------------------------------------------------------------------------
-// GoogLeNet conv1 im2col (7x7, stride 2, pad 3) with to_tensor and _transform_input folded in.
-// One block per (image, output row, segment of 56 output pixels): the 7 input rows it needs are staged in shared
-// memory as transformed floats (zero outside the image: padding is applied after the affine), then each thread
-// emits 16-byte groups; column (r*7+s)*3+c of pixel px is smem[r][6*px + s*3 + c], i.e. contiguous in (s,c).
-static constexpr int kG1Seg = 56;
-static constexpr int kG1RowFloats = (2 * kG1Seg + 5) * 3;  // 117 input pixels x 3 channels
-
-__global__ void __launch_bounds__(256) g1_im2col_kernel(const unsigned char* __restrict__ u8,
-                                                        const float* __restrict__ f32, uint4* __restrict__ out,
-                                                        int B, int S) {
-  __shared__ float sm[7][kG1RowFloats];
-  const int OS = S / 2;
-  const int segs = (OS + kG1Seg - 1) / kG1Seg;
-  const int seg = blockIdx.x % segs;
-  const int oy = (blockIdx.x / segs) % OS;
-  const int n = blockIdx.x / (segs * OS);
-  const int ox0 = seg * kG1Seg;
-  const int ix0 = 2 * ox0 - 3;
-  // torchvision GoogLeNet._transform_input: x_c * (std_c / 0.5) + (mean_c - 0.5) / 0.5
-  const float sc[3] = {0.229f / 0.5f, 0.224f / 0.5f, 0.225f / 0.5f};
-  const float sh[3] = {(0.485f - 0.5f) / 0.5f, (0.456f - 0.5f) / 0.5f, (0.406f - 0.5f) / 0.5f};
-  for (int i = threadIdx.x; i < 7 * kG1RowFloats; i += blockDim.x) {
-    const int r = i / kG1RowFloats, e = i - r * kG1RowFloats;
-    const int px = e / 3, c = e - px * 3;
-    const int iy = 2 * oy + r - 3, ix = ix0 + px;
-    float val = 0.0f;
-    if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
-      const float v = f32 ? __ldg(f32 + (((long long)n * 3 + c) * S + iy) * S + ix)
-                          : (float)u8[(((long long)n * S + iy) * S + ix) * 3 + c] / 255.0f;
-      val = v * sc[c] + sh[c];
-    }
-    sm[r][e] = val;
-  }
-  __syncthreads();
-  const int npx = min(kG1Seg, OS - ox0);
-  uint4* orow = out + (((long long)n * OS + oy) * OS + ox0) * 24;
-  for (int t = threadIdx.x; t < npx * 24; t += blockDim.x) {
-    const int px = t / 24, g = t - px * 24;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int col = g * 8 + j;
-      const int r = col / 21, rem = col - r * 21;
-      v[j] = col < 147 ? sm[r][6 * px + rem] : 0.0f;
-    }
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]);
-    o.w = pack_bf16x2(v[6], v[7]);
-    orow[t] = o;
-  }
-}
-
-int launch_g1_im2col(ug_engine* h, const ug_g1_im2col_desc* d, cudaStream_t s) {
-  if ((!d->u8 && !d->f32) || !d->out || d->B <= 0 || d->S <= 0 || d->S % 2)
-    return set_error(h, UG_EINVAL, "g1_im2col: bad args");
-  const int OS = d->S / 2;
-  const int segs = (OS + kG1Seg - 1) / kG1Seg;
-  g1_im2col_kernel<<<d->B * OS * segs, 256, 0, s>>>(d->u8, d->f32, reinterpret_cast<uint4*>(d->out), d->B, d->S);
-  h->launches++;
-  return check_cuda(h, cudaGetLastError(), "g1_im2col launch");
 }
 
 // ------------------------------------------------------------------------------------------------

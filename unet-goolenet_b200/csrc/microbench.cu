@@ -1,7 +1,9 @@
 // Micro-benchmarks used to size the conv kernels (not on the product path):
 //   ug_mma_microbench: cycles per tcgen05.mma (M=128, N, K=16, bf16, both operands in 128B-swizzled smem) when
 //   `n_acc` independent TMEM accumulators are interleaved and `n_cta` CTAs share an SM.
+#include <vector>
 #include "conv_common.cuh"
+#include "../../include/ugnet_dev.h"
 
 namespace ug {
 

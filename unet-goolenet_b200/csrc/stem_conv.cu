@@ -387,8 +387,7 @@ int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* L) {
 }
 
 int stem_launch(ug_engine* h, const StemLaunch* L, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->attr_stem) {
     cudaError_t e = cudaFuncSetAttribute((const void*)stem_conv_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          100 * 1024);
     if (e == cudaSuccess)
@@ -401,7 +400,7 @@ int stem_launch(ug_engine* h, const StemLaunch* L, cudaStream_t s) {
       e = cudaFuncSetAttribute((const void*)stem_conv_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                210 * 1024);
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(stem_conv_kernel)");
-    attr_set = true;
+    h->attr_stem = true;
   }
   cudaError_t le;
   if (L->kind == 0 && L->groups == 6) le = launch_pdl(h, stem_conv_kernel<0, 6>, L->grid, 768, L->smem, s, L->tmB, L->tmO, L->tmP, L->p);

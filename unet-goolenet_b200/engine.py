@@ -10,12 +10,17 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libugnet.so")
+# UG_DEV_LIB=1 (scripts/ only): load libugnet_dev.so = the same objects + the profiling / micro-benchmark hooks of
+# include/ugnet_dev.h, which are not part of the product ABI
+DEV_LIB_PATH = os.path.join(_HERE, "libugnet_dev.so")
+USE_DEV_LIB = os.environ.get("UG_DEV_LIB", "0") == "1"
 
 UG_OK = 0
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 EPI_STORE, EPI_ADD, EPI_GATE, EPI_OUTC = 0, 1, 2, 3
-(OP_CONV, OP_INC_IM2COL, OP_POOL, OP_LAYERNORM, OP_ATTN, OP_CHANSTATS, OP_GATE, OP_BBOX, OP_CROPRESIZE,
- OP_G1_IM2COL, OP_HEAD, OP_STEM, OP_RESIZE, OP_WAVELET) = range(1, 15)
+# (2 and 10 were round 1's stand-alone im2col packs; the numbers stay retired, see ugnet.h)
+OP_CONV, OP_POOL, OP_LAYERNORM, OP_ATTN, OP_CHANSTATS, OP_GATE, OP_BBOX, OP_CROPRESIZE = 1, 3, 4, 5, 6, 7, 8, 9
+OP_HEAD, OP_STEM, OP_RESIZE, OP_WAVELET = 11, 12, 13, 14
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
@@ -28,10 +33,6 @@ class ConvDesc(C.Structure):
                 ("outc_b", _f), ("logits", _vp), ("mask", _vp), ("pool_out", _vp), ("pool_cstride", _i),
                 ("stats_sum", _vp), ("stats_max", _vp), ("stats_tiles", _i),
                 ("TW", _i), ("TH", _i), ("TN", _i), ("BN", _i), ("stages", _i), ("variant", _i)]
-
-
-class IncIm2colDesc(C.Structure):
-    _fields_ = [("x", _vp), ("out", _vp), ("B", _i), ("H", _i), ("W", _i)]
 
 
 class PoolDesc(C.Structure):
@@ -66,10 +67,6 @@ class CropResizeDesc(C.Structure):
     _fields_ = [("img", _vp), ("boxes", _vp), ("out_u8", _vp), ("B", _i), ("H", _i), ("W", _i), ("S", _i)]
 
 
-class G1Im2colDesc(C.Structure):
-    _fields_ = [("u8", _vp), ("out", _vp), ("B", _i), ("S", _i), ("f32", _vp)]
-
-
 class HeadDesc(C.Structure):
     _fields_ = [("inp", _vp), ("w", _vp), ("b", _vp), ("logits", _vp), ("B", _i), ("HW", _i), ("C", _i),
                 ("ncls", _i)]
@@ -91,9 +88,9 @@ class WaveletDesc(C.Structure):
 
 
 class _OpUnion(C.Union):
-    _fields_ = [("conv", ConvDesc), ("inc", IncIm2colDesc), ("pool", PoolDesc), ("ln", LayerNormDesc),
+    _fields_ = [("conv", ConvDesc), ("pool", PoolDesc), ("ln", LayerNormDesc),
                 ("attn", AttnDesc), ("stats", ChanStatsDesc), ("gate", GateDesc), ("bbox", BBoxDesc),
-                ("crop", CropResizeDesc), ("g1", G1Im2colDesc), ("head", HeadDesc), ("stem", StemDesc),
+                ("crop", CropResizeDesc), ("head", HeadDesc), ("stem", StemDesc),
                 ("resize", ResizeDesc), ("wavelet", WaveletDesc)]
 
 
@@ -105,24 +102,24 @@ class Copy(C.Structure):
     _fields_ = [("dst", _vp), ("src", _vp), ("bytes", C.c_size_t)]
 
 
-_KIND_FIELD = {OP_CONV: "conv", OP_INC_IM2COL: "inc", OP_POOL: "pool", OP_LAYERNORM: "ln", OP_ATTN: "attn",
+_KIND_FIELD = {OP_CONV: "conv", OP_POOL: "pool", OP_LAYERNORM: "ln", OP_ATTN: "attn",
                OP_CHANSTATS: "stats", OP_GATE: "gate", OP_BBOX: "bbox", OP_CROPRESIZE: "crop",
-               OP_G1_IM2COL: "g1", OP_HEAD: "head", OP_STEM: "stem", OP_RESIZE: "resize",
-               OP_WAVELET: "wavelet"}
-_DESC_KIND = {ConvDesc: OP_CONV, IncIm2colDesc: OP_INC_IM2COL, PoolDesc: OP_POOL, LayerNormDesc: OP_LAYERNORM,
+               OP_HEAD: "head", OP_STEM: "stem", OP_RESIZE: "resize", OP_WAVELET: "wavelet"}
+_DESC_KIND = {ConvDesc: OP_CONV, PoolDesc: OP_POOL, LayerNormDesc: OP_LAYERNORM,
               AttnDesc: OP_ATTN, ChanStatsDesc: OP_CHANSTATS, GateDesc: OP_GATE, BBoxDesc: OP_BBOX,
-              CropResizeDesc: OP_CROPRESIZE, G1Im2colDesc: OP_G1_IM2COL, HeadDesc: OP_HEAD, StemDesc: OP_STEM,
+              CropResizeDesc: OP_CROPRESIZE, HeadDesc: OP_HEAD, StemDesc: OP_STEM,
               ResizeDesc: OP_RESIZE, WaveletDesc: OP_WAVELET}
-_SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_INC_IM2COL: "ug_inc_im2col", OP_POOL: "ug_pool",
+_SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_POOL: "ug_pool",
                  OP_LAYERNORM: "ug_layernorm", OP_ATTN: "ug_attention", OP_CHANSTATS: "ug_chanstats",
                  OP_GATE: "ug_gate", OP_BBOX: "ug_bbox", OP_CROPRESIZE: "ug_cropresize",
-                 OP_G1_IM2COL: "ug_g1_im2col", OP_HEAD: "ug_head", OP_STEM: "ug_stem",
+                 OP_HEAD: "ug_head", OP_STEM: "ug_stem",
                  OP_RESIZE: "ug_resize_u8", OP_WAVELET: "ug_wavelet"}
 
 EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
-                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_host_pipelined", "ug_program_run_timed", "ug_program_autotune", "ug_conv_profile", "ug_mma_microbench",
-                    "ug_mma_microbench2", "ug_conv_profile16", "ug_wavelet_workspace_bytes"]
+                    "ug_program_destroy", "ug_program_run_host", "ug_program_run_host_pipelined",
+                    "ug_program_run_timed", "ug_program_autotune", "ug_wavelet_workspace_bytes"]
+DEV_SYMBOLS = ["ug_conv_profile", "ug_conv_profile16", "ug_mma_microbench", "ug_mma_microbench2"]
 
 _lib = None
 
@@ -132,10 +129,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+    path = DEV_LIB_PATH if USE_DEV_LIB else LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
                            f"g.build()'` (there is no fallback path)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.ug_version.restype = _i
     lib.ug_create.argtypes = [_i, C.POINTER(_vp)]
     lib.ug_destroy.argtypes = [_vp]
@@ -145,10 +143,11 @@ def load_library():
     lib.ug_launch_count.restype = _ll
     for name in _SINGLE_ENTRY.values():
         getattr(lib, name).argtypes = [_vp, _vp, _vp]
-    lib.ug_mma_microbench.argtypes = [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]
-    lib.ug_mma_microbench2.argtypes = [_vp, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]
-    lib.ug_conv_profile16.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_double)]
-    lib.ug_conv_profile.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_double)]
+    if USE_DEV_LIB:
+        lib.ug_mma_microbench.argtypes = [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]
+        lib.ug_mma_microbench2.argtypes = [_vp, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]
+        lib.ug_conv_profile16.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_double)]
+        lib.ug_conv_profile.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_double)]
     lib.ug_program_create.argtypes = [_vp, _vp, _i, C.POINTER(_vp)]
     lib.ug_program_run.argtypes = [_vp, _vp, _vp]
     lib.ug_program_num_launches.argtypes = [_vp]
@@ -277,7 +276,7 @@ class Engine:
         self._check(fn(self.handle, C.byref(desc), s))
 
     def conv_profile(self, desc, stream=None):
-        """Per-role cycle counters of the persistent conv kernel for one op (see ug_conv_profile)."""
+        """Per-role cycle counters of the persistent conv kernel for one op (ugnet_dev.h; needs UG_DEV_LIB=1)."""
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         out = (C.c_double * 10)()
         self._check(self.lib.ug_conv_profile(self.handle, C.byref(desc), s, out))
@@ -286,7 +285,7 @@ class Engine:
         return dict(zip(keys, list(out)))
 
     def conv_profile16(self, desc, stream=None):
-        """Per-role cycle counters of the multi-issuer 3x3 kernel for one op (see ug_conv_profile16)."""
+        """Per-role cycle counters of the multi-issuer 3x3 kernel for one op (ugnet_dev.h; needs UG_DEV_LIB=1)."""
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         out = (C.c_double * 16)()
         self._check(self.lib.ug_conv_profile16(self.handle, C.byref(desc), s, out))

@@ -25,17 +25,49 @@ class GoogLeNetClassifier(nn.Module):
     def _drop_runner(self, *args, **kwargs):
         self._runner = None
 
+    def invalidate(self):
+        """Forget the packed engine copy of the weights (it is rebuilt on the next forward)."""
+        self._runner = None
+
+    def _fingerprint(self):
+        # (storage address, in-place version counter) of every parameter / buffer: changes on load_state_dict, .to(),
+        # optimizer steps, p.copy_() / p.mul_() under no_grad, and on assigning a new Parameter or submodule.  Writes
+        # through `p.data` bypass the version counter: call invalidate() after those.
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_runner"] = None          # the engine handle / device workspaces are per process, never pickled
+        state.pop("_runner_key", None)
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        runner, self._runner = self._runner, None
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            new.__dict__ = copy.deepcopy({k: v for k, v in self.__dict__.items() if k != "_runner_key"}, memo)
+        finally:
+            self._runner = runner
+        return new
+
     def _apply(self, fn, *args, **kwargs):
         self._runner = None
         return super()._apply(fn, *args, **kwargs)
 
     def runner(self):
+        key = self._fingerprint()
+        if self._runner is not None and getattr(self, "_runner_key", None) != key:
+            self._runner = None          # weights were edited in place since the last pack
         if self._runner is None:
             from .lower import GoogLeNetRunner
             dev = self.googlenet.fc.weight.device
             if dev.type != "cuda":
                 raise RuntimeError("GoogLeNetClassifier runs on the ugnet CUDA engine only: call .to('cuda')")
             self._runner = GoogLeNetRunner(self.state_dict(), dev)
+            self._runner_key = key
         return self._runner
 
     def forward(self, x):

@@ -34,11 +34,41 @@ FUSE_STATS = int(os.environ.get("UG_FUSE_STATS", "0"))
 FUSE_REDUCE = os.environ.get("UG_FUSE_REDUCE", "1") != "0"
 
 
-def _finish(engine, ops, ws):
-    ws["program"] = engine.program(ops)
+# Plans (program + activation workspace) kept per runner: a loader with ragged / varying batch sizes would otherwise
+# pin one multi-GB workspace per distinct size for ever.  Least-recently-used plans beyond this many are dropped.
+MAX_PLANS = int(os.environ.get("UG_MAX_PLANS", "4"))
+
+
+def _finish(engine, ops, ws, keepalive=()):
+    """Compile `ops`.  The op descriptors hold raw device pointers only, so the program itself keeps every workspace
+    tensor they point into alive (`keepalive` = every allocation the builder(s) made while emitting)."""
+    ws["program"] = engine.program(ops, keepalive=list(keepalive))
     if AUTOTUNE:
         ws["tuned_ops"] = ws["program"].autotune()
     return ws
+
+
+class _PlanCache(dict):
+    """dict with least-recently-used eviction (insertion order = recency)."""
+
+    def __init__(self, limit=None, on_evict=None):
+        super().__init__()
+        self.limit = limit or MAX_PLANS
+        self.on_evict = on_evict
+
+    def get_or_build(self, key, build):
+        if key in self:
+            ws = self.pop(key)          # re-insert: most recently used last
+            self[key] = ws
+            return ws
+        ws = build()
+        self[key] = ws
+        while len(self) > self.limit:
+            old = next(iter(self))
+            dropped = self.pop(old)
+            if self.on_evict:
+                self.on_evict(old, dropped)
+        return ws
 
 
 class View:
@@ -58,8 +88,20 @@ class View:
         return View(self.t, C, self.off + off, self.cstride)
 
 
-def _f32(t, dev):
-    return t.detach().to(dev, torch.float32).contiguous()
+def _f32(t, dev=None):
+    """fp32 HOST copy of a state_dict tensor.  All folding / packing runs on the CPU; the packed set is uploaded once
+    (_Builder._upload), so building a runner issues no torch kernels on the GPU (`dev` is ignored, kept for callers)."""
+    return t.detach().to("cpu", torch.float32).contiguous()
+
+
+def _map_tensors(obj, fn):
+    if isinstance(obj, torch.Tensor):
+        return fn(obj)
+    if isinstance(obj, dict):
+        return {k: _map_tensors(v, fn) for k, v in obj.items()}
+    if isinstance(obj, (tuple, list)):
+        return type(obj)(_map_tensors(v, fn) for v in obj)
+    return obj
 
 
 class _Builder:
@@ -70,6 +112,39 @@ class _Builder:
         self.dev = dev
         self.w = {}          # packed tensors kept alive for the lifetime of the runner
         self.engine = E.Engine.get(dev)
+        self._allocs = []    # every workspace tensor handed out by buf() since begin()
+
+    def begin(self):
+        """Start collecting the allocations of one plan (see _finish)."""
+        self._allocs = []
+        return self._allocs
+
+    def _upload(self):
+        """Move the packed weight set (host tensors in self.w) to the device as ONE buffer + one H2D copy; every
+        entry becomes a 256-byte aligned view of it."""
+        slots = []
+
+        def collect(t):
+            slots.append(t)
+            return t
+        _map_tensors(self.w, collect)
+        off, offs = 0, []
+        for t in slots:
+            off = (off + 255) // 256 * 256
+            offs.append(off)
+            off += t.numel() * t.element_size()
+        host = torch.zeros(max(off, 256), dtype=torch.uint8)
+        for t, o in zip(slots, offs):
+            n = t.numel() * t.element_size()
+            host[o:o + n] = t.contiguous().view(-1).view(torch.uint8)
+        self.w_blob = host.to(self.dev)
+        it = iter(zip(slots, offs))
+
+        def view(t):
+            t0, o = next(it)
+            n = t0.numel() * t0.element_size()
+            return self.w_blob[o:o + n].view(t0.dtype).view(t0.shape)
+        self.w = _map_tensors(self.w, view)
 
     # ---- weights -------------------------------------------------------------------------------
     def conv_bn(self, key, conv, bn, eps, bias_key=None):
@@ -135,13 +210,15 @@ class _Builder:
         same tensor (the emission order is deterministic), so several op lists can share one workspace."""
         pool = getattr(self, "_pool", None)
         if pool is None:
-            return torch.empty(shape, device=self.dev, dtype=dtype)
-        i = self._pool_i
-        self._pool_i += 1
-        if i == len(pool):
-            pool.append(torch.empty(shape, device=self.dev, dtype=dtype))
-        t = pool[i]
-        assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, "workspace replay out of sync"
+            t = torch.empty(shape, device=self.dev, dtype=dtype)
+        else:
+            i = self._pool_i
+            self._pool_i += 1
+            if i == len(pool):
+                pool.append(torch.empty(shape, device=self.dev, dtype=dtype))
+            t = pool[i]
+            assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, "workspace replay out of sync"
+        self._allocs.append(t)       # the compiled program keeps it alive (raw pointers in the descriptors)
         return t
 
     def sharing(self, pool):
@@ -169,8 +246,9 @@ class UNetRunner(_Builder):
         assert head in ("seg", "cls")
         self.head = head          # "seg": basicUnet.py forward (logits map); "cls": 分类/nets/basicUnet.py forward
         self.max_batch = max_batch
-        self.plans = {}
+        self.plans = _PlanCache()
         self._pack()
+        self._upload()
 
     # ---------------------------------------------------------------------------- weights
     def _pack(self):
@@ -238,7 +316,7 @@ class UNetRunner(_Builder):
         # matrix (composed in float64, stored fp32); the mean over the 196 tokens is the head kernel's first step
         w1, b1 = sd["fc1.weight"].detach().double().cpu(), sd["fc1.bias"].detach().double().cpu()
         w2, b2 = sd["fc2.weight"].detach().double().cpu(), sd["fc2.bias"].detach().double().cpu()
-        self.w["cls_head"] = ((w2 @ w1).float().contiguous().to(dev), (w2 @ b1 + b2).float().contiguous().to(dev))
+        self.w["cls_head"] = ((w2 @ w1).float().contiguous(), (w2 @ b1 + b2).float().contiguous())
 
     # ---------------------------------------------------------------------------- program
     def _emit_encoder(self, B, ws, ops, io=None):
@@ -269,7 +347,6 @@ class UNetRunner(_Builder):
             if nxt is not None and not FUSE_POOL:
                 ops.append(E.PoolDesc(t1.data_ptr(), cout, nxt.data_ptr(), cout, cout, B, half, half, half // 2,
                                       half // 2, 2, 2, 0))
-            ws.setdefault("keep", []).append(pooled)
             pooled, size = nxt, half
             skips.append(t1)
             ws[blk] = t1
@@ -291,7 +368,6 @@ class UNetRunner(_Builder):
         for src, dst, n in ((X, xn, "x_att_norm"), (M, mn, "m_att_norm")):
             ops.append(E.LayerNormDesc(src.data_ptr(), dst.data_ptr(), self.w[n][0].data_ptr(),
                                        self.w[n][1].data_ptr(), T, 512, 1e-5))
-        ws.setdefault("keep", []).extend([X, M, xn, mn, out0])
         return X, M, xn, mn
 
     def _emit_unet(self, B, ws, ops, io=None):
@@ -353,10 +429,10 @@ class UNetRunner(_Builder):
                 self.conv(ops, self.w[blk + ".conv1_e"], View(skip), geom, View(e1))
                 ops.append(E.ChanStatsDesc(e1.data_ptr(), C, C, B, size * size, S, psum.data_ptr(), pmax.data_ptr()))
             gw = self.w[blk + ".gate"]
-            g, hid = buf(B, C, dtype=torch.float32), buf(B, C // 2, dtype=torch.float32)
+            g, ghid = buf(B, C, dtype=torch.float32), buf(B, C // 2, dtype=torch.float32)
             ops.append(E.GateDesc(psum.data_ptr(), pmax.data_ptr(), gw["w1"].data_ptr(), gw["b1"].data_ptr(),
                                   gw["w2"].data_ptr(), gw["b2"].data_ptr(), gw["w3"].data_ptr(), gw["b3"].data_ptr(),
-                                  g.data_ptr(), B, C, size * size, S, hid.data_ptr()))
+                                  g.data_ptr(), B, C, size * size, S, ghid.data_ptr()))
             self.conv(ops, self.w[blk + ".conv2_e"], View(cat, C, 0), geom, View(cat, C, C), mode=E.EPI_GATE,
                       add=View(e1), add_bstride=size * size * C, gate=g)
             n0 = buf(B, size, size, cout)
@@ -371,8 +447,6 @@ class UNetRunner(_Builder):
                 prev = n1
                 ws[blk] = n1
             psize = size
-            ws.setdefault("keep", []).extend([cat, e1, psum, pmax, g, hid, n0])
-        ws.setdefault("keep", []).extend([X, M, xn, mn, qkv, att, m1, cq, ckv, catt, m_in, mln, hid, out0])
 
     def _emit_cls(self, B, ws, ops, io=None):
         """Classifier-head forward (分类/nets/basicUnet.py:406-436): encoder, the `x` stream of the TransformerDecoder
@@ -410,24 +484,22 @@ class UNetRunner(_Builder):
         ws["cl_out"] = io["cl_out"] if io and "cl_out" in io else torch.empty((B, 1), device=self.dev)
         hw, hb = self.w["cls_head"]
         ops.append(E.HeadDesc(tok.data_ptr(), hw.data_ptr(), hb.data_ptr(), ws["cl_out"].data_ptr(), B, 196, 512, 1))
-        ws.setdefault("keep", []).extend([qkv, att, x1, cq, ckv, catt, x_in, xln, hid] + skips)
 
     def _emit_bbox(self, B, ws, ops, padding=30, boxes=None):
         ws["boxes"] = boxes if boxes is not None else torch.empty((B, 4), device=self.dev, dtype=torch.int32)
         ops.append(E.BBoxDesc(ws["mask"].data_ptr(), ws["boxes"].data_ptr(), B, IMG, IMG, padding))
 
     def plan(self, B, padding=30):
-        key = (B, padding)
-        if key not in self.plans:
+        def build():
             ws, ops = {}, []
+            allocs = self.begin()
             if self.head == "cls":
                 self._emit_cls(B, ws, ops)
             else:
                 self._emit_unet(B, ws, ops)
                 self._emit_bbox(B, ws, ops, padding)
-            _finish(self.engine, ops, ws)
-            self.plans[key] = ws
-        return self.plans[key]
+            return _finish(self.engine, ops, ws, allocs + [v for v in ws.values() if isinstance(v, torch.Tensor)])
+        return self.plans.get_or_build((B, padding), build)
 
     @torch.no_grad()
     def forward(self, x, with_mask_boxes=False, padding=30):
@@ -474,8 +546,9 @@ class GoogLeNetRunner(_Builder):
     def __init__(self, sd, dev, max_batch=256, prefix="googlenet."):
         super().__init__({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, torch.device(dev))
         self.max_batch = max_batch
-        self.plans = {}
+        self.plans = _PlanCache()
         self._pack()
+        self._upload()
 
     def _pack(self):
         sd, dev = self.sd, self.dev
@@ -485,7 +558,7 @@ class GoogLeNetRunner(_Builder):
         scale, bias = pack.fold_bn(None, _f32(sd["conv1.bn.weight"], dev), _f32(sd["conv1.bn.bias"], dev),
                                    _f32(sd["conv1.bn.running_mean"], dev), _f32(sd["conv1.bn.running_var"], dev),
                                    self.EPS)
-        gemm = torch.zeros(64, 7, 22, device=dev)
+        gemm = torch.zeros(64, 7, 22)
         gemm[:, :, :21] = wt.permute(0, 2, 3, 1).reshape(64, 7, 21)
         self.w["conv1"] = dict(w=pack.pack_linear_weight(gemm.reshape(64, 154), 64), scale=scale, bias=bias, N=64,
                                Cin=192, R=1, BN=64, algo_k=147)
@@ -520,14 +593,12 @@ class GoogLeNetRunner(_Builder):
         self.conv(ops, self.w["conv3"], View(c2), (B, 56, 56), View(c3))
         cur = buf(B, 28, 28, 192)
         ops.append(E.PoolDesc(c3.data_ptr(), 192, cur.data_ptr(), 192, 192, B, 56, 56, 28, 28, 3, 2, 0))
-        keep = [c1, p1, c2, c3, cur]
         size = 28
         for name, (cin, c1x1, c3r, c3x3, c5r, c5x5, pp, sp) in _INCEPTION_CFG.items():
             if sp != size:                                           # maxpool3 (3,s2,ceil) / maxpool4 (2,s2,ceil)
                 k = 3 if sp == 14 else 2
                 nxt = buf(B, sp, sp, cin)
                 ops.append(E.PoolDesc(cur.data_ptr(), cin, nxt.data_ptr(), cin, cin, B, size, size, sp, sp, k, 2, 0))
-                keep.append(nxt)
                 cur, size = nxt, sp
             cout = c1x1 + c3x3 + c5x5 + pp
             out = buf(B, sp, sp, cout)                               # torch.cat([b1,b2,b3,b4],1) target
@@ -539,39 +610,34 @@ class GoogLeNetRunner(_Builder):
                 r23 = buf(B, sp, sp, c3r + c5r)
                 self.conv(ops, self.w[name + ".reduce"], xin, flat, View(r23))
                 r2, r3 = View(r23, c3r, 0), View(r23, c5r, c3r)
-                keep.append(r23)
             else:
                 t2, t3 = buf(B, sp, sp, c3r), buf(B, sp, sp, c5r)
                 self.conv(ops, self.w[name + ".branch2.0"], xin, flat, View(t2))
                 self.conv(ops, self.w[name + ".branch3.0"], xin, flat, View(t3))
                 r2, r3 = View(t2), View(t3)
-                keep += [t2, t3]
             self.conv(ops, self.w[name + ".branch2.1"], r2, geom, View(out, c3x3, c1x1))
             self.conv(ops, self.w[name + ".branch3.1"], r3, geom, View(out, c5x5, c1x1 + c3x3))
             pl = buf(B, sp, sp, cin)
             ops.append(E.PoolDesc(cur.data_ptr(), cin, pl.data_ptr(), cin, cin, B, sp, sp, sp, sp, 3, 1, 1))
             self.conv(ops, self.w[name + ".branch4.1"], View(pl), flat, View(out, pp, c1x1 + c3x3 + c5x5))
-            keep += [out, pl]
             ws[name] = out
             cur = out
         ws["cls_logits"] = buf(B, self.ncls, dtype=torch.float32)
         ops.append(E.HeadDesc(cur.data_ptr(), self.w["fc"][0].data_ptr(), self.w["fc"][1].data_ptr(),
                               ws["cls_logits"].data_ptr(), B, 49, 1024, self.ncls))
-        ws.setdefault("keep", []).extend(keep)
 
     def plan(self, B, kind="f32"):
-        key = (B, kind)
-        if key not in self.plans:
+        def build():
             ws, ops = {}, []
+            allocs = self.begin()
             if kind == "u8":
                 ws["in"] = self.buf(B, IMG, IMG, 3, dtype=torch.uint8)
                 self._emit_googlenet(B, ws, ops, u8=ws["in"])
             else:
                 ws["in"] = self.buf(B, 3, IMG, IMG, dtype=torch.float32)
                 self._emit_googlenet(B, ws, ops, f32=ws["in"])
-            _finish(self.engine, ops, ws)
-            self.plans[key] = ws
-        return self.plans[key]
+            return _finish(self.engine, ops, ws, allocs)
+        return self.plans.get_or_build((B, kind), build)
 
     def _run(self, x, kind):
         if x.device.type != "cuda":
@@ -615,19 +681,27 @@ class PipelineRunner:
         self.micro_batch = micro_batch
         self.cls_batch = max(cls_batch, micro_batch) // micro_batch * micro_batch
         self.padding = padding
-        self.plans = {}
+        self.plans = _PlanCache(on_evict=self._evicted)
         self._pools = {}
+
+    def _evicted(self, key, ws):
+        """Drop the shared UNet workspace of a micro-batch size no remaining plan uses."""
+        live = {w["mb"] for w in self.plans.values()}
+        for mb in [m for m in self._pools if m not in live]:
+            del self._pools[mb]
 
     def plan(self, B, source=None):
         """Program for a batch of B images; B must be <= micro_batch or a multiple of it.  With `source` =
         (Hs, Ws) the program starts with the device front-end (PIL-exact resize of uint8 HWC sources + to_tensor,
         util/data_utils.py) writing the UNet input, and `ws["src_u8"]` is the program's input buffer."""
         key = B if source is None else (B,) + tuple(source)
-        if key not in self.plans:
+
+        def build():
             mb = min(B, self.micro_batch)
             assert B % mb == 0
             dev = self.dev
-            ws = dict(x_in=torch.empty((B, 3, IMG, IMG), device=dev),
+            ua, ga = self.unet.begin(), self.gnet.begin()
+            ws = dict(mb=mb, x_in=torch.empty((B, 3, IMG, IMG), device=dev),
                       logits=torch.empty((B, 1, IMG, IMG), device=dev),
                       mask=torch.empty((B, IMG, IMG), device=dev, dtype=torch.uint8),
                       boxes=torch.empty((B, 4), device=dev, dtype=torch.int32),
@@ -649,9 +723,8 @@ class PipelineRunner:
                                             ws["u8"][sl].data_ptr(), mb, IMG, IMG, IMG))
                 ws.setdefault("sub", []).append(sub)
             self.gnet._emit_googlenet(B, ws, ops, u8=ws["u8"])
-            _finish(self.engine, ops, ws)
-            self.plans[key] = ws
-        return self.plans[key]
+            return _finish(self.engine, ops, ws, ua + ga + [v for v in ws.values() if isinstance(v, torch.Tensor)])
+        return self.plans.get_or_build(key, build)
 
     def _chunks(self, n):
         """Split n images into plan-able chunks: multiples of micro_batch up to cls_batch, then the remainder."""

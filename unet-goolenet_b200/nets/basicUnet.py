@@ -83,22 +83,56 @@ class UNetTaskAligWeight(nn.Module):  # basicUnet.py:369-437
     def _drop_runner(self, *args, **kwargs):
         self._runner = None
 
+    def invalidate(self):
+        """Forget the packed engine copy of the weights (it is rebuilt on the next forward)."""
+        self._runner = None
+
+    def _fingerprint(self):
+        # (storage address, in-place version counter) of every parameter / buffer: changes on load_state_dict, .to(),
+        # optimizer steps, p.copy_() / p.mul_() under no_grad, and on assigning a new Parameter or submodule.  Writes
+        # through `p.data` bypass the version counter: call invalidate() after those.
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_runner"] = None          # the engine handle / device workspaces are per process, never pickled
+        state.pop("_runner_key", None)
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        runner, self._runner = self._runner, None
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            new.__dict__ = copy.deepcopy({k: v for k, v in self.__dict__.items() if k != "_runner_key"}, memo)
+        finally:
+            self._runner = runner
+        return new
+
     def _apply(self, fn, *args, **kwargs):
         self._runner = None  # .to()/.cuda() move parameters: re-pack lazily
         return super()._apply(fn, *args, **kwargs)
 
+    HEAD = "seg"   # "cls" in the classifier-head variant (nets/basicUnet_cls.py)
+
     def runner(self):
         """The engine-side compiled network (packed weights + per-batch programs)."""
+        key = self._fingerprint()
+        if self._runner is not None and getattr(self, "_runner_key", None) != key:
+            self._runner = None          # weights were edited in place since the last pack
         if self._runner is None:
             from ..lower import UNetRunner
             dev = self.outc.weight.device
             if dev.type != "cuda":
                 raise RuntimeError("UNetTaskAligWeight runs on the ugnet CUDA engine only: call .to('cuda') "
                                    "(there is no CPU path)")
-            if self.n_channels != 3 or self.n_classes != 1:
+            if self.n_channels != 3 or (self.HEAD == "seg" and self.n_classes != 1):
                 raise NotImplementedError("the engine lowers UNetTaskAligWeight(3, 1), the configuration every "
                                           "reference entry point instantiates")
-            self._runner = UNetRunner(self.state_dict(), dev)
+            self._runner = UNetRunner(self.state_dict(), dev, head=self.HEAD)
+            self._runner_key = key
         return self._runner
 
     def forward(self, x):

@@ -12,17 +12,7 @@ from .basicUnet import UNetTaskAligWeight as _SegShell
 
 
 class UNetTaskAligWeight(_SegShell):  # 分类/nets/basicUnet.py:369
-    def runner(self):
-        if self._runner is None:
-            from ..lower import UNetRunner
-            dev = self.outc.weight.device
-            if dev.type != "cuda":
-                raise RuntimeError("UNetTaskAligWeight runs on the ugnet CUDA engine only: call .to('cuda') "
-                                   "(there is no CPU path)")
-            if self.n_channels != 3:
-                raise NotImplementedError("the engine lowers the 3-channel network every reference entry point builds")
-            self._runner = UNetRunner(self.state_dict(), dev, head="cls")
-        return self._runner
+    HEAD = "cls"   # UNetRunner(head="cls"): encoder + x token stream + avgpool2/fc1/fc2 (lower._emit_cls)
 
     def forward(self, x):
         """-> cl_out fp32 [B, 1] (分类/nets/basicUnet.py:432-436)."""
