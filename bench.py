@@ -5,12 +5,16 @@
   python bench.py --impl reference ...                      (the reference's CPU arithmetic: the oracle port)
 
 A step is one pass of the whole path over this rank's batch of synthetic 224x224 images (default 256 per GPU,
-run as micro-batches of 128 — BASELINE.json config 4/5: 512 images on 2 GPUs, 2048 on 8), followed for N>1 by
-the path's only collective: an NCCL all-gather of masks and class logits.  Weak scaling: per-GPU work is fixed.
+run as micro-batches of 128 — BASELINE.json configs[3]/[4]: 512 images on 2 GPUs, 2048 on 8), followed for N>1 by
+the path's only collective: an NCCL gather of masks, boxes and class logits to rank 0 (double-buffered, on a side
+stream, so it overlaps the next step).  Default: weak scaling (per-GPU work fixed); `--scaling strong` fixes the
+GLOBAL batch (BASELINE configs[3]: 512) and gives every GPU global/N images.  Weights are the briefly-trained fixture
+(oracle/fixtures.py; SURVEY fact 5: random-init weights make every mask all-ones and the ROI stage trivial), and the
+contract's parity gates are evaluated against the oracle on this rank's first images BEFORE the timed region.
 
   value     device-timed whole-job images/s, inputs already resident in HBM (staging buffer of the program)
-  e2e       same metric through the C-ABI host entry (ug_program_run_host): pinned host inputs copied H2D and
-            masks/boxes/logits copied D2H inside the timed region, every step
+  e2e       same metric through the C-ABI host entry (ug_program_run_host_pipelined, direct form): pinned host inputs
+            copied H2D and masks/boxes/logits copied D2H inside the timed region, every step
   roofline  tensor-pipe roofline of the dominant kernel (conv_gemm_kernel): algorithmic conv/linear FLOPs per
             step / summed device time of its launches (event pair per launch, measured live in a separate
             profiling pass of the same program), against MEASURED_PEAKS.json bf16_tflops_sustained
@@ -126,8 +130,7 @@ def run_reference_arm(args, rank):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sample = args.cpu_sample
-    usd = fixtures.procedural_state(fixtures.unet_template(), seed=7)
-    gsd = fixtures.procedural_state(fixtures.googlenet_template(), seed=11)
+    usd, gsd = fixtures.trained_unet_state(), fixtures.trained_googlenet_state()   # same weights as the GPU arm
     imgs, _, _ = fixtures.synth_images(sample, seed=1234)
     x = torch.from_numpy(imgs)
 
@@ -162,8 +165,7 @@ def cpu_baseline(sample, budget_s=20.0):
     from oracle import fixtures, googlenet_ref, roi_ref, unet_ref
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    usd = fixtures.procedural_state(fixtures.unet_template(), seed=7)
-    gsd = fixtures.procedural_state(fixtures.googlenet_template(), seed=11)
+    usd, gsd = fixtures.trained_unet_state(), fixtures.trained_googlenet_state()   # same weights as the GPU arm
     imgs, _, _ = fixtures.synth_images(sample, seed=1234)
     x = torch.from_numpy(imgs)
 
@@ -194,8 +196,8 @@ def gpu_eager_yardstick(dev, iters=3):
     reference does on the host).  images/s = 1 / (t_unet / 64 + t_googlenet / 256)."""
     import torch
     from oracle import fixtures, googlenet_ref, unet_ref
-    usd = {k: v.to(dev) for k, v in fixtures.procedural_state(fixtures.unet_template(), seed=7).items()}
-    gsd = {k: v.to(dev) for k, v in fixtures.procedural_state(fixtures.googlenet_template(), seed=11).items()}
+    usd = {k: v.to(dev) for k, v in fixtures.trained_unet_state().items()}
+    gsd = {k: v.to(dev) for k, v in fixtures.trained_googlenet_state().items()}
     xu = torch.rand((64, 3, 224, 224), device=dev)
     xg = torch.rand((256, 3, 224, 224), device=dev)
     out = {}
@@ -230,27 +232,45 @@ def gpu_eager_yardstick(dev, iters=3):
     return out
 
 
+def _fixture_weights():
+    """Briefly-trained reference-format state_dicts (cached under tests/_cache, regenerated on this GPU if absent)."""
+    import torch
+    from oracle import fixtures
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    return fixtures.trained_unet_state(device=dev), fixtures.trained_googlenet_state(device=dev)
+
+
 def run_stage_alone(args, dev, rank):
     """BASELINE configs[1] (UNet forward, batch 64) / configs[2] (GoogLeNet forward on ROI crops, batch 256) on one GPU:
     device-resident inputs, CUDA-event timing, one JSON line (same keys as the headline line where they apply)."""
     import torch
-    from ugnet_b200 import engine as E
-    from ugnet_b200.googlenet import GoogLeNetClassifier
+    from oracle import gates
     from ugnet_b200.lower import GoogLeNetRunner, UNetRunner
-    from ugnet_b200.nets import UNetTaskAligWeight
-    torch.manual_seed(1234)
+    usd, gsd = _fixture_weights()
     B = args.batch if args.batch != 256 or args.workload == "googlenet" else 64
+    imgs = synth_batch(B, 1234, dev)
     if args.workload == "unet":
-        runner = UNetRunner(UNetTaskAligWeight(3, 1).state_dict(), dev, max_batch=B)
+        runner = UNetRunner(usd, dev, max_batch=B)
         ws = runner.plan(B)
-        ws["x_in"].copy_(synth_batch(B, 1234, dev))
+        ws["x_in"].copy_(imgs)
         name, flop_img = f"UNet forward + mask + bbox, batch {B} (BASELINE.json configs[1])", 78.54e9
     else:
-        runner = GoogLeNetRunner(GoogLeNetClassifier(6).state_dict(), dev, max_batch=B)
+        runner = GoogLeNetRunner(gsd, dev, max_batch=B)
         ws = runner.plan(B, "u8")
-        ws["in"].copy_((synth_batch(B, 1234, dev) * 255).to(torch.uint8).permute(0, 2, 3, 1))
+        ws["in"].copy_((imgs * 255).to(torch.uint8).permute(0, 2, 3, 1))
         name, flop_img = f"GoogLeNet forward on uint8 ROI crops, batch {B} (BASELINE.json configs[2])", 2.995e9
     prog = ws["program"]
+    prog.run()
+    torch.cuda.synchronize()
+    if args.workload == "unet":
+        parity, _ = gates.unet_gates(usd, imgs.cpu().numpy(), ws["mask"].cpu().numpy(), ws["boxes"].cpu().numpy(), dev,
+                                     seg_logits=ws["logits"])
+    else:
+        ref = gates.oracle_googlenet_logits(gsd, ws["in"].permute(0, 3, 1, 2).float().div(255).cpu(), dev)
+        rel = gates.logit_rel_err(ws["cls_logits"].cpu(), ref)
+        parity = {"images": B, "cls_logit_rel_err_max": float(rel.max()),
+                  "cls_argmax_equal": int((ws["cls_logits"].cpu().argmax(1) == ref.argmax(1)).sum()),
+                  "ok": bool(rel.max() <= gates.LOGIT_REL)}
     W = max(3, args.warmup)
     for _ in range(W):
         prog.run()
@@ -269,7 +289,7 @@ def run_stage_alone(args, dev, rank):
                           "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
                           "dtype": "bf16", "data": "synthetic", "config": {"workload": name, "batch": B},
                           "gpu_launches": runner.engine.launch_count - l0,
-                          "model_tflops": v * flop_img / 1e12}))
+                          "model_tflops": v * flop_img / 1e12, "parity": parity}))
 
 
 def main():
@@ -278,7 +298,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch images per GPU; strong: --global-batch images in total, split over the GPUs "
+                         "(BASELINE.json configs[3]: 512 over 2/4/8)")
+    ap.add_argument("--global-batch", type=int, default=512)
     ap.add_argument("--micro-batch", type=int, default=128, help="UNet micro-batch (images sharing one workspace)")
     ap.add_argument("--source-size", type=int, default=0,
                     help="N > 0: inputs are uint8 HWC NxN source images resized on the device by the front-end op "
@@ -289,8 +313,12 @@ def main():
                          "ROI crops (configs[2]: 256).  The stage-alone lines are parity/throughput cases, not the headline")
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--yardstick", action="store_true",
-                    help="also time the reference arithmetic under PyTorch eager on the GPU (fp32, bf16+channels_last)")
+    ap.add_argument("--parity-images", type=int, default=128, help="images checked against the oracle before timing")
+    ap.add_argument("--no-yardstick", action="store_true",
+                    help="skip the PyTorch-eager timing of the reference arithmetic on this GPU (N=1 only)")
+    ap.add_argument("--yardstick", action="store_true", help=argparse.SUPPRESS)   # (round-1 flag: now the default)
+    ap.add_argument("--collective", default="gather", choices=["gather", "all_gather"],
+                    help="gather: masks/boxes/logits to rank 0 on a side stream (default); all_gather: round 1's form")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -303,9 +331,9 @@ def main():
     import torch
     import torch.distributed as dist
     import ugnet_b200  # noqa: F401
-    from ugnet_b200.googlenet import GoogLeNetClassifier
+    from oracle import gates                                   # the checker of the in-run parity gates
+    from ugnet_b200.dist import RootGather
     from ugnet_b200.lower import PipelineRunner
-    from ugnet_b200.nets import UNetTaskAligWeight
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the engine has no CPU path")
@@ -316,36 +344,75 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
-    PB, MB = args.batch, args.micro_batch
+    if args.scaling == "strong":
+        assert args.global_batch % world == 0
+        PB = args.global_batch // world
+    else:
+        PB = args.batch
+    MB = min(args.micro_batch, PB)
     assert PB % MB == 0
 
-    torch.manual_seed(1234)                                   # identical random-init replica on every rank
-    unet_sd = UNetTaskAligWeight(3, 1).state_dict()
-    gnet_sd = GoogLeNetClassifier(6).state_dict()
+    unet_sd, gnet_sd = _fixture_weights()                     # identical trained-like replica on every rank
     pipe = PipelineRunner(unet_sd, gnet_sd, dev, micro_batch=MB, cls_batch=PB)
     eng = pipe.engine
     SRC = args.source_size
-    # one program per step: (front-end resize,) PB/MB UNet micro-batches + one GoogLeNet pass over PB crops
-    ws = pipe.plan(PB, source=(SRC, SRC) if SRC else None)
-    prog = ws["program"]
+    src = (SRC, SRC) if SRC else None
+    # one program per step: (front-end resize,) PB/MB UNet micro-batches + one GoogLeNet pass over PB crops; two slots
+    # (own input/output buffers over the same workspaces) for the host-fed loop
+    plans = [pipe.plan(PB, source=src, slot=k) for k in (0, 1)]
+    ws, prog = plans[0], plans[0]["program"]
     imgs = synth_batch(PB, 1234 + rank, dev)                  # this rank's slice of the global batch
     if SRC:                                                   # uint8 HWC sources, resized on the device every step
         big = torch.nn.functional.interpolate(imgs, size=(SRC, SRC), mode="bilinear", align_corners=False)
         src_u8 = (big * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
-        ws["src_u8"].copy_(src_u8)
         in_key, in_host_src = "src_u8", src_u8
     else:
-        ws["x_in"].copy_(imgs)                                # HBM-resident input of the program
         in_key, in_host_src = "x_in", imgs
+    for w_ in plans:
+        w_[in_key].copy_(in_host_src)                         # HBM-resident input of the program
+
+    # ---- correctness gates, same run, before any timing: engine vs the fp32 oracle on this GPU
+    prog.run()
+    torch.cuda.synchronize()
+    parity = None
+    if rank == 0:
+        n = min(args.parity_images, PB)
+        x224 = ws["x_in"][:n].cpu().numpy()                   # what the UNet saw (front-end output when --source-size)
+        parity = gates.pipeline_gates(unet_sd, gnet_sd, x224, ws["mask"][:n], ws["boxes"][:n], ws["cls_logits"][:n],
+                                      dev, crops_u8=ws["u8"][:n], seg_logits=ws["logits"][:n])
+        if SRC:
+            k = min(8, n)
+            parity["front_end_bit_exact_vs_pil"] = bool(
+                (gates.pil_front_end(src_u8[:k].cpu().numpy()) == x224[:k]).all())
+            parity["ok"] = bool(parity["ok"] and parity["front_end_bit_exact_vs_pil"])
+        plans[1]["program"].run()                             # the second slot computes the same thing
+        torch.cuda.synchronize()
+        parity["slots_identical"] = bool(torch.equal(plans[1]["mask"], ws["mask"]) and
+                                         torch.equal(plans[1]["cls_logits"], ws["cls_logits"]))
+        parity["ok"] = bool(parity["ok"] and parity["slots_identical"])
+        if not parity["ok"]:
+            print("bench.py: PARITY GATE FAILED " + json.dumps(parity), file=sys.stderr, flush=True)
+
+    gather = None
     if world > 1:
-        g_masks = torch.empty((world * PB, 224, 224), dtype=torch.uint8, device=dev)
-        g_cls = torch.empty((world * PB, 6), dtype=torch.float32, device=dev)
+        if args.collective == "gather":
+            gather = RootGather([ws["mask"], ws["boxes"], ws["cls_logits"]], root=0)
+        else:
+            g_masks = torch.empty((world * PB, 224, 224), dtype=torch.uint8, device=dev)
+            g_cls = torch.empty((world * PB, 6), dtype=torch.float32, device=dev)
+
+    def collective(w_):
+        if world == 1:
+            return
+        if gather is not None:                                 # the path's only collective, off the compute stream
+            gather.submit([w_["mask"], w_["boxes"], w_["cls_logits"]])
+        else:
+            dist.all_gather_into_tensor(g_masks, w_["mask"])
+            dist.all_gather_into_tensor(g_cls, w_["cls_logits"])
 
     def step_device():
         prog.run()
-        if world > 1:                                          # the path's only collective (NVLink all-gather)
-            dist.all_gather_into_tensor(g_masks, ws["mask"])
-            dist.all_gather_into_tensor(g_cls, ws["cls_logits"])
+        collective(ws)
 
     def timed(fn, steps):
         torch.cuda.synchronize()
@@ -355,14 +422,21 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if gather is not None:
+            gather.wait()                                      # the last step's gather is inside the timed region
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        own = e0.elapsed_time(e1)
+        ms = torch.tensor([own], device=dev)
+        per_rank = [own]
         if world > 1:
+            allms = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(allms, ms)
+            per_rank = [t.item() for t in allms]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+        return ms.item(), per_rank
 
     for _ in range(W):
         step_device()
@@ -370,10 +444,16 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = eng.launch_count
-    ms = timed(step_device, args.steps)
+    ms, per_rank_ms = timed(step_device, args.steps)
     launches = eng.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
     value = world * PB * args.steps / (ms / 1e3)
+    gathered_ok = None
+    if gather is not None:
+        res = gather.results()
+        if rank == 0:                                          # the root's own slice of the gathered result is its own output
+            gathered_ok = bool(torch.equal(res[0][:PB], ws["mask"]) and torch.equal(res[2][:PB], ws["cls_logits"]) and
+                               res[0].shape[0] == world * PB)
 
     # ---- end to end through the C-ABI host entry: pinned host buffers, H2D + D2H every step
     h_in = torch.empty(tuple(in_host_src.shape), dtype=in_host_src.dtype).pin_memory()
@@ -381,17 +461,24 @@ def main():
     h_masks = torch.empty((PB, 224, 224), dtype=torch.uint8).pin_memory()
     h_boxes = torch.empty((PB, 4), dtype=torch.int32).pin_memory()
     h_cls = torch.empty((PB, 6), dtype=torch.float32).pin_memory()
+    e2e_i = [0]
 
     def step_e2e():
-        # double-buffered serving loop: this step's H2D (pinned host -> device staging, copy stream) overlaps the
-        # kernels of the previous step; D2H of masks / boxes / logits every step; `timed` synchronizes at the end
-        prog.run_host_pipelined([(ws[in_key], h_in)],
-                                [(h_masks, ws["mask"]), (h_boxes, ws["boxes"]), (h_cls, ws["cls_logits"])])
+        # double-buffered serving loop: this step's H2D goes straight into the input buffer of program slot i&1 on the
+        # copy stream and overlaps the kernels of the previous step (other slot); D2H of masks / boxes / logits every
+        # step; `timed` synchronizes at the end
+        w_ = plans[e2e_i[0] & 1]
+        e2e_i[0] += 1
+        w_["program"].run_host_pipelined([(w_[in_key], h_in)],
+                                         [(h_masks, w_["mask"]), (h_boxes, w_["boxes"]), (h_cls, w_["cls_logits"])],
+                                         direct=True)
+        collective(w_)
 
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e, _ = timed(step_e2e, args.steps)
     e2e_value = world * PB * args.steps / (ms_e2e / 1e3)
+    e2e_same = bool(torch.equal(h_masks, ws["mask"].cpu()) and torch.equal(h_cls, ws["cls_logits"].cpu()))
     h2d = h_in.numel() * h_in.element_size()
     d2h = PB * (224 * 224 + 16 + 24)
 
@@ -410,44 +497,53 @@ def main():
     n_conv = sum(isinstance(d, tc_kinds) for d in prog.descs)
     achieved = total_flop / (conv_ms / 1e3) / 1e12
     traffic, traffic_src = None, None
-    try:                                                      # DRAM bytes per launch from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
-            tj = json.load(f)
-        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-    except Exception:
-        pass
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):   # DRAM bytes per launch from the committed ncu capture
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            break
+        except Exception:
+            pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "tcgen05 implicit-GEMM conv family (conv_multi_kernel, conv_gemm_persistent_kernel, "
                           "conv_gemm_kernel, stem_conv_kernel)", "launches_per_step": n_conv,
                 "avg_launch_ms": conv_ms / n_conv, "share_of_step": conv_ms / sum(per_op_ms),
+                "algorithmic_flop_per_step": total_flop,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"}
 
     if rank == 0:
+        what = ("end-to-end UNet->bbox crop->GoogLeNet at 224x224 (BASELINE.json configs[3]: batch sharded across GPUs)"
+                if not SRC else f"end-to-end device resize {SRC}x{SRC} uint8 -> 224 -> UNet->bbox crop->GoogLeNet "
+                                "(BASELINE.json configs[4])")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": ("end-to-end UNet->bbox crop->GoogLeNet at 224x224 (BASELINE.json configs[3]: "
-                                    "batch sharded across GPUs), random-init weights" if not SRC else
-                                    f"end-to-end device resize {SRC}x{SRC} uint8 -> 224 -> UNet->bbox crop->GoogLeNet "
-                                    "(BASELINE.json configs[4]), random-init weights"),
+            "config": {"workload": what + ", briefly-trained fixture weights",
                        "images_per_gpu_per_step": PB, "micro_batch": MB, "global_batch": world * PB,
-                       "collective": "nccl all_gather(masks u8, logits f32)" if world > 1 else "none",
+                       "collective": (("nccl gather to rank 0 (masks u8, boxes i32, logits f32), double-buffered on a "
+                                       "side stream" if gather is not None else
+                                       "nccl all_gather(masks u8, logits f32)") if world > 1 else "none"),
                        "autotuned_conv_ops": ws.get("tuned_ops"),
                        "l2": f"per-step inputs ({h2d / 1e6:.0f} MB) and activations (GBs) exceed the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps,
-                    "how": "ug_program_run_host_pipelined: pinned host input copied H2D every step (double-buffered "
-                           "staging, the copy of step i+1 overlaps the kernels of step i), masks/boxes/logits copied "
-                           "D2H every step, one synchronize after the K steps"},
+                    "ms_per_step": ms_e2e / args.steps, "outputs_equal_device_run": e2e_same,
+                    "how": "ug_program_run_host_pipelined (direct form): pinned host input copied H2D every step into "
+                           "the input buffer of one of two alternating program slots (the copy of step i+1 overlaps the "
+                           "kernels of step i, no device-to-device hop), masks/boxes/logits copied D2H every step, one "
+                           "synchronize after the K steps"},
             "gpu_launches": launches,
             "model_tflops": value * FLOP_PER_IMAGE / 1e12 / world,
-            "roofline": roofline, "clocks": clocks,
+            "roofline": roofline, "clocks": clocks, "parity": parity,
+            "per_rank_ms_per_step": [t / args.steps for t in per_rank_ms],
         }
+        if gathered_ok is not None:
+            line["gathered_result_checked"] = gathered_ok
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
-        if world == 1 and args.yardstick:
+        if world == 1 and not args.no_yardstick:
             line["gpu_eager_yardstick"] = gpu_eager_yardstick(dev)
         # per-op breakdown for profiles/ (not part of the contract line)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

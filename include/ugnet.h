@@ -296,11 +296,14 @@ typedef struct ug_copy {
 } ug_copy;
 int ug_program_run_host(ug_handle h, ug_program p, const ug_copy* h2d, int n_h2d, const ug_copy* d2h, int n_d2h,
                         void* stream);
-/* Double-buffered form for back-to-back steps (a serving loop): the H2D copies of this call go to device staging
- * buffers (stage0[i] / stage1[i], alternating per call, each at least h2d[i].bytes, caller-owned) on an engine-owned
- * copy stream, so the copy of step i+1 overlaps the kernels of step i; the compute stream then moves the staged
- * input into h2d[i].dst (device to device), runs the program and enqueues the D2H copies.  Does NOT synchronize:
- * results are valid after the caller synchronizes `stream`. */
+/* Double-buffered form for back-to-back steps (a serving loop): the H2D copies of this call run on an engine-owned
+ * copy stream, so the copy of step i+1 overlaps the kernels of step i; the compute stream then runs the program and
+ * enqueues the D2H copies.  Does NOT synchronize: results are valid after the caller synchronizes `stream`.  Two forms:
+ *   staged  (stage0 / stage1 non-NULL, each entry at least h2d[i].bytes, caller-owned, alternating per call): the copy
+ *           lands in the staging slot and the compute stream moves it into h2d[i].dst (device to device) — one program;
+ *   direct  (stage0 == stage1 == NULL): the copy lands in h2d[i].dst itself.  The caller must alternate between TWO
+ *           programs with their own input buffers from call to call (call i and call i+2 may share buffers, call i and
+ *           call i+1 may not); the extra device-to-device pass of the staged form disappears. */
 int ug_program_run_host_pipelined(ug_handle h, ug_program p, const ug_copy* h2d, void* const* stage0,
                                   void* const* stage1, int n_h2d, const ug_copy* d2h, int n_d2h, void* stream);
 

@@ -1,30 +1,34 @@
-# Round evidence run (one gpurun call): full GPU test suite, smoke, bench (both arms), ncu launch list of one step and
-# ncu --set full captures of the dominant conv kernels and of the memory-bound kernels (exported to CSV on the box;
-# the .ncu-rep files are dropped to stay under the 64 MiB return limit).
-# usage: bash scripts/gpu_evidence.sh <tag>      (outputs land in gpurun_out/<tag>_*)
-TAG=${1:-r01}
+# Round evidence run (one gpurun call): full GPU test suite, smoke, bench (both arms + the stage-alone / 512-source
+# configs), the ncu launch list of ONE pipeline pass restricted to the engine's kernels, and ncu --set full captures of
+# every kernel class of that pass (exported to CSV on the box; the .ncu-rep files are dropped to stay under the 64 MiB
+# return limit).   usage: bash scripts/gpu_evidence.sh <tag> [quick]      (outputs land in gpurun_out/<tag>_*)
+TAG=${1:-r02}
 O=gpurun_out
+K='regex:conv_multi|conv_gemm|conv_pair|stem_conv|pool_kernel|pool3x3s1|layernorm|attention_mma|chanstats|gate_hidden|gate_out|bbox_kernel|resize_u8|head_kernel'
 set -x
-python -m pytest tests -m gpu -q -x --tb=short -p no:cacheprovider > $O/${TAG}_gputests.log 2>&1; echo "pytest rc=$?"; tail -5 $O/${TAG}_gputests.log
+python -m pytest tests -m gpu -q -x --tb=short -p no:cacheprovider -rP > $O/${TAG}_gputests.log 2>&1; echo "pytest rc=$?"; tail -5 $O/${TAG}_gputests.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/${TAG}_smoke.log
-python bench.py --steps 20 --warmup 3 > $O/${TAG}_bench.log 2>&1; echo "bench rc=$?"; tail -c 2800 $O/${TAG}_bench.log
+python bench.py --steps 20 --warmup 3 > $O/${TAG}_bench.log 2>&1; echo "bench rc=$?"; tail -c 3800 $O/${TAG}_bench.log
 cp $O/bench_breakdown_n1.json $O/${TAG}_per_op.json
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline --source-size 512 > $O/${TAG}_bench_src512.log 2>&1; tail -c 600 $O/${TAG}_bench_src512.log
-python bench.py --workload unet --batch 64 --steps 20 > $O/${TAG}_bench_unet64.log 2>&1; tail -c 500 $O/${TAG}_bench_unet64.log
-python bench.py --workload googlenet --steps 20 > $O/${TAG}_bench_googlenet256.log 2>&1; tail -c 500 $O/${TAG}_bench_googlenet256.log
+if [ "$2" != "quick" ]; then
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-yardstick --source-size 512 > $O/${TAG}_bench_src512.log 2>&1; tail -c 900 $O/${TAG}_bench_src512.log
+python bench.py --workload unet --batch 64 --steps 20 > $O/${TAG}_bench_unet64.log 2>&1; tail -c 900 $O/${TAG}_bench_unet64.log
+python bench.py --workload googlenet --steps 20 > $O/${TAG}_bench_googlenet256.log 2>&1; tail -c 700 $O/${TAG}_bench_googlenet256.log
 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_ref.log 2>&1; tail -c 1200 $O/${TAG}_bench_ref.log
-CMD="python bench.py --steps 1 --warmup 3 --batch 128 --no-cpu-baseline"
-# launches per pass at batch 128: 57 (UNet) + 15 (tail ops) ... measured from the plain run's gpu_launches
-$CMD > $O/${TAG}_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 357 -c 119 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu1.log 2>&1
+fi
+# ---- ncu: one pass of the engine's kernels (the warm-up passes are skipped by counting ONLY matching kernels)
+CMD="python scripts/one_pass.py --batch 128 --passes 3"
+$CMD > $O/${TAG}_plain.log 2>&1 || { cat $O/${TAG}_plain.log; exit 1; }
+L=$(grep LAUNCHES_PER_PASS $O/${TAG}_plain.log | awk '{print $2}'); echo "launches per pass: $L"
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" --launch-skip $((2 * L)) --launch-count $L --csv \
+    --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu1.log 2>&1
 echo "ncu launches rc=$?"
+if grep -q elementwise_kernel $O/${TAG}_launches.csv; then echo "ERROR: torch kernels in the launch list"; fi
+grep -c '^"' $O/${TAG}_launches.csv
 $CMD > $O/${TAG}_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:conv_multi -s 132 -c 44 -o $O/${TAG}_conv $CMD > $O/${TAG}_ncu2.log 2>&1
-echo "ncu conv rc=$?"
-ncu -i $O/${TAG}_conv.ncu-rep --page raw --csv > $O/${TAG}_conv.raw.csv 2>/dev/null
-$CMD > $O/${TAG}_plain.log 2>&1 && \
-ncu --set full --clock-control none -k "regex:pool_kernel|chanstats|cropresize|bbox|layernorm|attention|head_kernel|gate_|stem_conv" -s 105 -c 35 -o $O/${TAG}_mem $CMD > $O/${TAG}_ncu3.log 2>&1
-echo "ncu mem rc=$?"
-ncu -i $O/${TAG}_mem.ncu-rep --page raw --csv > $O/${TAG}_mem.raw.csv 2>/dev/null
-rm -f $O/${TAG}_conv.ncu-rep $O/${TAG}_mem.ncu-rep
+ncu --set full --clock-control none --import-source on -k "$K" --launch-skip $((2 * L)) --launch-count $L -o $O/${TAG}_full $CMD > $O/${TAG}_ncu2.log 2>&1
+echo "ncu full rc=$?"
+ncu -i $O/${TAG}_full.ncu-rep --page raw --csv > $O/${TAG}_full.raw.csv 2>/dev/null
+ls -la $O/${TAG}_full.ncu-rep
+rm -f $O/${TAG}_full.ncu-rep
 ls -la $O | tail -14

@@ -8,7 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import ugnet_b200  # noqa: F401
-from ugnet_b200.dist import gather_shards, run_sharded, shard_range
+from ugnet_b200.dist import RootGather, gather_shards, run_sharded, shard_range
 
 
 def _fake_pipeline(x):
@@ -29,6 +29,23 @@ def _worker(rank, world, port, q):
     ok = torch.equal(masks, ref[0]) and torch.equal(boxes, ref[1]) and torch.equal(logits, ref[2])
     t = gather_shards(torch.full((3, 2), float(rank)))
     ok = ok and torch.equal(t, torch.tensor([0.0] * 6 + [1.0] * 6).reshape(6, 2))
+    # gather to one rank only (the path's final collective as BASELINE.json words it)
+    r0 = run_sharded(_fake_pipeline, imgs, dst=0)
+    if rank == 0:
+        ok = ok and all(torch.equal(a, b) for a, b in zip(r0, ref))
+    else:
+        ok = ok and all(t is None for t in r0)
+    # double-buffered gather of a serving loop: three steps through two staging slots, last step's result on the root
+    lo, hi = shard_range(8, rank, world)
+    rg = None
+    for step in range(3):
+        m, b, lg = _fake_pipeline(imgs[lo:hi] * (0.5 + 0.25 * step))
+        rg = rg or RootGather([m, b, lg], root=0)
+        rg.submit([m, b, lg])
+        m.zero_()                                        # the caller may overwrite its buffers right after submit
+    res = rg.results()
+    want = _fake_pipeline(imgs * 1.0)
+    ok = ok and ((res is None) if rank else all(torch.equal(a, b) for a, b in zip(res, want)))
     q.put((rank, ok))
     dist.destroy_process_group()
 

@@ -77,7 +77,10 @@ def test_unet_parity(engine, unet_sd, images, oracle_unet):
     agree = (mask.cpu().numpy() == ref_mask).mean()
     assert agree >= 0.999, f"mask agreement {agree:.5f} < 99.9 %"
     d = (logits.cpu() - ref_logits).abs()
-    assert d.mean() < 0.05 and d.max() < 0.1 * ref_logits.abs().max(), (d.mean().item(), d.max().item())
+    rel_fro = ((logits.cpu() - ref_logits).norm() / ref_logits.norm()).item()
+    # the contract gate for the segmentation stage is the mask (above); the logit map itself is held to the measured
+    # bf16 drift with 2x headroom: relative Frobenius error 1.2e-2, worst pixel 3 % of the logit range
+    assert rel_fro <= 2.5e-2 and d.max() <= 0.06 * ref_logits.abs().max(), (rel_fro, d.mean().item(), d.max().item())
     ref_boxes = np.array([roi_ref.bbox_from_mask(m) for m in ref_mask], np.int32)
     got_boxes = boxes.cpu().numpy()
     same_mask = [(mask[i].cpu().numpy() == ref_mask[i]).all() for i in range(N_IMG)]
@@ -86,7 +89,8 @@ def test_unet_parity(engine, unet_sd, images, oracle_unet):
         assert tuple(got_boxes[i]) == roi_ref.bbox_from_mask(mask[i].cpu().numpy())
         if same_mask[i]:
             assert tuple(got_boxes[i]) == tuple(ref_boxes[i])
-    print(f"mask agreement {agree:.6f}; mean|dlogit| {d.mean():.4f}; boxes equal "
+    print(f"mask agreement {agree:.6f}; mean|dlogit| {d.mean():.4f}; max|dlogit|/scale "
+          f"{(d.max() / ref_logits.abs().max()).item():.4f}; rel fro {rel_fro:.4f}; boxes equal "
           f"{(got_boxes == ref_boxes).all(1).sum()}/{N_IMG}")
 
 
@@ -109,8 +113,8 @@ def test_unet_shell_is_drop_in(engine, unet_sd, images, oracle_unet):
 def test_unet_cls_head_variant(engine, unet_sd, images):
     """分类/nets/basicUnet.py:369-436 (classifier-head UNetTaskAligWeight): same state_dict, forward ->
     cl_out [B,1].  Checked against the golden cl_out of the IMPORTED reference class (procedural weights, seed 7) and
-    against the fp32 oracle on the trained fixture.  Tolerance: 3e-2 of the output scale (bf16 activations through
-    10 conv layers + the transformer block, then a mean over 196 tokens and a 512-term dot product)."""
+    against the fp32 oracle on the trained fixture.  Tolerance: the contract's 1e-2 of the output scale (measured 4e-3:
+    bf16 activations through 10 conv layers + the transformer block, a mean over 196 tokens, a 512-term dot product)."""
     import os
     from oracle import fixtures, unet_ref
     from ugnet_b200.nets.basicUnet_cls import UNetTaskAligWeight
@@ -125,7 +129,7 @@ def test_unet_cls_head_variant(engine, unet_sd, images):
     assert out.shape == (2, 1) and out.dtype == torch.float32
     err = np.abs(out.cpu().numpy() - gold).max()
     print(f"cls-head golden: engine {out.cpu().numpy().ravel()} reference {gold.ravel()} err {err:.4f}")
-    assert err <= 3e-2 * max(1.0, np.abs(gold).max())
+    assert err <= 1e-2 * max(1.0, np.abs(gold).max())
     # trained encoder weights, 8 images, live oracle
     model.load_state_dict(unet_sd)
     x = torch.from_numpy(images[0])
@@ -134,7 +138,7 @@ def test_unet_cls_head_variant(engine, unet_sd, images):
         got = model(x.cuda()).cpu().numpy()
     err = np.abs(got - ref).max()
     print(f"cls-head trained fixture: err {err:.4f} of scale {np.abs(ref).max():.3f}")
-    assert err <= 3e-2 * max(1.0, np.abs(ref).max())
+    assert err <= 1e-2 * max(1.0, np.abs(ref).max())
     with pytest.raises(RuntimeError):
         model.forward_mask_boxes(x.cuda())
 

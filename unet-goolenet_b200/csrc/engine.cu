@@ -285,7 +285,8 @@ int ug_program_run_host(ug_handle h, ug_program p, const ug_copy* h2d, int n_h2d
 
 int ug_program_run_host_pipelined(ug_handle h, ug_program p, const ug_copy* h2d, void* const* stage0,
                                   void* const* stage1, int n_h2d, const ug_copy* d2h, int n_d2h, void* stream) {
-  if (!h || !p || (n_h2d > 0 && (!h2d || !stage0 || !stage1))) return UG_EINVAL;
+  const bool direct = !stage0 && !stage1;  // see ugnet.h: the caller alternates two programs with their own inputs
+  if (!h || !p || (n_h2d > 0 && (!h2d || (!direct && (!stage0 || !stage1))))) return UG_EINVAL;
   DeviceGuard guard(h);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!h->copy_stream) {
@@ -297,23 +298,27 @@ int ug_program_run_host_pipelined(ug_handle h, ug_program p, const ug_copy* h2d,
     if (rc != UG_OK) return rc;
   }
   const int slot = (int)(h->pipelined_steps & 1);
-  void* const* stage = slot ? stage1 : stage0;
-  // copy stream: wait until the step that last used this staging slot has copied it out, then H2D into the slot
+  void* const* stage = direct ? nullptr : (slot ? stage1 : stage0);
+  // copy stream: wait until the step that last used this slot no longer reads it, then H2D into the slot
   if (h->pipelined_steps >= 2) cudaStreamWaitEvent(h->copy_stream, h->ev_free[slot], 0);
   for (int i = 0; i < n_h2d; ++i) {
-    int rc = check_cuda(h, cudaMemcpyAsync(stage[i], h2d[i].src, h2d[i].bytes, cudaMemcpyHostToDevice, h->copy_stream), "H2D copy");
+    void* dst = direct ? h2d[i].dst : stage[i];
+    int rc = check_cuda(h, cudaMemcpyAsync(dst, h2d[i].src, h2d[i].bytes, cudaMemcpyHostToDevice, h->copy_stream), "H2D copy");
     if (rc != UG_OK) return rc;
   }
   cudaEventRecord(h->ev_h2d[slot], h->copy_stream);
-  // compute stream: staging slot -> the program's input buffers (device to device), run, results to the host
   cudaStreamWaitEvent(s, h->ev_h2d[slot], 0);
-  for (int i = 0; i < n_h2d; ++i) {
-    int rc = check_cuda(h, cudaMemcpyAsync(h2d[i].dst, stage[i], h2d[i].bytes, cudaMemcpyDeviceToDevice, s), "D2D copy");
-    if (rc != UG_OK) return rc;
+  if (!direct) {
+    // compute stream: staging slot -> the program's input buffers (device to device); the slot is free after that
+    for (int i = 0; i < n_h2d; ++i) {
+      int rc = check_cuda(h, cudaMemcpyAsync(h2d[i].dst, stage[i], h2d[i].bytes, cudaMemcpyDeviceToDevice, s), "D2D copy");
+      if (rc != UG_OK) return rc;
+    }
+    cudaEventRecord(h->ev_free[slot], s);
   }
-  cudaEventRecord(h->ev_free[slot], s);
   int rc = ug_program_run(h, p, stream);
   if (rc != UG_OK) return rc;
+  if (direct) cudaEventRecord(h->ev_free[slot], s);  // the program reads its input buffers until its last kernels
   for (int i = 0; i < n_d2h; ++i) {
     rc = check_cuda(h, cudaMemcpyAsync(d2h[i].dst, d2h[i].src, d2h[i].bytes, cudaMemcpyDeviceToHost, s), "D2H copy");
     if (rc != UG_OK) return rc;

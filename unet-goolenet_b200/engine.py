@@ -215,21 +215,27 @@ class Program:
         self.engine._check(self.engine.lib.ug_program_run_host(self.engine.handle, self.handle, C.byref(a), len(h2d),
                                                                C.byref(b), len(d2h), s))
 
-    def run_host_pipelined(self, h2d, d2h, stream=None):
+    def run_host_pipelined(self, h2d, d2h, stream=None, direct=False):
         """Like run_host but double-buffered and NOT synchronizing: the H2D copies of this call run on the engine's
-        copy stream into device staging buffers and overlap the kernels of the previous call (ug_program_run_host_
-        pipelined).  Results are valid after the caller synchronizes the stream."""
+        copy stream and overlap the kernels of the previous call (ug_program_run_host_pipelined).  Results are valid
+        after the caller synchronizes the stream.  direct=False: the copies land in device staging buffers and are
+        moved into place on the compute stream (one program).  direct=True: they land in the program's own input
+        buffers — the caller alternates between two programs with distinct buffers from call to call."""
         s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        if not hasattr(self, "_stage"):
-            self._stage = [[torch.empty_like(dst) for dst, _ in h2d] for _ in range(2)]
         a = (Copy * max(1, len(h2d)))()
-        st = [(_vp * max(1, len(h2d)))(), (_vp * max(1, len(h2d)))()]
         for i, (dst, src) in enumerate(h2d):
             a[i] = Copy(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size())
-            st[0][i], st[1][i] = self._stage[0][i].data_ptr(), self._stage[1][i].data_ptr()
         b = (Copy * max(1, len(d2h)))()
         for i, (dst, src) in enumerate(d2h):
             b[i] = Copy(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size())
+        if direct:
+            st = [None, None]
+        else:
+            if not hasattr(self, "_stage"):
+                self._stage = [[torch.empty_like(dst) for dst, _ in h2d] for _ in range(2)]
+            st = [(_vp * max(1, len(h2d)))(), (_vp * max(1, len(h2d)))()]
+            for i in range(len(h2d)):
+                st[0][i], st[1][i] = self._stage[0][i].data_ptr(), self._stage[1][i].data_ptr()
         self.engine._check(self.engine.lib.ug_program_run_host_pipelined(
             self.engine.handle, self.handle, C.byref(a), st[0], st[1], len(h2d), C.byref(b), len(d2h), s))
 

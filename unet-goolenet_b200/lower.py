@@ -682,26 +682,33 @@ class PipelineRunner:
         self.cls_batch = max(cls_batch, micro_batch) // micro_batch * micro_batch
         self.padding = padding
         self.plans = _PlanCache(on_evict=self._evicted)
-        self._pools = {}
+        self._pools = {}      # UNet activation workspace per micro-batch size (shared by every plan using it)
+        self._gpools = {}     # GoogLeNet activation workspace per batch size
 
     def _evicted(self, key, ws):
-        """Drop the shared UNet workspace of a micro-batch size no remaining plan uses."""
+        """Drop the shared workspaces no remaining plan uses."""
         live = {w["mb"] for w in self.plans.values()}
         for mb in [m for m in self._pools if m not in live]:
             del self._pools[mb]
+        liveb = {w["B"] for w in self.plans.values()}
+        for b in [m for m in self._gpools if m not in liveb]:
+            del self._gpools[b]
 
-    def plan(self, B, source=None):
+    def plan(self, B, source=None, slot=0):
         """Program for a batch of B images; B must be <= micro_batch or a multiple of it.  With `source` =
         (Hs, Ws) the program starts with the device front-end (PIL-exact resize of uint8 HWC sources + to_tensor,
-        util/data_utils.py) writing the UNet input, and `ws["src_u8"]` is the program's input buffer."""
-        key = B if source is None else (B,) + tuple(source)
+        util/data_utils.py) writing the UNet input, and `ws["src_u8"]` is the program's input buffer.
+        `slot` selects one of several programs of the same shape with their OWN input / output buffers (x_in, src_u8,
+        logits, mask, boxes, u8) over the SAME activation workspaces: a host-fed serving loop alternates slots so that
+        the H2D copy of step i+1 lands in place while step i computes (Program.run_host_pipelined(direct=True))."""
+        key = (B, slot) if source is None else (B, slot) + tuple(source)
 
         def build():
             mb = min(B, self.micro_batch)
             assert B % mb == 0
             dev = self.dev
             ua, ga = self.unet.begin(), self.gnet.begin()
-            ws = dict(mb=mb, x_in=torch.empty((B, 3, IMG, IMG), device=dev),
+            ws = dict(mb=mb, B=B, x_in=torch.empty((B, 3, IMG, IMG), device=dev),
                       logits=torch.empty((B, 1, IMG, IMG), device=dev),
                       mask=torch.empty((B, IMG, IMG), device=dev, dtype=torch.uint8),
                       boxes=torch.empty((B, 4), device=dev, dtype=torch.int32),
@@ -712,6 +719,7 @@ class PipelineRunner:
                 ops.append(E.ResizeDesc(ws["src_u8"].data_ptr(), ws["x_in"].data_ptr(), None, B, source[0], source[1],
                                         IMG))
             pool = self._pools.setdefault(mb, [])
+            gpool = self._gpools.setdefault(B, [])
             for s in range(0, B, mb):
                 sl = slice(s, s + mb)
                 sub = {}
@@ -722,7 +730,8 @@ class PipelineRunner:
                 ops.append(E.CropResizeDesc(ws["x_in"][sl].data_ptr(), ws["boxes"][sl].data_ptr(),
                                             ws["u8"][sl].data_ptr(), mb, IMG, IMG, IMG))
                 ws.setdefault("sub", []).append(sub)
-            self.gnet._emit_googlenet(B, ws, ops, u8=ws["u8"])
+            with self.gnet.sharing(gpool):
+                self.gnet._emit_googlenet(B, ws, ops, u8=ws["u8"])
             return _finish(self.engine, ops, ws, ua + ga + [v for v in ws.values() if isinstance(v, torch.Tensor)])
         return self.plans.get_or_build(key, build)
 
