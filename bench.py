@@ -53,37 +53,61 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Spawn nvidia-smi (20 ms period) and wait until its first row arrived: its start-up takes longer than a short
+        timed region.  Rows are time-stamped; only those between mark_begin() and mark_end() are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            deadline = time.time() + 5.0
+            while not self.rows and time.time() < deadline:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.02]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window_s": (t1 - t0) if self.t0 and self.t1 else None}
+
+
+def fixture_batch(n, seed, device):
+    """The fixture's own seeded synthetic ultrasound-like images (oracle/fixtures.synth_images: the distribution the
+    trained-like UNet weights segment — ~8 % foreground, boxes of every size), as a float tensor on `device`."""
+    import torch
+    from oracle import fixtures
+    imgs, _, _ = fixtures.synth_images(n, seed=seed)
+    return torch.from_numpy(imgs).to(device)
 
 
 def synth_batch(n, seed, device):
-    """Seeded synthetic ultrasound-like images generated on the device: low-frequency background, one dark
-    ellipse, speckle; 3 identical channels in [0,1]."""
+    """(round 1's generator, kept for the stage-alone GoogLeNet line) seeded images generated on the device:
+    low-frequency background, one dark ellipse, speckle; 3 identical channels in [0,1]."""
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
     S = 224
@@ -248,7 +272,7 @@ def run_stage_alone(args, dev, rank):
     from ugnet_b200.lower import GoogLeNetRunner, UNetRunner
     usd, gsd = _fixture_weights()
     B = args.batch if args.batch != 256 or args.workload == "googlenet" else 64
-    imgs = synth_batch(B, 1234, dev)
+    imgs = fixture_batch(B, 1234, dev)
     if args.workload == "unet":
         runner = UNetRunner(usd, dev, max_batch=B)
         ws = runner.plan(B)
@@ -361,7 +385,7 @@ def main():
     # (own input/output buffers over the same workspaces) for the host-fed loop
     plans = [pipe.plan(PB, source=src, slot=k) for k in (0, 1)]
     ws, prog = plans[0], plans[0]["program"]
-    imgs = synth_batch(PB, 1234 + rank, dev)                  # this rank's slice of the global batch
+    imgs = fixture_batch(PB, 1234 + rank, dev)                # this rank's slice of the global batch
     if SRC:                                                   # uint8 HWC sources, resized on the device every step
         big = torch.nn.functional.interpolate(imgs, size=(SRC, SRC), mode="bilinear", align_corners=False)
         src_u8 = (big * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
@@ -444,7 +468,9 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = eng.launch_count
+    sampler.mark_begin()
     ms, per_rank_ms = timed(step_device, args.steps)
+    sampler.mark_end()
     launches = eng.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
     value = world * PB * args.steps / (ms / 1e3)

@@ -29,6 +29,10 @@ int ug_mma_microbench(ug_handle h, int N, int n_acc, int iters, int ctas_per_sm,
 int ug_mma_microbench2(ug_handle h, int N, int n_acc, int issuers, int iters, int ctas_per_sm, int a_off, int a_sbo,
                        int acc_stride, double* out2);
 
+/* CTA pairs (cluster of 2) issuing tcgen05.mma.cta_group::2 (M = 256 over two SMs, N/2 of B per CTA) from `issuers`
+ * (1..4) warps of the leader CTA: out2[0] = cycles per M=256 MMA of one issuer, out2[1] = launch wall time in ms. */
+int ug_mma_microbench_pair(ug_handle h, int N, int issuers, int iters, double* out2);
+
 #ifdef __cplusplus
 }
 #endif

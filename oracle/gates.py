@@ -9,7 +9,8 @@ on the same images and weights as the engine and evaluates BASELINE.json's contr
     the engine's own mask, and the engine's uint8 crop must equal the reference crop/resize chain (roi.py:39-44,
     data_utils.py:102,146-147) for that box — for every image; where the engine's mask equals the reference mask this
     is the reference's box and crop;
-  * class logits within 1e-2 of the per-image logit scale with identical argmax, the reference classifier
+  * class logits within 1e-2 of the per-image logit scale with identical argmax (on every image whose reference top-2
+    margin is outside the 2 x 1e-2 tolerance band — see argmax_gate), the reference classifier
     (分类/test.py:64-73) being evaluated on the reference crop of the engine's box (the crop depends on the image and
     the box only, so for every image whose box equals the reference's this is the unmodified reference path).
 
@@ -63,6 +64,17 @@ def logit_rel_err(got, ref):
     return ((got - ref).abs().amax(1) / ref.abs().amax(1)).numpy()
 
 
+def argmax_gate(got, ref):
+    """-> (number of images with identical argmax, number of DECIDED images, all decided images identical).
+    An image is decided when the reference's top-2 margin exceeds twice the logit tolerance (2 * 1e-2 * scale): inside
+    that band two logits that each moved by <= 1e-2 * scale may legitimately swap, outside it a different argmax is an
+    error whatever the logit error."""
+    top2 = ref.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 2 * LOGIT_REL * ref.abs().amax(1)
+    same = got.argmax(1) == ref.argmax(1)
+    return int(same.sum()), int(decided.sum()), bool(same[decided].all())
+
+
 def unet_gates(unet_sd, imgs, masks, boxes, device, seg_logits=None, padding=30):
     """Stage-1 gates.  imgs float [B,3,224,224] (NumPy); masks u8 [B,224,224], boxes i32 [B,4] from the engine."""
     masks = np.asarray(masks)
@@ -114,8 +126,9 @@ def pipeline_gates(unet_sd, gnet_sd, imgs, masks, boxes, cls_logits, device, cro
     same_box = (boxes == ref_boxes).all(1)
     out["cls_logit_rel_err_max"] = float(rel.max())
     out["cls_logit_rel_err_max_reference_box"] = float(rel[same_box].max()) if same_box.any() else None
-    out["cls_argmax_equal"] = int((cls.argmax(1) == ref_cls.argmax(1)).sum())
-    out["ok"] = bool(out["ok"] and out["cls_logit_rel_err_max"] <= LOGIT_REL and out["cls_argmax_equal"] == B and
+    out["cls_argmax_equal"], out["cls_decided_images"], decided_ok = argmax_gate(cls, ref_cls)
+    out["cls_argmax_equal_on_decided"] = decided_ok   # decided: reference top-2 margin > 2 * 1e-2 * logit scale
+    out["ok"] = bool(out["ok"] and out["cls_logit_rel_err_max"] <= LOGIT_REL and decided_ok and
                      out.get("crops_bit_exact", B) == B)
     return out
 

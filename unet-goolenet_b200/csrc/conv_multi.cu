@@ -19,16 +19,26 @@
 //
 // Each issuer i owns a pixel-tile stream, a ring of activation stages, TMEM accumulators and a warpgroup of four
 // epilogue warps (folded BN/bias + activation, residual / CoordAtt3 combine / outc epilogues, bf16 tile staged in
-// swizzled smem and written with TMA stores).  Warp roles (384 threads): warps 0-3 / 4-7 epilogue of issuer 0 / 1,
-// warp 8 TMEM allocator + weight producer, warp 9 activation producer, warps 10-11 MMA issuers.
+// swizzled smem and written with TMA stores).  Warp roles: warps 0-3 / 4-7 epilogue of tile stream 0 / 1,
+// warp 8 TMEM allocator + weight producer, warp 9 activation producer, warps 10.. MMA issuers.
+//
+// K-split (kKS = 2, narrow tiles BN <= 64): the 36 (or 72) MMAs of a tile form ONE dependent chain on its accumulator
+// and a chain retires an MMA only every ~110 cycles whatever N is (profiles/r01_mma_multi_issuer.txt), so two chains
+// per SM left the N = 64 layers at 63 cycles per MMA against a shared-memory operand floor of 48.  With kKS = 2 every
+// tile stream has TWO issuing warps that take alternate (chunk, tap) items of the same tile into their OWN TMEM
+// accumulators (four independent chains per SM); the epilogue adds the two partial sums in fp32 while it reads them.
+// The epilogue mode is a template parameter as well: its branches on ADD / GATE / OUTC were a third of the
+// instructions of the chunk loop of a plain-store layer.
 #include <cfloat>
 #include <cstring>
+#include <cstdlib>
+#include <algorithm>
 #include "conv_common.cuh"
 
 namespace ug {
 
-static constexpr int kMultiThreads = 384;
-static constexpr int kMI = 2;           // MMA issuers per CTA
+static constexpr int kMI = 2;           // tile streams per CTA (each with its own epilogue warpgroup)
+__host__ __device__ constexpr int kMultiThreads(int ks) { return 32 * (4 * kMI + 2 + kMI * ks); }   // 384 (kKS = 1) / 448 (kKS = 2)
 static constexpr int kMPitch = 10;      // halo tile pitch: 8 output pixels + one border pixel on each side
 // Warp roles.  The warp scheduler prefers the highest warp id among eligible warps, and the MMA issuers are the
 // latency-critical warps (every late tcgen05.mma is a tensor-pipe bubble), so they get the highest ids, then the
@@ -37,7 +47,7 @@ static constexpr int kMPitch = 10;      // halo tile pitch: 8 output pixels + on
 // profiles/r01_conv_sweep_multi_issuer.txt.
 static constexpr int kMAllocWarp = 4 * kMI;          // 8: TMEM allocator + weight (B) producer
 static constexpr int kMProducerWarp = 4 * kMI + 1;   // 9: activation (A) producer
-static constexpr int kMIssuerWarp0 = 4 * kMI + 2;    // 10, 11
+static constexpr int kMIssuerWarp0 = 4 * kMI + 2;    // 10 ..: issuer of (stream i, K-half h) is warp 10 + i*kKS + h
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -88,11 +98,12 @@ struct StoreMaps {  // output maps: [0] for plain stores, [q] = quadrant (dy,dx)
   CUtensorMap m[4];
 };
 
-template <int kAct, int kTaps>
-__global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                      const __grid_constant__ CUtensorMap tmB,
-                                                                      const __grid_constant__ StoreMaps tmO,
-                                                                      const ConvKParams p, const MultiParams hp) {
+template <int kAct, int kTaps, int kMode, int kKS>
+__global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                           const __grid_constant__ CUtensorMap tmB,
+                                                                           const __grid_constant__ StoreMaps tmO,
+                                                                           const ConvKParams p, const MultiParams hp) {
+  constexpr int kThreadsCta = kMultiThreads(kKS);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   const int b_tile_bytes = p.BN * 128;
@@ -132,14 +143,14 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
     }
     for (int i = 0; i < kMI * hp.sa; ++i) {
       mbar_init(&a_full[i], 1);
-      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_empty[i], kKS);  // every issuer of the stream has finished reading the stage
     }
     for (int i = 0; i < hp.sb; ++i) {
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], kMI);  // released once every issuer has consumed (or skipped) the tile
     }
     for (int i = 0; i < kMI * p.acc_stages; ++i) {
-      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_full[i], kKS);  // every K-half of the tile is complete
       mbar_init(&acc_empty[i], 4);
     }
     fence_mbar_init();
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
     tmem_alloc(tmem_ptr, p.tmem_cols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.npad; i += kMultiThreads) {
+  for (int i = threadIdx.x; i < p.npad; i += kThreadsCta) {
     sScale[i] = (i < p.N) ? (p.scale ? p.scale[i] : 1.0f) : 0.0f;
     sBias[i] = (i < p.N && p.bias) ? p.bias[i] : 0.0f;
   }
@@ -254,7 +265,9 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
     if (p.prof && lane == 0) p.prof[blockIdx.x * 16 + 1] = w_b;
   } else if (warp >= kMIssuerWarp0) {
     // ------------------------------------------------------------------ MMA issuers (whole warp, one elected lane issues)
-    const int i = warp - kMIssuerWarp0;
+    const int iw = warp - kMIssuerWarp0;
+    const int i = iw / kKS;       // tile stream
+    const int h = iw - i * kKS;   // K-half: this warp issues the (chunk, tap) items whose index is h modulo kKS
     const uint32_t idesc = umma_idesc_bf16(128, p.BN);
     int as = 0, bs = 0, acc = 0;
     uint32_t aph = 0, bph = 0, acc_phase = 0;
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
         mbar_wait(&acc_empty[i * p.acc_stages + acc], acc_phase ^ 1);
         if (p.prof) w_acc += clock64() - tw0;
         tc_fence_after();
-        d_tmem = tmem_base + (i * p.acc_stages + acc) * p.BN;
+        d_tmem = tmem_base + ((i * p.acc_stages + acc) * kKS + h) * p.BN;
       }
       for (int kc = 0; kc < p.kchunks; ++kc) {
         uint64_t ad0 = 0;
@@ -290,33 +303,37 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
 #pragma unroll 3
         for (int tap = 0; tap < kTaps; ++tap) {
           const int r = tap / 3, sx = tap - r * 3;
-          uint32_t b_addr;
+          const int item = kc * kTaps + tap;
+          const bool mine = kKS == 1 || (item % kKS) == h;
+          uint32_t b_addr = 0;
           if (hp.b_resident) {
             b_addr = sB_u32 + (kc * kTaps + tap) * b_tile_bytes;
-          } else {
+          } else if (mine) {
             const long long tw0 = p.prof ? clock64() : 0;
             mbar_wait(&b_full[bs], bph);
             if (p.prof) w_bf += clock64() - tw0;
             tc_fence_after();
             b_addr = sB_u32 + bs * b_tile_bytes;
           }
-          if (valid) {
-            // tap (r, sx): the A rows start (r*10 + sx) halo pixels (128 B each) into the stage
-            const uint64_t ad = ad0 + (uint64_t)((r * kMPitch + sx) * 8);
-            const uint64_t bd = umma_desc_sw128(b_addr);
-            const uint32_t first = (kc | tap) != 0 ? 1u : 0u;
-            if (elect_one_sync()) {
-              umma_bf16(d_tmem, ad, bd, idesc, first);
-              umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-              umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-              umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
-              if (!hp.b_resident) umma_commit(&b_empty[bs]);
+          if (mine) {
+            if (valid) {
+              // tap (r, sx): the A rows start (r*10 + sx) halo pixels (128 B each) into the stage
+              const uint64_t ad = ad0 + (uint64_t)((r * kMPitch + sx) * 8);
+              const uint64_t bd = umma_desc_sw128(b_addr);
+              const uint32_t first = item >= kKS ? 1u : 0u;   // this issuer's first item of the tile overwrites
+              if (elect_one_sync()) {
+                umma_bf16(d_tmem, ad, bd, idesc, first);
+                umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                if (!hp.b_resident) umma_commit(&b_empty[bs]);
+              }
+              __syncwarp();
+            } else if (!hp.b_resident) {
+              // a tile-less stream (odd tile count, last round) still has to hand the slot back
+              if (elect_one_sync()) mbar_arrive(&b_empty[bs]);
+              __syncwarp();
             }
-            __syncwarp();
-          } else if (!hp.b_resident) {
-            // a tile-less issuer (odd tile count, last round) still has to hand the slot back
-            if (elect_one_sync()) mbar_arrive(&b_empty[bs]);
-            __syncwarp();
           }
           if (!hp.b_resident) {
             if (++bs == hp.sb) {
@@ -343,7 +360,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
         }
       }
     }
-    if (p.prof && lane == 0 && !((hp.debug & 8) && i == 1)) {
+    if (p.prof && lane == 0 && h == 0 && !((hp.debug & 8) && i == 1)) {
       p.prof[blockIdx.x * 16 + 4 + i * 4 + 0] = w_af;
       p.prof[blockIdx.x * 16 + 4 + i * 4 + 1] = w_bf;
       p.prof[blockIdx.x * 16 + 4 + i * 4 + 2] = w_acc;
@@ -369,7 +386,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
     // SUB-TILE AHEAD (right after the chunk loop of the previous sub-tile, whose residual registers are dead by
     // then): with the loads issued at the start of the same tile the HBM latency was exposed in the first chunk of
     // every tile of the epilogue-bound 64-channel layers (chunk loop 1000 cycles per chunk instead of 400).
-    const bool has_add = p.mode == UG_EPI_ADD || p.mode == UG_EPI_GATE;
+    constexpr bool has_add = kMode == UG_EPI_ADD || kMode == UG_EPI_GATE;
     uint4 addv[8];
     auto prefetch_add = [&](int s2, int sub2) {
       const int nt2 = hp.d_msuper.div(s2), mt2 = (s2 - nt2 * hp.m_super) * kMI + i;
@@ -404,21 +421,27 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
       const bool valid = row_in_tile && (x < p.W) && (y < p.H) && (n < p.B);
       const float* gate_row = p.gate + (long long)n * p.N + ncol0;
       const int ncols = min(p.BN, p.N - ncol0);
-      if (has_add && p.mode == UG_EPI_GATE && etid < ncols) sGate[i * 128 + etid] = 1.0f + __ldg(gate_row + etid);
+      if (kMode == UG_EPI_GATE && etid < ncols && n < p.B) sGate[i * 128 + etid] = 1.0f + __ldg(gate_row + etid);
       long long tw0 = p.prof ? clock64() : 0;
       mbar_wait(&acc_full[i * p.acc_stages + acc], acc_phase);
       if (p.prof) e_wacc += clock64() - tw0;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (i * p.acc_stages + acc) * p.BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (i * p.acc_stages + acc) * kKS * p.BN;
       float dot = 0.0f;
 
       uint32_t v[16];
+      uint32_t v2[kKS == 2 ? 16 : 1];   // partial sums of the second K-half
       __syncwarp();
       if (hp.debug & 1) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0u;
+        if (kKS == 2) {
+#pragma unroll
+          for (int j = 0; j < (kKS == 2 ? 16 : 1); ++j) v2[j] = 0u;
+        }
       } else {
         tmem_ld16(taddr, v);
+        if constexpr (kKS == 2) tmem_ld16(taddr + p.BN, reinterpret_cast<uint32_t(&)[16]>(v2));
       }
       for (int sub = 0; sub * 64 < ncols; ++sub) {
         if (p.tma_store) {
@@ -441,12 +464,19 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
           const int c0 = sub * 64 + cc * 16;
           if (c0 >= ncols) break;
           tmem_ld_wait();
+          if constexpr (kKS == 2) {   // the two K-halves of the tile were accumulated separately: add them in fp32
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j < (kKS == 2 ? 16 : 1) ? j : 0]));
+          }
           float f[16];
           epi_math16_linear<kAct>(v, f, sScale, sBias, ncol0 + c0);   // ReLU deferred (see conv_common.cuh)
           __syncwarp();
-          if (c0 + 16 < ncols && !(hp.debug & 1)) tmem_ld16(taddr + c0 + 16, v);
-          if (p.mode != UG_EPI_STORE) epi_relu16<kAct>(f);  // stores fold the ReLU into the bf16 conversion below
-          if (p.mode == UG_EPI_OUTC) {
+          if (c0 + 16 < ncols && !(hp.debug & 1)) {
+            tmem_ld16(taddr + c0 + 16, v);
+            if constexpr (kKS == 2) tmem_ld16(taddr + p.BN + c0 + 16, reinterpret_cast<uint32_t(&)[16]>(v2));
+          }
+          if (kMode != UG_EPI_STORE) epi_relu16<kAct>(f);  // stores fold the ReLU into the bf16 conversion below
+          if (kMode == UG_EPI_OUTC) {
             const float4* ow = reinterpret_cast<const float4*>(p.outc_w + ncol0 + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -464,7 +494,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
               case 2: a0 = addv[4]; a1 = addv[5]; break;
               default: a0 = addv[6]; a1 = addv[7]; break;
             }
-            if (p.mode == UG_EPI_GATE) {
+            if (kMode == UG_EPI_GATE) {
               const float4* gp = reinterpret_cast<const float4*>(sGate + i * 128 + c0);
               epi_gate8(f, a0, gp[0], gp[1]);
               if (groups == 2) epi_gate8(f + 8, a1, gp[2], gp[3]);
@@ -480,7 +510,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
               // (after a residual add / gate the values may be negative again: only the STORE epilogue's ReLU is
               // folded here; for the other modes f is already activated and the relu conversion is an identity on
               // the activation but NOT on the sum, so they use the plain conversion)
-              if (p.mode == UG_EPI_STORE) {
+              if (kMode == UG_EPI_STORE) {
                 o.x = epi_pack2<kAct>(f[g * 8 + 0], f[g * 8 + 1]);
                 o.y = epi_pack2<kAct>(f[g * 8 + 2], f[g * 8 + 3]);
                 o.z = epi_pack2<kAct>(f[g * 8 + 4], f[g * 8 + 5]);
@@ -515,7 +545,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
         }
         const long long tl1 = p.prof ? clock64() : 0;
         if (p.prof) e_loop += tl1 - tl0;
-        if (p.mode == UG_EPI_OUTC) continue;
+        if (kMode == UG_EPI_OUTC) continue;
         if ((sub + 1) * 64 >= ncols) {  // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
           tc_fence_before();
           __syncwarp();
@@ -578,7 +608,7 @@ __global__ void __launch_bounds__(kMultiThreads, 1) conv_multi_kernel(const __gr
         if (p.prof) e_tail += clock64() - tl1;
         if (p.obufs == 2) obuf ^= 1;
       }
-      if (p.mode == UG_EPI_OUTC) {
+      if (kMode == UG_EPI_OUTC) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
@@ -672,7 +702,16 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): fused channel statistics need a 3x3 STORE conv and stats_tiles == %d",
                      cdiv_m(d->W, 8) * cdiv_m(d->H, TH));
   const int obuf_bytes = tma_store ? kABytesPerStage + (pool ? kPoolBytes : 0) : 0;  // per staging buffer, for sizing
-  const int acc_stages = std::max(1, std::min(4, 512 / (kMI * BN)));
+  // K-split: two issuing warps per tile stream for narrow 3x3 tiles (see the header comment); UG_KSPLIT=0 turns it off
+  static const int ksplit_on = [] { const char* e = getenv("UG_KSPLIT"); return e ? atoi(e) : 1; }();
+  const int ks = (taps == 9 && BN <= 64 && ksplit_on && d->act == UG_ACT_RELU && d->mode != UG_EPI_ADD) ? 2 : 1;
+  // instantiated (activation, taps, epilogue) combinations: 3x3 = ReLU with any epilogue; 1x1 = plain stores with any
+  // activation, residual add without activation
+  if (taps == 9 && d->act != UG_ACT_RELU)
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): 3x3 layers are instantiated for ReLU only");
+  if (taps == 1 && !(d->mode == UG_EPI_STORE || (d->mode == UG_EPI_ADD && d->act == UG_ACT_NONE)))
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): 1x1 layers are instantiated for STORE (any activation) and ADD (no activation)");
+  const int acc_stages = std::max(1, std::min(4, 512 / (kMI * ks * BN)));
   const int a_bytes = taps == 9 ? kMPitch * (TH + 2) * 128 : TW * TH * TN * 128;
   const int a_stage = ((a_bytes + 1023) / 1024) * 1024;
   const int b_tile = BN * 128;
@@ -717,7 +756,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   p.kchunks = kchunks; p.num_k = taps * kchunks;
   p.N = d->N; p.BN = BN; p.stages = hp.sa;
   int tcols = 32;
-  while (tcols < kMI * acc_stages * BN) tcols <<= 1;
+  while (tcols < kMI * ks * acc_stages * BN) tcols <<= 1;
   p.tmem_cols = tcols;
   p.a_bytes = (unsigned)a_bytes; p.b_bytes = (unsigned)b_tile;
   p.scale = d->scale; p.bias = d->bias;
@@ -737,6 +776,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   L->halo_TH = TH; L->halo_a_stage = a_stage; L->halo_copy = hp.m_super;
   L->halo_sa = hp.sa; L->halo_sb = hp.sb; L->halo_bres = hp.b_resident;
   L->halo_debug = d->stages >= 100 ? d->stages - 100 : 0;  // profiling ablations (scripts/conv_prof.py)
+  L->halo_ks = ks;
 
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
@@ -802,31 +842,42 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   return UG_OK;
 }
 
-template <int kTaps>
-static cudaError_t launch_multi(const ug_engine* h, const ConvLaunch* L, const StoreMaps& maps, const MultiParams& hp,
-                                cudaStream_t s) {
-  const int act = L->p.act;
-  cudaError_t e;
-  if (act == UG_ACT_RELU)
-    e = launch_pdl(h, conv_multi_kernel<UG_ACT_RELU, kTaps>, L->grid, kMultiThreads, L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
-  else if (act == UG_ACT_GELU)
-    e = launch_pdl(h, conv_multi_kernel<UG_ACT_GELU, kTaps>, L->grid, kMultiThreads, L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
-  else
-    e = launch_pdl(h, conv_multi_kernel<UG_ACT_NONE, kTaps>, L->grid, kMultiThreads, L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
-  return e;
+template <int kAct, int kTaps, int kMode, int kKS>
+static cudaError_t launch_one(ug_engine* h, const ConvLaunch* L, const StoreMaps& maps, const MultiParams& hp,
+                              cudaStream_t s, bool set_attr) {
+  auto fn = conv_multi_kernel<kAct, kTaps, kMode, kKS>;
+  if (set_attr) return cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return launch_pdl(h, fn, L->grid, kMultiThreads(kKS), L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
+}
+
+// Dispatch over the instantiated (activation, taps, epilogue mode, K-split) combinations (conv_multi_prepare rejects the
+// others).  set_attr = true raises the dynamic shared memory limit of every instantiation instead of launching.
+static cudaError_t dispatch_multi(ug_engine* h, const ConvLaunch* L, const StoreMaps& maps, const MultiParams& hp,
+                                  cudaStream_t s, bool set_attr) {
+  cudaError_t e = cudaSuccess;
+  const int act = L->p.act, mode = L->p.mode, taps = L->halo_mode, ks = L->halo_ks;
+#define UG_MULTI_CASE(A, T, M, K)                                                        \
+  if (set_attr) {                                                                        \
+    if (e == cudaSuccess) e = launch_one<A, T, M, K>(h, L, maps, hp, s, true);           \
+  } else if (act == A && taps == T && mode == M && ks == K) {                            \
+    return launch_one<A, T, M, K>(h, L, maps, hp, s, false);                             \
+  }
+  UG_MULTI_CASE(UG_ACT_RELU, 9, UG_EPI_STORE, 1)
+  UG_MULTI_CASE(UG_ACT_RELU, 9, UG_EPI_STORE, 2)
+  UG_MULTI_CASE(UG_ACT_RELU, 9, UG_EPI_ADD, 1)
+  UG_MULTI_CASE(UG_ACT_RELU, 9, UG_EPI_GATE, 1)
+  UG_MULTI_CASE(UG_ACT_RELU, 9, UG_EPI_GATE, 2)
+  UG_MULTI_CASE(UG_ACT_RELU, 9, UG_EPI_OUTC, 1)
+  UG_MULTI_CASE(UG_ACT_RELU, 9, UG_EPI_OUTC, 2)
+  UG_MULTI_CASE(UG_ACT_NONE, 1, UG_EPI_STORE, 1)
+  UG_MULTI_CASE(UG_ACT_RELU, 1, UG_EPI_STORE, 1)
+  UG_MULTI_CASE(UG_ACT_GELU, 1, UG_EPI_STORE, 1)
+  UG_MULTI_CASE(UG_ACT_NONE, 1, UG_EPI_ADD, 1)
+#undef UG_MULTI_CASE
+  return set_attr ? e : cudaErrorInvalidValue;
 }
 
 int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
-  if (!h->attr_multi) {
-    cudaError_t e = cudaSuccess;
-    const void* fns[] = {(const void*)conv_multi_kernel<UG_ACT_NONE, 9>, (const void*)conv_multi_kernel<UG_ACT_RELU, 9>,
-                         (const void*)conv_multi_kernel<UG_ACT_GELU, 9>, (const void*)conv_multi_kernel<UG_ACT_NONE, 1>,
-                         (const void*)conv_multi_kernel<UG_ACT_RELU, 1>, (const void*)conv_multi_kernel<UG_ACT_GELU, 1>};
-    for (const void* f : fns)
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_multi_kernel)");
-    h->attr_multi = true;
-  }
   MultiParams hp;
   memset(&hp, 0, sizeof(hp));
   hp.TH = L->halo_TH; hp.a_stage_bytes = L->halo_a_stage;
@@ -840,7 +891,12 @@ int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   maps.m[1] = L->tmQ[0];
   maps.m[2] = L->tmQ[1];
   maps.m[3] = L->tmQ[2];
-  const cudaError_t e = L->halo_mode == 9 ? launch_multi<9>(h, L, maps, hp, s) : launch_multi<1>(h, L, maps, hp, s);
+  if (!h->attr_multi) {
+    const cudaError_t e = dispatch_multi(h, L, maps, hp, s, true);
+    if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_multi_kernel)");
+    h->attr_multi = true;
+  }
+  const cudaError_t e = dispatch_multi(h, L, maps, hp, s, false);
   h->launches++;
   return check_cuda(h, e != cudaSuccess ? e : cudaGetLastError(), "conv_multi_kernel launch");
 }

@@ -82,6 +82,7 @@ struct ConvLaunch {
   size_t smem;
   int variant;  // 0 = persistent, 1 = one tile per CTA, 5 = multi-issuer kernel (halo_mode = taps: 9 or 1)
   int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres, halo_debug;
+  int halo_ks;  // multi-issuer kernel: issuing warps per tile stream (K-split), 1 or 2
 };
 
 // Stem convolution (csrc/stem_conv.cu): kernel parameters and a prepared launch.

@@ -106,6 +106,71 @@ __global__ void __launch_bounds__(128) mma_bench2_kernel(int N, int n_acc, int i
   if (warp == 0) tmem_dealloc(tmem_base, cols);
 }
 
+
+// Third form: a CTA PAIR (cluster of 2) issuing tcgen05.mma.cta_group::2 (M = 256 across the two SMs, each CTA supplies
+// its own 128 A rows and N/2 of the B rows).  `issuers` warps of the LEADER CTA each run their own chain into their own
+// accumulator.  Answers what MMA rate a 2-CTA conv kernel could reach for N = 64 / 128 tiles.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __launch_bounds__(128) mma_bench_pair_kernel(int N, int issuers, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t tmem_ptr;
+  for (int i = threadIdx.x; i < (issuers * 16384 + (N / 2) * 128) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+  }
+  int cols = 32;
+  while (cols < issuers * N) cols <<= 1;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+  if (rank == 0 && warp < issuers && lane == 0) {
+    const uint32_t idesc = umma_idesc_bf16(256, N);
+    const uint64_t ad = umma_desc_sw128(smem_u32(smem + warp * 16384));
+    const uint64_t bd = umma_desc_sw128(smem_u32(smem + issuers * 16384));
+    const uint32_t d0 = tmem_base + warp * N;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d0),
+            "l"(ad + 2 * k), "l"(bd + 2 * k), "r"(idesc), "r"(1u)
+            : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[warp])) : "memory");
+    mbar_wait(&bar[warp], 0);
+    const long long t1 = clock64();
+    if (warp == 0) out[blockIdx.x >> 1] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+}
+
 }  // namespace ug
 
 extern "C" int ug_mma_microbench(ug_handle h, int N, int n_acc, int iters, int ctas_per_sm, int distinct_ab,
@@ -177,6 +242,51 @@ extern "C" int ug_mma_microbench2(ug_handle h, int N, int n_acc, int issuers, in
     double s = 0;
     for (long long v : host) s += (double)v;
     out2[0] = s / ctas / ((double)iters * 4 * n_acc);  // cycles per MMA of one issuer chain set
+  }
+  cudaFree(dev);
+  return rc;
+}
+
+extern "C" int ug_mma_microbench_pair(ug_handle h, int N, int issuers, int iters, double* out2) {
+  if (!h || !out2 || N % 16 || N < 32 || N > 256 || issuers < 1 || issuers > 4 || issuers * N > 512) return UG_EINVAL;
+  using namespace ug;
+  const int ctas = h->num_sms & ~1;
+  long long* dev = nullptr;
+  if (cudaMalloc(&dev, sizeof(long long) * ctas) != cudaSuccess) return UG_ENOMEM;
+  const size_t smem = 1024 + (size_t)issuers * 16384 + (size_t)(N / 2) * 128;
+  cudaFuncSetAttribute(mma_bench_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaMemset(dev, 0, sizeof(long long) * ctas);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, mma_bench_pair_kernel, N, issuers, 10, dev);  // warm-up
+  cudaEventRecord(e0);
+  if (le == cudaSuccess) le = cudaLaunchKernelEx(&cfg, mma_bench_pair_kernel, N, issuers, iters, dev);
+  cudaEventRecord(e1);
+  int rc = check_cuda(h, le != cudaSuccess ? le : cudaGetLastError(), "mma_bench_pair launch");
+  if (rc == UG_OK) rc = check_cuda(h, cudaDeviceSynchronize(), "mma_bench_pair");
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  out2[1] = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc == UG_OK) {
+    std::vector<long long> host(ctas / 2);
+    cudaMemcpy(host.data(), dev, sizeof(long long) * (ctas / 2), cudaMemcpyDeviceToHost);
+    double s = 0;
+    for (long long v : host) s += (double)v;
+    out2[0] = s / (ctas / 2) / ((double)iters * 4);  // cycles per M=256 MMA of one issuer
   }
   cudaFree(dev);
   return rc;

@@ -119,7 +119,8 @@ EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "u
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
                     "ug_program_destroy", "ug_program_run_host", "ug_program_run_host_pipelined",
                     "ug_program_run_timed", "ug_program_autotune", "ug_wavelet_workspace_bytes"]
-DEV_SYMBOLS = ["ug_conv_profile", "ug_conv_profile16", "ug_mma_microbench", "ug_mma_microbench2"]
+DEV_SYMBOLS = ["ug_conv_profile", "ug_conv_profile16", "ug_mma_microbench", "ug_mma_microbench2",
+               "ug_mma_microbench_pair"]
 
 _lib = None
 
@@ -147,6 +148,7 @@ def load_library():
         lib.ug_mma_microbench.argtypes = [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]
         lib.ug_mma_microbench2.argtypes = [_vp, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_double)]
         lib.ug_conv_profile16.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_double)]
+        lib.ug_mma_microbench_pair.argtypes = [_vp, _i, _i, _i, C.POINTER(C.c_double)]
         lib.ug_conv_profile.argtypes = [_vp, _vp, _vp, C.POINTER(C.c_double)]
     lib.ug_program_create.argtypes = [_vp, _vp, _i, C.POINTER(_vp)]
     lib.ug_program_run.argtypes = [_vp, _vp, _vp]
