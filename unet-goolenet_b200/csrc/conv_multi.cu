@@ -35,8 +35,13 @@
 #include <algorithm>
 #include "conv_common.cuh"
 
+#ifndef UG_EPI_UNROLL
+#define UG_EPI_UNROLL 1
+#endif
+
 namespace ug {
 
+static constexpr int kEpiUnroll = UG_EPI_UNROLL;   // unroll factor of the epilogue chunk loop
 static constexpr int kMI = 2;           // tile streams per CTA (each with its own epilogue warpgroup)
 __host__ __device__ constexpr int kMultiThreads(int ks) { return 32 * (4 * kMI + 2 + kMI * ks); }   // 384 (kKS = 1) / 448 (kKS = 2)
 static constexpr int kMPitch = 10;      // halo tile pitch: 8 output pixels + one border pixel on each side
@@ -456,10 +461,11 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
           if (p.prof) e_wobuf += clock64() - tw0;
         }
         uint8_t* so_row = sOi + obuf * obuf_bytes + row * 128;
-        // not unrolled on purpose: the four epilogue warps of an SMSP share its 6 KB L0 instruction cache with an
-        // MMA issuer / producer warp, and a 4x larger loop body measurably slowed the MMA issue (0.24 -> 0.29 ms)
+        // unroll factor of the chunk loop (UG_EPI_UNROLL, default see below): the epilogue warps of an SMSP share its
+        // 6 KB L0 instruction cache with an MMA issuer / producer warp; with run-time epilogue modes a 4x larger loop
+        // body measurably slowed the MMA issue (0.24 -> 0.29 ms), so round 1 did not unroll at all
         const long long tl0 = p.prof ? clock64() : 0;
-#pragma unroll 1
+#pragma unroll kEpiUnroll
         for (int cc = 0; cc < 4; ++cc) {
           const int c0 = sub * 64 + cc * 16;
           if (c0 >= ncols) break;

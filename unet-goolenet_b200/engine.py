@@ -131,6 +131,7 @@ def load_library():
     if _lib is not None:
         return _lib
     path = DEV_LIB_PATH if USE_DEV_LIB else LIB_PATH
+    path = os.environ.get("UG_LIB_PATH", path)    # scripts/ only: A/B of experimental builds of the library
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
                            f"g.build()'` (there is no fallback path)")
