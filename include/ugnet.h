@@ -78,6 +78,12 @@ typedef struct ug_conv_desc {
                                  AdaptiveAvg/MaxPool2d(1) (basicUnet.py:217-218) fused into the epilogue; fold with
                                  ug_gate (splits = stats_tiles).  Deterministic (no atomics). */
   int stats_tiles;            /* must equal ceil(W/8) * ceil(H/16) (pixel tiles per image); checked */
+  void* out2;                 /* optional second destination (1x1 layers, STORE epilogue): GEMM columns [0, n1) go to */
+  int out2_cstride;           /* `out`, columns [n_split, N) to out2[... * out2_cstride + (j - n_split)]; columns */
+  int n_split, n1;            /* [n1, n_split) are padding (zero weight rows), n_split % 64 == 0.  Used for the three
+                                 1x1 convolutions of an Inception block that read the same tensor (torchvision
+                                 Inception.forward: branch1, branch2[0], branch3[0]) as ONE GEMM: branch1 lands in the
+                                 block's concat output, the two reduce results in a scratch tensor */
   int TW, TH, TN, BN, stages; /* tiling; 0 = engine chooses */
   int variant;                /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel (TMEM multi-buffered
                                  accumulators, TMA-store epilogue); 5 = 3x3 multi-issuer kernel (one CTA per

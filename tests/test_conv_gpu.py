@@ -163,6 +163,16 @@ CASES = [
     dict(B=5, H=7, W=7, Cin=160, N=320, R=3, variant=5),           # GoogLeNet 5a-like, tiny map
     dict(B=2, H=16, W=16, Cin=64, N=64, R=3, mode=1, variant=5),   # residual add, resident weights
     dict(B=70, H=32, W=32, Cin=64, N=128, R=3, variant=5),        # several rounds per CTA
+    # row-strip tiles (28-wide and other narrow maps: SR full image rows per tile, see conv_multi.cu): K-split, every
+    # epilogue mode, fused pool from the staged tile, ragged last strip, odd tile count
+    dict(B=3, H=28, W=28, Cin=64, N=64, R=3, variant=5),
+    dict(B=2, H=28, W=28, Cin=512, N=512, R=3, mode=2, variant=5),
+    dict(B=2, H=28, W=28, Cin=64, N=64, R=3, mode=3, variant=5),
+    dict(B=3, H=28, W=28, Cin=64, N=64, R=3, pool=True),
+    dict(B=2, H=30, W=20, Cin=128, N=128, R=3, mode=1, variant=5),
+    dict(B=2, H=18, W=36, Cin=64, N=96, R=3, pool=True),
+    dict(B=9, H=28, W=28, Cin=128, N=192, R=3, variant=5),
+    dict(B=2, H=28, W=28, Cin=1024, N=256, R=3, variant=5),
     # fused 2x2 max-pool side output (DownBlock): exact tiles, ragged width (28 = 3.5 tiles), streamed and resident weights
     dict(B=2, H=112, W=112, Cin=128, N=128, R=3, pool=True),
     dict(B=3, H=28, W=28, Cin=256, N=512, R=3, pool=True, out_extra=64, out_off=32),
@@ -223,6 +233,51 @@ def test_conv_fused_channel_stats(engine, B, H, W, Cin, N):
     assert torch.allclose(psum.sum(1), of.sum((1, 2)), rtol=1e-4, atol=1e-2)
     assert torch.equal(pmax.amax(1), of.amax((1, 2)))
     d.stats_tiles = S + 1
+    with pytest.raises(RuntimeError):
+        engine.run_op(d)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,n1,n2,bn", [
+    (256, 28, 28, 192, 64, 112, 128),     # inception3a heads at the pipeline batch: persistent kernel
+    (64, 14, 14, 512, 112, 176, 128),     # 4d: n1 padded 112 -> 128, persistent kernel
+    (16, 14, 14, 512, 160, 136, 128),     # 4b: 160 -> 192 is not a multiple of BN: persistent kernel forced
+    (8, 7, 7, 832, 384, 240, 64),         # 5b at a small batch: one tile per CTA, BN = 64 divides n_split
+    (3, 14, 14, 480, 192, 112, 64),       # 4a, ragged pixel tiles
+])
+def test_conv_split_gemm(engine, B, H, W, Cin, n1, n2, bn):
+    """The three 1x1 heads of an Inception block as ONE GEMM with two destinations (ug_conv_desc.out2): columns [0, n1)
+    into a channel slice of the concat output, columns [n_split, N) into a scratch tensor, padding columns nowhere."""
+    from ugnet_b200 import engine as E
+    from ugnet_b200 import pack
+    g = torch.Generator(device="cuda").manual_seed(n1 + n2)
+    x = _mk((B, H, W, Cin), g).to(torch.bfloat16)
+    n_split = (n1 + 63) // 64 * 64
+    N = n_split + n2
+    wt = _mk((N, Cin, 1, 1), g, (1.0 / Cin) ** 0.5)
+    wt[n1:n_split] = 0
+    wp = pack.pack_conv_weight(wt, 128)
+    scale = torch.rand((N,), generator=g, device="cuda") + 0.5
+    bias = _mk((N,), g)
+    scale[n1:n_split] = 0
+    bias[n1:n_split] = 0
+    cs1 = n1 + 96
+    out1, ok1 = guarded((B, H, W, cs1), 7.0, torch.bfloat16)
+    out2, ok2 = guarded((B, H, W, n2), 5.0, torch.bfloat16)
+    d = E.ConvDesc()
+    d.inp = x.data_ptr(); d.in_cstride = Cin; d.Cin = Cin; d.B, d.H, d.W = 1, 1, B * H * W
+    d.R = d.S = 1; d.pad = 0; d.w = wp.data_ptr(); d.N = N
+    d.scale = scale.data_ptr(); d.bias = bias.data_ptr(); d.act = 1; d.mode = 0
+    d.out = out1.data_ptr() + 2 * 32; d.out_cstride = cs1; d.up = 1; d.BN = bn
+    d.out2 = out2.data_ptr(); d.out2_cstride = n2; d.n_split = n_split; d.n1 = n1
+    engine.run_op(d)
+    torch.cuda.synchronize()
+    ok1(); ok2()
+    y = torch.relu(torch.einsum("bhwc,nc->bhwn", x.float(), wt[:, :, 0, 0].to(torch.bfloat16).float()) * scale + bias)
+    for got, ref in ((out1[..., 32:32 + n1].float(), y[..., :n1]), (out2.float(), y[..., n_split:])):
+        bad = (got - ref).abs() > 2.0 ** -7 * ref.abs() + 2e-2
+        assert not bad.any(), f"{bad.sum().item()} mismatches, max err {(got - ref).abs().max().item():.4f}"
+    assert (out1[..., :32] == 7.0).all() and (out1[..., 32 + n1:] == 7.0).all(), "padding columns leaked into the output"
+    d.n_split = n_split + 8
     with pytest.raises(RuntimeError):
         engine.run_op(d)
 

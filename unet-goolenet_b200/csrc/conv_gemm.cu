@@ -146,6 +146,13 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     const long long pix = (long long)oy * p.OW + ox;
     __nv_bfloat16* out_row =
         reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)n * p.OH * p.OW + pix) * p.out_cstride + cbase;
+    int ncols = min(p.BN, p.N - ncol0);
+    if (p.n_split) {  // split 1x1 GEMM: this n-tile lies entirely in one of the two column groups (BN divides n_split)
+      if (ncol0 >= p.n_split)
+        out_row = reinterpret_cast<__nv_bfloat16*>(p.out2) + ((long long)n * p.OH * p.OW + pix) * p.out2_cstride + (ncol0 - p.n_split);
+      else
+        ncols = min(p.BN, p.n1 - ncol0);  // (<= 0 for a tile of padding columns: nothing is stored)
+    }
     const __nv_bfloat16* add_row =
         reinterpret_cast<const __nv_bfloat16*>(p.add) + (long long)n * p.add_bstride + pix * p.add_cstride + cbase;
     const float* gate_row = p.gate + (long long)n * p.N + ncol0;
@@ -155,7 +162,6 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float dot = 0.0f;
 
-    const int ncols = min(p.BN, p.N - ncol0);
     for (int c0 = 0; c0 < ncols; c0 += 16) {
       __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the guarded stores
       uint32_t v[16];
@@ -208,6 +214,7 @@ template <int kAct>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                            const __grid_constant__ CUtensorMap tmB,
                                                                            const __grid_constant__ CUtensorMap tmO,
+                                                                           const __grid_constant__ CUtensorMap tmO2,
                                                                            const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     if (p.tma_store) prefetch_tmap(&tmO);
+    if (p.tma_store && p.n_split) prefetch_tmap(&tmO2);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -447,8 +455,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         named_bar_sync(1, 128);
         if (etid == 0) {
-          for (int sub = 0; sub * 64 < ncols; ++sub)
-            tma_store_4d(&tmO, sO + obuf * obuf_bytes + sub * kABytesPerStage, ncol0 + sub * 64, x0, y0, n0);
+          for (int sub = 0; sub * 64 < ncols; ++sub) {
+            // split 1x1 GEMM: 64-column blocks at or beyond n_split belong to the second destination (the map of the
+            // first one ends at n1, so its padding columns are clipped)
+            const int col = ncol0 + sub * 64;
+            if (p.n_split && col >= p.n_split)
+              tma_store_4d(&tmO2, sO + obuf * obuf_bytes + sub * kABytesPerStage, col - p.n_split, x0, y0, n0);
+            else
+              tma_store_4d(&tmO, sO + obuf * obuf_bytes + sub * kABytesPerStage, col, x0, y0, n0);
+          }
           bulk_commit_group();
         }
         if (p.obufs == 2) obuf ^= 1;
@@ -573,6 +588,14 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
     if (d->mode == UG_EPI_GATE && !d->gate) return set_error(h, UG_EINVAL, "conv: GATE epilogue needs gate");
   }
 
+  const bool split = d->out2 != nullptr || d->n_split != 0;
+  if (split) {
+    if (d->R != 1 || up != 1 || d->mode != UG_EPI_STORE || !d->out2 || d->n_split % 64 || d->n_split <= 0 ||
+        d->n_split >= d->N || d->n1 <= 0 || d->n1 > d->n_split || d->n1 % 8 || d->out2_cstride % 8 ||
+        (reinterpret_cast<uintptr_t>(d->out2) & 15) || d->variant == 5 || d->pool_out || d->stats_sum)
+      return set_error(h, UG_EINVAL, "conv: a split GEMM is a 1x1 STORE layer with n_split %% 64 == 0 and 0 < n1 <= n_split < N");
+    if (BN % 64) return set_error(h, UG_EINVAL, "conv: a split GEMM needs BN %% 64 == 0");
+  }
   if (d->variant == 5) return conv_multi_prepare(h, d, d->R == 3 ? std::min(BN, 128) : BN, L);
   if (d->variant == 0 && up == 2 && d->H * d->W >= 784 && d->convt_cout % 64 == 0) {
     // ConvTranspose 2x2 s2 on maps of at least 28x28: multi-issuer kernel (two epilogue warpgroups, pixel shuffle as
@@ -615,7 +638,7 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   static const int gemm_rule = [] { const char* e = getenv("UG_GEMM_RULE"); return e ? atoi(e) : 1; }();
   int auto_persistent = BN == 256;
   if (gemm_rule && d->variant == 0 && d->R == 1 && d->S == 1 && up == 1 && d->mode != UG_EPI_OUTC) {
-    if (m_tiles_total >= 1024 && kchunks == 1 && (n_tiles == 1 || BN % 64 == 0)) {
+    if (m_tiles_total >= 1024 && kchunks == 1 && (n_tiles == 1 || BN % 64 == 0) && !split) {
       const int rc = conv_multi_prepare(h, d, BN, L);
       if (rc == UG_OK) return rc;
       if (rc != UG_EUNSUPPORTED) return rc;
@@ -624,7 +647,10 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
     const bool boxes_ok = n_tiles == 1 || BN % 64 == 0;
     if (boxes_ok && (m_tiles_total >= 1024 || (m_tiles_total >= 296 && BN > 64))) auto_persistent = 1;
   }
+  if (split && d->n_split % BN) auto_persistent = 1;  // the one-tile kernel needs whole n-tiles on either side of n_split
   const int variant = d->variant == 1 ? 1 : (d->variant == 2 ? 0 : (auto_persistent ? 0 : 1));
+  if (split && variant == 1 && d->n_split % BN)
+    return set_error(h, UG_EINVAL, "conv: split GEMM on the one-tile kernel needs BN to divide n_split (BN = 64)");
   const int tma_store = (variant == 0 && up == 1 && d->mode != UG_EPI_OUTC) ? 1 : 0;
   const int stage_copy = (variant == 0 && up == 2) ? 1 : 0;
   const int n_sub = ceil_div(BN, 64);
@@ -677,6 +703,7 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   p.logits = d->logits; p.mask = d->mask;
   p.m_tiles = m_tiles_total; p.n_tiles = n_tiles; p.acc_stages = acc_stages;
   p.tma_store = tma_store; p.obufs = obufs; p.npad = npad; p.stage_copy = stage_copy;
+  p.out2 = d->out2; p.out2_cstride = d->out2_cstride; p.n_split = split ? d->n_split : 0; p.n1 = d->n1;
   L->variant = variant;
   if (variant == 0) {
     int tcols = 32;
@@ -684,7 +711,7 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
     p.tmem_cols = tcols;
   }
   if (tma_store) {
-    cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t dims[4] = {(cuuint64_t)(split ? d->n1 : d->N), (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->out_cstride * 2, (cuuint64_t)d->W * d->out_cstride * 2,
                              (cuuint64_t)d->H * d->W * d->out_cstride * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
@@ -693,8 +720,19 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv: output tensor map encode failed (%d)", (int)r);
+    memset(&L->tmO2, 0, sizeof(L->tmO2));
+    if (split) {
+      cuuint64_t dims2[4] = {(cuuint64_t)(d->N - d->n_split), (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+      cuuint64_t strides2[3] = {(cuuint64_t)d->out2_cstride * 2, (cuuint64_t)d->W * d->out2_cstride * 2,
+                                (cuuint64_t)d->H * d->W * d->out2_cstride * 2};
+      r = encode(&L->tmO2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d->out2, dims2, strides2, box, es,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(h, UG_ECUDA, "conv: second output tensor map encode failed (%d)", (int)r);
+    }
   } else {
     memset(&L->tmO, 0, sizeof(L->tmO));
+    memset(&L->tmO2, 0, sizeof(L->tmO2));
   }
 
   {
@@ -755,11 +793,11 @@ int conv_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
     else le = launch_pdl(h, conv_gemm_kernel<UG_ACT_NONE>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->p);
   } else {
     if (act == UG_ACT_RELU)
-      le = launch_pdl(h, conv_gemm_persistent_kernel<UG_ACT_RELU>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->tmO, L->p);
+      le = launch_pdl(h, conv_gemm_persistent_kernel<UG_ACT_RELU>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->tmO, L->tmO2, L->p);
     else if (act == UG_ACT_GELU)
-      le = launch_pdl(h, conv_gemm_persistent_kernel<UG_ACT_GELU>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->tmO, L->p);
+      le = launch_pdl(h, conv_gemm_persistent_kernel<UG_ACT_GELU>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->tmO, L->tmO2, L->p);
     else
-      le = launch_pdl(h, conv_gemm_persistent_kernel<UG_ACT_NONE>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->tmO, L->p);
+      le = launch_pdl(h, conv_gemm_persistent_kernel<UG_ACT_NONE>, L->grid, kThreads, L->smem, s, L->tmA, L->tmB, L->tmO, L->tmO2, L->p);
   }
   h->launches++;
   return check_cuda(h, le != cudaSuccess ? le : cudaGetLastError(), "conv_gemm kernel launch");

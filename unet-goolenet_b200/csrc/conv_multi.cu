@@ -13,6 +13,14 @@
 //   * weights that fit (9*Cin_pad*BN*2 bytes, e.g. 72 KB for 64->64) stay RESIDENT in shared memory for the launch;
 //   * otherwise every streamed weight tile is consumed by both issuers (each for its own pixel tile) before its
 //     slot is released, which halves the weight traffic per FLOP (an effective 256 x BN CTA tile).
+// Row-strip tiles (hp.strip, maps 28 pixels wide): 8-pixel-wide tiles cover a 28-wide row with 3.5 tile columns, so
+// only 76.6 % of the MMA rows were output pixels.  In strip mode a tile is SR = 4 FULL image rows: the TMA box is
+// {64 ch, W+2 px, SR+2 rows}, the MMA rows are the FLATTENED halo positions m = j*(W+2) + x (8-row groups contiguous:
+// SBO 1024), tap (r, s) starts (r*(W+2) + s) pixels into the stage, and rows with x >= W (two per image row) plus the
+// tail m >= SR*(W+2) are computed but never stored: 112 of 128 rows useful (87.5 %), 7 tiles per image instead of 8.
+// The epilogue compacts its rows to the [SR][W] layout of the TMA store box; the fused 2x2 max-pool reads the staged
+// tile instead of exchanging registers (row neighbours are W+2 lanes apart).
+//
 // The issue loops are warp-uniform with the asynchronous instructions under elect_one_sync() (see common.cuh):
 // with `if (lane == 0)` loops the issuing thread needed ~16 SASS instructions per MMA and bounded every N <= 128
 // layer (224x224 64->64: 0.375 ms before, 0.236 ms after; profiles/r01_conv_sweep_multi_issuer.txt).
@@ -44,7 +52,7 @@ namespace ug {
 static constexpr int kEpiUnroll = UG_EPI_UNROLL;   // unroll factor of the epilogue chunk loop
 static constexpr int kMI = 2;           // tile streams per CTA (each with its own epilogue warpgroup)
 __host__ __device__ constexpr int kMultiThreads(int ks) { return 32 * (4 * kMI + 2 + kMI * ks); }   // 384 (kKS = 1) / 448 (kKS = 2)
-static constexpr int kMPitch = 10;      // halo tile pitch: 8 output pixels + one border pixel on each side
+static constexpr int kMPitch = 10;      // halo tile pitch of 8-pixel-wide tiles: 8 output pixels + one border pixel on each side
 // Warp roles.  The warp scheduler prefers the highest warp id among eligible warps, and the MMA issuers are the
 // latency-critical warps (every late tcgen05.mma is a tensor-pipe bubble), so they get the highest ids, then the
 // TMA producer; the epilogue warps (which have plenty of slack but dense instruction streams) get the lowest.
@@ -89,6 +97,10 @@ struct MultiParams {
   int b_resident;     // whole weight matrix kept in smem (requires n_tiles == 1)
   int m_super;        // ceil(m_tiles / kMI): pixel tiles are handed out in groups of kMI
   FastDiv d_msuper, d_tx, d_ty;   // dividers by m_super, tiles_x, tiles_y
+  int pitch;          // halo pixels per stage row: kMPitch (8-pixel-wide tiles) or W + 2 (row-strip tiles)
+  int sbo;            // byte distance of consecutive 8-row groups of the A operand: pitch * 128 (tiles) or 1024 (strips)
+  int strip;          // row-strip tiles (see the header comment); TH is then the number of image rows per tile
+  FastDiv d_pitch;    // divider by pitch (strip mode: MMA row -> (image row, x))
   int debug;          // ablation switches for profiling (results are wrong when set): 1 = no TMEM loads,
                       // 2 = no staging stores / TMA store, 4 = activation TMA loads only for the first stages
 };
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     // ------------------------------------------------------------------ activation producer (whole warp, elected lane issues)
     int as[kMI] = {0, 0};
     uint32_t aph[kMI] = {0, 0};
-    const uint32_t a_tx = kTaps == 9 ? (uint32_t)(kMPitch * (hp.TH + 2) * 128) : p.a_bytes;
+    const uint32_t a_tx = kTaps == 9 ? (uint32_t)(hp.pitch * (hp.TH + 2) * 128) : p.a_bytes;
     long long w_a = 0;
     const long long t_start = clock64();
     unsigned long long ns0 = 0;
@@ -301,7 +313,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
           mbar_wait(&a_full[i * hp.sa + as], aph);
           if (p.prof) w_af += clock64() - tw0;
           tc_fence_after();
-          ad0 = kTaps == 9 ? umma_desc_sw128_sbo(smem_u32(sA + (i * hp.sa + as) * hp.a_stage_bytes), kMPitch * 128)
+          ad0 = kTaps == 9 ? umma_desc_sw128_sbo(smem_u32(sA + (i * hp.sa + as) * hp.a_stage_bytes), hp.sbo)
                            : umma_desc_sw128(smem_u32(sA + (i * hp.sa + as) * hp.a_stage_bytes));
         }
         // (tap loop unrolled by one filter row only: keeps the issue loop inside the L0 instruction cache)
@@ -322,8 +334,8 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
           }
           if (mine) {
             if (valid) {
-              // tap (r, sx): the A rows start (r*10 + sx) halo pixels (128 B each) into the stage
-              const uint64_t ad = ad0 + (uint64_t)((r * kMPitch + sx) * 8);
+              // tap (r, sx): the A rows start (r*pitch + sx) halo pixels (128 B each) into the stage
+              const uint64_t ad = ad0 + (uint64_t)((r * hp.pitch + sx) * 8);
               const uint64_t bd = umma_desc_sw128(b_addr);
               const uint32_t first = item >= kKS ? 1u : 0u;   // this issuer's first item of the tile overwrites
               if (elect_one_sync()) {
@@ -377,10 +389,15 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int etid = threadIdx.x - i * 128;
-    const int tx = kTaps == 9 ? (row & 7) : row % p.TW;
-    const int ty = kTaps == 9 ? (row >> 3) : (row / p.TW) % p.TH;
+    // MMA row -> pixel of the tile.  8-pixel-wide 3x3 tiles: row = ty*8 + tx.  Row-strip 3x3 tiles: row = ty*pitch + tx
+    // with tx >= W garbage.  1x1 tiles: row = (tn*TH + ty)*TW + tx.  `srow` is the row of the staged output tile.
+    const bool strip = kTaps == 9 && hp.strip;
+    const int sty = hp.d_pitch.div(row);
+    const int tx = kTaps == 9 ? (strip ? row - sty * hp.pitch : (row & 7)) : row % p.TW;
+    const int ty = kTaps == 9 ? (strip ? sty : (row >> 3)) : (row / p.TW) % p.TH;
     const int tn = kTaps == 9 ? 0 : row / (p.TW * p.TH);
-    const bool row_in_tile = kTaps == 9 ? (ty < hp.TH) : (row < p.TW * p.TH * p.TN);
+    const bool row_in_tile = kTaps == 9 ? (ty < hp.TH && (!strip || tx < p.W)) : (row < p.TW * p.TH * p.TN);
+    const int srow = strip ? ty * p.W + tx : row;
     uint8_t* sOi = sO + i * p.obufs * obuf_bytes;
     int acc = 0, obuf = 0;
     uint32_t acc_phase = 0;
@@ -460,7 +477,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
           named_bar_sync(1 + i, 128);
           if (p.prof) e_wobuf += clock64() - tw0;
         }
-        uint8_t* so_row = sOi + obuf * obuf_bytes + row * 128;
+        uint8_t* so_row = sOi + obuf * obuf_bytes + srow * 128;
         // unroll factor of the chunk loop (UG_EPI_UNROLL, default see below): the epilogue warps of an SMSP share its
         // 6 KB L0 instruction cache with an MMA issuer / producer warp; with run-time epilogue modes a 4x larger loop
         // body measurably slowed the MMA issue (0.24 -> 0.29 ms), so round 1 did not unroll at all
@@ -528,8 +545,8 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
                 o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
               }
               const int chunk = cc * 2 + g;
-              if (!(hp.debug & 2)) *reinterpret_cast<uint4*>(so_row + ((chunk ^ (row & 7)) << 4)) = o;
-              if (p.pool) {
+              if (!(hp.debug & 2) && (!strip || row_in_tile)) *reinterpret_cast<uint4*>(so_row + ((chunk ^ (srow & 7)) << 4)) = o;
+              if (p.pool && !strip) {
                 // fused nn.MaxPool2d(2): the 2x2 window of pixel (tx, ty) lives in lanes ^1 (x) and ^8 (y) of this
                 // warp (row = ty*8 + tx); max of the rounded bf16 values == rounded max (rounding is monotonic)
                 uint4 m = o;
@@ -556,6 +573,32 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
+        }
+        if (p.pool && strip) {
+          // fused nn.MaxPool2d(2) of a row-strip tile: row neighbours are not warp neighbours here, so the 2x2 windows
+          // are read back from the staged tile ([TH][W] rows of 128 B) once every thread has written its row
+          named_bar_sync(1 + i, 128);
+          const uint8_t* sbuf = sOi + obuf * obuf_bytes;
+          uint8_t* pbuf = sP + (i * p.obufs + obuf) * kPoolBytes;
+          const int pw = p.W >> 1, items = (hp.TH >> 1) * pw * 8;
+          for (int it = etid; it < items; it += 128) {
+            const int ch = it & 7, pp = it >> 3;       // 16-byte channel chunk, pooled pixel of the tile
+            const int py = pp / pw, px = pp - py * pw;
+            uint4 m = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const int r = (2 * py + (w >> 1)) * p.W + 2 * px + (w & 1);
+              const uint4 v4 = *reinterpret_cast<const uint4*>(sbuf + r * 128 + ((ch ^ (r & 7)) << 4));
+              if (w == 0) m = v4;
+              else {
+                m.x = bf16x2_max(m.x, v4.x);
+                m.y = bf16x2_max(m.y, v4.y);
+                m.z = bf16x2_max(m.z, v4.z);
+                m.w = bf16x2_max(m.w, v4.w);
+              }
+            }
+            *reinterpret_cast<uint4*>(pbuf + pp * 128 + ((ch ^ (pp & 7)) << 4)) = m;
+          }
         }
         fence_proxy_async_smem();
         // (issued after the proxy fence: the fence waits for outstanding loads, which would expose their latency here)
@@ -684,10 +727,33 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): ConvTranspose needs cout %% 64 == 0 and BN %% 64 == 0");
   if (taps == 1 && d->mode == UG_EPI_OUTC) return set_error(h, UG_EUNSUPPORTED, "conv(multi): OUTC is a 3x3 epilogue");
   int TW, TH, TN;
+  int strip = 0, pitch = kMPitch;
   if (taps == 9) {
     TW = 8;
     TH = cdiv_m(d->H, cdiv_m(d->H, 16));  // <= 16 rows per tile, no wasted tile rows
     TN = 1;
+    // row-strip tiles (SR full image rows per tile) when they put more output pixels on the 128 MMA rows than the
+    // 8-pixel-wide tiles do: 28-wide maps (87.5 % instead of 76.6 %).  UG_STRIP=0 turns them off.
+    static const int strip_on = [] { const char* e = getenv("UG_STRIP"); return e ? atoi(e) : 1; }();
+    const int sr_max = 128 / (d->W + 2);
+    if (strip_on && sr_max >= 1 && !d->stats_sum) {
+      int sr = std::min(sr_max, d->H);
+      if (d->pool_out) sr &= ~1;                                   // pooled tiles need an even number of rows
+      if (sr >= 1) {
+        sr = cdiv_m(d->H, cdiv_m(d->H, sr));                       // no wasted tile rows
+        if (d->pool_out && (sr & 1)) sr = 0;
+      }
+      if (sr >= 1) {
+        const double fill_strip = (double)d->H * d->W / ((double)cdiv_m(d->H, sr) * 128.0);
+        const double fill_tile = (double)d->H * d->W / ((double)cdiv_m(d->W, 8) * cdiv_m(d->H, TH) * 128.0);
+        if (fill_strip > fill_tile + 1e-6) {
+          strip = 1;
+          pitch = d->W + 2;
+          TW = d->W;
+          TH = sr;
+        }
+      }
+    }
   } else {
     choose_tile(d->B, d->H, d->W, &TW, &TH, &TN);
     if (TW > 256 || TH > 256 || TN > 256) return set_error(h, UG_EUNSUPPORTED, "conv(multi): tile exceeds the TMA box limits");
@@ -700,7 +766,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   const int tma_store = d->mode != UG_EPI_OUTC;
   const int pool = d->pool_out != nullptr;
   if (pool && (taps != 9 || d->mode != UG_EPI_STORE || (d->H & 1) || (d->W & 1) || (TH & 1) || d->pool_cstride % 8 ||
-               (reinterpret_cast<uintptr_t>(d->pool_out) & 15)))
+               (reinterpret_cast<uintptr_t>(d->pool_out) & 15) || (TW / 2) * (TH / 2) * 128 > kPoolBytes))
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): fused max-pool needs a 3x3 STORE conv on an even map");
   const int stats = d->stats_sum != nullptr;
   if (stats && (taps != 9 || d->mode != UG_EPI_STORE || !d->stats_max ||
@@ -718,14 +784,19 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   if (taps == 1 && !(d->mode == UG_EPI_STORE || (d->mode == UG_EPI_ADD && d->act == UG_ACT_NONE)))
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): 1x1 layers are instantiated for STORE (any activation) and ADD (no activation)");
   const int acc_stages = std::max(1, std::min(4, 512 / (kMI * ks * BN)));
-  const int a_bytes = taps == 9 ? kMPitch * (TH + 2) * 128 : TW * TH * TN * 128;
-  const int a_stage = ((a_bytes + 1023) / 1024) * 1024;
+  const int a_bytes = taps == 9 ? pitch * (TH + 2) * 128 : TW * TH * TN * 128;
+  // strip mode: MMA row 127 of tap (2,2) reads halo position 127 + 2*pitch + 2, past the loaded box (garbage rows only)
+  const int a_span = strip ? std::max(a_bytes, (128 + 2 * pitch + 2) * 128) : a_bytes;
+  const int a_stage = ((a_span + 1023) / 1024) * 1024;
   const int b_tile = BN * 128;
 
   MultiParams hp;
   memset(&hp, 0, sizeof(hp));
   hp.TH = TH;
   hp.a_stage_bytes = a_stage;
+  hp.strip = strip;
+  hp.pitch = pitch;
+  hp.sbo = strip ? 1024 : pitch * 128;
   const int fixed = 1024 + 8 * (2 * kMI * 4 + 2 * 16 + 2 * kMI * 4) + 16 + 2 * npad * (int)sizeof(float) +
                     kMI * 128 * (int)sizeof(float) + (stats ? kMI * 512 * (int)sizeof(float) : 0);
   const long long budget = 227LL * 1024 - fixed;
@@ -783,12 +854,13 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   L->halo_sa = hp.sa; L->halo_sb = hp.sb; L->halo_bres = hp.b_resident;
   L->halo_debug = d->stages >= 100 ? d->stages - 100 : 0;  // profiling ablations (scripts/conv_prof.py)
   L->halo_ks = ks;
+  L->halo_strip = strip; L->halo_pitch = pitch;
 
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)d->W * d->in_cstride * 2,
                              (cuuint64_t)d->H * d->W * d->in_cstride * 2};
-    cuuint32_t box9[4] = {64, (cuuint32_t)kMPitch, (cuuint32_t)(TH + 2), 1};
+    cuuint32_t box9[4] = {64, (cuuint32_t)pitch, (cuuint32_t)(TH + 2), 1};
     cuuint32_t box1[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
     const int r = encode_map(encode, &L->tmA, const_cast<void*>(d->in), 4, dims, strides, taps == 9 ? box9 : box1,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
@@ -818,7 +890,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
         cuuint64_t pdims[4] = {(cuuint64_t)d->N, (cuuint64_t)(d->W / 2), (cuuint64_t)(d->H / 2), (cuuint64_t)d->B};
         cuuint64_t pstrides[3] = {(cuuint64_t)(pcs * 2), (cuuint64_t)((d->W / 2) * pcs * 2),
                                   (cuuint64_t)((long long)(d->H / 2) * (d->W / 2) * pcs * 2)};
-        cuuint32_t pbox[4] = {64, 4, (cuuint32_t)(TH / 2), 1};
+        cuuint32_t pbox[4] = {64, (cuuint32_t)(TW / 2), (cuuint32_t)(TH / 2), 1};
         const int rp = encode_map(encode, &L->tmQ[0], d->pool_out, 4, pdims, pstrides, pbox, CU_TENSOR_MAP_L2_PROMOTION_NONE);
         if (rp) return set_error(h, UG_ECUDA, "conv(multi): pooled output tensor map encode failed (%d)", rp);
       }
@@ -889,6 +961,9 @@ int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   hp.TH = L->halo_TH; hp.a_stage_bytes = L->halo_a_stage;
   hp.sa = L->halo_sa; hp.sb = L->halo_sb; hp.b_resident = L->halo_bres; hp.m_super = L->halo_copy;
   hp.debug = L->halo_debug;
+  hp.strip = L->halo_strip; hp.pitch = L->halo_pitch;
+  hp.sbo = hp.strip ? 1024 : hp.pitch * 128;
+  hp.d_pitch = make_fastdiv(hp.pitch);
   hp.d_msuper = make_fastdiv(hp.m_super);
   hp.d_tx = make_fastdiv(L->p.tiles_x);
   hp.d_ty = make_fastdiv(L->p.tiles_y);

@@ -68,6 +68,8 @@ struct ConvKParams {
   float* stats_sum;  // multi-issuer 3x3 kernel: per-tile channel sums / maxima of the stored output
   float* stats_max;
   int stage_copy;  // ConvTranspose scatter: stage the tile in smem, then coalesced cooperative copy-out
+  void* out2;      // second destination of a split 1x1 GEMM (see ug_conv_desc.out2): columns >= n_split
+  int out2_cstride, n_split, n1;
   long long* prof;  // optional per-CTA cycle counters [grid][8] (debug / profiling builds of the plan)
 };
 
@@ -76,12 +78,14 @@ struct ConvLaunch {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
   alignas(64) CUtensorMap tmO;  // output map for the TMA-store epilogues
+  alignas(64) CUtensorMap tmO2;    // persistent GEMM kernel: TMA-store map of the second destination (split 1x1 GEMM)
   alignas(64) CUtensorMap tmQ[3];  // multi-issuer kernel, ConvTranspose: output views of quadrants 1..3 (tmO = quadrant 0)
   ConvKParams p;
   dim3 grid;
   size_t smem;
   int variant;  // 0 = persistent, 1 = one tile per CTA, 5 = multi-issuer kernel (halo_mode = taps: 9 or 1)
   int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres, halo_debug;
+  int halo_strip, halo_pitch;  // multi-issuer kernel: row-strip tiles (full image rows per tile) and their halo pitch
   int halo_ks;  // multi-issuer kernel: issuing warps per tile stream (K-split), 1 or 2
 };
 

@@ -116,8 +116,12 @@ int launch_pool(ug_engine* h, const ug_pool_desc* d, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per token, C = 256 * kNV in {256, 512, 768, 1024}; two-pass statistics in registers (kNV is a
-// template parameter so that the row stays in registers: with a run-time trip count it lived in local memory).
+// LayerNorm: one warp per kLnTok consecutive tokens, C = 256 * kNV in {256, 512, 768, 1024}.  All rows of the warp are
+// fetched before any arithmetic (the 196-token x 512 maps are tiny: with one token per warp and two loads per lane the
+// kernel ran at 12 % of the HBM peak, bound by load latency), gamma / beta are read once per warp; two-pass statistics
+// in fp32 registers (kNV is a template parameter so that the rows stay in registers).
+static constexpr int kLnTok = 4;
+
 template <int kNV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ in,
                                                         __nv_bfloat16* __restrict__ out,
@@ -127,54 +131,78 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
-  constexpr int nv = kNV;  // 16-byte vectors per lane
-  const __nv_bfloat16* row = in + (long long)warp * C;
-  float v[kNV * 8];
-  float sum = 0.0f;
+  const int t0 = warp * kLnTok;
+  if (t0 >= M) return;
+  uint4 raw[kLnTok][kNV];
 #pragma unroll
-  for (int i = 0; i < nv; ++i) {
-    const uint4 u = *reinterpret_cast<const uint4*>(row + (i * 32 + lane) * 8);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int t = 0; t < kLnTok; ++t) {
+    const __nv_bfloat16* row = in + (long long)min(t0 + t, M - 1) * C;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[i * 8 + 2 * j] = bf16_lo(w[j]);
-      v[i * 8 + 2 * j + 1] = bf16_hi(w[j]);
-      sum += v[i * 8 + 2 * j] + v[i * 8 + 2 * j + 1];
-    }
+    for (int i = 0; i < kNV; ++i) raw[t][i] = __ldg(reinterpret_cast<const uint4*>(row + (i * 32 + lane) * 8));
   }
+  float4 ga[kNV][2], be[kNV][2];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float sq = 0.0f;
-#pragma unroll
-  for (int i = 0; i < nv * 8; ++i) {
-    const float dlt = v[i] - mean;
-    sq += dlt * dlt;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / C + eps);
-  __nv_bfloat16* orow = out + (long long)warp * C;
-#pragma unroll
-  for (int i = 0; i < nv; ++i) {
+  for (int i = 0; i < kNV; ++i) {
     const int c0 = (i * 32 + lane) * 8;
-    float r[8];
+    ga[i][0] = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    ga[i][1] = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    be[i][0] = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    be[i][1] = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = (v[i * 8 + j] - mean) * rstd * __ldg(gamma + c0 + j) + __ldg(beta + c0 + j);
-    uint4 o;
-    o.x = pack_bf16x2(r[0], r[1]);
-    o.y = pack_bf16x2(r[2], r[3]);
-    o.z = pack_bf16x2(r[4], r[5]);
-    o.w = pack_bf16x2(r[6], r[7]);
-    *reinterpret_cast<uint4*>(orow + c0) = o;
+  for (int t = 0; t < kLnTok; ++t) {
+    float v[kNV * 8];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kNV; ++i) {
+      const uint32_t w[4] = {raw[t][i].x, raw[t][i].y, raw[t][i].z, raw[t][i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[i * 8 + 2 * j] = bf16_lo(w[j]);
+        v[i * 8 + 2 * j + 1] = bf16_hi(w[j]);
+        sum += v[i * 8 + 2 * j] + v[i * 8 + 2 * j + 1];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kNV * 8; ++i) {
+      const float dlt = v[i] - mean;
+      sq += dlt * dlt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / C + eps);
+    if (t0 + t < M) {
+      __nv_bfloat16* orow = out + (long long)(t0 + t) * C;
+#pragma unroll
+      for (int i = 0; i < kNV; ++i) {
+        const float g8[8] = {ga[i][0].x, ga[i][0].y, ga[i][0].z, ga[i][0].w, ga[i][1].x, ga[i][1].y, ga[i][1].z, ga[i][1].w};
+        const float b8[8] = {be[i][0].x, be[i][0].y, be[i][0].z, be[i][0].w, be[i][1].x, be[i][1].y, be[i][1].z, be[i][1].w};
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = (v[i * 8 + j] - mean) * rstd * g8[j] + b8[j];
+        uint4 o;
+        o.x = pack_bf16x2(r[0], r[1]);
+        o.y = pack_bf16x2(r[2], r[3]);
+        o.z = pack_bf16x2(r[4], r[5]);
+        o.w = pack_bf16x2(r[6], r[7]);
+        *reinterpret_cast<uint4*>(orow + (i * 32 + lane) * 8) = o;
+      }
+    }
   }
 }
 
 int launch_layernorm(ug_engine* h, const ug_layernorm_desc* d, cudaStream_t s) {
   if (!d->in || !d->out || !d->gamma || !d->beta || d->M <= 0 || d->C % 256 || d->C > 1024 || d->C <= 0)
     return set_error(h, UG_EINVAL, "layernorm: C must be a multiple of 256 up to 1024");
-  const dim3 grid(cdiv((long long)d->M * 32, 256));
+  if ((reinterpret_cast<uintptr_t>(d->gamma) & 15) || (reinterpret_cast<uintptr_t>(d->beta) & 15) ||
+      (reinterpret_cast<uintptr_t>(d->in) & 15) || (reinterpret_cast<uintptr_t>(d->out) & 15))
+    return set_error(h, UG_EINVAL, "layernorm: in / out / gamma / beta must be 16-byte aligned");
+  const long long warps = ((long long)d->M + kLnTok - 1) / kLnTok;
+  const dim3 grid(cdiv(warps * 32, 256));
   const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d->in);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d->out);
   switch (d->C / 256) {
@@ -187,6 +215,7 @@ int launch_layernorm(ug_engine* h, const ug_layernorm_desc* d, cudaStream_t s) {
   return check_cuda(h, cudaGetLastError(), "layernorm launch");
 }
 
+// ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
 // Tensor-core attention for S <= 208 tokens (the 14x14 bottleneck: S = 196), dim_head = 64.
 // One CTA (4 warps) per (image, head).  K (row-major, padded pitch) and V^T are staged in shared memory; each warp

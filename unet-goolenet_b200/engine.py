@@ -32,6 +32,7 @@ class ConvDesc(C.Structure):
                 ("add", _vp), ("add_bstride", _ll), ("add_cstride", _i), ("gate", _vp), ("outc_w", _vp),
                 ("outc_b", _f), ("logits", _vp), ("mask", _vp), ("pool_out", _vp), ("pool_cstride", _i),
                 ("stats_sum", _vp), ("stats_max", _vp), ("stats_tiles", _i),
+                ("out2", _vp), ("out2_cstride", _i), ("n_split", _i), ("n1", _i),
                 ("TW", _i), ("TH", _i), ("TN", _i), ("BN", _i), ("stages", _i), ("variant", _i)]
 
 

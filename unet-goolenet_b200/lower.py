@@ -32,6 +32,10 @@ FUSE_STATS = int(os.environ.get("UG_FUSE_STATS", "0"))
 # UG_FUSE_REDUCE=0: run the two Inception reduce convolutions (branch2.0 / branch3.0, same input) as separate launches.
 # Same-box A/B: 9756 / 9721 img/s fused vs 9732 / 9742 separate (neutral); kept on, it removes 9 launches per batch.
 FUSE_REDUCE = os.environ.get("UG_FUSE_REDUCE", "1") != "0"
+# UG_FUSE_HEAD=0: keep Inception branch1 as its own 1x1 launch.  Default: ONE GEMM for the three 1x1 convolutions that
+# read the block input (branch1 | 3x3-reduce | 5x5-reduce; torchvision Inception.forward), branch1's columns stored
+# straight into the block's concat output and the two reduce results into a scratch tensor (ug_conv_desc.out2).
+FUSE_HEAD = os.environ.get("UG_FUSE_HEAD", "1") != "0" and FUSE_REDUCE
 
 
 # Plans (program + activation workspace) kept per runner: a loader with ragged / varying batch sizes would otherwise
@@ -162,12 +166,17 @@ class _Builder:
                            Cin=wt.shape[1], R=wt.shape[2], BN=bn_tile)
         return self.w[key]
 
-    def linear(self, key, weights, bias=None):
-        """Pack (a vertical concatenation of) nn.Linear weights [out, in]."""
+    def linear(self, key, weights, bias=None, along_k=False):
+        """Pack a concatenation of nn.Linear weights [out, in]: stacked outputs (several projections of ONE input as
+        one GEMM) or, with along_k, side-by-side inputs (the SUM of several projections of different inputs as one
+        GEMM over the concatenated inputs; `bias` is then a list whose entries are added)."""
         if key in self.w:
             return self.w[key]
-        wt = torch.cat([_f32(self.sd[k], self.dev) for k in weights], 0)
-        b = _f32(self.sd[bias], self.dev) if bias else None
+        wt = torch.cat([_f32(self.sd[k], self.dev) for k in weights], 1 if along_k else 0)
+        if along_k:
+            b = sum(_f32(self.sd[k], self.dev) for k in bias) if bias else None
+        else:
+            b = _f32(self.sd[bias], self.dev) if bias else None
         bn_tile = pack.choose_bn(wt.shape[0])
         self.w[key] = dict(w=pack.pack_linear_weight(wt, bn_tile), scale=None, bias=b, N=wt.shape[0],
                            Cin=wt.shape[1], R=1, BN=bn_tile)
@@ -175,7 +184,7 @@ class _Builder:
 
     # ---- ops -----------------------------------------------------------------------------------
     def conv(self, ops, wd, x, geom, out=None, act=E.ACT_RELU, mode=E.EPI_STORE, up=1, add=None, add_bstride=0,
-             gate=None, outc=None, pool_out=None, stats=None):
+             gate=None, outc=None, pool_out=None, stats=None, out2=None):
         B, H, W = geom
         d = E.ConvDesc()
         d.algo_k = wd.get("algo_k", wd["Cin"] * wd["R"] * wd["R"])   # true reduction length (for FLOP accounting)
@@ -200,6 +209,8 @@ class _Builder:
             d.pool_out, d.pool_cstride = pool_out.data_ptr(), pool_out.shape[-1]
         if stats is not None:                                        # fused per-tile channel sums / maxima
             d.stats_sum, d.stats_max, d.stats_tiles = stats[0].data_ptr(), stats[1].data_ptr(), stats[2]
+        if out2 is not None:                                         # split 1x1 GEMM (Inception heads)
+            d.out2, d.out2_cstride, d.n_split, d.n1 = out2.ptr, out2.cstride, wd["n_split"], wd["n1"]
         if outc is not None:
             d.outc_w, d.outc_b = outc["w"].data_ptr(), outc["b"]
             d.logits, d.mask = outc["logits"].data_ptr(), outc["mask"].data_ptr()
@@ -269,13 +280,19 @@ class UNetRunner(_Builder):
             pos = _f32(sd[f"task2.pos_embedding_decoder_{name[5:]}"], dev)[0]       # [512,14,14]
             self.w[f"pos_{name}"] = pos.permute(1, 2, 0).contiguous().to(torch.bfloat16)   # [14,14,512]
         L = "task2.layers.0."
-        self.linear("cq", [L + "cross_attention_cl.to_q.weight"])
         self.linear("ckv", [L + "cross_attention_cl.to_k.weight", L + "cross_attention_cl.to_v.weight"])
-        self.linear("cout", [L + "cross_attention_cl.to_out.0.weight"], L + "cross_attention_cl.to_out.0.bias")
+        # Multi_Attention (tasks.py:166-184), live stream s (m for the segmentation head, x for the classifier head):
+        #   s_in = s + to_out_self(attn(LN s)) + to_out_cross(attn(q = LN s, kv = LN other))
+        # * the self-attention qkv projection and the cross-attention q projection read the same LN(s): ONE GEMM with
+        #   N = 1536 + 512;
+        # * the two output projections are summed: ONE GEMM over the concatenated attention outputs [att | catt]
+        #   (K = 1024) with the biases added, the residual s added in its epilogue (fp32 accumulation of both products)
+        att = "attention1" if self.head == "cls" else "attention2"
+        self.linear("qkvq", [L + att + ".to_qkv.weight", L + "cross_attention_cl.to_q.weight"])
+        self.linear("outcat", [L + att + ".to_out.0.weight", L + "cross_attention_cl.to_out.0.weight"],
+                    [L + att + ".to_out.0.bias", L + "cross_attention_cl.to_out.0.bias"], along_k=True)
         if self.head == "cls":
             return self._pack_cls_head()
-        self.linear("qkv2", [L + "attention2.to_qkv.weight"])
-        self.linear("out2", [L + "attention2.to_out.0.weight"], L + "attention2.to_out.0.bias")
         self.linear("ff1", [L + "m_feed.net.0.weight"], L + "m_feed.net.0.bias")
         self.linear("ff2", [L + "m_feed.net.3.weight"], L + "m_feed.net.3.bias")
         for n in ("x_att_norm", "m_att_norm", "m_mlp_norm"):
@@ -306,8 +323,6 @@ class UNetRunner(_Builder):
         Multi_Attention (attention1, cross_attention_cl(x, m), x_mlp_norm, x_feed) + avgpool2 + fc1 + fc2."""
         sd, dev = self.sd, self.dev
         L = "task2.layers.0."
-        self.linear("qkv1", [L + "attention1.to_qkv.weight"])
-        self.linear("out1", [L + "attention1.to_out.0.weight"], L + "attention1.to_out.0.bias")
         self.linear("xff1", [L + "x_feed.net.0.weight"], L + "x_feed.net.0.bias")
         self.linear("xff2", [L + "x_feed.net.3.weight"], L + "x_feed.net.3.bias")
         for n in ("x_att_norm", "m_att_norm", "x_mlp_norm"):
@@ -370,6 +385,28 @@ class UNetRunner(_Builder):
                                        self.w[n][1].data_ptr(), T, 512, 1e-5))
         return X, M, xn, mn
 
+    def _emit_attention(self, B, ops, s_res, s_norm, other_norm):
+        """tasks.py:170-176 for the live token stream: returns s + self_attn(LN s) + cross_attn(LN s <- LN other) as ONE
+        fused projection GEMM + two attention launches + ONE fused output GEMM (see _pack)."""
+        buf = self.buf
+        T = B * 196
+        flat = (1, 1, T)
+        scale = 512 ** -0.5                                          # tasks.py:126 / :63 (dim ** -0.5)
+        qkvq = buf(T, 2048)                                          # [q | k | v of the self attention | cross q]
+        self.conv(ops, self.w["qkvq"], View(s_norm), flat, View(qkvq), act=E.ACT_NONE)
+        ckv = buf(T, 1024)
+        self.conv(ops, self.w["ckv"], View(other_norm), flat, View(ckv), act=E.ACT_NONE)
+        attcat = buf(T, 1024)                                        # [self-attention out | cross-attention out]
+        p0 = qkvq.data_ptr()
+        ops.append(E.AttnDesc(p0, p0 + 2 * 512, p0 + 2 * 1024, 2048, 2048, 2048, attcat.data_ptr(), 1024, B, 196, 8,
+                              scale))
+        ops.append(E.AttnDesc(p0 + 2 * 1536, ckv.data_ptr(), ckv.data_ptr() + 2 * 512, 2048, 1024, 1024,
+                              attcat.data_ptr() + 2 * 512, 1024, B, 196, 8, scale))
+        s_in = buf(T, 512)
+        self.conv(ops, self.w["outcat"], View(attcat), flat, View(s_in), act=E.ACT_NONE, mode=E.EPI_ADD,
+                  add=View(s_res))
+        return s_in
+
     def _emit_unet(self, B, ws, ops, io=None):
         """Append the ops of one UNet forward at batch B; `ws` receives the workspace tensors.  `io` may supply
         pre-allocated x_in / logits / mask tensors (slices of larger buffers)."""
@@ -383,22 +420,7 @@ class UNetRunner(_Builder):
         X, M, xn, mn = self._emit_tokens(B, ws, ops, out0)
         T = B * 196
         flat = (1, 1, T)
-        scale = 512 ** -0.5                                          # tasks.py:126 / :63 (dim ** -0.5)
-        qkv = buf(T, 1536)
-        self.conv(ops, self.w["qkv2"], View(mn), flat, View(qkv), act=E.ACT_NONE)
-        att = buf(T, 512)
-        ops.append(E.AttnDesc(qkv.data_ptr(), qkv.data_ptr() + 2 * 512, qkv.data_ptr() + 2 * 1024, 1536, 1536,
-                              1536, att.data_ptr(), 512, B, 196, 8, scale))
-        m1 = buf(T, 512)                                             # m + m_att
-        self.conv(ops, self.w["out2"], View(att), flat, View(m1), act=E.ACT_NONE, mode=E.EPI_ADD, add=View(M))
-        cq, ckv = buf(T, 512), buf(T, 1024)
-        self.conv(ops, self.w["cq"], View(mn), flat, View(cq), act=E.ACT_NONE)
-        self.conv(ops, self.w["ckv"], View(xn), flat, View(ckv), act=E.ACT_NONE)
-        catt = buf(T, 512)
-        ops.append(E.AttnDesc(cq.data_ptr(), ckv.data_ptr(), ckv.data_ptr() + 2 * 512, 512, 1024, 1024,
-                              catt.data_ptr(), 512, B, 196, 8, scale))
-        m_in = buf(T, 512)                                           # m_att + m_cross + m
-        self.conv(ops, self.w["cout"], View(catt), flat, View(m_in), act=E.ACT_NONE, mode=E.EPI_ADD, add=View(m1))
+        m_in = self._emit_attention(B, ops, M, mn, xn)               # m_att + m_cross + m
         mln = buf(T, 512)
         ops.append(E.LayerNormDesc(m_in.data_ptr(), mln.data_ptr(), self.w["m_mlp_norm"][0].data_ptr(),
                                    self.w["m_mlp_norm"][1].data_ptr(), T, 512, 1e-5))
@@ -457,22 +479,7 @@ class UNetRunner(_Builder):
         X, M, xn, mn = self._emit_tokens(B, ws, ops, out0)
         T = B * 196
         flat = (1, 1, T)
-        scale = 512 ** -0.5
-        qkv = buf(T, 1536)
-        self.conv(ops, self.w["qkv1"], View(xn), flat, View(qkv), act=E.ACT_NONE)
-        att = buf(T, 512)
-        ops.append(E.AttnDesc(qkv.data_ptr(), qkv.data_ptr() + 2 * 512, qkv.data_ptr() + 2 * 1024, 1536, 1536,
-                              1536, att.data_ptr(), 512, B, 196, 8, scale))
-        x1 = buf(T, 512)                                             # x + x_att
-        self.conv(ops, self.w["out1"], View(att), flat, View(x1), act=E.ACT_NONE, mode=E.EPI_ADD, add=View(X))
-        cq, ckv = buf(T, 512), buf(T, 1024)                          # cross_attention_cl(x_norm, m_norm): q <- x
-        self.conv(ops, self.w["cq"], View(xn), flat, View(cq), act=E.ACT_NONE)
-        self.conv(ops, self.w["ckv"], View(mn), flat, View(ckv), act=E.ACT_NONE)
-        catt = buf(T, 512)
-        ops.append(E.AttnDesc(cq.data_ptr(), ckv.data_ptr(), ckv.data_ptr() + 2 * 512, 512, 1024, 1024,
-                              catt.data_ptr(), 512, B, 196, 8, scale))
-        x_in = buf(T, 512)                                           # x_att + x_cross + x
-        self.conv(ops, self.w["cout"], View(catt), flat, View(x_in), act=E.ACT_NONE, mode=E.EPI_ADD, add=View(x1))
+        x_in = self._emit_attention(B, ops, X, xn, mn)               # x_att + x_cross + x (cross_attention_cl(x, m))
         xln = buf(T, 512)
         ops.append(E.LayerNormDesc(x_in.data_ptr(), xln.data_ptr(), self.w["x_mlp_norm"][0].data_ptr(),
                                    self.w["x_mlp_norm"][1].data_ptr(), T, 512, 1e-5))
@@ -575,6 +582,18 @@ class GoogLeNetRunner(_Builder):
             self.w[f"{name}.reduce"] = dict(w=pack.pack_conv_weight(wt, bn_tile), scale=torch.cat([a["scale"], b["scale"]]),
                                             bias=torch.cat([a["bias"], b["bias"]]), N=wt.shape[0], Cin=wt.shape[1], R=1,
                                             BN=bn_tile)
+            # all three 1x1 heads of the block as one GEMM: [branch1 | zero rows up to a multiple of 64 | reduce]
+            h1 = self.w[f"{name}.branch1"]
+            n1 = h1["N"]
+            n_split = pack.round_up(n1, 64)
+            w1 = _f32(sd[f"{name}.branch1.conv.weight"], dev)
+            padw = torch.zeros((n_split - n1,) + tuple(w1.shape[1:]))
+            padv = torch.zeros(n_split - n1)
+            self.w[f"{name}.head"] = dict(
+                w=pack.pack_conv_weight(torch.cat([w1, padw, wt], 0), 128),
+                scale=torch.cat([h1["scale"], padv, a["scale"], b["scale"]]),
+                bias=torch.cat([h1["bias"], padv, a["bias"], b["bias"]]),
+                N=n_split + wt.shape[0], Cin=wt.shape[1], R=1, BN=128, n1=n1, n_split=n_split)
         self.w["fc"] = (_f32(sd["fc.weight"], dev), _f32(sd["fc.bias"], dev))
         self.ncls = self.w["fc"][0].shape[0]
 
@@ -605,8 +624,18 @@ class GoogLeNetRunner(_Builder):
             flat = (1, 1, B * sp * sp)
             geom = (B, sp, sp)
             xin = View(cur)
-            self.conv(ops, self.w[name + ".branch1"], xin, flat, View(out, c1x1, 0))
-            if FUSE_REDUCE:
+            if FUSE_HEAD:
+                r23 = buf(B, sp, sp, c3r + c5r)
+                hw = dict(self.w[name + ".head"])
+                # (one tile per CTA below ~300 pixel tiles: whole 64-column n-tiles on either side of n_split)
+                hw["BN"] = 128 if B * sp * sp >= 296 * 128 else 64
+                self.conv(ops, hw, xin, flat, View(out, c1x1, 0), out2=View(r23))
+                r2, r3 = View(r23, c3r, 0), View(r23, c5r, c3r)
+            else:
+                self.conv(ops, self.w[name + ".branch1"], xin, flat, View(out, c1x1, 0))
+            if FUSE_HEAD:
+                pass                                                 # (r2 / r3 come from the fused head GEMM)
+            elif FUSE_REDUCE:
                 r23 = buf(B, sp, sp, c3r + c5r)
                 self.conv(ops, self.w[name + ".reduce"], xin, flat, View(r23))
                 r2, r3 = View(r23, c3r, 0), View(r23, c5r, c3r)
