@@ -313,6 +313,34 @@ int ug_program_run_host(ug_handle h, ug_program p, const ug_copy* h2d, int n_h2d
 int ug_program_run_host_pipelined(ug_handle h, ug_program p, const ug_copy* h2d, void* const* stage0,
                                   void* const* stage1, int n_h2d, const ug_copy* d2h, int n_d2h, void* stream);
 
+/* ---- plan images: the net-level entry points -------------------------------------------------------
+ * A plan image is a compiled program + its device memory layout + its constant data (BN-folded, packed weights of both
+ * networks) as ONE relocatable byte blob, produced once by the Python tooling (`PipelineRunner.export_plan(batch)`,
+ * `UNetRunner.export_plan`, `GoogLeNetRunner.export_plan`).  With it a host in any language runs the whole path
+ *   UNetTaskAligWeight.forward -> roi.py threshold / bbox / crop / resize -> GoogLeNetClassifier.forward
+ * through this C ABI alone (no Python, no CUDA runtime calls of its own):
+ *   ug_create -> ug_plan_load -> ug_plan_copy_in("x_in", images) -> ug_plan_run -> ug_plan_copy_out("mask" / "boxes" /
+ *   "cls_logits" / "logits" / "u8") -> ug_plan_destroy.     (examples/run_plan.c is exactly this.)
+ * Named io buffers of a pipeline plan: "x_in" f32 [B,3,224,224] (or "src_u8" u8 [B,Hs,Ws,3] for plans with the device
+ * front-end), "logits" f32 [B,1,224,224], "mask" u8 [B,224,224], "boxes" i32 [B,4], "u8" u8 [B,224,224,3] (the ROI
+ * crops), "cls_logits" f32 [B,6]. */
+typedef struct ug_plan_s* ug_plan;
+/* Parses the image (host memory, may be freed afterwards), allocates ONE device arena for every buffer of the plan
+ * (ug_plan_device_bytes), uploads the constants, relocates the op list and prepares the program. */
+int ug_plan_load(ug_handle h, const void* image, size_t image_bytes, ug_plan* out);
+int ug_plan_num_io(ug_plan p);
+const char* ug_plan_io_name(ug_plan p, int i);
+/* Device pointer and size of a named io buffer (UG_EINVAL if the plan has no such buffer). */
+int ug_plan_io(ug_plan p, const char* name, void** dev_ptr, size_t* bytes);
+size_t ug_plan_device_bytes(ug_plan p);
+/* The prepared program of the plan (for ug_program_run_host / _pipelined / _timed). */
+ug_program ug_plan_program(ug_plan p);
+/* Host -> named buffer (asynchronous on `stream`) / named buffer -> host (synchronizes `stream`). */
+int ug_plan_copy_in(ug_handle h, ug_plan p, const char* name, const void* host, size_t bytes, void* stream);
+int ug_plan_copy_out(ug_handle h, ug_plan p, const char* name, void* host, size_t bytes, void* stream);
+int ug_plan_run(ug_handle h, ug_plan p, void* stream);
+int ug_plan_destroy(ug_handle h, ug_plan p);
+
 #ifdef __cplusplus
 }
 #endif

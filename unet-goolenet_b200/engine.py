@@ -119,7 +119,9 @@ _SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_POOL: "ug_pool",
 EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",
                     "ug_program_destroy", "ug_program_run_host", "ug_program_run_host_pipelined",
-                    "ug_program_run_timed", "ug_program_autotune", "ug_wavelet_workspace_bytes"]
+                    "ug_program_run_timed", "ug_program_autotune", "ug_wavelet_workspace_bytes",
+                    "ug_plan_load", "ug_plan_num_io", "ug_plan_io_name", "ug_plan_io", "ug_plan_device_bytes",
+                    "ug_plan_program", "ug_plan_copy_in", "ug_plan_copy_out", "ug_plan_run", "ug_plan_destroy"]
 DEV_SYMBOLS = ["ug_conv_profile", "ug_conv_profile16", "ug_mma_microbench", "ug_mma_microbench2",
                "ug_mma_microbench_pair"]
 
@@ -162,6 +164,19 @@ def load_library():
     lib.ug_program_destroy.argtypes = [_vp, _vp]
     lib.ug_program_run_host.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _vp]
     lib.ug_program_run_host_pipelined.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]
+    lib.ug_plan_load.argtypes = [_vp, _vp, C.c_size_t, C.POINTER(_vp)]
+    lib.ug_plan_num_io.argtypes = [_vp]
+    lib.ug_plan_io_name.argtypes = [_vp, _i]
+    lib.ug_plan_io_name.restype = C.c_char_p
+    lib.ug_plan_io.argtypes = [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(C.c_size_t)]
+    lib.ug_plan_device_bytes.argtypes = [_vp]
+    lib.ug_plan_device_bytes.restype = C.c_size_t
+    lib.ug_plan_program.argtypes = [_vp]
+    lib.ug_plan_program.restype = _vp
+    lib.ug_plan_copy_in.argtypes = [_vp, _vp, C.c_char_p, _vp, C.c_size_t, _vp]
+    lib.ug_plan_copy_out.argtypes = [_vp, _vp, C.c_char_p, _vp, C.c_size_t, _vp]
+    lib.ug_plan_run.argtypes = [_vp, _vp, _vp]
+    lib.ug_plan_destroy.argtypes = [_vp, _vp]
     _lib = lib
     return lib
 
@@ -248,6 +263,136 @@ class Program:
             if self.handle:
                 self.engine.lib.ug_program_destroy(self.engine.handle, self.handle)
                 self.handle = None
+        except Exception:
+            pass
+
+
+PLAN_MAGIC = b"UGPLAN01"
+
+
+def export_plan(descs, io, tensors):
+    """Serialise a compiled op list as a relocatable plan image (layout: csrc/plan.cu; loaded by ug_plan_load).
+
+    descs   the op descriptors (as given to Engine.program)
+    io      {name: tensor}: buffers a host addresses by name (inputs, outputs)
+    tensors every tensor the descriptors may point into (workspace allocations, packed-weight blobs, io tensors).
+            Storages are the allocation units; a storage whose tensor is listed in `io` or that is written by the
+            program is left uninitialised, CONSTANT storages must be passed as (tensor, True) to embed their contents.
+    Every non-null pointer field of every descriptor must fall inside one of those storages (checked)."""
+    import struct
+    allocs, seen = [], {}
+    for item in tensors:
+        t, const = item if isinstance(item, tuple) else (item, False)
+        st = t.untyped_storage()
+        key = st.data_ptr()
+        if key in seen:
+            allocs[seen[key]][2] = allocs[seen[key]][2] or const
+            continue
+        seen[key] = len(allocs)
+        allocs.append([key, st.nbytes(), const, t])
+    order = sorted(range(len(allocs)), key=lambda i: allocs[i][0])
+    starts = [allocs[i][0] for i in order]
+
+    def locate(addr):
+        import bisect
+        j = bisect.bisect_right(starts, addr) - 1
+        if j < 0:
+            raise ValueError(f"pointer {addr:#x} is not inside any listed tensor")
+        i = order[j]
+        base, nbytes = allocs[i][0], allocs[i][1]
+        if not (base <= addr <= base + nbytes):
+            raise ValueError(f"pointer {addr:#x} is not inside any listed tensor")
+        return i, addr - base
+
+    arr = (Op * len(descs))()
+    relocs = []
+    for k, d in enumerate(descs):
+        kind = _DESC_KIND[type(d)]
+        arr[k].kind = kind
+        setattr(arr[k].u, _KIND_FIELD[kind], d)
+        ubase = Op.u.offset
+        for fname, ftype in d._fields_:
+            if ftype is _vp:
+                v = getattr(d, fname)
+                if v:
+                    ai, off = locate(v)
+                    relocs.append((k, ubase + getattr(type(d), fname).offset, ai, off))
+    ios = []
+    for name, t in io.items():
+        ai, off = locate(t.data_ptr())
+        ios.append((name.encode()[:31], ai, off, t.numel() * t.element_size()))
+    head = 8 + 4 * 4 + 8
+    tables = head + 24 * len(allocs) + C.sizeof(Op) * len(descs) + 24 * len(relocs) + 56 * len(ios)
+    blobs, cur, alloc_rows = [], (tables + 255) // 256 * 256, []
+    for base, nbytes, const, t in allocs:
+        if const:
+            raw = torch.empty(nbytes, dtype=torch.uint8)
+            flat = torch.tensor([], dtype=torch.uint8, device=t.device).set_(t.untyped_storage(), 0, (nbytes,))
+            raw.copy_(flat)
+            alloc_rows.append((nbytes, cur, nbytes))
+            blobs.append((cur, raw.numpy().tobytes()))
+            cur = (cur + nbytes + 255) // 256 * 256
+        else:
+            alloc_rows.append((nbytes, 0, 0))
+    out = bytearray(cur)
+    struct.pack_into("<8sIIIIQ", out, 0, PLAN_MAGIC, len(allocs), len(descs), len(relocs), len(ios), C.sizeof(Op))
+    o = head
+    for row in alloc_rows:
+        struct.pack_into("<QQQ", out, o, *row)
+        o += 24
+    out[o:o + C.sizeof(Op) * len(descs)] = bytes(arr)
+    o += C.sizeof(Op) * len(descs)
+    for r in relocs:
+        struct.pack_into("<IIIIQ", out, o, r[0], r[1], r[2], 0, r[3])
+        o += 24
+    for name, ai, off, nbytes in ios:
+        struct.pack_into("<32sIIQQ", out, o, name, ai, 0, off, nbytes)
+        o += 56
+    for pos, raw in blobs:
+        out[pos:pos + len(raw)] = raw
+    return bytes(out)
+
+
+class Plan:
+    """A plan image loaded through the C ABI (ug_plan_load): what a non-Python host does, from Python (tests)."""
+
+    def __init__(self, engine, image):
+        self.engine = engine
+        self.handle = _vp()
+        self._image = image
+        buf = (C.c_char * len(image)).from_buffer_copy(image)
+        engine._check(engine.lib.ug_plan_load(engine.handle, buf, len(image), C.byref(self.handle)))
+        self.names = [engine.lib.ug_plan_io_name(self.handle, i).decode()
+                      for i in range(engine.lib.ug_plan_num_io(self.handle))]
+        self.device_bytes = engine.lib.ug_plan_device_bytes(self.handle)
+
+    def copy_in(self, name, host_tensor, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        t = host_tensor.contiguous()
+        self.engine._check(self.engine.lib.ug_plan_copy_in(self.engine.handle, self.handle, name.encode(), t.data_ptr(),
+                                                           t.numel() * t.element_size(), s))
+        torch.cuda.current_stream().synchronize()   # `t` may be a temporary
+
+    def copy_out(self, name, host_tensor, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        assert host_tensor.is_contiguous()
+        self.engine._check(self.engine.lib.ug_plan_copy_out(self.engine.handle, self.handle, name.encode(),
+                                                            host_tensor.data_ptr(),
+                                                            host_tensor.numel() * host_tensor.element_size(), s))
+        return host_tensor
+
+    def run(self, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        self.engine._check(self.engine.lib.ug_plan_run(self.engine.handle, self.handle, s))
+
+    def close(self):
+        if self.handle:
+            self.engine.lib.ug_plan_destroy(self.engine.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 

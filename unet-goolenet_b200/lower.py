@@ -764,6 +764,16 @@ class PipelineRunner:
             return _finish(self.engine, ops, ws, ua + ga + [v for v in ws.values() if isinstance(v, torch.Tensor)])
         return self.plans.get_or_build(key, build)
 
+    def export_plan(self, B, source=None):
+        """The whole two-stage program for a batch of B images as a relocatable plan image (bytes): op list, device
+        memory layout, BN-folded packed weights of both networks.  A host in any language runs it through the C ABI
+        alone (ug_plan_load / ug_plan_copy_in / ug_plan_run / ug_plan_copy_out, include/ugnet.h; examples/run_plan.c)."""
+        ws = self.plan(B, source=source)
+        prog = ws["program"]
+        io = {k: ws[k] for k in ("x_in", "src_u8", "logits", "mask", "boxes", "u8", "cls_logits") if k in ws}
+        tensors = list(prog.keepalive) + list(io.values()) + [(self.unet.w_blob, True), (self.gnet.w_blob, True)]
+        return E.export_plan(prog.descs, io, tensors)
+
     def _chunks(self, n):
         """Split n images into plan-able chunks: multiples of micro_batch up to cls_batch, then the remainder."""
         out, s = [], 0
