@@ -12,7 +12,7 @@ eng = E.Engine.get(0)
 g = torch.Generator(device="cuda").manual_seed(0)
 
 
-def make(B, H, W, Cin, N, R, mode=0, bn=None, stages=0, variant=0, tile=None, up=1):
+def make(B, H, W, Cin, N, R, mode=0, bn=None, stages=0, variant=0, tile=None, up=1, act=1):
     x = torch.randn((B, H, W, Cin), generator=g, device="cuda").to(torch.bfloat16)
     wt = torch.randn((N, Cin, R, R), generator=g, device="cuda") * (Cin * R * R) ** -0.5
     BN = bn or (pack.choose_bn(N, N // 4) if up == 2 else pack.choose_bn(N))
@@ -22,13 +22,13 @@ def make(B, H, W, Cin, N, R, mode=0, bn=None, stages=0, variant=0, tile=None, up
     d = E.ConvDesc()
     d.inp = x.data_ptr(); d.in_cstride = Cin; d.Cin = Cin; d.B, d.H, d.W = B, H, W
     d.R = d.S = R; d.pad = (R - 1) // 2; d.w = wp.data_ptr(); d.N = N
-    d.scale = scale.data_ptr(); d.bias = bias.data_ptr(); d.act = 1; d.mode = mode
+    d.scale = scale.data_ptr(); d.bias = bias.data_ptr(); d.act = act; d.mode = mode
     d.out = out.data_ptr(); d.out_cstride = N // (up * up); d.up = up; d.BN = BN; d.stages = stages; d.variant = variant
     if up == 2:
         d.convt_cout = N // 4; d.act = 0
     if tile: d.TW, d.TH, d.TN = tile
     keep = [x, wp, out, scale, bias]
-    if mode == 2:
+    if mode in (1, 2):
         add = torch.randn((B, H, W, N), generator=g, device="cuda").to(torch.bfloat16)
         gate = torch.rand((B, N), device="cuda")
         d.add = add.data_ptr(); d.add_cstride = N; d.add_bstride = H * W * N; d.gate = gate.data_ptr()
@@ -64,13 +64,22 @@ CONFIGS = [dict(variant=1), dict(variant=2), dict(variant=2, bn=256), dict(varia
            dict(variant=5, bn=256)]
 if os.environ.get("UG_CONFIGS") == "v5":
     CONFIGS = [dict(variant=5), dict(variant=5, mode=2)]
+if os.environ.get("UG_CONFIGS") == "ffn":     # bottleneck linear layers: every kernel structure, the layer's own epilogue
+    A, M = int(os.environ.get("UG_ACT", "0")), int(os.environ.get("UG_MODE", "0"))
+    CONFIGS = [dict(variant=1, act=A, mode=M), dict(variant=1, act=A, mode=M, bn=256), dict(variant=2, act=A, mode=M),
+               dict(variant=2, act=A, mode=M, bn=256), dict(variant=5, act=A, mode=M), dict(variant=5, act=A, mode=M, bn=256),
+               dict(variant=0, act=A, mode=M)]
 if os.environ.get("UG_ABLATE"):
     CONFIGS = [dict(variant=5, stages=108), dict(variant=5, stages=108, mode=2)]
+if os.environ.get("UG_ABLATE") == "resid":    # GATE epilogue with / without its residual loads (results wrong without)
+    CONFIGS = [dict(variant=5, mode=2), dict(variant=5, mode=2, stages=116)]
 for shp in SHAPES:
     B, H, W, Cin, N, R = shp
     fl = 2.0 * B * H * W * N * Cin * max(R, 1) ** 2
     for cfg in CONFIGS:
         if cfg.get("bn", 0) > N or (cfg.get("mode") == 2 and (H * W < 784 or R != 3)):
+            continue
+        if cfg.get("bn") == 256 and N % 256:
             continue
         if cfg.get("variant") == 5 and cfg.get("bn") == 256 and R == 3:
             continue

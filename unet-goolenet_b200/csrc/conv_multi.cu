@@ -102,7 +102,8 @@ struct MultiParams {
   int strip;          // row-strip tiles (see the header comment); TH is then the number of image rows per tile
   FastDiv d_pitch;    // divider by pitch (strip mode: MMA row -> (image row, x))
   int debug;          // ablation switches for profiling (results are wrong when set): 1 = no TMEM loads,
-                      // 2 = no staging stores / TMA store, 4 = activation TMA loads only for the first stages
+                      // 2 = no staging stores / TMA store, 4 = activation TMA loads only for the first stages,
+                      // 16 = no residual loads (ADD / GATE epilogues)
 };
 
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
                                 ((long long)y2 * p.W + x2) * p.add_cstride + col2;
 #pragma unroll
       for (int g = 0; g < 8; ++g)
-        addv[g] = (v2 && col2 + g * 8 < p.N) ? __ldg(reinterpret_cast<const uint4*>(ar + g * 8)) : make_uint4(0, 0, 0, 0);
+        addv[g] = (v2 && col2 + g * 8 < p.N && !(hp.debug & 16)) ? __ldg(reinterpret_cast<const uint4*>(ar + g * 8)) : make_uint4(0, 0, 0, 0);
     };
     if (has_add) {
       int s0 = blockIdx.x;
