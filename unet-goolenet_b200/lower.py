@@ -166,7 +166,7 @@ class _Builder:
                            Cin=wt.shape[1], R=wt.shape[2], BN=bn_tile)
         return self.w[key]
 
-    def linear(self, key, weights, bias=None, along_k=False):
+    def linear(self, key, weights, bias=None, along_k=False, bn=None, variant=0):
         """Pack a concatenation of nn.Linear weights [out, in]: stacked outputs (several projections of ONE input as
         one GEMM) or, with along_k, side-by-side inputs (the SUM of several projections of different inputs as one
         GEMM over the concatenated inputs; `bias` is then a list whose entries are added)."""
@@ -177,9 +177,9 @@ class _Builder:
             b = sum(_f32(self.sd[k], self.dev) for k in bias) if bias else None
         else:
             b = _f32(self.sd[bias], self.dev) if bias else None
-        bn_tile = pack.choose_bn(wt.shape[0])
+        bn_tile = bn or pack.choose_bn(wt.shape[0])
         self.w[key] = dict(w=pack.pack_linear_weight(wt, bn_tile), scale=None, bias=b, N=wt.shape[0],
-                           Cin=wt.shape[1], R=1, BN=bn_tile)
+                           Cin=wt.shape[1], R=1, BN=bn_tile, variant=variant)
         return self.w[key]
 
     # ---- ops -----------------------------------------------------------------------------------
@@ -201,6 +201,7 @@ class _Builder:
         d.up = up
         d.convt_cout = wd["N"] // 4 if up == 2 else 0
         d.BN = wd["BN"]
+        d.variant = wd.get("variant", 0)
         if add is not None:
             d.add, d.add_cstride, d.add_bstride = add.ptr, add.cstride, add_bstride
         if gate is not None:
@@ -289,12 +290,15 @@ class UNetRunner(_Builder):
         #   (K = 1024) with the biases added, the residual s added in its epilogue (fp32 accumulation of both products)
         att = "attention1" if self.head == "cls" else "attention2"
         self.linear("qkvq", [L + att + ".to_qkv.weight", L + "cross_attention_cl.to_q.weight"])
+        # (kernel structure of the two residual GEMMs as measured at 25088 tokens, profiles/r02_bottleneck_gemms.txt:
+        #  K = 1024 -> 512 multi-issuer 0.046 ms against 0.058 for the static rule; 2048 -> 512 persistent with one
+        #  256-wide n-tile pair 0.067 against 0.091)
         self.linear("outcat", [L + att + ".to_out.0.weight", L + "cross_attention_cl.to_out.0.weight"],
-                    [L + att + ".to_out.0.bias", L + "cross_attention_cl.to_out.0.bias"], along_k=True)
+                    [L + att + ".to_out.0.bias", L + "cross_attention_cl.to_out.0.bias"], along_k=True, variant=5)
         if self.head == "cls":
             return self._pack_cls_head()
         self.linear("ff1", [L + "m_feed.net.0.weight"], L + "m_feed.net.0.bias")
-        self.linear("ff2", [L + "m_feed.net.3.weight"], L + "m_feed.net.3.bias")
+        self.linear("ff2", [L + "m_feed.net.3.weight"], L + "m_feed.net.3.bias", bn=256, variant=2)
         for n in ("x_att_norm", "m_att_norm", "m_mlp_norm"):
             self.w[n] = (_f32(sd[L + n + ".weight"], dev), _f32(sd[L + n + ".bias"], dev))
         for blk in ("up4", "up3", "up2", "up1"):
@@ -324,7 +328,7 @@ class UNetRunner(_Builder):
         sd, dev = self.sd, self.dev
         L = "task2.layers.0."
         self.linear("xff1", [L + "x_feed.net.0.weight"], L + "x_feed.net.0.bias")
-        self.linear("xff2", [L + "x_feed.net.3.weight"], L + "x_feed.net.3.bias")
+        self.linear("xff2", [L + "x_feed.net.3.weight"], L + "x_feed.net.3.bias", bn=256, variant=2)
         for n in ("x_att_norm", "m_att_norm", "x_mlp_norm"):
             self.w[n] = (_f32(sd[L + n + ".weight"], dev), _f32(sd[L + n + ".bias"], dev))
         # fc2(fc1(.)) has no activation in between (:433-434), so the two Linear layers compose into one [1, 512]
