@@ -51,19 +51,16 @@ namespace ug {
 
 static constexpr int kEpiUnroll = UG_EPI_UNROLL;   // unroll factor of the epilogue chunk loop
 static constexpr int kMI = 2;           // tile streams per CTA (each with its own epilogue warpgroup)
-// threads per CTA: 4 epilogue warps per (stream, epilogue group), two producer warps, kKS issuers per stream:
-// 384 (kKS = 1) / 448 (kKS = 2) / 640 (kEG = 2)
-__host__ __device__ constexpr int kMultiThreads(int ks, int eg = 1) { return 32 * (4 * kMI * eg + 2 + kMI * ks); }
+__host__ __device__ constexpr int kMultiThreads(int ks) { return 32 * (4 * kMI + 2 + kMI * ks); }   // 384 (kKS = 1) / 448 (kKS = 2)
 static constexpr int kMPitch = 10;      // halo tile pitch of 8-pixel-wide tiles: 8 output pixels + one border pixel on each side
 // Warp roles.  The warp scheduler prefers the highest warp id among eligible warps, and the MMA issuers are the
 // latency-critical warps (every late tcgen05.mma is a tensor-pipe bubble), so they get the highest ids, then the
 // TMA producer; the epilogue warps (which have plenty of slack but dense instruction streams) get the lowest.
 // Measured on the 224x224 64->64 layer: issuers at warps 1-2 below a tightened epilogue: 0.29 ms, here: see
 // profiles/r01_conv_sweep_multi_issuer.txt.
-// (with kEG epilogue groups per stream the epilogue occupies warps 0 .. 4*kMI*kEG-1 and the roles below follow it)
-__host__ __device__ constexpr int kMAllocWarp(int eg) { return 4 * kMI * eg; }          // 8: TMEM allocator + weight (B) producer
-__host__ __device__ constexpr int kMProducerWarp(int eg) { return 4 * kMI * eg + 1; }   // 9: activation (A) producer
-__host__ __device__ constexpr int kMIssuerWarp0(int eg) { return 4 * kMI * eg + 2; }    // 10 ..: issuer of (stream i, K-half h) is warp 10 + i*kKS + h
+static constexpr int kMAllocWarp = 4 * kMI;          // 8: TMEM allocator + weight (B) producer
+static constexpr int kMProducerWarp = 4 * kMI + 1;   // 9: activation (A) producer
+static constexpr int kMIssuerWarp0 = 4 * kMI + 2;    // 10 ..: issuer of (stream i, K-half h) is warp 10 + i*kKS + h
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -119,13 +116,12 @@ struct StoreMaps {  // output maps: [0] for plain stores, [q] = quadrant (dy,dx)
   CUtensorMap m[4];
 };
 
-template <int kAct, int kTaps, int kMode, int kKS, int kEG>
-__global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int kAct, int kTaps, int kMode, int kKS>
+__global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                            const __grid_constant__ CUtensorMap tmB,
                                                                            const __grid_constant__ StoreMaps tmO,
                                                                            const ConvKParams p, const MultiParams hp) {
-  constexpr int kThreadsCta = kMultiThreads(kKS, kEG);
-  constexpr int kAllocW = kMAllocWarp(kEG), kProdW = kMProducerWarp(kEG), kIssW0 = kMIssuerWarp0(kEG);
+  constexpr int kThreadsCta = kMultiThreads(kKS);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   const int b_tile_bytes = p.BN * 128;
@@ -134,7 +130,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
   uint8_t* sA = smem;                                        // [kMI][sa] activation stages
   uint8_t* sB = sA + kMI * hp.sa * hp.a_stage_bytes;
   uint8_t* sO = sB + nb_tiles * b_tile_bytes;                // [kMI][obufs] output staging
-  uint8_t* sP = sO + kMI * kEG * p.obufs * obuf_bytes;        // [kMI][obufs] pooled staging (4 KB each) when p.pool
+  uint8_t* sP = sO + kMI * p.obufs * obuf_bytes;              // [kMI][obufs] pooled staging (4 KB each) when p.pool
   float* sScale = reinterpret_cast<float*>(sP + (p.pool ? kMI * p.obufs * kPoolBytes : 0));  // 16-byte aligned
   float* sBias = sScale + p.npad;
   float* sGate = sBias + p.npad;                              // [kMI][128]: 1 + gate of the tile's image (GATE epilogue)
@@ -151,7 +147,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
   const int lane = threadIdx.x & 31;
   const int total_super = hp.m_super * p.n_tiles;
 
-  if (warp == kProdW && lane == 0) {
+  if (warp == kMProducerWarp && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     if (p.tma_store) {
@@ -173,11 +169,11 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
     }
     for (int i = 0; i < kMI * p.acc_stages; ++i) {
       mbar_init(&acc_full[i], kKS);  // every K-half of the tile is complete
-      mbar_init(&acc_empty[i], 4 * kEG);  // one arrival per epilogue warp of the stream
+      mbar_init(&acc_empty[i], 4);
     }
     fence_mbar_init();
   }
-  if (warp == kAllocW) {
+  if (warp == kMAllocWarp) {
     tmem_alloc(tmem_ptr, p.tmem_cols);
     tmem_relinquish();
   }
@@ -192,10 +188,10 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
   // Everything above touched only kernel parameters and constant weights; from here on the roles read activations /
   // write outputs, which must wait for the previous kernel of the stream.  The weight producer (kMAllocWarp) streams
   // constants only and starts right away.
-  if (warp != kAllocW) pdl_wait();
+  if (warp != kMAllocWarp) pdl_wait();
   pdl_launch_dependents();
 
-  if (warp == kProdW) {
+  if (warp == kMProducerWarp) {
     // ------------------------------------------------------------------ activation producer (whole warp, elected lane issues)
     int as[kMI] = {0, 0};
     uint32_t aph[kMI] = {0, 0};
@@ -249,7 +245,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
       p.prof[blockIdx.x * 16 + 2] = clock64() - t_start;
       p.prof[blockIdx.x * 16 + 3] = (long long)(ns1 - ns0);
     }
-  } else if (warp == kAllocW) {
+  } else if (warp == kMAllocWarp) {
     // ------------------------------------------------------------------ weight producer (its own warp: a full weight
     // ring must not delay the activation loads of the next chunk, and vice versa)
     long long w_b = 0;
@@ -285,9 +281,9 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
       }
     }
     if (p.prof && lane == 0) p.prof[blockIdx.x * 16 + 1] = w_b;
-  } else if (warp >= kIssW0) {
+  } else if (warp >= kMIssuerWarp0) {
     // ------------------------------------------------------------------ MMA issuers (whole warp, one elected lane issues)
-    const int iw = warp - kIssW0;
+    const int iw = warp - kMIssuerWarp0;
     const int i = iw / kKS;       // tile stream
     const int h = iw - i * kKS;   // K-half: this warp issues the (chunk, tap) items whose index is h modulo kKS
     const uint32_t idesc = umma_idesc_bf16(128, p.BN);
@@ -388,16 +384,12 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
       p.prof[blockIdx.x * 16 + 4 + i * 4 + 2] = w_acc;
       p.prof[blockIdx.x * 16 + 4 + i * 4 + 3] = clock64() - t_start;
     }
-  } else if (warp < 4 * kMI * kEG) {
-    // ------------------------------------------------------------------ epilogue (4 warps per group).  kEG = 1: one
-    // group per stream.  kEG = 2 (wide 1x1 / ConvTranspose tiles, whose 2-4 sub-tiles of 64 columns made the epilogue
-    // the bottleneck): two groups per stream, group (i, eh) takes the sub-tiles eh, eh + 2 of the stream's tile.
-    const int g = warp >> 2;            // epilogue group: staging buffers and named barrier of its own
-    const int i = g % kMI;              // tile stream
-    const int eh = g / kMI;             // first sub-tile of this group
+  } else if (warp < 4 * kMI) {
+    // ------------------------------------------------------------------ epilogue (4 warps per issuer)
+    const int i = warp >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int etid = threadIdx.x - g * 128;
+    const int etid = threadIdx.x - i * 128;
     // MMA row -> pixel of the tile.  8-pixel-wide 3x3 tiles: row = ty*8 + tx.  Row-strip 3x3 tiles: row = ty*pitch + tx
     // with tx >= W garbage.  1x1 tiles: row = (tn*TH + ty)*TW + tx.  `srow` is the row of the staged output tile.
     const bool strip = kTaps == 9 && hp.strip;
@@ -407,7 +399,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
     const int tn = kTaps == 9 ? 0 : row / (p.TW * p.TH);
     const bool row_in_tile = kTaps == 9 ? (ty < hp.TH && (!strip || tx < p.W)) : (row < p.TW * p.TH * p.TN);
     const int srow = strip ? ty * p.W + tx : row;
-    uint8_t* sOi = sO + g * p.obufs * obuf_bytes;
+    uint8_t* sOi = sO + i * p.obufs * obuf_bytes;
     int acc = 0, obuf = 0;
     uint32_t acc_phase = 0;
     long long e_wacc = 0, e_wobuf = 0, e_tiles = 0, e_loop = 0, e_tail = 0;
@@ -470,11 +462,11 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
 #pragma unroll
           for (int j = 0; j < (kKS == 2 ? 16 : 1); ++j) v2[j] = 0u;
         }
-      } else if (eh * 64 < ncols) {
-        tmem_ld16(taddr + eh * 64, v);
-        if constexpr (kKS == 2) tmem_ld16(taddr + p.BN + eh * 64, reinterpret_cast<uint32_t(&)[16]>(v2));
+      } else {
+        tmem_ld16(taddr, v);
+        if constexpr (kKS == 2) tmem_ld16(taddr + p.BN, reinterpret_cast<uint32_t(&)[16]>(v2));
       }
-      for (int sub = eh; sub * 64 < ncols; sub += kEG) {
+      for (int sub = 0; sub * 64 < ncols; ++sub) {
         if (p.tma_store) {
           // staging buffer `obuf` must no longer be read by the TMA store issued obufs sub-tiles ago
           // (the barrier also publishes sGate of this tile)
@@ -483,7 +475,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
             if (p.obufs == 2) bulk_wait_group_read<1>();
             else bulk_wait_group_read<0>();
           }
-          named_bar_sync(1 + g, 128);
+          named_bar_sync(1 + i, 128);
           if (p.prof) e_wobuf += clock64() - tw0;
         }
         uint8_t* so_row = sOi + obuf * obuf_bytes + srow * 128;
@@ -503,11 +495,9 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
           float f[16];
           epi_math16_linear<kAct>(v, f, sScale, sBias, ncol0 + c0);   // ReLU deferred (see conv_common.cuh)
           __syncwarp();
-          // next chunk of this group: the following 16 columns, or the first chunk of its next sub-tile
-          const int nc0 = (kEG == 1 || cc < 3) ? c0 + 16 : (sub + kEG) * 64;
-          if (nc0 < ncols && !(hp.debug & 1)) {
-            tmem_ld16(taddr + nc0, v);
-            if constexpr (kKS == 2) tmem_ld16(taddr + p.BN + nc0, reinterpret_cast<uint32_t(&)[16]>(v2));
+          if (c0 + 16 < ncols && !(hp.debug & 1)) {
+            tmem_ld16(taddr + c0 + 16, v);
+            if constexpr (kKS == 2) tmem_ld16(taddr + p.BN + c0 + 16, reinterpret_cast<uint32_t(&)[16]>(v2));
           }
           if (kMode != UG_EPI_STORE) epi_relu16<kAct>(f);  // stores fold the ReLU into the bf16 conversion below
           if (kMode == UG_EPI_OUTC) {
@@ -580,7 +570,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
         const long long tl1 = p.prof ? clock64() : 0;
         if (p.prof) e_loop += tl1 - tl0;
         if (kMode == UG_EPI_OUTC) continue;
-        if ((sub + kEG) * 64 >= ncols) {  // all TMEM reads of this group are done: hand the accumulator back
+        if ((sub + 1) * 64 >= ncols) {  // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
@@ -588,7 +578,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
         if (p.pool && strip) {
           // fused nn.MaxPool2d(2) of a row-strip tile: row neighbours are not warp neighbours here, so the 2x2 windows
           // are read back from the staged tile ([TH][W] rows of 128 B) once every thread has written its row
-          named_bar_sync(1 + g, 128);
+          named_bar_sync(1 + i, 128);
           const uint8_t* sbuf = sOi + obuf * obuf_bytes;
           uint8_t* pbuf = sP + (i * p.obufs + obuf) * kPoolBytes;
           const int pw = p.W >> 1, items = (hp.TH >> 1) * pw * 8;
@@ -621,7 +611,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
             if (s2 < total_super && ((s2 - hp.d_msuper.div(s2) * hp.m_super) * kMI + i) < p.m_tiles) prefetch_add(s2, 0);
           }
         }
-        named_bar_sync(1 + g, 128);
+        named_bar_sync(1 + i, 128);
         if (etid == 0 && !(hp.debug & 2)) {
           const int col = ncol0 + sub * 64;
           if (p.up == 2) {  // ConvTranspose 2x2 s2: column block -> quadrant (dy,dx) map, channel inside the quadrant
@@ -653,7 +643,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
             m1 = fmaxf(m1, b);
           }
           *reinterpret_cast<float4*>(sStat + i * 512 + rq * 128 + cp * 4) = make_float4(s0, m0, s1, m1);
-          named_bar_sync(1 + g, 128);
+          named_bar_sync(1 + i, 128);
           const int nsub = min(64, ncols - sub * 64);
           if (etid < nsub) {
             const float* q0 = sStat + i * 512 + (etid >> 1) * 4 + (etid & 1) * 2;
@@ -667,11 +657,6 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
         }
         if (p.prof) e_tail += clock64() - tl1;
         if (p.obufs == 2) obuf ^= 1;
-      }
-      if (kEG > 1 && eh * 64 >= ncols) {  // a narrow last n-tile leaves this group without a sub-tile: release only
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
       }
       if (kMode == UG_EPI_OUTC) {
         tc_fence_before();
@@ -691,7 +676,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
       }
     }
     if (p.tma_store && etid == 0) bulk_wait_group_all();
-    if (p.prof && etid == 0 && g == 0) {
+    if (p.prof && etid == 0 && i == 0) {
       p.prof[blockIdx.x * 16 + 12] = e_wacc;
       p.prof[blockIdx.x * 16 + 13] = e_wobuf;
       p.prof[blockIdx.x * 16 + 14] = clock64() - e_start;
@@ -705,7 +690,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kEG), 1) conv_multi_kernel(
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kAllocW) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == kMAllocWarp) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -800,10 +785,6 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   if (taps == 1 && !(d->mode == UG_EPI_STORE || (d->mode == UG_EPI_ADD && d->act == UG_ACT_NONE)))
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): 1x1 layers are instantiated for STORE (any activation) and ADD (no activation)");
   const int acc_stages = std::max(1, std::min(4, 512 / (kMI * ks * BN)));
-  // wide epilogue: two epilogue groups per stream for 1x1 / ConvTranspose tiles of >= 128 columns (2-4 sub-tiles of 64
-  // columns per 64..512-deep tile made the epilogue, not the tensor pipe or HBM, the bound); UG_WIDE_EPI=0 turns it off
-  static const int wide_on = [] { const char* e = getenv("UG_WIDE_EPI"); return e ? atoi(e) : 1; }();
-  const int eg = (taps == 1 && d->mode == UG_EPI_STORE && d->act == UG_ACT_NONE && BN >= 128 && wide_on) ? 2 : 1;
   const int a_bytes = taps == 9 ? pitch * (TH + 2) * 128 : TW * TH * TN * 128;
   // strip mode: MMA row 127 of tap (2,2) reads halo position 127 + 2*pitch + 2, past the loaded box (garbage rows only)
   const int a_span = strip ? std::max(a_bytes, (128 + 2 * pitch + 2) * 128) : a_bytes;
@@ -821,13 +802,12 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
                     kMI * 128 * (int)sizeof(float) + (stats ? kMI * 512 * (int)sizeof(float) : 0);
   const long long budget = 227LL * 1024 - fixed;
   int obufs = tma_store ? 2 : 0;
-  const int ng = kMI * eg;   // epilogue groups (each with its own staging buffers)
   const long long resB = (long long)taps * kchunks * b_tile;
-  if (n_tiles == 1 && resB + kMI * 2LL * a_stage + (tma_store ? ng * obuf_bytes : 0) <= budget) {
+  if (n_tiles == 1 && resB + kMI * 2LL * a_stage + (tma_store ? kMI * obuf_bytes : 0) <= budget) {
     hp.b_resident = 1;
     hp.sb = 1;
-    if (resB + kMI * 2LL * a_stage + ng * obufs * obuf_bytes > budget) obufs = 1;
-    hp.sa = (int)std::min<long long>(4, (budget - resB - ng * obufs * obuf_bytes) / (kMI * a_stage));
+    if (resB + kMI * 2LL * a_stage + kMI * obufs * obuf_bytes > budget) obufs = 1;
+    hp.sa = (int)std::min<long long>(4, (budget - resB - kMI * obufs * obuf_bytes) / (kMI * a_stage));
   } else {
     // streamed weights: the MMA time per tile is long, so one staging buffer per epilogue group is enough and the
     // shared memory goes to a deep weight ring instead (a slot is only handed back when the MMAs that read it have
@@ -835,7 +815,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     hp.b_resident = 0;
     hp.sa = 2;
     if (obufs == 2) obufs = 1;
-    long long rest = budget - kMI * 2LL * a_stage - ng * obufs * obuf_bytes;
+    long long rest = budget - kMI * 2LL * a_stage - kMI * obufs * obuf_bytes;
     hp.sb = (int)std::min<long long>(16, rest / b_tile);
     if (hp.sb < 3) return set_error(h, UG_EUNSUPPORTED, "conv(multi): tile does not fit in shared memory");
     if (hp.sb >= 12 && rest - 10LL * b_tile >= kMI * a_stage) {  // room for a third activation stage
@@ -875,7 +855,6 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   L->halo_sa = hp.sa; L->halo_sb = hp.sb; L->halo_bres = hp.b_resident;
   L->halo_debug = d->stages >= 100 ? d->stages - 100 : 0;  // profiling ablations (scripts/conv_prof.py)
   L->halo_ks = ks;
-  L->halo_eg = eg;
   L->halo_strip = strip; L->halo_pitch = pitch;
 
   {
@@ -934,7 +913,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   const long long total_super = (long long)hp.m_super * n_tiles;
   L->grid = dim3((unsigned)std::min<long long>(total_super, (long long)h->num_sms), 1, 1);
   const int nb_tiles = hp.b_resident ? taps * kchunks : hp.sb;
-  L->smem = 1024 + (size_t)kMI * hp.sa * a_stage + (size_t)nb_tiles * b_tile + (size_t)ng * obufs * obuf_bytes +
+  L->smem = 1024 + (size_t)kMI * hp.sa * a_stage + (size_t)nb_tiles * b_tile + (size_t)kMI * obufs * obuf_bytes +
             8 * (2 * kMI * hp.sa + 2 * hp.sb + 2 * kMI * acc_stages) + 16 + 2 * (size_t)npad * sizeof(float) +
             kMI * 128 * sizeof(float) + (stats ? kMI * 512 * sizeof(float) : 0);
   if (L->smem > (size_t)227 * 1024)
@@ -942,12 +921,12 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   return UG_OK;
 }
 
-template <int kAct, int kTaps, int kMode, int kKS, int kEG = 1>
+template <int kAct, int kTaps, int kMode, int kKS>
 static cudaError_t launch_one(ug_engine* h, const ConvLaunch* L, const StoreMaps& maps, const MultiParams& hp,
                               cudaStream_t s, bool set_attr) {
-  auto fn = conv_multi_kernel<kAct, kTaps, kMode, kKS, kEG>;
+  auto fn = conv_multi_kernel<kAct, kTaps, kMode, kKS>;
   if (set_attr) return cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  return launch_pdl(h, fn, L->grid, kMultiThreads(kKS, kEG), L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
+  return launch_pdl(h, fn, L->grid, kMultiThreads(kKS), L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
 }
 
 // Dispatch over the instantiated (activation, taps, epilogue mode, K-split) combinations (conv_multi_prepare rejects the
@@ -955,12 +934,7 @@ static cudaError_t launch_one(ug_engine* h, const ConvLaunch* L, const StoreMaps
 static cudaError_t dispatch_multi(ug_engine* h, const ConvLaunch* L, const StoreMaps& maps, const MultiParams& hp,
                                   cudaStream_t s, bool set_attr) {
   cudaError_t e = cudaSuccess;
-  const int act = L->p.act, mode = L->p.mode, taps = L->halo_mode, ks = L->halo_ks, eg = L->halo_eg;
-  if (set_attr) {
-    if (e == cudaSuccess) e = launch_one<UG_ACT_NONE, 1, UG_EPI_STORE, 1, 2>(h, L, maps, hp, s, true);
-  } else if (eg == 2) {  // wide epilogue: the only instantiation (conv_multi_prepare sets eg = 2 for exactly this case)
-    return launch_one<UG_ACT_NONE, 1, UG_EPI_STORE, 1, 2>(h, L, maps, hp, s, false);
-  }
+  const int act = L->p.act, mode = L->p.mode, taps = L->halo_mode, ks = L->halo_ks;
 #define UG_MULTI_CASE(A, T, M, K)                                                        \
   if (set_attr) {                                                                        \
     if (e == cudaSuccess) e = launch_one<A, T, M, K>(h, L, maps, hp, s, true);           \

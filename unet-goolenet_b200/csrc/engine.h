@@ -86,7 +86,6 @@ struct ConvLaunch {
   int variant;  // 0 = persistent, 1 = one tile per CTA, 5 = multi-issuer kernel (halo_mode = taps: 9 or 1)
   int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres, halo_debug;
   int halo_strip, halo_pitch;  // multi-issuer kernel: row-strip tiles (full image rows per tile) and their halo pitch
-  int halo_eg;  // multi-issuer kernel: epilogue groups per tile stream (wide 1x1 / ConvTranspose tiles), 1 or 2
   int halo_ks;  // multi-issuer kernel: issuing warps per tile stream (K-split), 1 or 2
 };
 
