@@ -1,0 +1,53 @@
+"""Copy the outputs of scripts/gpu_evidence.sh <tag> from gpurun_out/ into profiles/ under round names (rNN_*).
+usage: store_evidence.py r02b r02"""
+import csv, json, re, shutil, subprocess, sys
+tag, rnd = sys.argv[1], sys.argv[2]
+O, P = "gpurun_out", "profiles"
+rows = [l for l in open(f"{O}/{tag}_launches.csv") if l.startswith('"')]
+assert not any("elementwise" in r for r in rows), "torch kernels in the launch list"
+open(f"{P}/{rnd}_launches.csv", "w").writelines(rows)
+rd = list(csv.reader(rows))
+ix = {h: i for i, h in enumerate(rd[0])}
+tot = {}
+for r in rd[1:]:
+    name = re.sub(r"<.*", "", r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("ug::", ""))
+    t = float(r[ix["Metric Value"]])
+    t = t / 1e3 if r[ix["Metric Unit"]] in ("ns", "nsecond") else t
+    tot.setdefault(name, [0, 0.0])
+    tot[name][0] += 1
+    tot[name][1] += t
+allt = sum(v[1] for v in tot.values())
+lines = [f"# Kernel classes of ONE 128-image pipeline pass (ncu --metrics gpu__time_duration.sum, engine kernels only;",
+         f"# source: profiles/{rnd}_launches.csv = scripts/gpu_evidence.sh {tag}; serialised, cold-cache launches, so shares, not absolutes)",
+         "", "| kernel | launches | us | share |", "|---|---|---|---|"]
+for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+    lines.append(f"| {k} | {v[0]} | {v[1]:.1f} | {100 * v[1] / allt:.1f} % |")
+lines.append(f"| total | {sum(v[0] for v in tot.values())} | {allt:.1f} | 100 % |")
+open(f"{P}/{rnd}_kernel_shares.md", "w").write("\n".join(lines) + "\n")
+print("\n".join(lines))
+shutil.copy(f"{O}/{tag}_per_op.json", f"{P}/{rnd}_per_op.json")
+for a, b in (("bench.log", "bench.json"), ("bench_src512.log", "bench_src512.json"), ("bench_unet64.log", "bench_unet64.json"),
+             ("bench_googlenet256.log", "bench_googlenet256.json"), ("bench_ref.log", "bench_reference_arm.json")):
+    last = [l for l in open(f"{O}/{tag}_{a}") if l.startswith("{")][-1]
+    open(f"{P}/{rnd}_{b}", "w").write(last)
+table = subprocess.run([sys.executable, "scripts/ncu_summary.py", f"{O}/{tag}_full.raw.csv"], capture_output=True, text=True, check=True).stdout
+hdr = (f"# ncu --set full --clock-control none of ONE 128-image pipeline pass, engine kernels only, program order (scripts/gpu_evidence.sh {tag})\n"
+       "# rows 0-56: UNet micro-batch of 128 + bbox + crop-resize; rows 57-: GoogLeNet over 128 crops\n"
+       "# tensor pipe % = sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed (at the full 1.965 GHz clock)\n"
+       "# % of HBM peak divides by the COPY peak 6552.6 GB/s; write-dominated kernels are bounded by the write roof 3.86 TB/s (r02_bandwidth_probe.txt)\n\n")
+open(f"{P}/{rnd}_ncu_kernels.md", "w").write(hdr + table)
+# DRAM bytes per launch of the dominant kernel family (conv_multi_kernel)
+rows = list(csv.reader(open(f"{O}/{tag}_full.raw.csv")))
+h, units = rows[0], rows[1]
+ixx = {n: i for i, n in enumerate(h)}
+SC = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+tb, n = 0.0, 0
+for r in rows[2:]:
+    if "conv_multi_kernel" in r[ixx["Kernel Name"]]:
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tb += float(r[ixx[m]]) * SC.get(units[ixx[m]], 1)
+        n += 1
+json.dump({"dram_bytes_per_launch": int(tb / n), "launches": n,
+           "source": f"profiles/{rnd}_ncu_kernels.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum averaged over the {n} "
+                     "conv_multi_kernel launches of one 128-image pipeline pass)"}, open(f"{P}/{rnd}_ncu_traffic.json", "w"))
+print("traffic per launch", int(tb / n), "over", n)

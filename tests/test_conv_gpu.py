@@ -173,6 +173,12 @@ CASES = [
     dict(B=2, H=18, W=36, Cin=64, N=96, R=3, pool=True),
     dict(B=9, H=28, W=28, Cin=128, N=192, R=3, variant=5),
     dict(B=2, H=28, W=28, Cin=1024, N=256, R=3, variant=5),
+    # CoordAtt3 combine on 64-channel layers: residual tile TMA-loaded into the staging buffer, combined in place (kRT)
+    dict(B=2, H=224, W=224, Cin=64, N=64, R=3, mode=2, in_extra=64, out_extra=64, out_off=64),   # up1.cca.conv2_e layout
+    dict(B=3, H=56, W=56, Cin=64, N=64, R=3, mode=2),
+    dict(B=2, H=30, W=44, Cin=64, N=64, R=3, mode=2, variant=5),      # ragged tiles in both directions
+    dict(B=5, H=16, W=8, Cin=64, N=64, R=3, mode=2, variant=5),       # odd tile count: one stream idles in the last round
+    dict(B=37, H=32, W=32, Cin=64, N=64, R=3, mode=2, variant=5),     # many rounds per CTA: staging-buffer hand-over
     # fused 2x2 max-pool side output (DownBlock): exact tiles, ragged width (28 = 3.5 tiles), streamed and resident weights
     dict(B=2, H=112, W=112, Cin=128, N=128, R=3, pool=True),
     dict(B=3, H=28, W=28, Cin=256, N=512, R=3, pool=True, out_extra=64, out_off=32),

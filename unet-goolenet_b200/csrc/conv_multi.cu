@@ -21,6 +21,13 @@
 // The epilogue compacts its rows to the [SR][W] layout of the TMA store box; the fused 2x2 max-pool reads the staged
 // tile instead of exchanging registers (row neighbours are W+2 lanes apart).
 //
+// TMA residual (kRT = 1, CoordAtt3 combine on 64-channel layers): the GATE epilogue adds the e1 tile.  Read by the
+// epilogue threads themselves (16 bytes per lane at a 128-byte lane stride, eight times per tile) those loads were a
+// fifth of the layer (0.348 -> 0.276 ms at 224x224 without them).  With kRT the otherwise idle weight-producer warp
+// TMA-loads the residual tile of the NEXT sub-tile straight into the other output staging buffer (same box and swizzle
+// as the store); the epilogue combines IN PLACE — every (row, 16-byte chunk) is read and rewritten by exactly one
+// thread — and hands the buffer back (r_free) once the TMA store that followed has finished reading it.
+//
 // The issue loops are warp-uniform with the asynchronous instructions under elect_one_sync() (see common.cuh):
 // with `if (lane == 0)` loops the issuing thread needed ~16 SASS instructions per MMA and bounded every N <= 128
 // layer (224x224 64->64: 0.375 ms before, 0.236 ms after; profiles/r01_conv_sweep_multi_issuer.txt).
@@ -101,6 +108,7 @@ struct MultiParams {
   int sbo;            // byte distance of consecutive 8-row groups of the A operand: pitch * 128 (tiles) or 1024 (strips)
   int strip;          // row-strip tiles (see the header comment); TH is then the number of image rows per tile
   FastDiv d_pitch;    // divider by pitch (strip mode: MMA row -> (image row, x))
+  int resid_tma;      // kRT kernels: residual tiles arrive by TMA in the staging buffers (see the header comment)
   int debug;          // ablation switches for profiling (results are wrong when set): 1 = no TMEM loads,
                       // 2 = no staging stores / TMA store, 4 = activation TMA loads only for the first stages,
                       // 16 = no residual loads (ADD / GATE epilogues)
@@ -112,11 +120,11 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 }
 static constexpr int kPoolBytes = 4096;   // pooled sub-tile staging: 4 x TH/2 <= 32 pixels x 64 channels bf16
 
-struct StoreMaps {  // output maps: [0] for plain stores, [q] = quadrant (dy,dx) of a ConvTranspose 2x2 s2 scatter
-  CUtensorMap m[4];
+struct StoreMaps {  // output maps: [0] for plain stores, [q] = quadrant (dy,dx) of a ConvTranspose 2x2 s2 scatter;
+  CUtensorMap m[5];  // [4] = load map of the residual tensor (kRT)
 };
 
-template <int kAct, int kTaps, int kMode, int kKS>
+template <int kAct, int kTaps, int kMode, int kKS, int kRT>
 __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                            const __grid_constant__ CUtensorMap tmB,
                                                                            const __grid_constant__ StoreMaps tmO,
@@ -141,7 +149,9 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
   uint64_t* b_empty = b_full + hp.sb;
   uint64_t* acc_full = b_empty + hp.sb;                      // [kMI][acc_stages]
   uint64_t* acc_empty = acc_full + kMI * p.acc_stages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + kMI * p.acc_stages);
+  uint64_t* r_full = acc_empty + kMI * p.acc_stages;          // [kMI][2] residual tile landed in staging buffer b (kRT)
+  uint64_t* r_free = r_full + kMI * 2;                        // [kMI][2] staging buffer b may be overwritten (kRT)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(r_free + kMI * 2);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -171,6 +181,11 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
       mbar_init(&acc_full[i], kKS);  // every K-half of the tile is complete
       mbar_init(&acc_empty[i], 4);
     }
+    for (int i = 0; i < kMI * 2; ++i) {
+      mbar_init(&r_full[i], 1);
+      mbar_init(&r_free[i], 1);
+    }
+    if (kRT) prefetch_tmap(&tmO.m[4]);
     fence_mbar_init();
   }
   if (warp == kMAllocWarp) {
@@ -257,6 +272,35 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
             tma_load_2d(sB + (kc * kTaps + tap) * b_tile_bytes, &tmB, &b_full[0], (tap * p.kchunks + kc) * 64, 0);
       }
       __syncwarp();
+      if constexpr (kRT) {
+        // residual producer: the tile sequence of both streams, one sub-tile (= one tile: BN <= 64) ahead of the
+        // epilogue; the residual is an activation written by an earlier kernel of the stream
+        pdl_wait();
+        const uint32_t r_tx = (uint32_t)(p.TW * p.TH * 128);
+        const int obuf_b = kABytesPerStage;
+        int rb[kMI] = {0, 0};
+        uint32_t rph[kMI] = {0, 0};
+        for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+          const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
+#pragma unroll
+          for (int i = 0; i < kMI; ++i) {
+            const int mt = ms * kMI + i;
+            if (mt >= p.m_tiles) continue;
+            const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
+            const int x0 = (mt - t1 * p.tiles_x) * p.TW, y0 = (t1 - t2 * p.tiles_y) * p.TH, n0 = t2 * p.TN;
+            mbar_wait(&r_free[i * 2 + rb[i]], rph[i] ^ 1);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&r_full[i * 2 + rb[i]], r_tx);
+              tma_load_4d(sO + (i * p.obufs + rb[i]) * obuf_b, &tmO.m[4], &r_full[i * 2 + rb[i]], nt * p.BN, x0, y0, n0);
+            }
+            __syncwarp();
+            if (++rb[i] == 2) {
+              rb[i] = 0;
+              rph[i] ^= 1;
+            }
+          }
+        }
+      }
     } else {
       int bs = 0;
       uint32_t bph = 0;
@@ -409,7 +453,9 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     // SUB-TILE AHEAD (right after the chunk loop of the previous sub-tile, whose residual registers are dead by
     // then): with the loads issued at the start of the same tile the HBM latency was exposed in the first chunk of
     // every tile of the epilogue-bound 64-channel layers (chunk loop 1000 cycles per chunk instead of 400).
-    constexpr bool has_add = kMode == UG_EPI_ADD || kMode == UG_EPI_GATE;
+    constexpr bool has_add = (kMode == UG_EPI_ADD || kMode == UG_EPI_GATE) && !kRT;   // register-prefetched residual
+    constexpr bool smem_add = (kMode == UG_EPI_ADD || kMode == UG_EPI_GATE) && kRT;   // TMA-loaded residual, in place
+    uint32_t r_uses = 0;   // kRT: sub-tiles processed so far by this group (buffer = r_uses & 1, phase = (r_uses >> 1) & 1)
     uint4 addv[8];
     auto prefetch_add = [&](int s2, int sub2) {
       const int nt2 = hp.d_msuper.div(s2), mt2 = (s2 - nt2 * hp.m_super) * kMI + i;
@@ -471,7 +517,16 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
           // staging buffer `obuf` must no longer be read by the TMA store issued obufs sub-tiles ago
           // (the barrier also publishes sGate of this tile)
           tw0 = p.prof ? clock64() : 0;
-          if (etid == 0) {
+          if constexpr (smem_add) {
+            // the store of the previous sub-tile (other buffer) has finished reading: hand that buffer to the residual
+            // producer for the NEXT sub-tile, then wait for this sub-tile's residual (loaded one sub-tile ago)
+            if (etid == 0 && r_uses > 0) {
+              bulk_wait_group_read<0>();
+              mbar_arrive(&r_free[i * 2 + (obuf ^ 1)]);
+            }
+            mbar_wait(&r_full[i * 2 + obuf], (r_uses >> 1) & 1);
+            ++r_uses;
+          } else if (etid == 0) {
             if (p.obufs == 2) bulk_wait_group_read<1>();
             else bulk_wait_group_read<0>();
           }
@@ -510,6 +565,18 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
             continue;
           }
           const int groups = (c0 + 16 <= ncols) ? 2 : 1;
+          if constexpr (smem_add) {   // residual pieces of this chunk sit where the result will be written
+            const uint4 a0 = *reinterpret_cast<const uint4*>(so_row + (((cc * 2) ^ (srow & 7)) << 4));
+            const uint4 a1 = *reinterpret_cast<const uint4*>(so_row + (((cc * 2 + 1) ^ (srow & 7)) << 4));
+            if (kMode == UG_EPI_GATE) {
+              const float4* gp = reinterpret_cast<const float4*>(sGate + i * 128 + c0);
+              epi_gate8(f, a0, gp[0], gp[1]);
+              if (groups == 2) epi_gate8(f + 8, a1, gp[2], gp[3]);
+            } else {
+              epi_add8(f, a0);
+              if (groups == 2) epi_add8(f + 8, a1);
+            }
+          }
           if (has_add) {
             uint4 a0, a1;  // prefetched residual pieces of this chunk (register indices must be compile-time)
             switch (cc) {
@@ -785,6 +852,19 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   if (taps == 1 && !(d->mode == UG_EPI_STORE || (d->mode == UG_EPI_ADD && d->act == UG_ACT_NONE)))
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): 1x1 layers are instantiated for STORE (any activation) and ADD (no activation)");
   const int acc_stages = std::max(1, std::min(4, 512 / (kMI * ks * BN)));
+  // TMA residual (see the header comment): CoordAtt3 combine layers with one 64-column n-tile and resident weights.
+  // Needs two staging buffers per stream next to the weights: tiles of <= 14 rows make room (the layer is bound by its
+  // epilogue, not by the 12.5 % of MMA rows this leaves empty).  UG_RESID_TMA=0 turns it off.
+  static const int rt_on = [] { const char* e = getenv("UG_RESID_TMA"); return e ? atoi(e) : 1; }();
+  int rt = (rt_on && taps == 9 && !strip && ks == 2 && d->mode == UG_EPI_GATE && d->N <= 64 && BN == 64 && d->add_bstride > 0 &&
+            !pool && !stats) ? 1 : 0;
+  if (rt) {
+    const int th2 = cdiv_m(d->H, cdiv_m(d->H, 14));
+    const long long need = (long long)taps * kchunks * BN * 128 + kMI * 2LL * (((kMPitch * (th2 + 2) * 128) + 1023) / 1024 * 1024) +
+                           kMI * 2LL * kABytesPerStage + 4096;
+    if (need <= 227LL * 1024) TH = th2;
+    else rt = 0;
+  }
   const int a_bytes = taps == 9 ? pitch * (TH + 2) * 128 : TW * TH * TN * 128;
   // strip mode: MMA row 127 of tap (2,2) reads halo position 127 + 2*pitch + 2, past the loaded box (garbage rows only)
   const int a_span = strip ? std::max(a_bytes, (128 + 2 * pitch + 2) * 128) : a_bytes;
@@ -798,7 +878,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   hp.strip = strip;
   hp.pitch = pitch;
   hp.sbo = strip ? 1024 : pitch * 128;
-  const int fixed = 1024 + 8 * (2 * kMI * 4 + 2 * 16 + 2 * kMI * 4) + 16 + 2 * npad * (int)sizeof(float) +
+  const int fixed = 1024 + 8 * (2 * kMI * 4 + 2 * 16 + 2 * kMI * 4 + 4 * kMI) + 16 + 2 * npad * (int)sizeof(float) +
                     kMI * 128 * (int)sizeof(float) + (stats ? kMI * 512 * (int)sizeof(float) : 0);
   const long long budget = 227LL * 1024 - fixed;
   int obufs = tma_store ? 2 : 0;
@@ -823,6 +903,9 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
       hp.sb = (int)std::min<long long>(16, (rest - kMI * a_stage) / b_tile);
     }
   }
+
+  if (rt && !(hp.b_resident && obufs == 2)) rt = 0;   // (does not fit after all: register-prefetched residual)
+  hp.resid_tma = rt;
 
   ConvKParams& p = L->p;
   memset(&p, 0, sizeof(p));
@@ -855,6 +938,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   L->halo_sa = hp.sa; L->halo_sb = hp.sb; L->halo_bres = hp.b_resident;
   L->halo_debug = d->stages >= 100 ? d->stages - 100 : 0;  // profiling ablations (scripts/conv_prof.py)
   L->halo_ks = ks;
+  L->halo_rt = rt;
   L->halo_strip = strip; L->halo_pitch = pitch;
 
   {
@@ -878,6 +962,14 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   }
   memset(L->tmQ, 0, sizeof(L->tmQ));
   memset(&L->tmO, 0, sizeof(L->tmO));
+  memset(&L->tmR, 0, sizeof(L->tmR));
+  if (rt) {  // load map of the residual tensor, same box as the output store
+    cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->add_cstride * 2, (cuuint64_t)d->W * d->add_cstride * 2, (cuuint64_t)d->add_bstride * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    const int r = encode_map(encode, &L->tmR, const_cast<void*>(d->add), 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (r) return set_error(h, UG_ECUDA, "conv(multi): residual tensor map encode failed (%d)", r);
+  }
   if (tma_store) {
     cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
     if (up == 1) {
@@ -914,17 +1006,17 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   L->grid = dim3((unsigned)std::min<long long>(total_super, (long long)h->num_sms), 1, 1);
   const int nb_tiles = hp.b_resident ? taps * kchunks : hp.sb;
   L->smem = 1024 + (size_t)kMI * hp.sa * a_stage + (size_t)nb_tiles * b_tile + (size_t)kMI * obufs * obuf_bytes +
-            8 * (2 * kMI * hp.sa + 2 * hp.sb + 2 * kMI * acc_stages) + 16 + 2 * (size_t)npad * sizeof(float) +
+            8 * (2 * kMI * hp.sa + 2 * hp.sb + 2 * kMI * acc_stages + 4 * kMI) + 16 + 2 * (size_t)npad * sizeof(float) +
             kMI * 128 * sizeof(float) + (stats ? kMI * 512 * sizeof(float) : 0);
   if (L->smem > (size_t)227 * 1024)
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): shared memory request %zu too large", L->smem);
   return UG_OK;
 }
 
-template <int kAct, int kTaps, int kMode, int kKS>
+template <int kAct, int kTaps, int kMode, int kKS, int kRT = 0>
 static cudaError_t launch_one(ug_engine* h, const ConvLaunch* L, const StoreMaps& maps, const MultiParams& hp,
                               cudaStream_t s, bool set_attr) {
-  auto fn = conv_multi_kernel<kAct, kTaps, kMode, kKS>;
+  auto fn = conv_multi_kernel<kAct, kTaps, kMode, kKS, kRT>;
   if (set_attr) return cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   return launch_pdl(h, fn, L->grid, kMultiThreads(kKS), L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
 }
@@ -935,6 +1027,11 @@ static cudaError_t dispatch_multi(ug_engine* h, const ConvLaunch* L, const Store
                                   cudaStream_t s, bool set_attr) {
   cudaError_t e = cudaSuccess;
   const int act = L->p.act, mode = L->p.mode, taps = L->halo_mode, ks = L->halo_ks;
+  if (set_attr) {
+    if (e == cudaSuccess) e = launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 2, 1>(h, L, maps, hp, s, true);
+  } else if (L->halo_rt) {  // TMA residual: the only instantiation (conv_multi_prepare sets rt for exactly this case)
+    return launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 2, 1>(h, L, maps, hp, s, false);
+  }
 #define UG_MULTI_CASE(A, T, M, K)                                                        \
   if (set_attr) {                                                                        \
     if (e == cudaSuccess) e = launch_one<A, T, M, K>(h, L, maps, hp, s, true);           \
@@ -962,6 +1059,7 @@ int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   hp.TH = L->halo_TH; hp.a_stage_bytes = L->halo_a_stage;
   hp.sa = L->halo_sa; hp.sb = L->halo_sb; hp.b_resident = L->halo_bres; hp.m_super = L->halo_copy;
   hp.debug = L->halo_debug;
+  hp.resid_tma = L->halo_rt;
   hp.strip = L->halo_strip; hp.pitch = L->halo_pitch;
   hp.sbo = hp.strip ? 1024 : hp.pitch * 128;
   hp.d_pitch = make_fastdiv(hp.pitch);
@@ -973,6 +1071,7 @@ int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   maps.m[1] = L->tmQ[0];
   maps.m[2] = L->tmQ[1];
   maps.m[3] = L->tmQ[2];
+  maps.m[4] = L->tmR;
   if (!h->attr_multi) {
     const cudaError_t e = dispatch_multi(h, L, maps, hp, s, true);
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_multi_kernel)");

@@ -79,6 +79,7 @@ struct ConvLaunch {
   alignas(64) CUtensorMap tmB;
   alignas(64) CUtensorMap tmO;  // output map for the TMA-store epilogues
   alignas(64) CUtensorMap tmO2;    // persistent GEMM kernel: TMA-store map of the second destination (split 1x1 GEMM)
+  alignas(64) CUtensorMap tmR;     // multi-issuer kernel: TMA load map of the residual tensor (kRT kernels)
   alignas(64) CUtensorMap tmQ[3];  // multi-issuer kernel, ConvTranspose: output views of quadrants 1..3 (tmO = quadrant 0)
   ConvKParams p;
   dim3 grid;
@@ -86,6 +87,7 @@ struct ConvLaunch {
   int variant;  // 0 = persistent, 1 = one tile per CTA, 5 = multi-issuer kernel (halo_mode = taps: 9 or 1)
   int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres, halo_debug;
   int halo_strip, halo_pitch;  // multi-issuer kernel: row-strip tiles (full image rows per tile) and their halo pitch
+  int halo_rt;  // multi-issuer kernel: residual tiles by TMA into the staging buffers (CoordAtt3 combine, 64 channels)
   int halo_ks;  // multi-issuer kernel: issuing warps per tile stream (K-split), 1 or 2
 };
 
