@@ -84,6 +84,12 @@ typedef struct ug_conv_desc {
                                  1x1 convolutions of an Inception block that read the same tensor (torchvision
                                  Inception.forward: branch1, branch2[0], branch3[0]) as ONE GEMM: branch1 lands in the
                                  block's concat output, the two reduce results in a scratch tensor */
+  long long in_rstride;       /* optional explicit input strides in elements (0 = dense: W*in_cstride, H*W*in_cstride). */
+  long long in_bstride;       /* With in_cstride < Cin the 64-channel rows of neighbouring pixels OVERLAP (a TMA tensor
+                                 map with a pixel stride below its inner box): together with R > 1, S == 1, pad == 0
+                                 ("row taps": out(y,x) = sum_r W_r . in(y+r, x), input map H+R-1 rows, Cin <= 64) this
+                                 runs a KxK strided stem convolution as a regular implicit GEMM over a space-to-depth
+                                 image (GoogLeNet conv1 7x7 s2 = 4 row taps x [4 px x 16 ch] windows, see ug_s2d_desc) */
   int TW, TH, TN, BN, stages; /* tiling; 0 = engine chooses */
   int variant;                /* 0 = auto; 1 = one tile per CTA; 2 = persistent kernel (TMEM multi-buffered
                                  accumulators, TMA-store epilogue); 5 = 3x3 multi-issuer kernel (one CTA per
@@ -188,6 +194,20 @@ typedef struct ug_stem_desc {
   int pool_cstride;
 } ug_stem_desc;
 
+/* Space-to-depth pack for GoogLeNet conv1 (torchvision BasicConv2d 7x7 s2 p3; 分类/test.py:68-73): the uint8 HWC crop
+ * [B,S,S,3] (or a float NCHW image in [0,1]) -> bf16 [B][S/2+3][S/2+3][16]:
+ *   q[n][Y][X][(dy*2+dx)*3 + c] = T(img[n][2Y+dy-3][2X+dx-3][c])  (0 outside the image: padding after the affine),
+ *   T = to_tensor (/255) followed by torchvision's _transform_input; channels 12..15 are zero.
+ * Then conv1(y,x) = sum_{r2<4} sum_{s2<4} W2[r2][s2] . q[y+r2][x+s2]: with in_cstride = 16 the 64-element window
+ * q[y+r2][x .. x+3] is ONE overlapping 128-byte row of a TMA tensor map, so the layer runs on the implicit-GEMM kernel
+ * with four row taps (K = 4 x 64, ug_conv_desc.in_rstride) and no thread-built im2col. */
+typedef struct ug_s2d_desc {
+  const unsigned char* in_u8;
+  const float* in_f32;
+  void* out;
+  int B, S;
+} ug_s2d_desc;
+
 /* Device front-end: the reference's CDDataAugmentation.transform live lines
  * (分类/util/data_utils.py:146-147, 分割/util/data_utils.py): F.resize(PIL image, (S,S), BILINEAR) + F.to_tensor.
  * src: uint8 HWC [B][Hs][Ws][3] of any size up to 8*S per side (e.g. the 512x512 sources of BASELINE config 5);
@@ -236,7 +256,8 @@ enum {
   UG_OP_HEAD = 11,
   UG_OP_STEM = 12,
   UG_OP_RESIZE = 13,
-  UG_OP_WAVELET = 14
+  UG_OP_WAVELET = 14,
+  UG_OP_S2D = 15
 };
 
 typedef struct ug_op {
@@ -255,6 +276,7 @@ typedef struct ug_op {
     ug_stem_desc stem;
     ug_resize_desc resize;
     ug_wavelet_desc wavelet;
+    ug_s2d_desc s2d;
   } u;
 } ug_op;
 
@@ -278,6 +300,7 @@ int ug_head(ug_handle h, const ug_head_desc* d, void* stream);
 int ug_stem(ug_handle h, const ug_stem_desc* d, void* stream);
 int ug_resize_u8(ug_handle h, const ug_resize_desc* d, void* stream);
 int ug_wavelet(ug_handle h, const ug_wavelet_desc* d, void* stream);
+int ug_s2d_pack(ug_handle h, const ug_s2d_desc* d, void* stream);
 size_t ug_wavelet_workspace_bytes(int B, int H, int W);
 
 /* Programs: a validated op list with tensor maps and launch geometry prepared once; run = launches only. */

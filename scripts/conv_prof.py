@@ -69,6 +69,8 @@ if os.environ.get("UG_CONFIGS") == "ffn":     # bottleneck linear layers: every 
     CONFIGS = [dict(variant=1, act=A, mode=M), dict(variant=1, act=A, mode=M, bn=256), dict(variant=2, act=A, mode=M),
                dict(variant=2, act=A, mode=M, bn=256), dict(variant=5, act=A, mode=M), dict(variant=5, act=A, mode=M, bn=256),
                dict(variant=0, act=A, mode=M)]
+if os.environ.get("UG_CONFIGS") == "convt":   # ConvTranspose shapes (R = 0 in the shape): every kernel structure
+    CONFIGS = [dict(variant=1), dict(variant=2), dict(variant=5), dict(variant=0)]
 if os.environ.get("UG_ABLATE"):
     CONFIGS = [dict(variant=5, stages=108), dict(variant=5, stages=108, mode=2)]
 if os.environ.get("UG_ABLATE") == "resid":    # GATE epilogue with / without its residual loads (results wrong without)

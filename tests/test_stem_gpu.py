@@ -82,6 +82,48 @@ def test_stem_conv1(engine, B, S, src):
     _check(out.float(), ref.permute(0, 2, 3, 1))
 
 
+@pytest.mark.parametrize("B,S,src", [(1, 224, "u8"), (5, 224, "u8"), (2, 224, "f32"), (3, 64, "u8"), (40, 32, "f32")])
+def test_conv1_space_to_depth(engine, B, S, src):
+    """GoogLeNet conv1 as ug_s2d_pack + a four-row-tap implicit GEMM over overlapping TMA windows (ug_conv_desc.in_rstride)
+    against F.conv2d(7x7, stride 2, padding 3) on the transformed image; the packed tensor itself is checked exactly."""
+    from ugnet_b200 import engine as E
+    from ugnet_b200 import pack
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + S)
+    wt = torch.randn((64, 3, 7, 7), generator=g, device="cuda") * 0.1
+    scale = torch.rand((64,), generator=g, device="cuda") + 0.5
+    bias = torch.randn((64,), generator=g, device="cuda")
+    wp = pack.pack_conv1_s2d(wt)
+    Q, O = S // 2 + 3, S // 2
+    q, q_intact = guarded((B, Q, Q, 16), 7.0, torch.bfloat16)
+    out, o_intact = guarded((B, O, O, 64), 7.0, torch.bfloat16)
+    if src == "u8":
+        u8 = torch.randint(0, 256, (B, S, S, 3), generator=g, device="cuda", dtype=torch.uint8)
+        xf = (u8.float() / 255.0).permute(0, 3, 1, 2)
+        engine.run_op(E.S2dDesc(u8.data_ptr(), None, q.data_ptr(), B, S))
+    else:
+        xf = torch.rand((B, 3, S, S), generator=g, device="cuda")
+        engine.run_op(E.S2dDesc(None, xf.data_ptr(), q.data_ptr(), B, S))
+    xt = xf * _SC.cuda()[None, :, None, None] + _SH.cuda()[None, :, None, None]   # GoogLeNet._transform_input
+    # the pack: q[n, Y, X, (dy*2+dx)*3 + c] = padded(xt)[n, c, 2Y+dy, 2X+dx]
+    xp = F.pad(xt, (3, 3, 3, 3))
+    want = xp.reshape(B, 3, Q, 2, Q, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Q, Q, 12).to(torch.bfloat16)
+    torch.cuda.synchronize()
+    q_intact()
+    assert torch.equal(q[..., :12], want) and (q[..., 12:] == 0).all()
+    d = E.ConvDesc()
+    d.inp = q.data_ptr(); d.in_cstride = 16; d.Cin = 64; d.B, d.H, d.W = B, O, O
+    d.R, d.S, d.pad = 4, 1, 0
+    d.in_rstride, d.in_bstride = Q * 16, Q * Q * 16
+    d.w = wp.data_ptr(); d.N = 64; d.scale = scale.data_ptr(); d.bias = bias.data_ptr(); d.act = 1; d.mode = 0
+    d.out = out.data_ptr(); d.out_cstride = 64; d.up = 1; d.BN = 64
+    engine.run_op(d)
+    torch.cuda.synchronize()
+    o_intact()
+    xq, wq = xt.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    ref = torch.relu(F.conv2d(xq, wq, stride=2, padding=3) * scale[None, :, None, None] + bias[None, :, None, None])
+    _check(out.float(), ref.permute(0, 2, 3, 1))
+
+
 def test_stem_rejects_bad_args(engine):
     from ugnet_b200 import engine as E
     w = torch.zeros((64, 64), device="cuda", dtype=torch.bfloat16)

@@ -555,8 +555,11 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->N <= 0)
     return set_error(h, UG_EINVAL, "conv: non-positive shape");
   if (d->act < UG_ACT_NONE || d->act > UG_ACT_GELU) return set_error(h, UG_EINVAL, "conv: unknown activation");
-  if (d->R <= 0 || d->S <= 0 || 2 * d->pad != d->R - 1 || d->R != d->S)
-    return set_error(h, UG_EINVAL, "conv: only square stride-1 'same' filters (2*pad == R-1) are supported");
+  const bool rowtaps = d->R > 1 && d->S == 1 && d->pad == 0 && d->up != 2 && d->Cin <= 64;   // ug_conv_desc.in_rstride
+  if (!rowtaps && (d->R <= 0 || d->S <= 0 || 2 * d->pad != d->R - 1 || d->R != d->S))
+    return set_error(h, UG_EINVAL, "conv: only square stride-1 'same' filters (2*pad == R-1) or R x 1 row taps are supported");
+  if ((d->in_rstride || d->in_bstride) && !(rowtaps || (d->R == 1 && d->variant == 5)))
+    return set_error(h, UG_EINVAL, "conv: explicit input strides are for row-tap layers (multi-issuer kernel)");
   if (d->in_cstride % 8 || (reinterpret_cast<uintptr_t>(d->in) & 15))
     return set_error(h, UG_EINVAL, "conv: input channel stride must be a multiple of 8 and base 16B aligned");
   if (d->N % 8) return set_error(h, UG_EINVAL, "conv: N must be a multiple of 8");
@@ -596,9 +599,13 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
       return set_error(h, UG_EINVAL, "conv: a split GEMM is a 1x1 STORE layer with n_split %% 64 == 0 and 0 < n1 <= n_split < N");
     if (BN % 64) return set_error(h, UG_EINVAL, "conv: a split GEMM needs BN %% 64 == 0");
   }
+  if (rowtaps) {
+    if (split || d->variant == 1 || d->variant == 2) return set_error(h, UG_EINVAL, "conv: row-tap layers run on the multi-issuer kernel");
+    return conv_multi_prepare(h, d, BN, L);
+  }
   if (d->variant == 5) return conv_multi_prepare(h, d, d->R == 3 ? std::min(BN, 128) : BN, L);
-  if (d->variant == 0 && up == 2 && d->H * d->W >= 784 && d->convt_cout % 64 == 0) {
-    // ConvTranspose 2x2 s2 on maps of at least 28x28: multi-issuer kernel (two epilogue warpgroups, pixel shuffle as
+  if (d->variant == 0 && up == 2 && d->H * d->W >= 196 && d->convt_cout % 64 == 0) {
+    // ConvTranspose 2x2 s2 on maps of at least 14x14 (profiles/r02_convt_variants.txt): multi-issuer kernel (two epilogue warpgroups, pixel shuffle as
     // four strided TMA-store views); one 256-wide n-tile when that covers all four quadrants
     const int rc = conv_multi_prepare(h, d, d->N == 256 ? 256 : 128, L);
     if (rc == UG_OK) return rc;

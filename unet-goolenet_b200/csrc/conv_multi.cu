@@ -108,6 +108,7 @@ struct MultiParams {
   int sbo;            // byte distance of consecutive 8-row groups of the A operand: pitch * 128 (tiles) or 1024 (strips)
   int strip;          // row-strip tiles (see the header comment); TH is then the number of image rows per tile
   FastDiv d_pitch;    // divider by pitch (strip mode: MMA row -> (image row, x))
+  int rowtaps;        // 1x1 tiles: k-chunk kc is ROW TAP kc of an overlapping-window input (A box at row y0 + kc, channel 0)
   int resid_tma;      // kRT kernels: residual tiles arrive by TMA in the staging buffers (see the header comment)
   int debug;          // ablation switches for profiling (results are wrong when set): 1 = no TMEM loads,
                       // 2 = no staging stores / TMA store, 4 = activation TMA loads only for the first stages,
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
             } else {
               mbar_arrive_expect_tx(&a_full[slot], a_tx);
               if (kTaps == 9) tma_load_4d(sA + slot * hp.a_stage_bytes, &tmA, &a_full[slot], kc * 64, x0 - 1, y0 - 1, n);
+              else if (hp.rowtaps) tma_load_4d(sA + slot * hp.a_stage_bytes, &tmA, &a_full[slot], 0, x0, y0 + kc, n);
               else tma_load_4d(sA + slot * hp.a_stage_bytes, &tmA, &a_full[slot], kc * 64, x0, y0, n);
             }
           }
@@ -783,9 +785,14 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return set_error(h, UG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   const int up = d->up == 2 ? 2 : 1;
-  const int taps = d->R == 3 ? 9 : 1;
-  if (!((d->R == 3 && d->S == 3 && d->pad == 1 && up == 1) || (d->R == 1 && d->S == 1 && d->pad == 0)))
-    return set_error(h, UG_EUNSUPPORTED, "conv(multi): 3x3 pad-1 or 1x1 stride-1 convolutions only");
+  // row taps (see ug_conv_desc.in_rstride): R x 1 "valid" convolution over an overlapping-window input, one 64-element
+  // window per tap: runs as a 1x1 tile whose R k-chunks are the taps
+  const int rowtaps = (d->R > 1 && d->S == 1 && d->pad == 0 && up == 1 && d->Cin <= 64) ? 1 : 0;
+  const int taps = d->R == 3 && !rowtaps ? 9 : 1;
+  if (!((d->R == 3 && d->S == 3 && d->pad == 1 && up == 1) || (d->R == 1 && d->S == 1 && d->pad == 0) || rowtaps))
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): 3x3 pad-1, 1x1, or R x 1 row-tap convolutions only");
+  if ((d->in_rstride || d->in_bstride) && taps == 9)
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi): explicit input strides are for 1x1 / row-tap layers");
   if (BN > 256) return set_error(h, UG_EUNSUPPORTED, "conv(multi): BN <= 256");
   // 3x3 with one n-tile wider than 128 columns (GoogLeNet N = 192 ... 224): plain stores only (the gate / statistics
   // staging is sized for 128 columns), one accumulator per issuer
@@ -827,10 +834,10 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     if (TW > 256 || TH > 256 || TN > 256) return set_error(h, UG_EUNSUPPORTED, "conv(multi): tile exceeds the TMA box limits");
   }
   const int cin_pad = cdiv_m(d->Cin, 64) * 64;
-  const int kchunks = cin_pad / 64;
+  const int kchunks = rowtaps ? d->R : cin_pad / 64;
   const int n_tiles = cdiv_m(d->N, BN);
   const int npad = n_tiles * BN;
-  const long long ktot = (long long)taps * cin_pad;
+  const long long ktot = rowtaps ? (long long)d->R * 64 : (long long)taps * cin_pad;
   const int tma_store = d->mode != UG_EPI_OUTC;
   const int pool = d->pool_out != nullptr;
   if (pool && (taps != 9 || d->mode != UG_EPI_STORE || (d->H & 1) || (d->W & 1) || (TH & 1) || d->pool_cstride % 8 ||
@@ -906,6 +913,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
 
   if (rt && !(hp.b_resident && obufs == 2)) rt = 0;   // (does not fit after all: register-prefetched residual)
   hp.resid_tma = rt;
+  hp.rowtaps = rowtaps;
 
   ConvKParams& p = L->p;
   memset(&p, 0, sizeof(p));
@@ -939,12 +947,16 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   L->halo_debug = d->stages >= 100 ? d->stages - 100 : 0;  // profiling ablations (scripts/conv_prof.py)
   L->halo_ks = ks;
   L->halo_rt = rt;
+  L->halo_rowtaps = rowtaps;
   L->halo_strip = strip; L->halo_pitch = pitch;
 
   {
-    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
-    cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)d->W * d->in_cstride * 2,
-                             (cuuint64_t)d->H * d->W * d->in_cstride * 2};
+    const long long in_h = d->H + (rowtaps ? d->R - 1 : 0);
+    const long long rs = d->in_rstride ? d->in_rstride : (long long)d->W * d->in_cstride;
+    const long long bs = d->in_bstride ? d->in_bstride : in_h * rs;
+    if (rs % 8 || bs % 8) return set_error(h, UG_EINVAL, "conv(multi): input strides must be multiples of 8 elements");
+    cuuint64_t dims[4] = {(cuuint64_t)(rowtaps ? 64 : d->Cin), (cuuint64_t)d->W, (cuuint64_t)in_h, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)rs * 2, (cuuint64_t)bs * 2};
     cuuint32_t box9[4] = {64, (cuuint32_t)pitch, (cuuint32_t)(TH + 2), 1};
     cuuint32_t box1[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
     const int r = encode_map(encode, &L->tmA, const_cast<void*>(d->in), 4, dims, strides, taps == 9 ? box9 : box1,
@@ -1060,6 +1072,7 @@ int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   hp.sa = L->halo_sa; hp.sb = L->halo_sb; hp.b_resident = L->halo_bres; hp.m_super = L->halo_copy;
   hp.debug = L->halo_debug;
   hp.resid_tma = L->halo_rt;
+  hp.rowtaps = L->halo_rowtaps;
   hp.strip = L->halo_strip; hp.pitch = L->halo_pitch;
   hp.sbo = hp.strip ? 1024 : hp.pitch * 128;
   hp.d_pitch = make_fastdiv(hp.pitch);

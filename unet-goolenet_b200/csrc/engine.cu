@@ -52,6 +52,7 @@ static int run_simple(ug_engine* h, const ug_op* op, cudaStream_t s) {
     case UG_OP_HEAD: return launch_head(h, &op->u.head, s);
     case UG_OP_RESIZE: return launch_resize_u8(h, &op->u.resize, s);
     case UG_OP_WAVELET: return launch_wavelet(h, &op->u.wavelet, s);
+    case UG_OP_S2D: return launch_s2d_pack(h, &op->u.s2d, s);
     default: return set_error(h, UG_EINVAL, "unknown op kind %d", op->kind);
   }
 }
@@ -133,6 +134,7 @@ UG_SIMPLE_ENTRY(ug_cropresize, ug_cropresize_desc, launch_cropresize)
 UG_SIMPLE_ENTRY(ug_head, ug_head_desc, launch_head)
 UG_SIMPLE_ENTRY(ug_resize_u8, ug_resize_desc, launch_resize_u8)
 UG_SIMPLE_ENTRY(ug_wavelet, ug_wavelet_desc, launch_wavelet)
+UG_SIMPLE_ENTRY(ug_s2d_pack, ug_s2d_desc, launch_s2d_pack)
 
 int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out) {
   if (!h || !ops || n_ops <= 0 || !out) return UG_EINVAL;
@@ -160,7 +162,7 @@ int ug_program_create(ug_handle h, const ug_op* ops, int n_ops, ug_program* out)
         delete p;
         return rc;
       }
-    } else if (po.kind < UG_OP_CONV || po.kind > UG_OP_WAVELET) {
+    } else if (po.kind < UG_OP_CONV || po.kind > UG_OP_S2D) {
       delete p;
       return set_error(h, UG_EINVAL, "op %d: unknown kind %d", i, po.kind);
     }

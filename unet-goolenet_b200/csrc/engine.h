@@ -88,6 +88,7 @@ struct ConvLaunch {
   int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres, halo_debug;
   int halo_strip, halo_pitch;  // multi-issuer kernel: row-strip tiles (full image rows per tile) and their halo pitch
   int halo_rt;  // multi-issuer kernel: residual tiles by TMA into the staging buffers (CoordAtt3 combine, 64 channels)
+  int halo_rowtaps;  // multi-issuer kernel, 1x1 tiles: the k-chunks are R row taps of an overlapping-window input
   int halo_ks;  // multi-issuer kernel: issuing warps per tile stream (K-split), 1 or 2
 };
 
@@ -153,5 +154,6 @@ int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s)
 int launch_head(ug_engine* h, const ug_head_desc* d, cudaStream_t s);
 int launch_resize_u8(ug_engine* h, const ug_resize_desc* d, cudaStream_t s);
 int launch_wavelet(ug_engine* h, const ug_wavelet_desc* d, cudaStream_t s);
+int launch_s2d_pack(ug_engine* h, const ug_s2d_desc* d, cudaStream_t s);
 
 }  // namespace ug

@@ -767,6 +767,65 @@ int launch_cropresize(ug_engine* h, const ug_cropresize_desc* d, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Space-to-depth pack for GoogLeNet conv1 (ug_s2d_desc): one thread per packed pixel (n, Y, X) writes its 16 bf16
+// channels (32 contiguous bytes): the 2x2 block of source pixels (2Y+dy-3, 2X+dx-3) x 3 channels, to_tensor and
+// _transform_input applied, zero outside the image and in channels 12..15.
+__global__ void __launch_bounds__(256) s2d_pack_kernel(ug_s2d_desc d) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
+  const int Q = d.S / 2 + 3;
+  const long long total = (long long)d.B * Q * Q;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int X = (int)(t % Q);
+  const int Y = (int)((t / Q) % Q);
+  const int n = (int)(t / ((long long)Q * Q));
+  // torchvision GoogLeNet._transform_input: x_c * (std_c / 0.5) + (mean_c - 0.5) / 0.5
+  const float sc[3] = {0.229f / 0.5f, 0.224f / 0.5f, 0.225f / 0.5f};
+  const float sh[3] = {(0.485f - 0.5f) / 0.5f, (0.456f - 0.5f) / 0.5f, (0.406f - 0.5f) / 0.5f};
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const int iy = 2 * Y + dy - 3;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int ix = 2 * X + dx - 3;
+      if (iy < 0 || iy >= d.S || ix < 0 || ix >= d.S) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float x = d.in_f32 ? __ldg(d.in_f32 + (((long long)n * 3 + c) * d.S + iy) * d.S + ix)
+                                 : (float)__ldg(d.in_u8 + (((long long)n * d.S + iy) * d.S + ix) * 3 + c) / 255.0f;
+        v[(dy * 2 + dx) * 3 + c] = x * sc[c] + sh[c];
+      }
+    }
+  }
+  uint4 o0, o1;
+  o0.x = pack_bf16x2(v[0], v[1]);
+  o0.y = pack_bf16x2(v[2], v[3]);
+  o0.z = pack_bf16x2(v[4], v[5]);
+  o0.w = pack_bf16x2(v[6], v[7]);
+  o1.x = pack_bf16x2(v[8], v[9]);
+  o1.y = pack_bf16x2(v[10], v[11]);
+  o1.z = pack_bf16x2(v[12], v[13]);
+  o1.w = pack_bf16x2(v[14], v[15]);
+  uint4* out = reinterpret_cast<uint4*>(d.out) + t * 2;
+  out[0] = o0;
+  out[1] = o1;
+}
+
+int launch_s2d_pack(ug_engine* h, const ug_s2d_desc* d, cudaStream_t s) {
+  if ((!d->in_u8 && !d->in_f32) || !d->out || d->B <= 0 || d->S <= 0 || (d->S & 1) || (reinterpret_cast<uintptr_t>(d->out) & 15))
+    return set_error(h, UG_EINVAL, "s2d_pack: bad args (even image side, 16-byte aligned output)");
+  const int Q = d->S / 2 + 3;
+  const long long total = (long long)d->B * Q * Q;
+  launch_pdl(h, s2d_pack_kernel, cdiv(total, 256), 256, 0, s, *d);
+  h->launches++;
+  return check_cuda(h, cudaGetLastError(), "s2d_pack launch");
+}
+
+// ------------------------------------------------------------------------------------------------
 // GoogLeNet head: global average pool + fc, one block per image.
 __global__ void __launch_bounds__(256) head_kernel(ug_head_desc d) {
   pdl_wait();  // programmatic dependent launch: see common.cuh

@@ -20,7 +20,7 @@ ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 EPI_STORE, EPI_ADD, EPI_GATE, EPI_OUTC = 0, 1, 2, 3
 # (2 and 10 were round 1's stand-alone im2col packs; the numbers stay retired, see ugnet.h)
 OP_CONV, OP_POOL, OP_LAYERNORM, OP_ATTN, OP_CHANSTATS, OP_GATE, OP_BBOX, OP_CROPRESIZE = 1, 3, 4, 5, 6, 7, 8, 9
-OP_HEAD, OP_STEM, OP_RESIZE, OP_WAVELET = 11, 12, 13, 14
+OP_HEAD, OP_STEM, OP_RESIZE, OP_WAVELET, OP_S2D = 11, 12, 13, 14, 15
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
@@ -33,6 +33,7 @@ class ConvDesc(C.Structure):
                 ("outc_b", _f), ("logits", _vp), ("mask", _vp), ("pool_out", _vp), ("pool_cstride", _i),
                 ("stats_sum", _vp), ("stats_max", _vp), ("stats_tiles", _i),
                 ("out2", _vp), ("out2_cstride", _i), ("n_split", _i), ("n1", _i),
+                ("in_rstride", _ll), ("in_bstride", _ll),
                 ("TW", _i), ("TH", _i), ("TN", _i), ("BN", _i), ("stages", _i), ("variant", _i)]
 
 
@@ -88,11 +89,15 @@ class WaveletDesc(C.Structure):
                 ("H", _i), ("W", _i)]
 
 
+class S2dDesc(C.Structure):
+    _fields_ = [("in_u8", _vp), ("in_f32", _vp), ("out", _vp), ("B", _i), ("S", _i)]
+
+
 class _OpUnion(C.Union):
     _fields_ = [("conv", ConvDesc), ("pool", PoolDesc), ("ln", LayerNormDesc),
                 ("attn", AttnDesc), ("stats", ChanStatsDesc), ("gate", GateDesc), ("bbox", BBoxDesc),
                 ("crop", CropResizeDesc), ("head", HeadDesc), ("stem", StemDesc),
-                ("resize", ResizeDesc), ("wavelet", WaveletDesc)]
+                ("resize", ResizeDesc), ("wavelet", WaveletDesc), ("s2d", S2dDesc)]
 
 
 class Op(C.Structure):
@@ -105,16 +110,16 @@ class Copy(C.Structure):
 
 _KIND_FIELD = {OP_CONV: "conv", OP_POOL: "pool", OP_LAYERNORM: "ln", OP_ATTN: "attn",
                OP_CHANSTATS: "stats", OP_GATE: "gate", OP_BBOX: "bbox", OP_CROPRESIZE: "crop",
-               OP_HEAD: "head", OP_STEM: "stem", OP_RESIZE: "resize", OP_WAVELET: "wavelet"}
+               OP_HEAD: "head", OP_STEM: "stem", OP_RESIZE: "resize", OP_WAVELET: "wavelet", OP_S2D: "s2d"}
 _DESC_KIND = {ConvDesc: OP_CONV, PoolDesc: OP_POOL, LayerNormDesc: OP_LAYERNORM,
               AttnDesc: OP_ATTN, ChanStatsDesc: OP_CHANSTATS, GateDesc: OP_GATE, BBoxDesc: OP_BBOX,
               CropResizeDesc: OP_CROPRESIZE, HeadDesc: OP_HEAD, StemDesc: OP_STEM,
-              ResizeDesc: OP_RESIZE, WaveletDesc: OP_WAVELET}
+              ResizeDesc: OP_RESIZE, WaveletDesc: OP_WAVELET, S2dDesc: OP_S2D}
 _SINGLE_ENTRY = {OP_CONV: "ug_conv", OP_POOL: "ug_pool",
                  OP_LAYERNORM: "ug_layernorm", OP_ATTN: "ug_attention", OP_CHANSTATS: "ug_chanstats",
                  OP_GATE: "ug_gate", OP_BBOX: "ug_bbox", OP_CROPRESIZE: "ug_cropresize",
                  OP_HEAD: "ug_head", OP_STEM: "ug_stem",
-                 OP_RESIZE: "ug_resize_u8", OP_WAVELET: "ug_wavelet"}
+                 OP_RESIZE: "ug_resize_u8", OP_WAVELET: "ug_wavelet", OP_S2D: "ug_s2d_pack"}
 
 EXPORTED_SYMBOLS = ["ug_version", "ug_create", "ug_destroy", "ug_last_error", "ug_launch_count",
                     *_SINGLE_ENTRY.values(), "ug_program_create", "ug_program_run", "ug_program_num_launches",

@@ -36,6 +36,9 @@ FUSE_REDUCE = os.environ.get("UG_FUSE_REDUCE", "1") != "0"
 # read the block input (branch1 | 3x3-reduce | 5x5-reduce; torchvision Inception.forward), branch1's columns stored
 # straight into the block's concat output and the two reduce results into a scratch tensor (ug_conv_desc.out2).
 FUSE_HEAD = os.environ.get("UG_FUSE_HEAD", "1") != "0" and FUSE_REDUCE
+# UG_CONV1_S2D=0: GoogLeNet conv1 (7x7 s2) on the thread-built im2col stem kernel.  Default: a space-to-depth pack of the
+# crop (ug_s2d_pack) followed by a regular TMA implicit GEMM with four row taps over overlapping 128-byte windows.
+CONV1_S2D = os.environ.get("UG_CONV1_S2D", "1") != "0"
 
 
 # Plans (program + activation workspace) kept per runner: a loader with ragged / varying batch sizes would otherwise
@@ -184,7 +187,7 @@ class _Builder:
 
     # ---- ops -----------------------------------------------------------------------------------
     def conv(self, ops, wd, x, geom, out=None, act=E.ACT_RELU, mode=E.EPI_STORE, up=1, add=None, add_bstride=0,
-             gate=None, outc=None, pool_out=None, stats=None, out2=None):
+             gate=None, outc=None, pool_out=None, stats=None, out2=None, in_strides=None):
         B, H, W = geom
         d = E.ConvDesc()
         d.algo_k = wd.get("algo_k", wd["Cin"] * wd["R"] * wd["R"])   # true reduction length (for FLOP accounting)
@@ -193,6 +196,10 @@ class _Builder:
         d.B, d.H, d.W = B, H, W
         d.R = d.S = wd["R"]
         d.pad = (wd["R"] - 1) // 2
+        if "S" in wd:                                                # row-tap layer (R x 1, valid): see ug_conv_desc
+            d.S, d.pad = wd["S"], wd["pad"]
+        if in_strides is not None:
+            d.in_rstride, d.in_bstride = in_strides
         d.w, d.N = wd["w"].data_ptr(), wd["N"]
         d.scale, d.bias = E.ptr(wd["scale"]), E.ptr(wd["bias"])
         d.act, d.mode = act, mode
@@ -573,6 +580,8 @@ class GoogLeNetRunner(_Builder):
         gemm[:, :, :21] = wt.permute(0, 2, 3, 1).reshape(64, 7, 21)
         self.w["conv1"] = dict(w=pack.pack_linear_weight(gemm.reshape(64, 154), 64), scale=scale, bias=bias, N=64,
                                Cin=192, R=1, BN=64, algo_k=147)
+        self.w["conv1_s2d"] = dict(w=pack.pack_conv1_s2d(wt), scale=scale, bias=bias, N=64, Cin=64, R=4, S=1, pad=0,
+                                   BN=64, algo_k=147)
         self.conv_bn("conv2", "conv2.conv", "conv2.bn", self.EPS)
         self.conv_bn("conv3", "conv3.conv", "conv3.bn", self.EPS)
         for name in _INCEPTION_CFG:
@@ -604,10 +613,19 @@ class GoogLeNetRunner(_Builder):
     def _emit_googlenet(self, B, ws, ops, u8=None, f32=None):
         """u8: [B,224,224,3] uint8 crops (HWC, channel order as the reference's roi_rgb), or f32: float NCHW."""
         buf = self.buf
-        c1 = buf(B, 112, 112, 64)                                    # conv1: im2col built in smem (stem_conv.cu)
-        w1 = self.w["conv1"]
-        ops.append(E.StemDesc(1, E.ptr(f32), E.ptr(u8), w1["w"].data_ptr(), w1["scale"].data_ptr(),
-                              w1["bias"].data_ptr(), c1.data_ptr(), 64, B, IMG, IMG))
+        c1 = buf(B, 112, 112, 64)
+        if CONV1_S2D:
+            # conv1 7x7 s2 as a TMA implicit GEMM: space-to-depth pack of the crop (to_tensor + _transform_input folded,
+            # padding materialised), then four row taps over overlapping [4 px x 16 ch] windows (K = 4 x 64)
+            Q = IMG // 2 + 3
+            q = buf(B, Q, Q, 16)
+            ops.append(E.S2dDesc(E.ptr(u8), E.ptr(f32), q.data_ptr(), B, IMG))
+            self.conv(ops, self.w["conv1_s2d"], View(q, 64, 0, 16), (B, 112, 112), View(c1),
+                      in_strides=(Q * 16, Q * Q * 16))
+        else:                                                        # im2col built in smem (stem_conv.cu)
+            w1 = self.w["conv1"]
+            ops.append(E.StemDesc(1, E.ptr(f32), E.ptr(u8), w1["w"].data_ptr(), w1["scale"].data_ptr(),
+                                  w1["bias"].data_ptr(), c1.data_ptr(), 64, B, IMG, IMG))
         p1 = buf(B, 56, 56, 64)
         ops.append(E.PoolDesc(c1.data_ptr(), 64, p1.data_ptr(), 64, 64, B, 112, 112, 56, 56, 3, 2, 0))
         c2 = buf(B, 56, 56, 64)

@@ -77,3 +77,17 @@ def pack_convt_weight(w, bias, bn):
     assert kh == 2 and kw == 2
     g = w.permute(2, 3, 1, 0).reshape(4 * cout, cin)  # row (kh*2+kw)*cout + co, col ci
     return pack_linear_weight(g, bn), bias.float().repeat(4).contiguous()
+
+
+def pack_conv1_s2d(w):
+    """torchvision GoogLeNet conv1 weight [64, 3, 7, 7] (stride 2, pad 3) -> the GEMM weight of its space-to-depth form
+    (ug_s2d_desc): bf16 [64][4*64], K index = r2*64 + s2*16 + (dy*2+dx)*3 + c = w[:, c, 2*r2+dy, 2*s2+dx] (zero where the
+    7x7 filter has no tap 7 and in the padding channels 12..15)."""
+    assert tuple(w.shape[1:]) == (3, 7, 7)
+    cout = w.shape[0]
+    w8 = torch.zeros(cout, 3, 8, 8, dtype=torch.float32, device=w.device)
+    w8[:, :, :7, :7] = w.float()
+    g = w8.reshape(cout, 3, 4, 2, 4, 2).permute(0, 2, 4, 3, 5, 1).reshape(cout, 4, 4, 12)   # [co, r2, s2, (dy,dx,c)]
+    out = torch.zeros(cout, 4, 4, 16, dtype=torch.float32, device=w.device)
+    out[..., :12] = g
+    return out.reshape(cout, 256).to(torch.bfloat16).contiguous()
