@@ -109,7 +109,9 @@ def test_conv1_space_to_depth(engine, B, S, src):
     want = xp.reshape(B, 3, Q, 2, Q, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Q, Q, 12).to(torch.bfloat16)
     torch.cuda.synchronize()
     q_intact()
-    assert torch.equal(q[..., :12], want) and (q[..., 12:] == 0).all()
+    # (the kernel applies the affine with one fused multiply-add, torch with two roundings: 1 bf16 ulp at most)
+    assert ((q[..., :12].float() - want.float()).abs() <= 2.0 ** -7 * want.float().abs() + 1e-6).all()
+    assert (q[..., 12:] == 0).all() and ((want == 0) <= (q[..., :12] == 0)).all(), "padding must stay exactly zero"
     d = E.ConvDesc()
     d.inp = q.data_ptr(); d.in_cstride = 16; d.Cin = 64; d.B, d.H, d.W = B, O, O
     d.R, d.S, d.pad = 4, 1, 0
