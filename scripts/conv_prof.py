@@ -28,6 +28,11 @@ def make(B, H, W, Cin, N, R, mode=0, bn=None, stages=0, variant=0, tile=None, up
         d.convt_cout = N // 4; d.act = 0
     if tile: d.TW, d.TH, d.TN = tile
     keep = [x, wp, out, scale, bias]
+    if mode == 3:
+        ow = torch.randn(N, generator=g, device="cuda") * 0.2
+        lg = torch.zeros((B, H, W), device="cuda"); mk = torch.zeros((B, H, W), device="cuda", dtype=torch.uint8)
+        d.outc_w = ow.data_ptr(); d.outc_b = 0.05; d.logits = lg.data_ptr(); d.mask = mk.data_ptr()
+        keep += [ow, lg, mk]
     if mode in (1, 2):
         add = torch.randn((B, H, W, N), generator=g, device="cuda").to(torch.bfloat16)
         gate = torch.rand((B, N), device="cuda")
@@ -71,6 +76,8 @@ if os.environ.get("UG_CONFIGS") == "ffn":     # bottleneck linear layers: every 
                dict(variant=0, act=A, mode=M)]
 if os.environ.get("UG_CONFIGS") == "convt":   # ConvTranspose shapes (R = 0 in the shape): every kernel structure
     CONFIGS = [dict(variant=1), dict(variant=2), dict(variant=5), dict(variant=0)]
+if os.environ.get("UG_CONFIGS") == "pair":    # 64-output-channel 3x3 layers: multi-issuer K-split kernel vs the CTA-pair kernel
+    CONFIGS = [dict(variant=5), dict(variant=6), dict(variant=5, mode=3), dict(variant=6, mode=3)]
 if os.environ.get("UG_ABLATE"):
     CONFIGS = [dict(variant=5, stages=108), dict(variant=5, stages=108, mode=2)]
 if os.environ.get("UG_ABLATE") == "resid":    # GATE epilogue with / without its residual loads (results wrong without)
@@ -97,7 +104,7 @@ for shp in SHAPES:
             if cfg.get("variant", 0) == 2:
                 pr = eng.conv_profile(d)
                 line += " | " + " ".join(f"{k}={v:.0f}" for k, v in pr.items())
-            if cfg.get("variant", 0) == 5:
+            if cfg.get("variant", 0) == 5 and cfg.get("mode", 0) != 3:
                 pr = eng.conv_profile16(d)
                 line += f" | clk {pr['prod_cycles'] / max(pr['prod_ns'], 1):.3f} GHz " + " ".join(
                     f"{k}={v:.0f}" for k, v in pr.items())

@@ -195,6 +195,16 @@ CASES = [
     dict(B=1, H=112, W=112, Cin=64, N=256, R=1, up=2, act=0, out_extra=64, variant=5),  # ConvT into a concat buffer
     dict(B=3, H=28, W=28, Cin=256, N=1024, R=1, up=2, act=0, out_extra=256, variant=5),  # ConvT, odd tile count
     dict(B=70, H=14, W=14, Cin=480, N=192, R=1, variant=5),                   # several rounds, ragged channel chunk
+    # CTA-pair kernel (conv_pair.cu, tcgen05.mma.cta_group::2): 3x3 ReLU layers with <= 64 output channels
+    dict(B=1, H=224, W=224, Cin=64, N=64, R=3, variant=6),            # 448 tiles = 112 quads over 74 pairs
+    dict(B=2, H=224, W=224, Cin=128, N=64, R=3, variant=6),           # two k-chunks (nConvs.0 of the last UpBlock)
+    dict(B=3, H=16, W=8, Cin=64, N=64, R=3, variant=6),               # 3 tiles: one quad, last tile past the end
+    dict(B=5, H=30, W=44, Cin=64, N=64, R=3, variant=6, out_extra=64, out_off=64, in_extra=64, in_off=64),   # ragged both ways, channel slices
+    dict(B=2, H=32, W=48, Cin=64, N=64, R=3, mode=3, variant=6),      # fused outc + sigmoid + threshold
+    dict(B=3, H=224, W=224, Cin=64, N=64, R=3, mode=3, variant=6),
+    dict(B=2, H=56, W=56, Cin=64, N=64, R=3, pool=True, variant=6),   # fused 2x2 max-pool side output
+    dict(B=37, H=32, W=32, Cin=24, N=48, R=3, variant=6),             # many rounds per pair; ragged channels both sides
+    dict(B=2, H=112, W=112, Cin=192, N=64, R=3, variant=6),           # three k-chunks, TH = 16
     # legacy one-tile-per-CTA variant stays covered
     dict(B=2, H=16, W=16, Cin=64, N=64, R=3, variant=1),
     dict(B=2, H=56, W=56, Cin=256, N=128, R=3, variant=1),

@@ -604,6 +604,14 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
     return conv_multi_prepare(h, d, BN, L);
   }
   if (d->variant == 5) return conv_multi_prepare(h, d, d->R == 3 ? std::min(BN, 128) : BN, L);
+  if (d->variant == 6) return conv_pair_prepare(h, d, L);
+  // UG_PAIR=1: 3x3 layers with <= 64 output channels on large maps go to the CTA-pair kernel (conv_pair.cu)
+  static const int use_pair = [] { const char* e = getenv("UG_PAIR"); return e ? atoi(e) : 0; }();
+  if (use_pair && d->variant == 0 && d->R == 3 && up == 1 && d->N <= 64 && d->H * d->W >= 112 * 112) {
+    const int rc = conv_pair_prepare(h, d, L);
+    if (rc == UG_OK) return rc;
+    if (rc != UG_EUNSUPPORTED) return rc;
+  }
   if (d->variant == 0 && up == 2 && d->H * d->W >= 196 && d->convt_cout % 64 == 0) {
     // ConvTranspose 2x2 s2 on maps of at least 14x14 (profiles/r02_convt_variants.txt): multi-issuer kernel (two epilogue warpgroups, pixel shuffle as
     // four strided TMA-store views); one 256-wide n-tile when that covers all four quadrants
@@ -792,6 +800,7 @@ int conv_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
     h->attr_gemm = true;
   }
   if (L->variant == 5) return conv_multi_launch(h, L, s);
+  if (L->variant == 6) return conv_pair_launch(h, L, s);
   const int act = L->p.act;
   cudaError_t le;
   if (L->variant == 1) {

@@ -19,7 +19,7 @@ struct ug_engine {
   int pdl = 1;  // launch kernels with programmatic stream serialization (UG_PDL=0 turns it off)
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the device that is current at the call, so the
   // "already raised" flags are per handle (= per device), not process-wide
-  bool attr_gemm = false, attr_multi = false, attr_stem = false, attr_attn = false;
+  bool attr_gemm = false, attr_multi = false, attr_pair = false, attr_stem = false, attr_attn = false;
   size_t attr_resize = 0, attr_crop = 0;
 };
 
@@ -84,7 +84,7 @@ struct ConvLaunch {
   ConvKParams p;
   dim3 grid;
   size_t smem;
-  int variant;  // 0 = persistent, 1 = one tile per CTA, 5 = multi-issuer kernel (halo_mode = taps: 9 or 1)
+  int variant;  // 0 = persistent, 1 = one tile per CTA, 5 = multi-issuer kernel (halo_mode = taps: 9 or 1), 6 = CTA-pair kernel
   int halo_mode, halo_TH, halo_a_stage, halo_copy, halo_sa, halo_sb, halo_bres, halo_debug;
   int halo_strip, halo_pitch;  // multi-issuer kernel: row-strip tiles (full image rows per tile) and their halo pitch
   int halo_rt;  // multi-issuer kernel: residual tiles by TMA into the staging buffers (CoordAtt3 combine, 64 channels)
@@ -140,6 +140,9 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
 int conv_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* out);
 int conv_multi_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
+// CTA-pair kernel (csrc/conv_pair.cu): 3x3 ReLU layers with <= 64 output channels, tcgen05.mma.cta_group::2
+int conv_pair_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
+int conv_pair_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 
 int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* out);
 int stem_launch(ug_engine* h, const StemLaunch* l, cudaStream_t s);
