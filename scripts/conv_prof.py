@@ -77,7 +77,8 @@ if os.environ.get("UG_CONFIGS") == "ffn":     # bottleneck linear layers: every 
 if os.environ.get("UG_CONFIGS") == "convt":   # ConvTranspose shapes (R = 0 in the shape): every kernel structure
     CONFIGS = [dict(variant=1), dict(variant=2), dict(variant=5), dict(variant=0)]
 if os.environ.get("UG_CONFIGS") == "pair":    # 64-output-channel 3x3 layers: multi-issuer K-split kernel vs the CTA-pair kernel
-    CONFIGS = [dict(variant=5), dict(variant=6), dict(variant=5, mode=3), dict(variant=6, mode=3)]
+    CONFIGS = [dict(variant=5), dict(variant=6), dict(variant=5, mode=3), dict(variant=6, mode=3), dict(variant=5, mode=2),
+               dict(variant=6, mode=2)]
 if os.environ.get("UG_ABLATE"):
     CONFIGS = [dict(variant=5, stages=108), dict(variant=5, stages=108, mode=2)]
 if os.environ.get("UG_ABLATE") == "resid":    # GATE epilogue with / without its residual loads (results wrong without)
@@ -104,7 +105,7 @@ for shp in SHAPES:
             if cfg.get("variant", 0) == 2:
                 pr = eng.conv_profile(d)
                 line += " | " + " ".join(f"{k}={v:.0f}" for k, v in pr.items())
-            if cfg.get("variant", 0) == 5 and cfg.get("mode", 0) != 3:
+            if cfg.get("variant", 0) == 5 and cfg.get("mode", 0) == 0:
                 pr = eng.conv_profile16(d)
                 line += f" | clk {pr['prod_cycles'] / max(pr['prod_ns'], 1):.3f} GHz " + " ".join(
                     f"{k}={v:.0f}" for k, v in pr.items())

@@ -204,7 +204,13 @@ CASES = [
     dict(B=3, H=224, W=224, Cin=64, N=64, R=3, mode=3, variant=6),
     dict(B=2, H=56, W=56, Cin=64, N=64, R=3, pool=True, variant=6),   # fused 2x2 max-pool side output
     dict(B=37, H=32, W=32, Cin=24, N=48, R=3, variant=6),             # many rounds per pair; ragged channels both sides
-    dict(B=2, H=112, W=112, Cin=192, N=64, R=3, variant=6),           # three k-chunks, TH = 16
+    dict(B=2, H=112, W=112, Cin=192, N=64, R=3, variant=6),           # three k-chunks: one tile stream per CTA, 3 stages
+    dict(B=3, H=112, W=112, Cin=256, N=64, R=3, variant=6),           # up2.nConvs.0: one stream, 2 stages, 144 KB of weights
+    dict(B=5, H=24, W=8, Cin=256, N=64, R=3, mode=3, variant=6),      # one stream + fused outc, odd tile count
+    dict(B=2, H=224, W=224, Cin=64, N=64, R=3, mode=2, variant=6, in_extra=64, out_extra=64, out_off=64),   # up1.cca.conv2_e layout
+    dict(B=2, H=30, W=44, Cin=64, N=64, R=3, mode=2, variant=6),      # GATE, ragged tiles in both directions
+    dict(B=5, H=16, W=8, Cin=128, N=64, R=3, mode=2, variant=6),      # GATE, odd tile count (tiles past the end)
+    dict(B=37, H=32, W=32, Cin=64, N=48, R=3, mode=2, variant=6),     # GATE, many rounds: staging-buffer hand-over; N < 64
     # legacy one-tile-per-CTA variant stays covered
     dict(B=2, H=16, W=16, Cin=64, N=64, R=3, variant=1),
     dict(B=2, H=56, W=56, Cin=256, N=128, R=3, variant=1),

@@ -18,7 +18,12 @@
 //   * the peer's epilogue warps hand accumulators back with remote arrives on the leader's acc_empty;
 //   * TMEM: each CTA allocates all 512 columns with cta_group::2, so accumulator addresses coincide in both CTAs;
 //   * tiles are handed out in groups of four (2 streams x 2 CTAs); a tile index past the end maps to an image index
-//     >= B: TMA zero-fills its loads and clips its stores, so every role runs the same number of rounds.
+//     >= B: TMA zero-fills its loads and clips its stores, so every role runs the same number of rounds;
+//   * layers whose resident weight halves leave no room for two streams (192 / 256 input channels: 108 / 144 KB per
+//     CTA) run ONE stream per CTA (hp.streams = 1; its two K-split issuers still keep the pair's tensor pipes at the
+//     two-chain rate of profiles/r02_mma_pair.txt, and the epilogue of such a layer is 1/4 of its MMA time);
+//   * the CoordAtt3 combine (GATE epilogue, kRT) uses the residual-by-TMA protocol of conv_multi.cu: the weight warp
+//     loads the residual tile of the NEXT tile into the free staging buffer, the epilogue combines in place.
 #include <cfloat>
 #include <cstring>
 #include <cstdlib>
@@ -49,12 +54,13 @@ static PairDiv make_pairdiv(int d) {
 }
 
 struct PairParams {
-  int TH, a_stage_bytes, sa, n_quads;   // rows per tile, bytes of one activation stage, stages per stream, ceil(m_tiles / 4)
+  int TH, a_stage_bytes, sa, n_quads;   // rows per tile, bytes of one activation stage, stages per stream, tile groups
+  int streams;                          // tile streams per CTA: 2, or 1 when the resident weights leave room for one
   PairDiv d_tx, d_ty;
 };
 
 struct PairMaps {
-  CUtensorMap out, pool;
+  CUtensorMap out, pool, resid;
 };
 
 __device__ __forceinline__ uint32_t pair_rank() {
@@ -119,7 +125,7 @@ __device__ __forceinline__ uint32_t pair_bf16x2_max(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int kMode>
+template <int kMode, int kRT>
 __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const __grid_constant__ PairMaps tmO, const ConvKParams p,
@@ -129,18 +135,22 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
   constexpr int kBTile = 32 * 128;                       // this CTA's half of a 64-row weight tile
   const int nb_tiles = 9 * p.kchunks;
   const int obuf_bytes = p.tma_store ? kABytesPerStage : 0;
-  uint8_t* sA = smem;                                    // [kPI][sa] activation stages
-  uint8_t* sB = sA + kPI * hp.sa * hp.a_stage_bytes;     // [kchunks][9] weight half-tiles (resident)
-  uint8_t* sO = sB + nb_tiles * kBTile;                  // [kPI][obufs] output staging
-  uint8_t* sP = sO + kPI * p.obufs * obuf_bytes;         // [kPI][obufs] pooled staging when p.pool
-  float* sScale = reinterpret_cast<float*>(sP + (p.pool ? kPI * p.obufs * kPPoolBytes : 0));
+  const int nstr = hp.streams;
+  uint8_t* sA = smem;                                    // [streams][sa] activation stages
+  uint8_t* sB = sA + nstr * hp.sa * hp.a_stage_bytes;    // [kchunks][9] weight half-tiles (resident)
+  uint8_t* sO = sB + nb_tiles * kBTile;                  // [streams][obufs] output staging
+  uint8_t* sP = sO + nstr * p.obufs * obuf_bytes;        // [streams][obufs] pooled staging when p.pool
+  float* sScale = reinterpret_cast<float*>(sP + (p.pool ? nstr * p.obufs * kPPoolBytes : 0));
   float* sBias = sScale + 64;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sBias + 64);   // [kPI][sa]   (leader's instance is the live one)
+  float* sGate = sBias + 64;                                    // [kPI][64]: 1 + gate of the tile's image (GATE epilogue)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sGate + kPI * 64);   // [kPI][sa]   (leader's instance is the live one)
   uint64_t* a_empty = a_full + kPI * hp.sa;                     // [kPI][sa]   (own instance, multicast commits)
   uint64_t* b_full = a_empty + kPI * hp.sa;                     // [1]         (leader's)
   uint64_t* acc_full = b_full + 1;                              // [kPI][kPAcc] (own instance, multicast commits)
   uint64_t* acc_empty = acc_full + kPI * kPAcc;                 // [kPI][kPAcc] (leader's, 8 arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + kPI * kPAcc);
+  uint64_t* r_full = acc_empty + kPI * kPAcc;                   // [kPI][2] residual tile landed in staging buffer b (kRT, own)
+  uint64_t* r_free = r_full + kPI * 2;                          // [kPI][2] staging buffer b may be overwritten (kRT, own)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(r_free + kPI * 2);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -163,6 +173,11 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
       mbar_init(&acc_full[i], kPKS);   // both K-halves of the tile are complete (multicast commits)
       mbar_init(&acc_empty[i], 8);     // the four epilogue warps of the stream in BOTH CTAs
     }
+    for (int i = 0; i < kPI * 2; ++i) {
+      mbar_init(&r_full[i], 1);
+      mbar_init(&r_free[i], 1);
+    }
+    if (kRT) prefetch_tmap(&tmO.resid);
     fence_mbar_init();
   }
   if (warp == kPAllocWarp) {
@@ -182,7 +197,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
   pdl_launch_dependents();
 
   // tile (quad s, stream i) of this CTA: tiles are numbered quad-major, then stream, then CTA rank
-  auto tile_of = [&](int s, int i) { return (s * kPI + i) * 2 + (int)rank; };
+  auto tile_of = [&](int s, int i) { return (s * nstr + i) * 2 + (int)rank; };
 
   if (warp == kPProducerWarp) {
     // ------------------------------------------------------------------ activation producer (both CTAs, own tiles)
@@ -193,7 +208,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
       int cx[kPI], cy[kPI], cn[kPI];
 #pragma unroll
       for (int i = 0; i < kPI; ++i) {
-        const int mt = tile_of(s, i);
+        const int mt = tile_of(s, i);   // (unused for i >= streams)
         const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
         cx[i] = (mt - t1 * p.tiles_x) * 8;
         cy[i] = (t1 - t2 * p.tiles_y) * hp.TH;
@@ -202,6 +217,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
       for (int kc = 0; kc < p.kchunks; ++kc) {
 #pragma unroll
         for (int i = 0; i < kPI; ++i) {
+          if (i >= nstr) continue;
           const int slot = i * hp.sa + as[i];
           mbar_wait(&a_empty[slot], aph[i] ^ 1);
           if (elect_one_sync()) {
@@ -226,10 +242,37 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
           tma_load_2d_pair(sB + (kc * 9 + tap) * kBTile, &tmB, bar, (tap * p.kchunks + kc) * 64, (int)rank * 32);
     }
     __syncwarp();
+    if constexpr (kRT) {
+      // residual producer: this CTA's tile sequence, one tile ahead of the epilogue (the residual is an activation
+      // written by an earlier kernel of the stream); plain loads into this CTA's staging buffers and barriers
+      pdl_wait();
+      const uint32_t r_tx = (uint32_t)(8 * hp.TH * 128);
+      int rb[kPI] = {0, 0};
+      uint32_t rph[kPI] = {0, 0};
+      for (int s = pair; s < hp.n_quads; s += npairs) {
+#pragma unroll
+        for (int i = 0; i < kPI; ++i) {
+          if (i >= nstr) continue;
+          const int mt = tile_of(s, i);
+          const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
+          const int x0 = (mt - t1 * p.tiles_x) * 8, y0 = (t1 - t2 * p.tiles_y) * hp.TH;
+          mbar_wait(&r_free[i * 2 + rb[i]], rph[i] ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&r_full[i * 2 + rb[i]], r_tx);
+            tma_load_4d(sO + (i * p.obufs + rb[i]) * kABytesPerStage, &tmO.resid, &r_full[i * 2 + rb[i]], 0, x0, y0, t2);
+          }
+          __syncwarp();
+          if (++rb[i] == 2) {
+            rb[i] = 0;
+            rph[i] ^= 1;
+          }
+        }
+      }
+    }
   } else if (warp >= kPIssuerWarp0) {
     // ------------------------------------------------------------------ MMA issuers (leader CTA only)
-    if (rank == 0) {
-      const int iw = warp - kPIssuerWarp0;
+    const int iw = warp - kPIssuerWarp0;
+    if (rank == 0 && iw / kPKS < nstr) {
       const int i = iw / kPKS, h = iw - i * kPKS;
       const uint32_t idesc = umma_idesc_bf16(256, 64);
       int as = 0, acc = 0;
@@ -287,7 +330,8 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
     uint8_t* sOi = sO + i * p.obufs * obuf_bytes;
     int acc = 0, obuf = 0;
     uint32_t acc_phase = 0;
-    for (int s = pair; s < hp.n_quads; s += npairs) {
+    uint32_t r_uses = 0;   // kRT: tiles processed so far by this group (buffer = r_uses & 1, phase = (r_uses >> 1) & 1)
+    for (int s = pair; s < (i < nstr ? hp.n_quads : 0); s += npairs) {
       const int mt = tile_of(s, i);
       const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
       const int x0 = (mt - t1 * p.tiles_x) * 8;
@@ -295,6 +339,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
       const int n = t2;
       const int x = x0 + tx, y = y0 + ty;
       const bool valid = row_in_tile && (x < p.W) && (y < p.H) && (n < p.B);
+      if (kMode == UG_EPI_GATE && etid < p.N && n < p.B) sGate[i * 64 + etid] = 1.0f + __ldg(p.gate + (long long)n * p.N + etid);
       mbar_wait(&acc_full[i * kPAcc + acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (i * kPAcc + acc) * kPKS * 64;
@@ -305,7 +350,17 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
       tmem_ld16(taddr + 64, v2);
       if (p.tma_store) {
         // staging buffer `obuf` must no longer be read by the TMA store issued obufs tiles ago
-        if (etid == 0) {
+        // (the barrier also publishes sGate of this tile)
+        if constexpr (kRT) {
+          // the store of the previous tile (other buffer) has finished reading: hand that buffer to the residual
+          // producer for the NEXT tile, then wait for this tile's residual (loaded one tile ago)
+          if (etid == 0 && r_uses > 0) {
+            bulk_wait_group_read<0>();
+            mbar_arrive(&r_free[i * 2 + (obuf ^ 1)]);
+          }
+          mbar_wait(&r_full[i * 2 + obuf], (r_uses >> 1) & 1);
+          ++r_uses;
+        } else if (etid == 0) {
           if (p.obufs == 2) bulk_wait_group_read<1>();
           else bulk_wait_group_read<0>();
         }
@@ -334,13 +389,28 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
             dot += f[4 * j] * w4.x + f[4 * j + 1] * w4.y + f[4 * j + 2] * w4.z + f[4 * j + 3] * w4.w;
           }
         } else {
+        if constexpr (kMode == UG_EPI_GATE) {   // e1 + d * (1 + g): the residual pieces sit where the result will be written
+          epi_relu16<UG_ACT_RELU>(f);
+          const uint4 a0 = *reinterpret_cast<const uint4*>(so_row + (((cc * 2) ^ (row & 7)) << 4));
+          const uint4 a1 = *reinterpret_cast<const uint4*>(so_row + (((cc * 2 + 1) ^ (row & 7)) << 4));
+          const float4* gp = reinterpret_cast<const float4*>(sGate + i * 64 + c0);
+          epi_gate8(f, a0, gp[0], gp[1]);
+          epi_gate8(f + 8, a1, gp[2], gp[3]);
+        }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           uint4 o;
-          o.x = pack_bf16x2_relu(f[g * 8 + 0], f[g * 8 + 1]);
-          o.y = pack_bf16x2_relu(f[g * 8 + 2], f[g * 8 + 3]);
-          o.z = pack_bf16x2_relu(f[g * 8 + 4], f[g * 8 + 5]);
-          o.w = pack_bf16x2_relu(f[g * 8 + 6], f[g * 8 + 7]);
+          if constexpr (kMode == UG_EPI_GATE) {   // the combined value may be negative: plain conversion
+            o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+            o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+            o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+            o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+          } else {
+            o.x = pack_bf16x2_relu(f[g * 8 + 0], f[g * 8 + 1]);
+            o.y = pack_bf16x2_relu(f[g * 8 + 2], f[g * 8 + 3]);
+            o.z = pack_bf16x2_relu(f[g * 8 + 4], f[g * 8 + 5]);
+            o.w = pack_bf16x2_relu(f[g * 8 + 6], f[g * 8 + 7]);
+          }
           const int chunk = cc * 2 + g;
           *reinterpret_cast<uint4*>(so_row + ((chunk ^ (row & 7)) << 4)) = o;
           if (p.pool) {
@@ -369,7 +439,7 @@ __global__ void __launch_bounds__(kPThreads, 1) conv_pair_kernel(const __grid_co
         if (rank == 0) mbar_arrive(&acc_empty[i * kPAcc + acc]);
         else mbar_arrive_cluster(pair_map(&acc_empty[i * kPAcc + acc], 0));
       }
-      if (kMode == UG_EPI_OUTC) {
+      if constexpr (kMode == UG_EPI_OUTC) {
         if (valid) {
           const float logit = dot + p.outc_b;
           const long long o = ((long long)n * p.H + y) * p.W + x;
@@ -419,31 +489,46 @@ static int encode_pair(EncodeTiledFn encode, CUtensorMap* m, void* base, int ran
 
 // Fills L for the CTA-pair kernel.  UG_EUNSUPPORTED when the layer is not one it takes (the caller falls back to
 // conv_multi_prepare): 3x3 pad 1, ReLU, <= 64 output channels in one 64-column n-tile, STORE (optionally with the fused
-// 2x2 pool) or OUTC epilogue, weights resident at 36 KB per 64 input channels per CTA, an even number of SMs.
+// 2x2 pool), OUTC or GATE epilogue, weights resident at 36 KB per 64 input channels per CTA, an even number of SMs.
 int conv_pair_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return set_error(h, UG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (!(d->R == 3 && d->S == 3 && d->pad == 1 && d->up != 2) || d->act != UG_ACT_RELU || d->N > 64 || d->N % 8 ||
-      !(d->mode == UG_EPI_STORE || d->mode == UG_EPI_OUTC) || d->stats_sum || d->out2 || d->in_rstride || d->in_bstride ||
-      (h->num_sms & 1))
-    return set_error(h, UG_EUNSUPPORTED, "conv(pair): 3x3 ReLU layers with <= 64 output channels, STORE / OUTC epilogue");
-  const int TH = cdiv_p(d->H, cdiv_p(d->H, 16));
+      !(d->mode == UG_EPI_STORE || d->mode == UG_EPI_OUTC || d->mode == UG_EPI_GATE) || d->stats_sum || d->out2 ||
+      d->in_rstride || d->in_bstride || (h->num_sms & 1))
+    return set_error(h, UG_EUNSUPPORTED, "conv(pair): 3x3 ReLU layers with <= 64 output channels, STORE / OUTC / GATE epilogue");
+  const int gate = d->mode == UG_EPI_GATE;
+  if (gate && (!d->add || !d->gate || d->add_bstride <= 0 || d->add_cstride % 8 || (reinterpret_cast<uintptr_t>(d->add) & 15) ||
+               d->pool_out))
+    return set_error(h, UG_EUNSUPPORTED, "conv(pair): the GATE epilogue needs a per-image residual tensor (16-byte aligned rows)");
   const int cin_pad = cdiv_p(d->Cin, 64) * 64;
   const int kchunks = cin_pad / 64;
   const long long ktot = 9LL * cin_pad;
   const int tma_store = d->mode != UG_EPI_OUTC;
   const int pool = d->pool_out != nullptr;
-  if (pool && (!tma_store || (d->H & 1) || (d->W & 1) || (TH & 1) || d->pool_cstride % 8 || (reinterpret_cast<uintptr_t>(d->pool_out) & 15)))
-    return set_error(h, UG_EUNSUPPORTED, "conv(pair): fused max-pool needs a STORE conv on an even map");
-  const int a_stage = ((kPPitch * (TH + 2) * 128 + 1023) / 1024) * 1024;
-  const int sa = 2;
   const long long resB = 9LL * kchunks * 32 * 128;
   const int obuf_unit = tma_store ? kABytesPerStage + (pool ? kPPoolBytes : 0) : 0;
-  const long long fixed = 1024 + 2 * 64 * sizeof(float) + 8 * (2 * kPI * sa + 1 + 2 * kPI * kPAcc) + 16;
-  int obufs = tma_store ? 2 : 0;
-  if (fixed + kPI * sa * (long long)a_stage + resB + kPI * obufs * (long long)obuf_unit > 227LL * 1024) obufs = tma_store ? 1 : 0;
-  const long long smem = fixed + kPI * sa * (long long)a_stage + resB + kPI * obufs * (long long)obuf_unit;
-  if (smem > 227LL * 1024) return set_error(h, UG_EUNSUPPORTED, "conv(pair): weights of %d input channels do not fit", d->Cin);
+  const long long fixed = 1024 + 3 * 64 * sizeof(float) + 64 * sizeof(float) + 8 * (2 * kPI * 3 + 1 + 2 * kPI * kPAcc + 4 * kPI) + 16;
+  // shared-memory plan, first fit: two tile streams with two activation stages each; else ONE stream with up to three
+  // stages (resident weights of 192 / 256 input channels).  GATE needs both staging buffers (residual one tile ahead).
+  const int TH = cdiv_p(d->H, cdiv_p(d->H, 16));
+  const int a_stage = ((kPPitch * (TH + 2) * 128 + 1023) / 1024) * 1024;
+  static const int cand[6][3] = {{2, 2, 2}, {2, 2, 1}, {1, 3, 2}, {1, 3, 1}, {1, 2, 2}, {1, 2, 1}};   // streams, stages, staging buffers
+  int streams = 0, sa = 0, obufs = 0;
+  long long smem = 0;
+  for (int c = 0; c < 6; ++c) {
+    const int ob = tma_store ? cand[c][2] : 0;
+    if (gate && ob != 2) continue;
+    if (!tma_store && cand[c][2] != 2) continue;   // (OUTC has no staging buffers: one candidate per shape)
+    const long long need = fixed + cand[c][0] * cand[c][1] * (long long)a_stage + resB + cand[c][0] * ob * (long long)obuf_unit;
+    if (need <= 227LL * 1024) {
+      streams = cand[c][0]; sa = cand[c][1]; obufs = ob; smem = need;
+      break;
+    }
+  }
+  if (!streams) return set_error(h, UG_EUNSUPPORTED, "conv(pair): weights of %d input channels do not fit", d->Cin);
+  if (pool && (!tma_store || (d->H & 1) || (d->W & 1) || (TH & 1) || d->pool_cstride % 8 || (reinterpret_cast<uintptr_t>(d->pool_out) & 15)))
+    return set_error(h, UG_EUNSUPPORTED, "conv(pair): fused max-pool needs a STORE conv on an even map");
 
   ConvKParams& p = L->p;
   memset(&p, 0, sizeof(p));
@@ -459,11 +544,14 @@ int conv_pair_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   p.out = d->out; p.out_cstride = d->out_cstride;
   p.up = 1; p.OH = d->H; p.OW = d->W;
   p.outc_w = d->outc_w; p.outc_b = d->outc_b; p.logits = d->logits; p.mask = d->mask;
+  p.add = d->add; p.add_bstride = d->add_bstride; p.add_cstride = d->add_cstride; p.gate = d->gate;
   p.m_tiles = p.tiles_x * p.tiles_y * d->B; p.n_tiles = 1; p.acc_stages = kPAcc;
   p.tma_store = tma_store; p.obufs = obufs; p.npad = 64; p.pool = pool;
   L->variant = 6;
   L->halo_TH = TH; L->halo_a_stage = a_stage; L->halo_sa = sa;
-  L->halo_copy = cdiv_p(p.m_tiles, 4);   // quads
+  L->halo_copy = cdiv_p(p.m_tiles, 2 * streams);   // tile groups: streams x 2 CTAs
+  L->halo_mode = streams;
+  L->halo_rt = gate;
 
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
@@ -482,6 +570,14 @@ int conv_pair_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   }
   memset(L->tmQ, 0, sizeof(L->tmQ));
   memset(&L->tmO, 0, sizeof(L->tmO));
+  memset(&L->tmR, 0, sizeof(L->tmR));
+  if (gate) {  // load map of the residual tensor, same box as the output store
+    cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
+    cuuint64_t strides[3] = {(cuuint64_t)d->add_cstride * 2, (cuuint64_t)d->W * d->add_cstride * 2, (cuuint64_t)d->add_bstride * 2};
+    cuuint32_t box[4] = {64, 8, (cuuint32_t)TH, 1};
+    const int r = encode_pair(encode, &L->tmR, const_cast<void*>(d->add), 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (r) return set_error(h, UG_ECUDA, "conv(pair): residual tensor map encode failed (%d)", r);
+  }
   if (tma_store) {
     cuuint32_t box[4] = {64, 8, (cuuint32_t)TH, 1};
     cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B};
@@ -508,20 +604,24 @@ int conv_pair_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
 
 int conv_pair_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   if (!h->attr_pair) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)conv_pair_kernel<UG_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute((const void*)conv_pair_kernel<UG_EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute((const void*)conv_pair_kernel<UG_EPI_OUTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute((const void*)conv_pair_kernel<UG_EPI_OUTC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute((const void*)conv_pair_kernel<UG_EPI_GATE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return check_cuda(h, e, "cudaFuncSetAttribute(conv_pair_kernel)");
     h->attr_pair = true;
   }
   PairParams hp;
   memset(&hp, 0, sizeof(hp));
   hp.TH = L->halo_TH; hp.a_stage_bytes = L->halo_a_stage; hp.sa = L->halo_sa; hp.n_quads = L->halo_copy;
+  hp.streams = L->halo_mode;
   hp.d_tx = make_pairdiv(L->p.tiles_x);
   hp.d_ty = make_pairdiv(L->p.tiles_y);
   PairMaps maps;
   maps.out = L->tmO;
   maps.pool = L->tmQ[0];
+  maps.resid = L->tmR;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = L->grid;
   cfg.blockDim = dim3(kPThreads);
@@ -537,8 +637,9 @@ int conv_pair_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   cfg.attrs = at;
   cfg.numAttrs = h->pdl ? 2 : 1;
   cudaError_t e;
-  if (L->p.mode == UG_EPI_OUTC) e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<UG_EPI_OUTC>, L->tmA, L->tmB, maps, L->p, hp);
-  else e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<UG_EPI_STORE>, L->tmA, L->tmB, maps, L->p, hp);
+  if (L->p.mode == UG_EPI_OUTC) e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<UG_EPI_OUTC, 0>, L->tmA, L->tmB, maps, L->p, hp);
+  else if (L->p.mode == UG_EPI_GATE) e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<UG_EPI_GATE, 1>, L->tmA, L->tmB, maps, L->p, hp);
+  else e = cudaLaunchKernelEx(&cfg, conv_pair_kernel<UG_EPI_STORE, 0>, L->tmA, L->tmB, maps, L->p, hp);
   h->launches++;
   return check_cuda(h, e != cudaSuccess ? e : cudaGetLastError(), "conv_pair_kernel launch");
 }
