@@ -533,8 +533,8 @@ def main():
             pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "tcgen05 implicit-GEMM conv family (conv_multi_kernel, conv_gemm_persistent_kernel, "
-                          "conv_gemm_kernel, stem_conv_kernel)", "launches_per_step": n_conv,
+                "kernel": "tcgen05 implicit-GEMM conv family (conv_multi_kernel, conv_pair_kernel, "
+                          "conv_gemm_persistent_kernel, conv_gemm_kernel, stem_conv_kernel)", "launches_per_step": n_conv,
                 "avg_launch_ms": conv_ms / n_conv, "share_of_step": conv_ms / sum(per_op_ms),
                 "algorithmic_flop_per_step": total_flop,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"}

@@ -95,7 +95,9 @@ typedef struct ug_conv_desc {
                                  accumulators, TMA-store epilogue); 5 = 3x3 multi-issuer kernel (one CTA per
                                  SM, two MMA-issuing warps sharing resident or streamed weights, activation
                                  halo tile fetched once per 64-channel chunk for all nine taps; see
-                                 csrc/conv_multi.cu) */
+                                 csrc/conv_multi.cu); 6 = CTA-pair kernel (csrc/conv_pair.cu: clusters of two CTAs,
+                                 tcgen05.mma.cta_group::2 with M = 256 over both SMs, each CTA holding half of the
+                                 weight rows; 3x3 ReLU layers with N <= 64, STORE / OUTC / GATE epilogues) */
 } ug_conv_desc;
 
 /* Max pooling on NHWC bf16 with -inf padding (nn.MaxPool2d(2), basicUnet.py:47; torchvision GoogLeNet

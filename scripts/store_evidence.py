@@ -36,18 +36,18 @@ hdr = (f"# ncu --set full --clock-control none of ONE 128-image pipeline pass, e
        "# tensor pipe % = sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed (at the full 1.965 GHz clock)\n"
        "# % of HBM peak divides by the COPY peak 6552.6 GB/s; write-dominated kernels are bounded by the write roof 3.86 TB/s (r02_bandwidth_probe.txt)\n\n")
 open(f"{P}/{rnd}_ncu_kernels.md", "w").write(hdr + table)
-# DRAM bytes per launch of the dominant kernel family (conv_multi_kernel)
+# DRAM bytes per launch of the dominant kernel family (conv_multi_kernel + conv_pair_kernel)
 rows = list(csv.reader(open(f"{O}/{tag}_full.raw.csv")))
 h, units = rows[0], rows[1]
 ixx = {n: i for i, n in enumerate(h)}
 SC = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 tb, n = 0.0, 0
 for r in rows[2:]:
-    if "conv_multi_kernel" in r[ixx["Kernel Name"]]:
+    if "conv_multi_kernel" in r[ixx["Kernel Name"]] or "conv_pair_kernel" in r[ixx["Kernel Name"]]:
         for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tb += float(r[ixx[m]]) * SC.get(units[ixx[m]], 1)
         n += 1
 json.dump({"dram_bytes_per_launch": int(tb / n), "launches": n,
            "source": f"profiles/{rnd}_ncu_kernels.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum averaged over the {n} "
-                     "conv_multi_kernel launches of one 128-image pipeline pass)"}, open(f"{P}/{rnd}_ncu_traffic.json", "w"))
+                     "conv_multi_kernel / conv_pair_kernel launches of one 128-image pipeline pass)"}, open(f"{P}/{rnd}_ncu_traffic.json", "w"))
 print("traffic per launch", int(tb / n), "over", n)

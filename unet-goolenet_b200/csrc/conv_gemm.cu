@@ -605,9 +605,14 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   }
   if (d->variant == 5) return conv_multi_prepare(h, d, d->R == 3 ? std::min(BN, 128) : BN, L);
   if (d->variant == 6) return conv_pair_prepare(h, d, L);
-  // UG_PAIR=1: 3x3 layers with <= 64 output channels on large maps go to the CTA-pair kernel (conv_pair.cu)
-  static const int use_pair = [] { const char* e = getenv("UG_PAIR"); return e ? atoi(e) : 0; }();
-  if (use_pair && d->variant == 0 && d->R == 3 && up == 1 && d->N <= 64 && d->H * d->W >= 112 * 112) {
+  // 3x3 layers with <= 64 output channels on maps of at least 112x112 (the UNet's two finest levels): CTA-pair kernel
+  // (conv_pair.cu, tcgen05.mma.cta_group::2) — profiles/r02_pair_kernel.txt: 64->64 0.221 -> 0.201 ms, + outc 0.208 ->
+  // 0.176, 128->64 0.451 -> 0.359, 256->64 at 112x112 0.218 -> 0.188 per 64 images.  The CoordAtt3 combine on 64 input
+  // channels is bound by its epilogue, not by the MMA, and stays on the multi-issuer kernel (0.277 against 0.291 ms).
+  // UG_PAIR=0 turns the rule off.
+  static const int use_pair = [] { const char* e = getenv("UG_PAIR"); return e ? atoi(e) : 1; }();
+  if (use_pair && d->variant == 0 && d->R == 3 && up == 1 && d->N <= 64 && d->H * d->W >= 112 * 112 &&
+      !(d->mode == UG_EPI_GATE && d->Cin <= 64)) {
     const int rc = conv_pair_prepare(h, d, L);
     if (rc == UG_OK) return rc;
     if (rc != UG_EUNSUPPORTED) return rc;
