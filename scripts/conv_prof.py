@@ -79,6 +79,8 @@ if os.environ.get("UG_CONFIGS") == "convt":   # ConvTranspose shapes (R = 0 in t
 if os.environ.get("UG_CONFIGS") == "pair":    # 64-output-channel 3x3 layers: multi-issuer K-split kernel vs the CTA-pair kernel
     CONFIGS = [dict(variant=5), dict(variant=6), dict(variant=5, mode=3), dict(variant=6, mode=3), dict(variant=5, mode=2),
                dict(variant=6, mode=2)]
+if os.environ.get("UG_CONFIGS") == "pair128":  # 128-column n-tiles: multi-issuer kernel with / without CTA pairs
+    CONFIGS = [dict(variant=5), dict(variant=7), dict(variant=5, mode=2), dict(variant=7, mode=2)]
 if os.environ.get("UG_ABLATE"):
     CONFIGS = [dict(variant=5, stages=108), dict(variant=5, stages=108, mode=2)]
 if os.environ.get("UG_ABLATE") == "resid":    # GATE epilogue with / without its residual loads (results wrong without)
@@ -105,7 +107,7 @@ for shp in SHAPES:
             if cfg.get("variant", 0) == 2:
                 pr = eng.conv_profile(d)
                 line += " | " + " ".join(f"{k}={v:.0f}" for k, v in pr.items())
-            if cfg.get("variant", 0) == 5 and cfg.get("mode", 0) == 0:
+            if cfg.get("variant", 0) in (5, 7) and cfg.get("mode", 0) == 0:
                 pr = eng.conv_profile16(d)
                 line += f" | clk {pr['prod_cycles'] / max(pr['prod_ns'], 1):.3f} GHz " + " ".join(
                     f"{k}={v:.0f}" for k, v in pr.items())

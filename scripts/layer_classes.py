@@ -3,7 +3,7 @@ usage: layer_classes.py gpurun_out/bench_breakdown_n1.json > profiles/rNN_layer_
 import json, sys
 d = json.load(open(sys.argv[1]))
 ops = d["per_op"]
-first_g = next(i for i, o in enumerate(ops) if o["kind"] == "StemDesc" and o["shape"][5] == 7)   # GoogLeNet conv1
+first_g = next(i for i, o in enumerate(ops) if o["kind"] == "S2dDesc" or (o["kind"] == "StemDesc" and o["shape"][5] == 7))   # GoogLeNet conv1
 
 
 def cls(i, o):
@@ -13,13 +13,15 @@ def cls(i, o):
         return "stem convs (inc, conv1)"
     if k == "ConvDesc":
         B, H, W, Cin, N, R = sh
+        if g and R == 4:
+            return "stem convs (inc, conv1)"        # conv1 as a four-row-tap GEMM over the space-to-depth image
         if g:
             return "GoogLeNet 3x3" if R == 3 else "GoogLeNet 1x1 (fused heads, branch4, conv2)"
         if R == 3:
             return f"UNet 3x3 {H}x{W} N={'64' if N <= 64 else '>=128'}"
         return "UNet 1x1 (ConvTranspose, linear layers)"
     return {"PoolDesc": "max-pools (GoogLeNet)", "ChanStatsDesc": "CoordAtt3 statistics + gate", "GateDesc": "CoordAtt3 statistics + gate",
-            "LayerNormDesc": "LayerNorm + attention", "AttnDesc": "LayerNorm + attention"}.get(k, "bbox / crop-resize / head / front-end")
+            "S2dDesc": "stem convs (inc, conv1)", "LayerNormDesc": "LayerNorm + attention", "AttnDesc": "LayerNorm + attention"}.get(k, "bbox / crop-resize / head / front-end")
 
 
 acc = {}

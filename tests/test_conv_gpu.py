@@ -211,6 +211,17 @@ CASES = [
     dict(B=2, H=30, W=44, Cin=64, N=64, R=3, mode=2, variant=6),      # GATE, ragged tiles in both directions
     dict(B=5, H=16, W=8, Cin=128, N=64, R=3, mode=2, variant=6),      # GATE, odd tile count (tiles past the end)
     dict(B=37, H=32, W=32, Cin=64, N=48, R=3, mode=2, variant=6),     # GATE, many rounds: staging-buffer hand-over; N < 64
+    # CTA pairs on the multi-issuer kernel (variant 7): 128-column n-tiles, each CTA streams half of every weight tile
+    dict(B=2, H=112, W=112, Cin=128, N=128, R=3, variant=7),          # 8-pixel-wide tiles, TH = 16, streamed weights
+    dict(B=3, H=56, W=56, Cin=256, N=256, R=3, variant=7),            # two n-tiles
+    dict(B=3, H=28, W=28, Cin=512, N=512, R=3, variant=7),            # row-strip tiles, four n-tiles
+    dict(B=5, H=28, W=28, Cin=1024, N=256, R=3, variant=7),           # 16 k-chunks, odd tile count (tiles past the end)
+    dict(B=2, H=112, W=112, Cin=64, N=128, R=3, variant=7, pool=True),   # resident weight halves + fused 2x2 max-pool
+    dict(B=3, H=28, W=28, Cin=256, N=512, R=3, pool=True, out_extra=64, out_off=32, variant=7),   # strips + pool from the staged tile
+    dict(B=2, H=56, W=56, Cin=256, N=128, R=3, mode=2, variant=7),    # CoordAtt3 combine (register-prefetched residual)
+    dict(B=3, H=28, W=28, Cin=512, N=512, R=3, mode=2, variant=7),    # combine on strips, four n-tiles
+    dict(B=5, H=14, W=14, Cin=512, N=512, R=3, variant=7),            # 14x14: two tiles per image, 10 tiles = 3 groups
+    dict(B=37, H=30, W=20, Cin=128, N=128, R=3, variant=7, in_extra=64, in_off=64),   # ragged both ways, many rounds
     # legacy one-tile-per-CTA variant stays covered
     dict(B=2, H=16, W=16, Cin=64, N=64, R=3, variant=1),
     dict(B=2, H=56, W=56, Cin=256, N=128, R=3, variant=1),

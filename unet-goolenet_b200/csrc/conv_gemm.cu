@@ -605,6 +605,7 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   }
   if (d->variant == 5) return conv_multi_prepare(h, d, d->R == 3 ? std::min(BN, 128) : BN, L);
   if (d->variant == 6) return conv_pair_prepare(h, d, L);
+  if (d->variant == 7) return conv_multi_prepare(h, d, 128, L, 1);
   // 3x3 layers with <= 64 output channels on maps of at least 112x112 (the UNet's two finest levels): CTA-pair kernel
   // (conv_pair.cu, tcgen05.mma.cta_group::2) — profiles/r02_pair_kernel.txt: 64->64 0.221 -> 0.201 ms, + outc 0.208 ->
   // 0.176, 128->64 0.451 -> 0.359, 256->64 at 112x112 0.218 -> 0.188 per 64 images.  The CoordAtt3 combine on 64 input
@@ -621,6 +622,18 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
     // ConvTranspose 2x2 s2 on maps of at least 14x14 (profiles/r02_convt_variants.txt): multi-issuer kernel (two epilogue warpgroups, pixel shuffle as
     // four strided TMA-store views); one 256-wide n-tile when that covers all four quadrants
     const int rc = conv_multi_prepare(h, d, d->N == 256 ? 256 : 128, L);
+    if (rc == UG_OK) return rc;
+    if (rc != UG_EUNSUPPORTED) return rc;
+  }
+  // 3x3 layers with 128-column n-tiles and streamed weights: clusters of two CTAs on the multi-issuer kernel (each CTA
+  // streams half of every weight tile; conv_multi.cu header).  profiles/r02_pair128.txt, per 64 images: 112x112 128->128
+  // 0.172 -> 0.148 ms (1600 TFLOP/s), 56x56 256->256 0.185 -> 0.164, 28x28 512->512 0.182 -> 0.169, 1024->256 0.204 ->
+  // 0.186; the 256-image step +4.9 %.  Not routed: 64 input channels (resident weights, bound by the epilogue: 0.094 ->
+  // 0.112 ms) and the CoordAtt3 combine below 256 input channels (0.192 -> 0.198 ms).  UG_PAIR128=0 turns the rule off.
+  static const int use_pair128 = [] { const char* e = getenv("UG_PAIR128"); return e ? atoi(e) : 1; }();
+  if (use_pair128 && d->variant == 0 && d->R == 3 && up == 1 && d->N % 128 == 0 && d->H * d->W >= 196 && !d->stats_sum &&
+      ((d->mode == UG_EPI_STORE && d->Cin > 64) || (d->mode == UG_EPI_GATE && d->Cin >= 256))) {
+    const int rc = conv_multi_prepare(h, d, 128, L, 1);
     if (rc == UG_OK) return rc;
     if (rc != UG_EUNSUPPORTED) return rc;
   }

@@ -44,6 +44,16 @@
 // accumulators (four independent chains per SM); the epilogue adds the two partial sums in fp32 while it reads them.
 // The epilogue mode is a template parameter as well: its branches on ADD / GATE / OUTC were a third of the
 // instructions of the chunk loop of a plain-store layer.
+//
+// CTA pairs (kPair = 1, 128-column n-tiles with streamed weights): the issuers of these layers waited for weight tiles
+// 18 % of their time (profiles/r02_pair_kernel.txt) — every CTA streams the whole weight matrix from L2 once per two pixel
+// tiles, ~2 GB per layer and ~7.5 TB/s of L2 -> SM traffic at 128 images.  A cluster of two CTAs runs
+// tcgen05.mma.cta_group::2 (M = 256 over both SMs): each CTA loads only HALF of the rows of every weight tile (the
+// tensor cores exchange them), so the weight traffic per SM halves and the ring holds twice as many tiles.  Protocol as
+// in conv_pair.cu: only the leader CTA issues; its a_full / b_full barriers collect the TMA bytes of both CTAs;
+// tcgen05.commit multicasts to the a_empty / b_empty / acc_full barriers of both; the peer's epilogue warps return
+// accumulators with remote arrives on the leader's acc_empty; pixel tiles past the end are zero-filled / clipped by TMA
+// so that both CTAs run the same number of rounds.
 #include <cfloat>
 #include <cstring>
 #include <cstdlib>
@@ -119,21 +129,79 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
   __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
-static constexpr int kPoolBytes = 4096;   // pooled sub-tile staging: 4 x TH/2 <= 32 pixels x 64 channels bf16
+static constexpr int kPoolBytes = 4096;
+
+// ---- CTA-pair (cta_group::2) forms
+__device__ __forceinline__ uint32_t mp_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void mp_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mp_leader_addr(const void* p) {   // shared::cluster address of `p` in the leader CTA
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(0u));
+  return r;
+}
+__device__ __forceinline__ void mp_arrive_leader(const void* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mp_leader_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mp_tma_load_4d(void* dst, const CUtensorMap* m, const void* leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(mp_leader_addr(leader_bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mp_tma_load_2d(void* dst, const CUtensorMap* m, const void* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mp_leader_addr(leader_bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int kPair>
+__device__ __forceinline__ void mp_umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+  }
+}
+// arrive on `bar` once the MMAs issued so far have completed; pairs: on the barrier at that offset in BOTH CTAs
+template <int kPair>
+__device__ __forceinline__ void mp_commit(uint64_t* bar) {
+  if constexpr (kPair) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+  } else {
+    umma_commit(bar);
+  }
+}   // pooled sub-tile staging: 4 x TH/2 <= 32 pixels x 64 channels bf16
 
 struct StoreMaps {  // output maps: [0] for plain stores, [q] = quadrant (dy,dx) of a ConvTranspose 2x2 s2 scatter;
   CUtensorMap m[5];  // [4] = load map of the residual tensor (kRT)
 };
 
-template <int kAct, int kTaps, int kMode, int kKS, int kRT>
+template <int kAct, int kTaps, int kMode, int kKS, int kRT, int kPair>
 __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                            const __grid_constant__ CUtensorMap tmB,
                                                                            const __grid_constant__ StoreMaps tmO,
                                                                            const ConvKParams p, const MultiParams hp) {
   constexpr int kThreadsCta = kMultiThreads(kKS);
+  static_assert(!kPair || (kTaps == 9 && !kRT), "CTA pairs: 3x3 halo tiles, register-prefetched residual");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
-  const int b_tile_bytes = p.BN * 128;
+  const int b_tile_bytes = (kPair ? p.BN / 2 : p.BN) * 128;   // pairs: this CTA's half of the rows of a weight tile
   const int obuf_bytes = p.tma_store ? kABytesPerStage : 0;  // one 64-channel sub-tile per staging buffer
   const int nb_tiles = hp.b_resident ? kTaps * p.kchunks : hp.sb;
   uint8_t* sA = smem;                                        // [kMI][sa] activation stages
@@ -157,6 +225,13 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int total_super = hp.m_super * p.n_tiles;
+  const uint32_t rank = kPair ? mp_rank() : 0u;                         // CTA of the pair (0 = leader: issues every MMA)
+  const int cta0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // first work item / stride of the persistent loops
+  const int ncta = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // pixel tile of (group ms, stream i): pairs interleave the two CTAs; tiles past the end stay in the loops of a pair
+  // (zero-filled loads, clipped stores) so that both CTAs run the same rounds
+  auto tile_of = [&](int ms, int i) { return kPair ? (ms * kMI + i) * 2 + (int)rank : ms * kMI + i; };
+  auto tile_live = [&](int mt) { return kPair ? true : mt < p.m_tiles; };
 
   if (warp == kMProducerWarp && lane == 0) {
     prefetch_tmap(&tmA);
@@ -180,7 +255,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     }
     for (int i = 0; i < kMI * p.acc_stages; ++i) {
       mbar_init(&acc_full[i], kKS);  // every K-half of the tile is complete
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], kPair ? 8 : 4);   // the epilogue warps of the stream (of both CTAs of a pair)
     }
     for (int i = 0; i < kMI * 2; ++i) {
       mbar_init(&r_full[i], 1);
@@ -190,8 +265,13 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     fence_mbar_init();
   }
   if (warp == kMAllocWarp) {
-    tmem_alloc(tmem_ptr, p.tmem_cols);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(tmem_ptr, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   for (int i = threadIdx.x; i < p.npad; i += kThreadsCta) {
     sScale[i] = (i < p.N) ? (p.scale ? p.scale[i] : 1.0f) : 0.0f;
@@ -199,6 +279,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) mp_cluster_sync();   // the barriers of both CTAs exist before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   // Everything above touched only kernel parameters and constant weights; from here on the roles read activations /
@@ -216,12 +297,12 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     const long long t_start = clock64();
     unsigned long long ns0 = 0;
     if (p.prof) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns0));
-    for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+    for (int s = cta0; s < total_super; s += ncta) {
       const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
       int cx[kMI], cy[kMI], cn[kMI];
 #pragma unroll
       for (int i = 0; i < kMI; ++i) {
-        const int mt = ms * kMI + i;
+        const int mt = tile_of(ms, i);
         const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
         cx[i] = (mt - t1 * p.tiles_x) * p.TW;
         cy[i] = (t1 - t2 * p.tiles_y) * p.TH;
@@ -230,15 +311,17 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
       for (int kc = 0; kc < p.kchunks; ++kc) {
 #pragma unroll
         for (int i = 0; i < kMI; ++i) {
-          const int mt = ms * kMI + i;
-          if (mt >= p.m_tiles) continue;
+          if (!tile_live(tile_of(ms, i))) continue;
           const int x0 = cx[i], y0 = cy[i], n = cn[i];
           const int slot = i * hp.sa + as[i];
           const long long tw0 = p.prof ? clock64() : 0;
           mbar_wait(&a_empty[slot], aph[i] ^ 1);
           if (p.prof) w_a += clock64() - tw0;
           if (elect_one_sync()) {
-            if ((hp.debug & 4) && s >= (int)gridDim.x * 2) {
+            if constexpr (kPair) {   // the leader's barrier collects the bytes of both CTAs' loads
+              if (rank == 0) mbar_arrive_expect_tx(&a_full[slot], 2 * a_tx);
+              mp_tma_load_4d(sA + slot * hp.a_stage_bytes, &tmA, &a_full[slot], kc * 64, x0 - 1, y0 - 1, n);
+            } else if ((hp.debug & 4) && s >= (int)gridDim.x * 2) {
               mbar_arrive(&a_full[slot]);
             } else {
               mbar_arrive_expect_tx(&a_full[slot], a_tx);
@@ -268,10 +351,18 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     long long w_b = 0;
     if (hp.b_resident) {
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(&b_full[0], (uint32_t)(kTaps * p.kchunks * b_tile_bytes));
-        for (int kc = 0; kc < p.kchunks; ++kc)
-          for (int tap = 0; tap < kTaps; ++tap)
-            tma_load_2d(sB + (kc * kTaps + tap) * b_tile_bytes, &tmB, &b_full[0], (tap * p.kchunks + kc) * 64, 0);
+        if constexpr (kPair) {
+          if (rank == 0) mbar_arrive_expect_tx(&b_full[0], (uint32_t)(2 * kTaps * p.kchunks * b_tile_bytes));
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            for (int tap = 0; tap < kTaps; ++tap)
+              mp_tma_load_2d(sB + (kc * kTaps + tap) * b_tile_bytes, &tmB, &b_full[0], (tap * p.kchunks + kc) * 64,
+                             (int)rank * (p.BN / 2));
+        } else {
+          mbar_arrive_expect_tx(&b_full[0], (uint32_t)(kTaps * p.kchunks * b_tile_bytes));
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            for (int tap = 0; tap < kTaps; ++tap)
+              tma_load_2d(sB + (kc * kTaps + tap) * b_tile_bytes, &tmB, &b_full[0], (tap * p.kchunks + kc) * 64, 0);
+        }
       }
       __syncwarp();
       if constexpr (kRT) {
@@ -282,12 +373,12 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
         const int obuf_b = kABytesPerStage;
         int rb[kMI] = {0, 0};
         uint32_t rph[kMI] = {0, 0};
-        for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+        for (int s = cta0; s < total_super; s += ncta) {
           const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
 #pragma unroll
           for (int i = 0; i < kMI; ++i) {
-            const int mt = ms * kMI + i;
-            if (mt >= p.m_tiles) continue;
+            const int mt = tile_of(ms, i);
+            if (!tile_live(mt)) continue;
             const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
             const int x0 = (mt - t1 * p.tiles_x) * p.TW, y0 = (t1 - t2 * p.tiles_y) * p.TH, n0 = t2 * p.TN;
             mbar_wait(&r_free[i * 2 + rb[i]], rph[i] ^ 1);
@@ -306,7 +397,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     } else {
       int bs = 0;
       uint32_t bph = 0;
-      for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+      for (int s = cta0; s < total_super; s += ncta) {
         const int nt = hp.d_msuper.div(s);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int tap = 0; tap < kTaps; ++tap) {
@@ -314,8 +405,14 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
             mbar_wait(&b_empty[bs], bph ^ 1);
             if (p.prof) w_b += clock64() - tw0;
             if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_tile_bytes);
-              tma_load_2d(sB + bs * b_tile_bytes, &tmB, &b_full[bs], (tap * p.kchunks + kc) * 64, nt * p.BN);
+              if constexpr (kPair) {
+                if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], (uint32_t)(2 * b_tile_bytes));
+                mp_tma_load_2d(sB + bs * b_tile_bytes, &tmB, &b_full[bs], (tap * p.kchunks + kc) * 64,
+                               nt * p.BN + (int)rank * (p.BN / 2));
+              } else {
+                mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_tile_bytes);
+                tma_load_2d(sB + bs * b_tile_bytes, &tmB, &b_full[bs], (tap * p.kchunks + kc) * 64, nt * p.BN);
+              }
             }
             __syncwarp();
             if (++bs == hp.sb) {
@@ -327,12 +424,14 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
       }
     }
     if (p.prof && lane == 0) p.prof[blockIdx.x * 16 + 1] = w_b;
+  } else if (warp >= kMIssuerWarp0 && rank != 0) {
+    // (the peer CTA of a pair issues nothing: the leader's MMAs read both CTAs' shared memory and write both TMEMs)
   } else if (warp >= kMIssuerWarp0) {
     // ------------------------------------------------------------------ MMA issuers (whole warp, one elected lane issues)
     const int iw = warp - kMIssuerWarp0;
     const int i = iw / kKS;       // tile stream
     const int h = iw - i * kKS;   // K-half: this warp issues the (chunk, tap) items whose index is h modulo kKS
-    const uint32_t idesc = umma_idesc_bf16(128, p.BN);
+    const uint32_t idesc = umma_idesc_bf16(kPair ? 256 : 128, p.BN);
     int as = 0, bs = 0, acc = 0;
     uint32_t aph = 0, bph = 0, acc_phase = 0;
     long long w_af = 0, w_bf = 0, w_acc = 0;
@@ -342,9 +441,9 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
       tc_fence_after();
     }
     const uint32_t sB_u32 = smem_u32(sB);
-    for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+    for (int s = cta0; s < total_super; s += ncta) {
       const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
-      const bool valid = ms * kMI + i < p.m_tiles;
+      const bool valid = tile_live(tile_of(ms, i));
       uint32_t d_tmem = 0;
       if (valid) {
         const long long tw0 = p.prof ? clock64() : 0;
@@ -386,11 +485,11 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
               const uint64_t bd = umma_desc_sw128(b_addr);
               const uint32_t first = item >= kKS ? 1u : 0u;   // this issuer's first item of the tile overwrites
               if (elect_one_sync()) {
-                umma_bf16(d_tmem, ad, bd, idesc, first);
-                umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-                umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-                umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
-                if (!hp.b_resident) umma_commit(&b_empty[bs]);
+                mp_umma<kPair>(d_tmem, ad, bd, idesc, first);
+                mp_umma<kPair>(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                mp_umma<kPair>(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                mp_umma<kPair>(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                if (!hp.b_resident) mp_commit<kPair>(&b_empty[bs]);
               }
               __syncwarp();
             } else if (!hp.b_resident) {
@@ -407,7 +506,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
           }
         }
         if (valid) {
-          if (elect_one_sync()) umma_commit(&a_empty[i * hp.sa + as]);
+          if (elect_one_sync()) mp_commit<kPair>(&a_empty[i * hp.sa + as]);
           __syncwarp();
           if (++as == hp.sa) {
             as = 0;
@@ -416,7 +515,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
         }
       }
       if (valid) {
-        if (elect_one_sync()) umma_commit(&acc_full[i * p.acc_stages + acc]);
+        if (elect_one_sync()) mp_commit<kPair>(&acc_full[i * p.acc_stages + acc]);
         __syncwarp();
         if (++acc == p.acc_stages) {
           acc = 0;
@@ -460,7 +559,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     uint32_t r_uses = 0;   // kRT: sub-tiles processed so far by this group (buffer = r_uses & 1, phase = (r_uses >> 1) & 1)
     uint4 addv[8];
     auto prefetch_add = [&](int s2, int sub2) {
-      const int nt2 = hp.d_msuper.div(s2), mt2 = (s2 - nt2 * hp.m_super) * kMI + i;
+      const int nt2 = hp.d_msuper.div(s2), mt2 = tile_of(s2 - nt2 * hp.m_super, i);
       const int u1 = hp.d_tx.div(mt2), u2 = hp.d_ty.div(u1);
       const int x2 = (mt2 - u1 * p.tiles_x) * p.TW + tx, y2 = (u1 - u2 * p.tiles_y) * p.TH + ty, n2 = u2 * p.TN + tn;
       const bool v2 = row_in_tile && (x2 < p.W) && (y2 < p.H) && (n2 < p.B);
@@ -472,15 +571,15 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
         addv[g] = (v2 && col2 + g * 8 < p.N && !(hp.debug & 16)) ? __ldg(reinterpret_cast<const uint4*>(ar + g * 8)) : make_uint4(0, 0, 0, 0);
     };
     if (has_add) {
-      int s0 = blockIdx.x;
-      while (s0 < total_super && ((s0 - hp.d_msuper.div(s0) * hp.m_super) * kMI + i) >= p.m_tiles) s0 += gridDim.x;
+      int s0 = cta0;
+      while (s0 < total_super && !tile_live(tile_of(s0 - hp.d_msuper.div(s0) * hp.m_super, i))) s0 += ncta;
       if (s0 < total_super) prefetch_add(s0, 0);
     }
 
-    for (int s = blockIdx.x; s < total_super; s += gridDim.x) {
+    for (int s = cta0; s < total_super; s += ncta) {
       const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
-      const int mt = ms * kMI + i;
-      if (mt >= p.m_tiles) continue;
+      const int mt = tile_of(ms, i);
+      if (!tile_live(mt)) continue;
       ++e_tiles;
       const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
       const int x0 = (mt - t1 * p.tiles_x) * p.TW;
@@ -642,7 +741,10 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
         if ((sub + 1) * 64 >= ncols) {  // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
+          if (lane == 0) {
+            if (kPair && rank != 0) mp_arrive_leader(&acc_empty[i * p.acc_stages + acc]);
+            else mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
+          }
         }
         if (p.pool && strip) {
           // fused nn.MaxPool2d(2) of a row-strip tile: row neighbours are not warp neighbours here, so the 2x2 windows
@@ -676,8 +778,8 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
           if ((sub + 1) * 64 < ncols) {
             prefetch_add(s, sub + 1);
           } else {
-            const int s2 = s + gridDim.x;
-            if (s2 < total_super && ((s2 - hp.d_msuper.div(s2) * hp.m_super) * kMI + i) < p.m_tiles) prefetch_add(s2, 0);
+            const int s2 = s + ncta;
+            if (s2 < total_super && tile_live(tile_of(s2 - hp.d_msuper.div(s2) * hp.m_super, i))) prefetch_add(s2, 0);
           }
         }
         named_bar_sync(1 + i, 128);
@@ -730,7 +832,10 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
       if (kMode == UG_EPI_OUTC) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
+        if (lane == 0) {
+          if (kPair && rank != 0) mp_arrive_leader(&acc_empty[i * p.acc_stages + acc]);
+          else mbar_arrive(&acc_empty[i * p.acc_stages + acc]);
+        }
         if (valid) {
           const float logit = dot + p.outc_b;
           const long long o = ((long long)n * p.H + y) * p.W + x;
@@ -759,7 +864,13 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMAllocWarp) tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (kPair) {
+    mp_cluster_sync();   // the leader's MMAs write the peer's tensor memory until both CTAs are done
+    if (warp == kMAllocWarp)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  } else {
+    if (warp == kMAllocWarp) tmem_dealloc(tmem_base, p.tmem_cols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -781,7 +892,7 @@ static int encode_map(EncodeTiledFn encode, CUtensorMap* m, void* base, int rank
 
 // Fills L for the multi-issuer kernel: 3x3 pad-1 convolutions (halo tiles) and 1x1 convolutions / linear layers /
 // ConvTranspose 2x2 s2 (plain pixel tiles).  Returns UG_EUNSUPPORTED when the shape does not fit it.
-int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* L) {
+int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* L, int pair) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return set_error(h, UG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   const int up = d->up == 2 ? 2 : 1;
@@ -844,6 +955,11 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
                (reinterpret_cast<uintptr_t>(d->pool_out) & 15) || (TW / 2) * (TH / 2) * 128 > kPoolBytes))
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): fused max-pool needs a 3x3 STORE conv on an even map");
   const int stats = d->stats_sum != nullptr;
+  // CTA pairs (see the header comment): 3x3 ReLU layers with 128-column n-tiles, plain stores (optionally pooled) or the
+  // CoordAtt3 combine; narrower layers have their own pair kernel (conv_pair.cu)
+  if (pair && (taps != 9 || BN != 128 || d->N % 128 || stats || (h->num_sms & 1) ||
+               !(d->mode == UG_EPI_STORE || d->mode == UG_EPI_GATE)))
+    return set_error(h, UG_EUNSUPPORTED, "conv(multi, pairs): 3x3 layers with 128-column n-tiles, STORE / GATE epilogue");
   if (stats && (taps != 9 || d->mode != UG_EPI_STORE || !d->stats_max ||
                 d->stats_tiles != cdiv_m(d->W, 8) * cdiv_m(d->H, TH)))
     return set_error(h, UG_EUNSUPPORTED, "conv(multi): fused channel statistics need a 3x3 STORE conv and stats_tiles == %d",
@@ -851,7 +967,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   const int obuf_bytes = tma_store ? kABytesPerStage + (pool ? kPoolBytes : 0) : 0;  // per staging buffer, for sizing
   // K-split: two issuing warps per tile stream for narrow 3x3 tiles (see the header comment); UG_KSPLIT=0 turns it off
   static const int ksplit_on = [] { const char* e = getenv("UG_KSPLIT"); return e ? atoi(e) : 1; }();
-  const int ks = (taps == 9 && BN <= 64 && ksplit_on && d->act == UG_ACT_RELU && d->mode != UG_EPI_ADD) ? 2 : 1;
+  const int ks = (taps == 9 && BN <= 64 && !pair && ksplit_on && d->act == UG_ACT_RELU && d->mode != UG_EPI_ADD) ? 2 : 1;
   // instantiated (activation, taps, epilogue) combinations: 3x3 = ReLU with any epilogue; 1x1 = plain stores with any
   // activation, residual add without activation
   if (taps == 9 && d->act != UG_ACT_RELU)
@@ -863,7 +979,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   // Needs two staging buffers per stream next to the weights: tiles of <= 14 rows make room (the layer is bound by its
   // epilogue, not by the 12.5 % of MMA rows this leaves empty).  UG_RESID_TMA=0 turns it off.
   static const int rt_on = [] { const char* e = getenv("UG_RESID_TMA"); return e ? atoi(e) : 1; }();
-  int rt = (rt_on && taps == 9 && !strip && ks == 2 && d->mode == UG_EPI_GATE && d->N <= 64 && BN == 64 && d->add_bstride > 0 &&
+  int rt = (rt_on && !pair && taps == 9 && !strip && ks == 2 && d->mode == UG_EPI_GATE && d->N <= 64 && BN == 64 && d->add_bstride > 0 &&
             !pool && !stats) ? 1 : 0;
   if (rt) {
     const int th2 = cdiv_m(d->H, cdiv_m(d->H, 14));
@@ -876,7 +992,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   // strip mode: MMA row 127 of tap (2,2) reads halo position 127 + 2*pitch + 2, past the loaded box (garbage rows only)
   const int a_span = strip ? std::max(a_bytes, (128 + 2 * pitch + 2) * 128) : a_bytes;
   const int a_stage = ((a_span + 1023) / 1024) * 1024;
-  const int b_tile = BN * 128;
+  const int b_tile = (pair ? BN / 2 : BN) * 128;   // pairs: each CTA holds half of the rows of a weight tile
 
   MultiParams hp;
   memset(&hp, 0, sizeof(hp));
@@ -926,7 +1042,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   p.N = d->N; p.BN = BN; p.stages = hp.sa;
   int tcols = 32;
   while (tcols < kMI * ks * acc_stages * BN) tcols <<= 1;
-  p.tmem_cols = tcols;
+  p.tmem_cols = pair ? 512 : tcols;   // (pairs: whole tensor memory, so that the addresses coincide in both CTAs)
   p.a_bytes = (unsigned)a_bytes; p.b_bytes = (unsigned)b_tile;
   p.scale = d->scale; p.bias = d->bias;
   p.act = d->act; p.mode = d->mode;
@@ -939,8 +1055,9 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   p.m_tiles = p.tiles_x * p.tiles_y * cdiv_m(d->B, TN); p.n_tiles = n_tiles; p.acc_stages = acc_stages;
   p.tma_store = tma_store; p.obufs = obufs; p.npad = npad; p.pool = pool;
   p.stats_sum = d->stats_sum; p.stats_max = d->stats_max;
-  hp.m_super = cdiv_m(p.m_tiles, kMI);
+  hp.m_super = cdiv_m(p.m_tiles, kMI * (pair ? 2 : 1));
   L->variant = 5;
+  L->halo_pair = pair;
   L->halo_mode = taps;
   L->halo_TH = TH; L->halo_a_stage = a_stage; L->halo_copy = hp.m_super;
   L->halo_sa = hp.sa; L->halo_sb = hp.sb; L->halo_bres = hp.b_resident;
@@ -968,7 +1085,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     // packer's own tile, which may differ from BN)
     cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d->N};
     cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? BN / 2 : BN)};
     const int r = encode_map(encode, &L->tmB, const_cast<void*>(d->w), 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (r) return set_error(h, UG_ECUDA, "conv(multi): weight tensor map encode failed (%d)", r);
   }
@@ -1015,7 +1132,8 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     }
   }
   const long long total_super = (long long)hp.m_super * n_tiles;
-  L->grid = dim3((unsigned)std::min<long long>(total_super, (long long)h->num_sms), 1, 1);
+  if (pair) L->grid = dim3(2u * (unsigned)std::min<long long>(total_super, (long long)(h->num_sms / 2)), 1, 1);
+  else L->grid = dim3((unsigned)std::min<long long>(total_super, (long long)h->num_sms), 1, 1);
   const int nb_tiles = hp.b_resident ? taps * kchunks : hp.sb;
   L->smem = 1024 + (size_t)kMI * hp.sa * a_stage + (size_t)nb_tiles * b_tile + (size_t)kMI * obufs * obuf_bytes +
             8 * (2 * kMI * hp.sa + 2 * hp.sb + 2 * kMI * acc_stages + 4 * kMI) + 16 + 2 * (size_t)npad * sizeof(float) +
@@ -1025,12 +1143,30 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   return UG_OK;
 }
 
-template <int kAct, int kTaps, int kMode, int kKS, int kRT = 0>
+template <int kAct, int kTaps, int kMode, int kKS, int kRT = 0, int kPair = 0>
 static cudaError_t launch_one(ug_engine* h, const ConvLaunch* L, const StoreMaps& maps, const MultiParams& hp,
                               cudaStream_t s, bool set_attr) {
-  auto fn = conv_multi_kernel<kAct, kTaps, kMode, kKS, kRT>;
+  auto fn = conv_multi_kernel<kAct, kTaps, kMode, kKS, kRT, kPair>;
   if (set_attr) return cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  return launch_pdl(h, fn, L->grid, kMultiThreads(kKS), L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
+  if constexpr (kPair) {   // clusters of two CTAs (+ programmatic dependent launch)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = L->grid;
+    cfg.blockDim = dim3(kMultiThreads(kKS));
+    cfg.dynamicSmemBytes = L->smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = h->pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, fn, L->tmA, L->tmB, maps, L->p, hp);
+  } else {
+    return launch_pdl(h, fn, L->grid, kMultiThreads(kKS), L->smem, s, L->tmA, L->tmB, maps, L->p, hp);
+  }
 }
 
 // Dispatch over the instantiated (activation, taps, epilogue mode, K-split) combinations (conv_multi_prepare rejects the
@@ -1041,6 +1177,11 @@ static cudaError_t dispatch_multi(ug_engine* h, const ConvLaunch* L, const Store
   const int act = L->p.act, mode = L->p.mode, taps = L->halo_mode, ks = L->halo_ks;
   if (set_attr) {
     if (e == cudaSuccess) e = launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 2, 1>(h, L, maps, hp, s, true);
+    if (e == cudaSuccess) e = launch_one<UG_ACT_RELU, 9, UG_EPI_STORE, 1, 0, 1>(h, L, maps, hp, s, true);
+    if (e == cudaSuccess) e = launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 1, 0, 1>(h, L, maps, hp, s, true);
+  } else if (L->halo_pair) {   // CTA pairs: two instantiations (conv_multi_prepare admits exactly these)
+    if (mode == UG_EPI_GATE) return launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 1, 0, 1>(h, L, maps, hp, s, false);
+    return launch_one<UG_ACT_RELU, 9, UG_EPI_STORE, 1, 0, 1>(h, L, maps, hp, s, false);
   } else if (L->halo_rt) {  // TMA residual: the only instantiation (conv_multi_prepare sets rt for exactly this case)
     return launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 2, 1>(h, L, maps, hp, s, false);
   }

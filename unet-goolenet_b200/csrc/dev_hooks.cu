@@ -61,7 +61,8 @@ int ug_conv_profile16(ug_handle h, const ug_conv_desc* d, void* stream, double* 
   for (int j = 0; j < 16; ++j) {
     double a = 0;
     for (int c = 0; c < ctas; ++c) a += (double)host[c * 16 + j];
-    out16[j] = a / ctas;
+    // (CTA pairs: only the leader CTAs have issuers, slots 4-11)
+    out16[j] = a / ((L.halo_pair && j >= 4 && j < 12) ? ctas / 2 : ctas);
   }
   return UG_OK;
 }

@@ -90,6 +90,7 @@ struct ConvLaunch {
   int halo_rt;  // multi-issuer kernel: residual tiles by TMA into the staging buffers (CoordAtt3 combine, 64 channels)
   int halo_rowtaps;  // multi-issuer kernel, 1x1 tiles: the k-chunks are R row taps of an overlapping-window input
   int halo_ks;  // multi-issuer kernel: issuing warps per tile stream (K-split), 1 or 2
+  int halo_pair;  // multi-issuer kernel: clusters of two CTAs issuing tcgen05.mma.cta_group::2 (128-column n-tiles)
 };
 
 // Stem convolution (csrc/stem_conv.cu): kernel parameters and a prepared launch.
@@ -138,7 +139,7 @@ inline cudaError_t launch_pdl(const ug_engine* h, void (*kernel)(KArgs...), dim3
 
 int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
 int conv_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
-int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* out);
+int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* out, int pair = 0);
 int conv_multi_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 // CTA-pair kernel (csrc/conv_pair.cu): 3x3 ReLU layers with <= 64 output channels, tcgen05.mma.cta_group::2
 int conv_pair_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
