@@ -957,7 +957,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   const int stats = d->stats_sum != nullptr;
   // CTA pairs (see the header comment): 3x3 ReLU layers with 128-column n-tiles, plain stores (optionally pooled) or the
   // CoordAtt3 combine; narrower layers have their own pair kernel (conv_pair.cu)
-  if (pair && (taps != 9 || BN != 128 || d->N % 128 || stats || (h->num_sms & 1) ||
+  if (pair && (taps != 9 || BN != 128 || d->N < 128 || stats || (h->num_sms & 1) ||
                !(d->mode == UG_EPI_STORE || d->mode == UG_EPI_GATE)))
     return set_error(h, UG_EUNSUPPORTED, "conv(multi, pairs): 3x3 layers with 128-column n-tiles, STORE / GATE epilogue");
   if (stats && (taps != 9 || d->mode != UG_EPI_STORE || !d->stats_max ||
