@@ -1,7 +1,9 @@
 """Copy the outputs of scripts/gpu_evidence.sh <tag> from gpurun_out/ into profiles/ under round names (rNN_*).
-usage: store_evidence.py r02b r02"""
+usage: store_evidence.py <tag> <round> [bench_tag]      (bench_tag: the run that holds the test / bench logs when <tag> was an
+"ncu"-only run of gpu_evidence.sh)"""
 import csv, json, re, shutil, subprocess, sys
 tag, rnd = sys.argv[1], sys.argv[2]
+btag = sys.argv[3] if len(sys.argv) > 3 else tag
 O, P = "gpurun_out", "profiles"
 rows = [l for l in open(f"{O}/{tag}_launches.csv") if l.startswith('"')]
 assert not any("elementwise" in r for r in rows), "torch kernels in the launch list"
@@ -25,14 +27,15 @@ for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
 lines.append(f"| total | {sum(v[0] for v in tot.values())} | {allt:.1f} | 100 % |")
 open(f"{P}/{rnd}_kernel_shares.md", "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
-shutil.copy(f"{O}/{tag}_per_op.json", f"{P}/{rnd}_per_op.json")
+shutil.copy(f"{O}/{btag}_per_op.json", f"{P}/{rnd}_per_op.json")
 for a, b in (("bench.log", "bench.json"), ("bench_src512.log", "bench_src512.json"), ("bench_unet64.log", "bench_unet64.json"),
              ("bench_googlenet256.log", "bench_googlenet256.json"), ("bench_ref.log", "bench_reference_arm.json")):
-    last = [l for l in open(f"{O}/{tag}_{a}") if l.startswith("{")][-1]
+    last = [l for l in open(f"{O}/{btag}_{a}") if l.startswith("{")][-1]
     open(f"{P}/{rnd}_{b}", "w").write(last)
 table = subprocess.run([sys.executable, "scripts/ncu_summary.py", f"{O}/{tag}_full.raw.csv"], capture_output=True, text=True, check=True).stdout
 hdr = (f"# ncu --set full --clock-control none of ONE 128-image pipeline pass, engine kernels only, program order (scripts/gpu_evidence.sh {tag})\n"
-       "# rows 0-56: UNet micro-batch of 128 + bbox + crop-resize; rows 57-: GoogLeNet over 128 crops\n"
+       "# rows up to resize_u8_kernel: UNet micro-batch of 128 + bbox + crop-resize; from s2d_pack_kernel on: GoogLeNet over 128 crops\n"
+       "# conv_multi_kernel<act, taps, epilogue mode, K-split, TMA residual, CTA pairs>; conv_pair_kernel<epilogue mode, TMA residual>\n"
        "# tensor pipe % = sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed (at the full 1.965 GHz clock)\n"
        "# % of HBM peak divides by the COPY peak 6552.6 GB/s; write-dominated kernels are bounded by the write roof 3.86 TB/s (r02_bandwidth_probe.txt)\n\n")
 open(f"{P}/{rnd}_ncu_kernels.md", "w").write(hdr + table)

@@ -233,7 +233,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(128) attention_mma_kernel(ug_attn_desc d) {
+__global__ void __launch_bounds__(128, 3) attention_mma_kernel(ug_attn_desc d) {
   pdl_wait();  // programmatic dependent launch: see common.cuh
   pdl_launch_dependents();
   extern __shared__ uint4 attn_smem[];
