@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
     long long w_empty = 0;
     const long long t_start = clock64();
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+      // (m-major order: the n-tiles of a pixel tile run on neighbouring CTAs at the same time and share its HBM read)
+      const int mt = p.m_major ? t / p.n_tiles : t % p.m_tiles, nt = p.m_major ? t % p.n_tiles : t / p.m_tiles;
       const int x0 = (mt % p.tiles_x) * p.TW;
       const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.TH;
       const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.TN;
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_persistent_kernel(const
     uint32_t acc_phase = 0;
 
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int mt = t % p.m_tiles, nt = t / p.m_tiles;
+      // (m-major order: the n-tiles of a pixel tile run on neighbouring CTAs at the same time and share its HBM read)
+      const int mt = p.m_major ? t / p.n_tiles : t % p.m_tiles, nt = p.m_major ? t % p.n_tiles : t / p.m_tiles;
       const int x0 = (mt % p.tiles_x) * p.TW;
       const int y0 = ((mt / p.tiles_x) % p.tiles_y) * p.TH;
       const int n0 = (mt / (p.tiles_x * p.tiles_y)) * p.TN;
@@ -737,6 +739,8 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   p.gate = d->gate; p.outc_w = d->outc_w; p.outc_b = d->outc_b;
   p.logits = d->logits; p.mask = d->mask;
   p.m_tiles = m_tiles_total; p.n_tiles = n_tiles; p.acc_stages = acc_stages;
+  static const int m_major_on = [] { const char* e = getenv("UG_M_MAJOR"); return e ? atoi(e) : 1; }();
+  p.m_major = (m_major_on && n_tiles > 1) ? 1 : 0;
   p.tma_store = tma_store; p.obufs = obufs; p.npad = npad; p.stage_copy = stage_copy;
   p.out2 = d->out2; p.out2_cstride = d->out2_cstride; p.n_split = split ? d->n_split : 0; p.n1 = d->n1;
   L->variant = variant;

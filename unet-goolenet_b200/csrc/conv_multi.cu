@@ -114,6 +114,10 @@ struct MultiParams {
   int b_resident;     // whole weight matrix kept in smem (requires n_tiles == 1)
   int m_super;        // ceil(m_tiles / kMI): pixel tiles are handed out in groups of kMI
   FastDiv d_msuper, d_tx, d_ty;   // dividers by m_super, tiles_x, tiles_y
+  int m_major;        // work item s -> (pixel-tile group s / n_tiles, n-tile s % n_tiles): the n-tiles of one pixel-tile group
+                      // run on neighbouring CTAs at the same time, so the activation tile comes from HBM once and from L2
+                      // for the other n-tiles (n-major order re-read the whole input from HBM once per n-tile)
+  FastDiv d_nt;       // divider by n_tiles
   int pitch;          // halo pixels per stage row: kMPitch (8-pixel-wide tiles) or W + 2 (row-strip tiles)
   int sbo;            // byte distance of consecutive 8-row groups of the A operand: pitch * 128 (tiles) or 1024 (strips)
   int strip;          // row-strip tiles (see the header comment); TH is then the number of image rows per tile
@@ -232,6 +236,16 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
   // (zero-filled loads, clipped stores) so that both CTAs run the same rounds
   auto tile_of = [&](int ms, int i) { return kPair ? (ms * kMI + i) * 2 + (int)rank : ms * kMI + i; };
   auto tile_live = [&](int mt) { return kPair ? true : mt < p.m_tiles; };
+  // work item -> (n-tile, pixel-tile group)
+  auto decode = [&](int s, int& nt, int& ms) {
+    if (hp.m_major) {
+      ms = hp.d_nt.div(s);
+      nt = s - ms * p.n_tiles;
+    } else {
+      nt = hp.d_msuper.div(s);
+      ms = s - nt * hp.m_super;
+    }
+  };
 
   if (warp == kMProducerWarp && lane == 0) {
     prefetch_tmap(&tmA);
@@ -298,7 +312,8 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     unsigned long long ns0 = 0;
     if (p.prof) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns0));
     for (int s = cta0; s < total_super; s += ncta) {
-      const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
+      int nt, ms;
+      decode(s, nt, ms);
       int cx[kMI], cy[kMI], cn[kMI];
 #pragma unroll
       for (int i = 0; i < kMI; ++i) {
@@ -374,7 +389,8 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
         int rb[kMI] = {0, 0};
         uint32_t rph[kMI] = {0, 0};
         for (int s = cta0; s < total_super; s += ncta) {
-          const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
+          int nt, ms;
+          decode(s, nt, ms);
 #pragma unroll
           for (int i = 0; i < kMI; ++i) {
             const int mt = tile_of(ms, i);
@@ -398,7 +414,8 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
       int bs = 0;
       uint32_t bph = 0;
       for (int s = cta0; s < total_super; s += ncta) {
-        const int nt = hp.d_msuper.div(s);
+        int nt, ms_unused;
+        decode(s, nt, ms_unused);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int tap = 0; tap < kTaps; ++tap) {
             const long long tw0 = p.prof ? clock64() : 0;
@@ -442,7 +459,8 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     }
     const uint32_t sB_u32 = smem_u32(sB);
     for (int s = cta0; s < total_super; s += ncta) {
-      const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
+      int nt, ms;
+      decode(s, nt, ms);
       const bool valid = tile_live(tile_of(ms, i));
       uint32_t d_tmem = 0;
       if (valid) {
@@ -559,7 +577,9 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     uint32_t r_uses = 0;   // kRT: sub-tiles processed so far by this group (buffer = r_uses & 1, phase = (r_uses >> 1) & 1)
     uint4 addv[8];
     auto prefetch_add = [&](int s2, int sub2) {
-      const int nt2 = hp.d_msuper.div(s2), mt2 = tile_of(s2 - nt2 * hp.m_super, i);
+      int nt2, ms2;
+      decode(s2, nt2, ms2);
+      const int mt2 = tile_of(ms2, i);
       const int u1 = hp.d_tx.div(mt2), u2 = hp.d_ty.div(u1);
       const int x2 = (mt2 - u1 * p.tiles_x) * p.TW + tx, y2 = (u1 - u2 * p.tiles_y) * p.TH + ty, n2 = u2 * p.TN + tn;
       const bool v2 = row_in_tile && (x2 < p.W) && (y2 < p.H) && (n2 < p.B);
@@ -572,12 +592,14 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
     };
     if (has_add) {
       int s0 = cta0;
-      while (s0 < total_super && !tile_live(tile_of(s0 - hp.d_msuper.div(s0) * hp.m_super, i))) s0 += ncta;
+      auto group_of = [&](int sx) { int a, b; decode(sx, a, b); return b; };
+      while (s0 < total_super && !tile_live(tile_of(group_of(s0), i))) s0 += ncta;
       if (s0 < total_super) prefetch_add(s0, 0);
     }
 
     for (int s = cta0; s < total_super; s += ncta) {
-      const int nt = hp.d_msuper.div(s), ms = s - nt * hp.m_super;
+      int nt, ms;
+      decode(s, nt, ms);
       const int mt = tile_of(ms, i);
       if (!tile_live(mt)) continue;
       ++e_tiles;
@@ -779,7 +801,9 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
             prefetch_add(s, sub + 1);
           } else {
             const int s2 = s + ncta;
-            if (s2 < total_super && tile_live(tile_of(s2 - hp.d_msuper.div(s2) * hp.m_super, i))) prefetch_add(s2, 0);
+            int nt3, ms3;
+            decode(s2 < total_super ? s2 : s, nt3, ms3);
+            if (s2 < total_super && tile_live(tile_of(ms3, i))) prefetch_add(s2, 0);
           }
         }
         named_bar_sync(1 + i, 128);
@@ -1218,6 +1242,9 @@ int conv_multi_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   hp.sbo = hp.strip ? 1024 : hp.pitch * 128;
   hp.d_pitch = make_fastdiv(hp.pitch);
   hp.d_msuper = make_fastdiv(hp.m_super);
+  static const int m_major_on = [] { const char* e = getenv("UG_M_MAJOR"); return e ? atoi(e) : 1; }();
+  hp.m_major = (m_major_on && L->p.n_tiles > 1) ? 1 : 0;
+  hp.d_nt = make_fastdiv(L->p.n_tiles);
   hp.d_tx = make_fastdiv(L->p.tiles_x);
   hp.d_ty = make_fastdiv(L->p.tiles_y);
   StoreMaps maps;

@@ -65,6 +65,7 @@ struct ConvKParams {
   // persistent variant
   int m_tiles, n_tiles, acc_stages, tma_store, obufs, npad;
   int pool;        // multi-issuer 3x3 kernel: fused 2x2 max-pool side output (second TMA store per sub-tile)
+  int m_major;     // persistent GEMM kernel: tile order (pixel tile, n-tile) instead of (n-tile, pixel tile)
   float* stats_sum;  // multi-issuer 3x3 kernel: per-tile channel sums / maxima of the stored output
   float* stats_max;
   int stage_copy;  // ConvTranspose scatter: stage the tile in smem, then coalesced cooperative copy-out
