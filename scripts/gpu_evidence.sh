@@ -4,7 +4,7 @@
 # return limit).   usage: bash scripts/gpu_evidence.sh <tag> [quick|ncu]     (outputs land in gpurun_out/<tag>_*)
 TAG=${1:-r02}
 O=gpurun_out
-K='regex:conv_multi|conv_gemm|conv_pair|stem_conv|s2d_pack|pool_kernel|pool3x3s1|layernorm|attention_mma|chanstats|gate_hidden|gate_out|bbox_kernel|resize_u8|head_kernel'
+K='regex:conv_multi|conv_gemm|conv_pair|stem_conv|s2d_pack|pool_kernel|pool3x3s|layernorm|attention_mma|chanstats|gate_hidden|gate_out|bbox_kernel|resize_u8|head_kernel'
 set -x
 if [ "$2" != "ncu" ]; then
 python -m pytest tests -m gpu -q -x --tb=short -p no:cacheprovider -rP > $O/${TAG}_gputests.log 2>&1; echo "pytest rc=$?"; tail -5 $O/${TAG}_gputests.log

@@ -16,7 +16,9 @@ def _gen(seed=0):
 
 @pytest.mark.parametrize("k,stride,pad,H,W", [(2, 2, 0, 28, 28), (3, 2, 0, 112, 112), (3, 2, 0, 56, 56),
                                               (3, 1, 1, 14, 14), (2, 2, 0, 14, 14), (3, 2, 0, 13, 15),
-                                              (3, 1, 1, 28, 28), (3, 1, 1, 7, 7), (3, 1, 1, 1, 5), (3, 1, 1, 9, 1)])
+                                              (3, 1, 1, 28, 28), (3, 1, 1, 7, 7), (3, 1, 1, 1, 5), (3, 1, 1, 9, 1),
+                                              (3, 2, 0, 28, 28), (3, 2, 0, 14, 14), (3, 2, 0, 8, 9), (3, 2, 0, 3, 3),
+                                              (3, 2, 1, 14, 14)])
 def test_pool(engine, k, stride, pad, H, W):
     from ugnet_b200 import engine as E
     g = _gen(2)

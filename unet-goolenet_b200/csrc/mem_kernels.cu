@@ -96,17 +96,148 @@ __global__ void __launch_bounds__(256) pool3x3s1_kernel(const __nv_bfloat16* __r
   }
 }
 
+// 3x3 stride-2 pad-0 ceil-mode max pooling (GoogLeNet maxpool1-4): one thread per (image, 2x2 block of output pixels,
+// 8-channel group).  The four windows of a block cover 5x5 input pixels: 25 independent loads for four outputs (6.25
+// per output instead of 9; the generic kernel ran at 52-55 % of the HBM peak with the L2 -> SM path at ~7 TB/s).
+// A sliding-window form (one thread per output row, 6 loads per output) was slower: too few, too serial threads
+// (profiles/r02_pool_s2.txt).  Columns / rows past the map (ceil mode) are skipped = -inf padding.
+__global__ void __launch_bounds__(256) pool3x3s2_kernel(const __nv_bfloat16* __restrict__ in,
+                                                        __nv_bfloat16* __restrict__ out, ug_pool_desc d) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
+  const int cg = d.C / 8;
+  const int bw = (d.OW + 1) >> 1, bh = (d.OH + 1) >> 1;
+  const int total = d.B * bh * bw * cg;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int g = t % cg;
+  int pp = t / cg;
+  const int bx = pp % bw;
+  pp /= bw;
+  const int by = pp % bh;
+  const int n = pp / bh;
+  const uint32_t ninf = 0xFF80FF80u;  // (-inf, -inf) in bf16
+  const uint4 vinf = make_uint4(ninf, ninf, ninf, ninf);
+  auto vmax = [](const uint4& a, const uint4& b) {
+    return make_uint4(bf16x2_max(a.x, b.x), bf16x2_max(a.y, b.y), bf16x2_max(a.z, b.z), bf16x2_max(a.w, b.w));
+  };
+  const int y0 = 4 * by, x0 = 4 * bx;
+  const __nv_bfloat16* base = in + ((long long)n * d.H * d.W) * d.in_cstride + g * 8;
+  uint4 o[2][2] = {{vinf, vinf}, {vinf, vinf}};
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    uint4 v[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+      v[r] = (y0 + r < d.H && x0 + c < d.W)
+                 ? *reinterpret_cast<const uint4*>(base + ((long long)(y0 + r) * d.W + x0 + c) * d.in_cstride)
+                 : vinf;
+    const uint4 top = vmax(vmax(v[0], v[1]), v[2]), bot = vmax(vmax(v[2], v[3]), v[4]);
+    if (c <= 2) {
+      o[0][0] = vmax(o[0][0], top);
+      o[1][0] = vmax(o[1][0], bot);
+    }
+    if (c >= 2) {
+      o[0][1] = vmax(o[0][1], top);
+      o[1][1] = vmax(o[1][1], bot);
+    }
+  }
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int oy = 2 * by + dy, ox = 2 * bx + dx;
+      if (oy < d.OH && ox < d.OW)
+        *reinterpret_cast<uint4*>(out + (((long long)n * d.OH + oy) * d.OW + ox) * d.out_cstride + g * 8) = o[dy][dx];
+    }
+}
+
+// 3x3 stride-1 pad-1 max pooling, block form: one thread per (image, 2x2 block of output pixels, 8-channel group): the four
+// windows cover 4x4 input pixels, 16 independent loads for four outputs.
+__global__ void __launch_bounds__(256) pool3x3s1_block_kernel(const __nv_bfloat16* __restrict__ in,
+                                                              __nv_bfloat16* __restrict__ out, ug_pool_desc d) {
+  pdl_wait();  // programmatic dependent launch: see common.cuh
+  pdl_launch_dependents();
+  const int cg = d.C / 8;
+  const int bw = (d.W + 1) >> 1, bh = (d.H + 1) >> 1;
+  const int total = d.B * bh * bw * cg;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int g = t % cg;
+  int pp = t / cg;
+  const int bx = pp % bw;
+  pp /= bw;
+  const int by = pp % bh;
+  const int n = pp / bh;
+  const uint32_t ninf = 0xFF80FF80u;  // (-inf, -inf) in bf16
+  const uint4 vinf = make_uint4(ninf, ninf, ninf, ninf);
+  auto vmax = [](const uint4& a, const uint4& b) {
+    return make_uint4(bf16x2_max(a.x, b.x), bf16x2_max(a.y, b.y), bf16x2_max(a.z, b.z), bf16x2_max(a.w, b.w));
+  };
+  const int y0 = 2 * by - 1, x0 = 2 * bx - 1;
+  const __nv_bfloat16* base = in + ((long long)n * d.H * d.W) * d.in_cstride + g * 8;
+  uint4 o[2][2] = {{vinf, vinf}, {vinf, vinf}};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int y = y0 + r, x = x0 + c;
+      v[r] = (y >= 0 && y < d.H && x >= 0 && x < d.W)
+                 ? *reinterpret_cast<const uint4*>(base + ((long long)y * d.W + x) * d.in_cstride)
+                 : vinf;
+    }
+    const uint4 mid = vmax(v[1], v[2]);
+    const uint4 top = vmax(v[0], mid), bot = vmax(mid, v[3]);
+    if (c <= 2) {
+      o[0][0] = vmax(o[0][0], top);
+      o[1][0] = vmax(o[1][0], bot);
+    }
+    if (c >= 1) {
+      o[0][1] = vmax(o[0][1], top);
+      o[1][1] = vmax(o[1][1], bot);
+    }
+  }
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int oy = 2 * by + dy, ox = 2 * bx + dx;
+      if (oy < d.H && ox < d.W)
+        *reinterpret_cast<uint4*>(out + (((long long)n * d.H + oy) * d.W + ox) * d.out_cstride + g * 8) = o[dy][dx];
+    }
+}
+
 int launch_pool(ug_engine* h, const ug_pool_desc* d, cudaStream_t s) {
   if (!d->in || !d->out || d->C % 8 || d->in_cstride % 8 || d->out_cstride % 8 || d->k <= 0 || d->stride <= 0)
     return set_error(h, UG_EINVAL, "pool: bad args (C and strides must be multiples of 8)");
   if ((d->OH - 1) * d->stride - d->pad >= d->H || (d->OW - 1) * d->stride - d->pad >= d->W)
     return set_error(h, UG_EINVAL, "pool: last window starts outside the input");
+  // UG_POOL_BLOCK=0: the previous kernels (generic for stride 2, sliding rows for stride 1) for A/B runs.  Block forms
+  // (profiles/r02_pool_s2.txt): maxpool1 0.1505 -> 0.107 ms per 256 images (4.8 TB/s of DRAM traffic), maxpool2 0.118 ->
+  // 0.086, the branch-4 pools on 28x28 / 14x14 maps 0.074 / 0.042 -> 0.058 / 0.033; the 7x7 maps stay on sliding rows
+  // (0.015 against 0.0195 ms).
+  static const int pool_block = [] { const char* e = getenv("UG_POOL_BLOCK"); return e ? atoi(e) : 1; }();
+  if (pool_block && d->k == 3 && d->stride == 1 && d->pad == 1 && d->OH == d->H && d->OW == d->W && d->H * d->W >= 196) {
+    const long long total = (long long)d->B * ((d->H + 1) / 2) * ((d->W + 1) / 2) * (d->C / 8);
+    launch_pdl(h, pool3x3s1_block_kernel, cdiv(total, 256), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(d->in),
+                                                            reinterpret_cast<__nv_bfloat16*>(d->out), *d);
+    h->launches++;
+    return check_cuda(h, cudaGetLastError(), "pool3x3s1 launch");
+  }
   if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->OH == d->H && d->OW == d->W) {
     const long long total = (long long)d->B * d->H * (d->C / 8);
     launch_pdl(h, pool3x3s1_kernel, cdiv(total, 256), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(d->in),
                                                       reinterpret_cast<__nv_bfloat16*>(d->out), *d);
     h->launches++;
     return check_cuda(h, cudaGetLastError(), "pool3x3s1 launch");
+  }
+  if (pool_block && d->k == 3 && d->stride == 2 && d->pad == 0 && 2 * (d->OH - 1) < d->H && 2 * (d->OW - 1) < d->W) {
+    const long long total = (long long)d->B * ((d->OH + 1) / 2) * ((d->OW + 1) / 2) * (d->C / 8);
+    launch_pdl(h, pool3x3s2_kernel, cdiv(total, 256), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(d->in),
+                                                      reinterpret_cast<__nv_bfloat16*>(d->out), *d);
+    h->launches++;
+    return check_cuda(h, cudaGetLastError(), "pool3x3s2 launch");
   }
   const long long total = (long long)d->B * d->OH * d->OW * (d->C / 8);
   launch_pdl(h, pool_kernel, cdiv(total, 256), 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(d->in),
