@@ -81,6 +81,8 @@ if os.environ.get("UG_CONFIGS") == "pair":    # 64-output-channel 3x3 layers: mu
                dict(variant=6, mode=2)]
 if os.environ.get("UG_CONFIGS") == "v5only":   # the static rule's choice only
     CONFIGS = [dict(variant=0)]
+if os.environ.get("UG_CONFIGS") == "gate128":  # CoordAtt3 combine on 128-column tiles: single CTA / pairs, plain store beside it
+    CONFIGS = [dict(variant=5, mode=2), dict(variant=7, mode=2), dict(variant=7)]
 if os.environ.get("UG_CONFIGS") == "pair128":  # 128-column n-tiles: multi-issuer kernel with / without CTA pairs
     CONFIGS = [dict(variant=5), dict(variant=7), dict(variant=5, mode=2), dict(variant=7, mode=2)]
 if os.environ.get("UG_ABLATE"):

@@ -222,6 +222,9 @@ CASES = [
     dict(B=3, H=28, W=28, Cin=512, N=512, R=3, mode=2, variant=7),    # combine on strips, four n-tiles
     dict(B=5, H=14, W=14, Cin=512, N=512, R=3, variant=7),            # 14x14: two tiles per image, 10 tiles = 3 groups
     dict(B=37, H=30, W=20, Cin=128, N=128, R=3, variant=7, in_extra=64, in_off=64),   # ragged both ways, many rounds
+    dict(B=2, H=112, W=112, Cin=128, N=128, R=3, mode=2, variant=7),  # combine, residual sub-tiles by TMA (two per tile)
+    dict(B=37, H=20, W=16, Cin=128, N=256, R=3, mode=2, variant=7),   # combine: many rounds (staging-buffer hand-over), ragged tiles
+    dict(B=5, H=14, W=14, Cin=256, N=192, R=3, bn=128, mode=2, variant=7),   # combine with a ragged last n-tile (one sub-tile)
     dict(B=3, H=56, W=56, Cin=64, N=192, R=3, bn=128, variant=7),     # GoogLeNet conv3: ragged second n-tile (64 of 128 columns)
     dict(B=5, H=14, W=14, Cin=160, N=320, R=3, variant=7),            # three n-tiles, last one half full; ragged k-chunk
     dict(B=4, H=14, W=14, Cin=96, N=208, R=3, bn=128, variant=7, out_extra=48, out_off=16),   # N = 208: last store box clipped

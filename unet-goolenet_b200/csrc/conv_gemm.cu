@@ -631,12 +631,13 @@ int conv_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   // streams half of every weight tile; conv_multi.cu header).  profiles/r02_pair128.txt, per 64 images: 112x112 128->128
   // 0.172 -> 0.148 ms (1600 TFLOP/s), 56x56 256->256 0.185 -> 0.164, 28x28 512->512 0.182 -> 0.169, 1024->256 0.204 ->
   // 0.186; the 256-image step +4.9 %.  Not routed: 64 input channels (resident weights, bound by the epilogue: 0.094 ->
-  // 0.112 ms; GoogLeNet conv3 64->192 neutral) and the CoordAtt3 combine below 256 input channels (0.192 -> 0.198 ms).
+  // 0.112 ms; GoogLeNet conv3 64->192 neutral).  The CoordAtt3 combine runs in pair mode with its residual sub-tiles
+  // TMA-loaded by an extra warp (UG_RESID_TMA128, profiles/r02_resid_tma128.txt): 112x112 128->128 0.197 -> 0.165 ms.
   // GoogLeNet's 3x3 layers with N >= 128 (ragged last n-tile) gain 8-13 % each, the stage 2.151 -> 2.124 ms.
   // UG_PAIR128=0 turns the rule off.
   static const int use_pair128 = [] { const char* e = getenv("UG_PAIR128"); return e ? atoi(e) : 1; }();
   if (use_pair128 && d->variant == 0 && d->R == 3 && up == 1 && d->H * d->W >= 196 && !d->stats_sum && d->N >= 128 &&
-      ((d->mode == UG_EPI_STORE && d->Cin > 64) || (d->mode == UG_EPI_GATE && d->Cin >= 256))) {
+      ((d->mode == UG_EPI_STORE && d->Cin > 64) || (d->mode == UG_EPI_GATE && d->Cin >= 128))) {
     const int rc = conv_multi_prepare(h, d, 128, L, 1);
     if (rc == UG_OK) return rc;
     if (rc != UG_EUNSUPPORTED) return rc;

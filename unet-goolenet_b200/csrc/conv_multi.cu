@@ -68,7 +68,9 @@ namespace ug {
 
 static constexpr int kEpiUnroll = UG_EPI_UNROLL;   // unroll factor of the epilogue chunk loop
 static constexpr int kMI = 2;           // tile streams per CTA (each with its own epilogue warpgroup)
-__host__ __device__ constexpr int kMultiThreads(int ks) { return 32 * (4 * kMI + 2 + kMI * ks); }   // 384 (kKS = 1) / 448 (kKS = 2)
+// threads per CTA: 384 (kKS = 1) / 448 (kKS = 2); + one warp (residual producer) for the TMA-residual pair kernels, whose
+// weight warp is busy streaming
+__host__ __device__ constexpr int kMultiThreads(int ks, int extra = 0) { return 32 * (4 * kMI + 2 + kMI * ks + extra); }
 static constexpr int kMPitch = 10;      // halo tile pitch of 8-pixel-wide tiles: 8 output pixels + one border pixel on each side
 // Warp roles.  The warp scheduler prefers the highest warp id among eligible warps, and the MMA issuers are the
 // latency-critical warps (every late tcgen05.mma is a tensor-pipe bubble), so they get the highest ids, then the
@@ -197,12 +199,13 @@ struct StoreMaps {  // output maps: [0] for plain stores, [q] = quadrant (dy,dx)
 };
 
 template <int kAct, int kTaps, int kMode, int kKS, int kRT, int kPair>
-__global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kMultiThreads(kKS, kRT && kPair), 1) conv_multi_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                            const __grid_constant__ CUtensorMap tmB,
                                                                            const __grid_constant__ StoreMaps tmO,
                                                                            const ConvKParams p, const MultiParams hp) {
-  constexpr int kThreadsCta = kMultiThreads(kKS);
-  static_assert(!kPair || (kTaps == 9 && !kRT), "CTA pairs: 3x3 halo tiles, register-prefetched residual");
+  constexpr int kThreadsCta = kMultiThreads(kKS, kRT && kPair);
+  constexpr int kResidWarp = kMIssuerWarp0 + kMI * kKS;   // extra warp of the TMA-residual pair kernels
+  static_assert(!kPair || kTaps == 9, "CTA pairs: 3x3 halo tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   const int b_tile_bytes = (kPair ? p.BN / 2 : p.BN) * 128;   // pairs: this CTA's half of the rows of a weight tile
@@ -302,6 +305,39 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
   if (warp != kMAllocWarp) pdl_wait();
   pdl_launch_dependents();
 
+  // Residual producer (kRT): the (tile, 64-column sub-tile) sequence of both streams, one sub-tile ahead of the epilogue,
+  // TMA-loaded into the free staging buffer; the residual is an activation written by an earlier kernel of the stream.
+  auto resid_loop = [&]() {
+    const uint32_t r_tx = (uint32_t)(p.TW * p.TH * 128);
+    const int obuf_b = kABytesPerStage;
+    int rb[kMI] = {0, 0};
+    uint32_t rph[kMI] = {0, 0};
+    for (int s = cta0; s < total_super; s += ncta) {
+      int nt, ms;
+      decode(s, nt, ms);
+      const int ncols = min(p.BN, p.N - nt * p.BN);
+#pragma unroll
+      for (int i = 0; i < kMI; ++i) {
+        const int mt = tile_of(ms, i);
+        if (!tile_live(mt)) continue;
+        const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
+        const int x0 = (mt - t1 * p.tiles_x) * p.TW, y0 = (t1 - t2 * p.tiles_y) * p.TH, n0 = t2 * p.TN;
+        for (int sub = 0; sub * 64 < ncols; ++sub) {
+          mbar_wait(&r_free[i * 2 + rb[i]], rph[i] ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&r_full[i * 2 + rb[i]], r_tx);
+            tma_load_4d(sO + (i * p.obufs + rb[i]) * obuf_b, &tmO.m[4], &r_full[i * 2 + rb[i]], nt * p.BN + sub * 64, x0, y0, n0);
+          }
+          __syncwarp();
+          if (++rb[i] == 2) {
+            rb[i] = 0;
+            rph[i] ^= 1;
+          }
+        }
+      }
+    }
+  };
+
   if (warp == kMProducerWarp) {
     // ------------------------------------------------------------------ activation producer (whole warp, elected lane issues)
     int as[kMI] = {0, 0};
@@ -380,35 +416,9 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
         }
       }
       __syncwarp();
-      if constexpr (kRT) {
-        // residual producer: the tile sequence of both streams, one sub-tile (= one tile: BN <= 64) ahead of the
-        // epilogue; the residual is an activation written by an earlier kernel of the stream
+      if constexpr (kRT && !kPair) {   // the weight warp is idle from here on: it produces the residual tiles
         pdl_wait();
-        const uint32_t r_tx = (uint32_t)(p.TW * p.TH * 128);
-        const int obuf_b = kABytesPerStage;
-        int rb[kMI] = {0, 0};
-        uint32_t rph[kMI] = {0, 0};
-        for (int s = cta0; s < total_super; s += ncta) {
-          int nt, ms;
-          decode(s, nt, ms);
-#pragma unroll
-          for (int i = 0; i < kMI; ++i) {
-            const int mt = tile_of(ms, i);
-            if (!tile_live(mt)) continue;
-            const int t1 = hp.d_tx.div(mt), t2 = hp.d_ty.div(t1);
-            const int x0 = (mt - t1 * p.tiles_x) * p.TW, y0 = (t1 - t2 * p.tiles_y) * p.TH, n0 = t2 * p.TN;
-            mbar_wait(&r_free[i * 2 + rb[i]], rph[i] ^ 1);
-            if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&r_full[i * 2 + rb[i]], r_tx);
-              tma_load_4d(sO + (i * p.obufs + rb[i]) * obuf_b, &tmO.m[4], &r_full[i * 2 + rb[i]], nt * p.BN, x0, y0, n0);
-            }
-            __syncwarp();
-            if (++rb[i] == 2) {
-              rb[i] = 0;
-              rph[i] ^= 1;
-            }
-          }
-        }
+        resid_loop();
       }
     } else {
       int bs = 0;
@@ -441,6 +451,8 @@ __global__ void __launch_bounds__(kMultiThreads(kKS), 1) conv_multi_kernel(const
       }
     }
     if (p.prof && lane == 0) p.prof[blockIdx.x * 16 + 1] = w_b;
+  } else if ((kRT && kPair) && warp == kResidWarp) {
+    resid_loop();   // (this warp executed pdl_wait above)
   } else if (warp >= kMIssuerWarp0 && rank != 0) {
     // (the peer CTA of a pair issues nothing: the leader's MMAs read both CTAs' shared memory and write both TMEMs)
   } else if (warp >= kMIssuerWarp0) {
@@ -1005,7 +1017,13 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   static const int rt_on = [] { const char* e = getenv("UG_RESID_TMA"); return e ? atoi(e) : 1; }();
   int rt = (rt_on && !pair && taps == 9 && !strip && ks == 2 && d->mode == UG_EPI_GATE && d->N <= 64 && BN == 64 && d->add_bstride > 0 &&
             !pool && !stats) ? 1 : 0;
-  if (rt) {
+  // pair mode: the residual of every 64-column sub-tile by TMA (an extra warp produces them: the weight warp is streaming);
+  // costs the second staging buffer per stream, i.e. four of the 8 KB weight-ring slots
+  static const int rt128_on = [] { const char* e = getenv("UG_RESID_TMA128"); return e ? atoi(e) : 1; }();
+  const int rt_pair = (rt_on && rt128_on && pair && d->mode == UG_EPI_GATE && d->add_bstride > 0 && d->add_cstride % 8 == 0 &&
+                       !(reinterpret_cast<uintptr_t>(d->add) & 15)) ? 1 : 0;
+  if (rt_pair) rt = 1;
+  if (rt && !pair) {
     const int th2 = cdiv_m(d->H, cdiv_m(d->H, 14));
     const long long need = (long long)taps * kchunks * BN * 128 + kMI * 2LL * (((kMPitch * (th2 + 2) * 128) + 1023) / 1024 * 1024) +
                            kMI * 2LL * kABytesPerStage + 4096;
@@ -1041,7 +1059,8 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     // COMPLETED, so several slots are always "in flight"; with 8 slots the issuers waited on weights 18 % of the time)
     hp.b_resident = 0;
     hp.sa = 2;
-    if (obufs == 2) obufs = 1;
+    // (the TMA residual of pair mode keeps both staging buffers if that leaves at least six 8 KB ring slots)
+    if (obufs == 2 && !(rt_pair && (budget - kMI * 2LL * a_stage - kMI * 2LL * obuf_bytes) / b_tile >= 6)) obufs = 1;
     long long rest = budget - kMI * 2LL * a_stage - kMI * obufs * obuf_bytes;
     hp.sb = (int)std::min<long long>(16, rest / b_tile);
     if (hp.sb < 3) return set_error(h, UG_EUNSUPPORTED, "conv(multi): tile does not fit in shared memory");
@@ -1051,7 +1070,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     }
   }
 
-  if (rt && !(hp.b_resident && obufs == 2)) rt = 0;   // (does not fit after all: register-prefetched residual)
+  if (rt && !(obufs == 2 && (hp.b_resident || pair))) rt = 0;   // (does not fit after all: register-prefetched residual)
   hp.resid_tma = rt;
   hp.rowtaps = rowtaps;
 
@@ -1175,7 +1194,7 @@ static cudaError_t launch_one(ug_engine* h, const ConvLaunch* L, const StoreMaps
   if constexpr (kPair) {   // clusters of two CTAs (+ programmatic dependent launch)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = L->grid;
-    cfg.blockDim = dim3(kMultiThreads(kKS));
+    cfg.blockDim = dim3(kMultiThreads(kKS, kRT && kPair));
     cfg.dynamicSmemBytes = L->smem;
     cfg.stream = s;
     cudaLaunchAttribute at[2];
@@ -1203,7 +1222,9 @@ static cudaError_t dispatch_multi(ug_engine* h, const ConvLaunch* L, const Store
     if (e == cudaSuccess) e = launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 2, 1>(h, L, maps, hp, s, true);
     if (e == cudaSuccess) e = launch_one<UG_ACT_RELU, 9, UG_EPI_STORE, 1, 0, 1>(h, L, maps, hp, s, true);
     if (e == cudaSuccess) e = launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 1, 0, 1>(h, L, maps, hp, s, true);
-  } else if (L->halo_pair) {   // CTA pairs: two instantiations (conv_multi_prepare admits exactly these)
+    if (e == cudaSuccess) e = launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 1, 1, 1>(h, L, maps, hp, s, true);
+  } else if (L->halo_pair) {   // CTA pairs: three instantiations (conv_multi_prepare admits exactly these)
+    if (mode == UG_EPI_GATE && L->halo_rt) return launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 1, 1, 1>(h, L, maps, hp, s, false);
     if (mode == UG_EPI_GATE) return launch_one<UG_ACT_RELU, 9, UG_EPI_GATE, 1, 0, 1>(h, L, maps, hp, s, false);
     return launch_one<UG_ACT_RELU, 9, UG_EPI_STORE, 1, 0, 1>(h, L, maps, hp, s, false);
   } else if (L->halo_rt) {  // TMA residual: the only instantiation (conv_multi_prepare sets rt for exactly this case)
