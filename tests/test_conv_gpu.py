@@ -16,7 +16,7 @@ from guard import guarded
 
 
 def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_extra=0, in_off=0, out_off=0,
-             seed=0, tile=None, bn=None, stages=0, add_broadcast=False, variant=0, pool=False):
+             seed=0, tile=None, bn=None, stages=0, add_broadcast=False, variant=0, pool=False, want_out=False):
     from ugnet_b200 import engine as E
     from ugnet_b200 import pack
     g = torch.Generator(device="cuda").manual_seed(seed)
@@ -77,6 +77,8 @@ def run_conv(engine, B, H, W, Cin, N, R, act=1, mode=0, up=1, in_extra=0, out_ex
     o_intact()
     if pool:
         p_intact()
+    if want_out:        # raw results, for bit-level comparisons between kernel structures
+        return (logits.clone(), mask.clone()) if mode == E.EPI_OUTC else (obuf.clone(), pbuf.clone() if pool else None)
 
     # ---- reference in fp32 on the same bf16-rounded operands
     xf = x.float().permute(0, 3, 1, 2)
@@ -241,6 +243,25 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
 def test_conv_parity(engine, case):
     run_conv(engine, **case)
+
+
+@pytest.mark.parametrize("case,a,b", [
+    (dict(B=3, H=56, W=56, Cin=256, N=256, R=3), 5, 7),
+    (dict(B=3, H=28, W=28, Cin=512, N=512, R=3, pool=True), 5, 7),
+    (dict(B=2, H=112, W=112, Cin=128, N=128, R=3, mode=2), 5, 7),
+    (dict(B=5, H=14, W=14, Cin=160, N=320, R=3), 5, 7),
+    (dict(B=2, H=224, W=224, Cin=128, N=64, R=3), 5, 6),
+    (dict(B=2, H=112, W=112, Cin=64, N=64, R=3, mode=3), 5, 6),
+    (dict(B=2, H=30, W=44, Cin=64, N=64, R=3, mode=2), 5, 6),
+], ids=lambda v: "-".join(f"{k}{x}" for k, x in v.items()) if isinstance(v, dict) else str(v))
+def test_conv_pair_kernels_bit_identical(engine, case, a, b):
+    """The CTA-pair kernels (variant 6: conv_pair.cu, 7: pair mode of the multi-issuer kernel) accumulate the same
+    products in the same order as the single-CTA multi-issuer kernel (5): results must be identical to the last bit."""
+    ra = run_conv(engine, variant=a, want_out=True, **case)
+    rb = run_conv(engine, variant=b, want_out=True, **case)
+    assert torch.equal(ra[0], rb[0])
+    if ra[1] is not None:
+        assert torch.equal(ra[1], rb[1])
 
 
 @pytest.mark.parametrize("B,H,W,Cin,N", [(2, 56, 56, 64, 64), (3, 28, 28, 128, 256), (2, 112, 112, 64, 128), (2, 20, 36, 64, 96)])

@@ -124,7 +124,9 @@ struct MultiParams {
   int sbo;            // byte distance of consecutive 8-row groups of the A operand: pitch * 128 (tiles) or 1024 (strips)
   int strip;          // row-strip tiles (see the header comment); TH is then the number of image rows per tile
   FastDiv d_pitch;    // divider by pitch (strip mode: MMA row -> (image row, x))
-  int rowtaps;        // 1x1 tiles: k-chunk kc is ROW TAP kc of an overlapping-window input (A box at row y0 + kc, channel 0)
+  int rowtaps;        // 1x1 tiles: k-chunk kc is ROW TAP kc of an overlapping-window input.  1: one A box per tap (at row
+                      // y0 + kc); 2: ONE box of TH + R - 1 rows per tile, tap kc reads it TW * 128 * kc bytes further in
+                      // (a "row halo": the window rows of neighbouring taps are the same bytes)
   int resid_tma;      // kRT kernels: residual tiles arrive by TMA in the staging buffers (see the header comment)
   int debug;          // ablation switches for profiling (results are wrong when set): 1 = no TMEM loads,
                       // 2 = no staging stores / TMA store, 4 = activation TMA loads only for the first stages,
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kRT && kPair), 1) conv_mult
 #pragma unroll
         for (int i = 0; i < kMI; ++i) {
           if (!tile_live(tile_of(ms, i))) continue;
+          if (kTaps == 1 && hp.rowtaps == 2 && kc > 0) continue;   // row halo: the tile's single box was loaded at kc == 0
           const int x0 = cx[i], y0 = cy[i], n = cn[i];
           const int slot = i * hp.sa + as[i];
           const long long tw0 = p.prof ? clock64() : 0;
@@ -484,13 +487,16 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kRT && kPair), 1) conv_mult
       }
       for (int kc = 0; kc < p.kchunks; ++kc) {
         uint64_t ad0 = 0;
+        const bool row_halo = kTaps == 1 && hp.rowtaps == 2;
         if (valid) {
-          const long long tw0 = p.prof ? clock64() : 0;
-          mbar_wait(&a_full[i * hp.sa + as], aph);
-          if (p.prof) w_af += clock64() - tw0;
-          tc_fence_after();
+          if (!(row_halo && kc > 0)) {
+            const long long tw0 = p.prof ? clock64() : 0;
+            mbar_wait(&a_full[i * hp.sa + as], aph);
+            if (p.prof) w_af += clock64() - tw0;
+            tc_fence_after();
+          }
           ad0 = kTaps == 9 ? umma_desc_sw128_sbo(smem_u32(sA + (i * hp.sa + as) * hp.a_stage_bytes), hp.sbo)
-                           : umma_desc_sw128(smem_u32(sA + (i * hp.sa + as) * hp.a_stage_bytes));
+                           : umma_desc_sw128(smem_u32(sA + (i * hp.sa + as) * hp.a_stage_bytes) + (row_halo ? kc * p.TW * 128 : 0));
         }
         // (tap loop unrolled by one filter row only: keeps the issue loop inside the L0 instruction cache)
 #pragma unroll 3
@@ -535,7 +541,7 @@ __global__ void __launch_bounds__(kMultiThreads(kKS, kRT && kPair), 1) conv_mult
             }
           }
         }
-        if (valid) {
+        if (valid && !(row_halo && kc + 1 < p.kchunks)) {   // (row halo: the stage is released after its last tap)
           if (elect_one_sync()) mp_commit<kPair>(&a_empty[i * hp.sa + as]);
           __syncwarp();
           if (++as == hp.sa) {
@@ -1030,7 +1036,11 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     if (need <= 227LL * 1024) TH = th2;
     else rt = 0;
   }
-  const int a_bytes = taps == 9 ? pitch * (TH + 2) * 128 : TW * TH * TN * 128;
+  // row halo (rowtaps 2): one box of TH + R - 1 rows per tile instead of R boxes of TH rows; needs whole 1024-byte swizzle
+  // atoms per tile row (TW % 8 == 0) and one image per tile.  UG_ROW_HALO=0 keeps one box per tap.
+  static const int row_halo_on = [] { const char* e = getenv("UG_ROW_HALO"); return e ? atoi(e) : 1; }();
+  const int row_halo = (rowtaps && row_halo_on && TW % 8 == 0 && TN == 1) ? 1 : 0;
+  const int a_bytes = taps == 9 ? pitch * (TH + 2) * 128 : TW * (TH + (row_halo ? d->R - 1 : 0)) * TN * 128;
   // strip mode: MMA row 127 of tap (2,2) reads halo position 127 + 2*pitch + 2, past the loaded box (garbage rows only)
   const int a_span = strip ? std::max(a_bytes, (128 + 2 * pitch + 2) * 128) : a_bytes;
   const int a_stage = ((a_span + 1023) / 1024) * 1024;
@@ -1072,7 +1082,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
 
   if (rt && !(obufs == 2 && (hp.b_resident || pair))) rt = 0;   // (does not fit after all: register-prefetched residual)
   hp.resid_tma = rt;
-  hp.rowtaps = rowtaps;
+  hp.rowtaps = rowtaps ? 1 + row_halo : 0;
 
   ConvKParams& p = L->p;
   memset(&p, 0, sizeof(p));
@@ -1107,7 +1117,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
   L->halo_debug = d->stages >= 100 ? d->stages - 100 : 0;  // profiling ablations (scripts/conv_prof.py)
   L->halo_ks = ks;
   L->halo_rt = rt;
-  L->halo_rowtaps = rowtaps;
+  L->halo_rowtaps = hp.rowtaps;
   L->halo_strip = strip; L->halo_pitch = pitch;
 
   {
@@ -1118,7 +1128,7 @@ int conv_multi_prepare(ug_engine* h, const ug_conv_desc* d, int BN, ConvLaunch* 
     cuuint64_t dims[4] = {(cuuint64_t)(rowtaps ? 64 : d->Cin), (cuuint64_t)d->W, (cuuint64_t)in_h, (cuuint64_t)d->B};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)rs * 2, (cuuint64_t)bs * 2};
     cuuint32_t box9[4] = {64, (cuuint32_t)pitch, (cuuint32_t)(TH + 2), 1};
-    cuuint32_t box1[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t box1[4] = {64, (cuuint32_t)TW, (cuuint32_t)(TH + (row_halo ? d->R - 1 : 0)), (cuuint32_t)TN};
     const int r = encode_map(encode, &L->tmA, const_cast<void*>(d->in), 4, dims, strides, taps == 9 ? box9 : box1,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (r) return set_error(h, UG_ECUDA, "conv(multi): activation tensor map encode failed (%d)", r);
