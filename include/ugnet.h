@@ -97,7 +97,10 @@ typedef struct ug_conv_desc {
                                  halo tile fetched once per 64-channel chunk for all nine taps; see
                                  csrc/conv_multi.cu); 6 = CTA-pair kernel (csrc/conv_pair.cu: clusters of two CTAs,
                                  tcgen05.mma.cta_group::2 with M = 256 over both SMs, each CTA holding half of the
-                                 weight rows; 3x3 ReLU layers with N <= 64, STORE / OUTC / GATE epilogues) */
+                                 weight rows; 3x3 ReLU layers with N <= 64, STORE / OUTC / GATE epilogues);
+                                 7 = the multi-issuer kernel in CTA-pair mode (3x3 ReLU layers with 128-column
+                                 n-tiles, STORE / GATE epilogues; each CTA streams half of every weight tile).
+                                 0 picks by the measured static rule of csrc/conv_gemm.cu (conv_prepare) */
 } ug_conv_desc;
 
 /* Max pooling on NHWC bf16 with -inf padding (nn.MaxPool2d(2), basicUnet.py:47; torchvision GoogLeNet

@@ -209,7 +209,7 @@ int ug_program_run_timed(ug_handle h, ug_program p, void* stream, float* ms_per_
 }
 
 // Measured kernel-variant choice: every conv op of the program is timed on its own buffers with each kernel
-// structure that accepts it (one tile per CTA, persistent, multi-issuer) and keeps the fastest.  All conv ops are
+// structure that accepts it (one tile per CTA, persistent, multi-issuer, the two CTA-pair forms) and keeps the fastest.  All conv ops are
 // pure functions of their inputs, so re-running them before the first real run is harmless.
 int ug_program_autotune(ug_handle h, ug_program p, void* stream, int* n_changed) {
   if (!h || !p) return UG_EINVAL;
@@ -236,7 +236,7 @@ int ug_program_autotune(ug_handle h, ug_program p, void* stream, int* n_changed)
     float best = 0.f;
     rc = time_launch(po.conv, &best);
     if (rc != UG_OK) break;
-    const int variants[3] = {1, 2, 5};
+    const int variants[5] = {1, 2, 5, 6, 7};
     for (int v : variants) {
       ug_conv_desc d = po.op.u.conv;
       d.variant = v;
