@@ -569,88 +569,58 @@ int launch_chanstats(ug_engine* h, const ug_chanstats_desc* d, cudaStream_t s) {
 //   gate_out_kernel:    g = sigmoid(W3 hid + b3)                                                     (slice of g)
 static constexpr int kGateSplit = 8;
 
-// (Round 2: every block handles kGateImgs images, so a weight row is read once per kGateImgs images instead of once per
-// image — the one-image blocks pulled the 1-1.5 MB of fp32 weights from L2 once per image, 29 + 15 us at C = 512.  The
-// per-image summation order — lane-strided partial sums, then the xor tree — is unchanged, so results are bit-identical.)
-static constexpr int kGateImgs = 8;
-
 __global__ void __launch_bounds__(256) gate_hidden_kernel(ug_gate_desc d, float* __restrict__ hid_out) {
   pdl_wait();  // programmatic dependent launch: see common.cuh
   pdl_launch_dependents();
-  __shared__ float s_avg[kGateImgs][512], s_max[kGateImgs][512];
-  const int n0 = blockIdx.y * kGateImgs;
-  const int nimg = min(kGateImgs, d.B - n0);
+  __shared__ float s_avg[512], s_max[512];
+  const int n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int e = threadIdx.x; e < nimg * d.C; e += blockDim.x) {
-    const int im = e / d.C, c = e - im * d.C;
+  for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
     float a = 0.0f, b = -FLT_MAX;
     for (int sp = 0; sp < d.splits; ++sp) {
-      const long long o = ((long long)(n0 + im) * d.splits + sp) * d.C + c;
+      const long long o = ((long long)n * d.splits + sp) * d.C + c;
       a += d.psum[o];
       b = fmaxf(b, d.pmax[o]);
     }
-    s_avg[im][c] = a / (float)d.HW;
-    s_max[im][c] = b;
+    s_avg[c] = a / (float)d.HW;
+    s_max[c] = b;
   }
   __syncthreads();
   const int hid = d.C / 2;
   const int per = (hid + kGateSplit - 1) / kGateSplit;
   const int j0 = blockIdx.x * per, j1 = min(hid, j0 + per);
   for (int j = j0 + warp; j < j1; j += 8) {
-    float a[kGateImgs], b[kGateImgs];
-#pragma unroll
-    for (int im = 0; im < kGateImgs; ++im) a[im] = b[im] = 0.0f;
+    float a = 0.0f, b = 0.0f;
     for (int c = lane; c < d.C; c += 32) {
-      const float w1 = __ldg(d.w1 + (long long)j * d.C + c), w2 = __ldg(d.w2 + (long long)j * d.C + c);
-#pragma unroll
-      for (int im = 0; im < kGateImgs; ++im) {
-        a[im] += w1 * s_avg[im][c];
-        b[im] += w2 * s_max[im][c];
-      }
+      a += __ldg(d.w1 + (long long)j * d.C + c) * s_avg[c];
+      b += __ldg(d.w2 + (long long)j * d.C + c) * s_max[c];
     }
 #pragma unroll
-    for (int im = 0; im < kGateImgs; ++im) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        a[im] += __shfl_xor_sync(0xffffffffu, a[im], o);
-        b[im] += __shfl_xor_sync(0xffffffffu, b[im], o);
-      }
-      if (lane == 0 && im < nimg)
-        hid_out[(long long)(n0 + im) * hid + j] = fmaxf(a[im] + d.b1[j], 0.0f) + fmaxf(b[im] + d.b2[j], 0.0f);
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
     }
+    if (lane == 0) hid_out[(long long)n * hid + j] = fmaxf(a + d.b1[j], 0.0f) + fmaxf(b + d.b2[j], 0.0f);
   }
 }
 
 __global__ void __launch_bounds__(256) gate_out_kernel(ug_gate_desc d, const float* __restrict__ hid_in) {
   pdl_wait();  // programmatic dependent launch: see common.cuh
   pdl_launch_dependents();
-  __shared__ float s_hid[kGateImgs][256];
-  const int n0 = blockIdx.y * kGateImgs;
-  const int nimg = min(kGateImgs, d.B - n0);
+  __shared__ float s_hid[256];
+  const int n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hid = d.C / 2;
-  for (int e = threadIdx.x; e < kGateImgs * hid; e += blockDim.x) {
-    const int im = e / hid, j = e - im * hid;
-    s_hid[im][j] = im < nimg ? hid_in[(long long)(n0 + im) * hid + j] : 0.0f;
-  }
+  for (int j = threadIdx.x; j < hid; j += blockDim.x) s_hid[j] = hid_in[(long long)n * hid + j];
   __syncthreads();
   const int per = (d.C + kGateSplit - 1) / kGateSplit;
   const int c0 = blockIdx.x * per, c1 = min(d.C, c0 + per);
   for (int c = c0 + warp; c < c1; c += 8) {
-    float a[kGateImgs];
+    float a = 0.0f;
+    for (int j = lane; j < hid; j += 32) a += __ldg(d.w3 + (long long)c * hid + j) * s_hid[j];
 #pragma unroll
-    for (int im = 0; im < kGateImgs; ++im) a[im] = 0.0f;
-    for (int j = lane; j < hid; j += 32) {
-      const float w3 = __ldg(d.w3 + (long long)c * hid + j);
-#pragma unroll
-      for (int im = 0; im < kGateImgs; ++im) a[im] += w3 * s_hid[im][j];
-    }
-#pragma unroll
-    for (int im = 0; im < kGateImgs; ++im) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a[im] += __shfl_xor_sync(0xffffffffu, a[im], o);
-      if (lane == 0 && im < nimg) d.g[(long long)(n0 + im) * d.C + c] = 1.0f / (1.0f + expf(-(a[im] + d.b3[c])));
-    }
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) d.g[(long long)n * d.C + c] = 1.0f / (1.0f + expf(-(a + d.b3[c])));
   }
 }
 
@@ -658,9 +628,8 @@ int launch_gate(ug_engine* h, const ug_gate_desc* d, cudaStream_t s) {
   if (!d->psum || !d->pmax || !d->w1 || !d->w2 || !d->w3 || !d->b1 || !d->b2 || !d->b3 || !d->g || !d->hid ||
       d->C > 512 || d->C % 2 || d->HW <= 0 || d->splits <= 0)
     return set_error(h, UG_EINVAL, "gate: bad args (C <= 512, hid scratch required)");
-  const int img_blocks = (d->B + kGateImgs - 1) / kGateImgs;
-  launch_pdl(h, gate_hidden_kernel, dim3(kGateSplit, img_blocks), 256, 0, s, *d, d->hid);
-  launch_pdl(h, gate_out_kernel, dim3(kGateSplit, img_blocks), 256, 0, s, *d, d->hid);
+  launch_pdl(h, gate_hidden_kernel, dim3(kGateSplit, d->B), 256, 0, s, *d, d->hid);
+  launch_pdl(h, gate_out_kernel, dim3(kGateSplit, d->B), 256, 0, s, *d, d->hid);
   h->launches += 2;
   return check_cuda(h, cudaGetLastError(), "gate launch");
 }
