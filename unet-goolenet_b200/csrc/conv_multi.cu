@@ -1203,7 +1203,7 @@ static cudaError_t launch_one(ug_engine* h, const ConvLaunch* L, const StoreMaps
   if (set_attr) return cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if constexpr (kPair) {   // clusters of two CTAs (+ programmatic dependent launch)
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = L->grid;
+    cfg.gridDim = dim3(std::min(L->grid.x, 2u * (unsigned)max_cluster_pairs(h)));   // persistent loops: any even grid works
     cfg.blockDim = dim3(kMultiThreads(kKS, kRT && kPair));
     cfg.dynamicSmemBytes = L->smem;
     cfg.stream = s;

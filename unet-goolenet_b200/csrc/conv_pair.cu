@@ -25,6 +25,7 @@
 //   * the CoordAtt3 combine (GATE epilogue, kRT) uses the residual-by-TMA protocol of conv_multi.cu: the weight warp
 //     loads the residual tile of the NEXT tile into the free staging buffer, the epilogue combines in place.
 #include <cfloat>
+#include <cstdio>
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
@@ -602,6 +603,32 @@ int conv_pair_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* L) {
   return UG_OK;
 }
 
+int max_cluster_pairs(ug_engine* h) {
+  if (h->max_pairs >= 0) return h->max_pairs;
+  int pairs = h->num_sms / 2;
+  cudaError_t e = cudaFuncSetAttribute((const void*)conv_pair_kernel<UG_EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * (h->num_sms / 2)));
+    cfg.blockDim = dim3(kPThreads);
+    cfg.dynamicSmemBytes = 200 * 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, (const void*)conv_pair_kernel<UG_EPI_STORE, 0>, &cfg);
+    if (e == cudaSuccess && n > 0) pairs = std::min(pairs, n);
+  }
+  if (e != cudaSuccess) cudaGetLastError();   // (the query is advisory: fall back to num_sms / 2)
+  if (getenv("UG_VERBOSE")) fprintf(stderr, "ugnet: %d co-resident CTA pairs on %d SMs\n", pairs, h->num_sms);
+  h->max_pairs = pairs;
+  return pairs;
+}
+
 int conv_pair_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   if (!h->attr_pair) {
     cudaError_t e = cudaFuncSetAttribute((const void*)conv_pair_kernel<UG_EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -623,7 +650,7 @@ int conv_pair_launch(ug_engine* h, const ConvLaunch* L, cudaStream_t s) {
   maps.pool = L->tmQ[0];
   maps.resid = L->tmR;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = L->grid;
+  cfg.gridDim = dim3(std::min(L->grid.x, 2u * (unsigned)max_cluster_pairs(h)));   // persistent loops: any even grid works
   cfg.blockDim = dim3(kPThreads);
   cfg.dynamicSmemBytes = L->smem;
   cfg.stream = s;

@@ -20,6 +20,7 @@ struct ug_engine {
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the device that is current at the call, so the
   // "already raised" flags are per handle (= per device), not process-wide
   bool attr_gemm = false, attr_multi = false, attr_pair = false, attr_stem = false, attr_attn = false;
+  int max_pairs = -1;  // co-resident clusters of two ~200 KB CTAs on this device (cudaOccupancyMaxActiveClusters), -1 = not queried
   size_t attr_resize = 0, attr_crop = 0;
 };
 
@@ -145,6 +146,10 @@ int conv_multi_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
 // CTA-pair kernel (csrc/conv_pair.cu): 3x3 ReLU layers with <= 64 output channels, tcgen05.mma.cta_group::2
 int conv_pair_prepare(ug_engine* h, const ug_conv_desc* d, ConvLaunch* out);
 int conv_pair_launch(ug_engine* h, const ConvLaunch* l, cudaStream_t s);
+// Number of CTA pairs (clusters of two CTAs with ~200 KB of shared memory each) the device can keep resident at once:
+// the persistent pair kernels must not launch more, or the surplus clusters would run as a second wave.  Usually
+// num_sms / 2; fewer when a GPC has an odd number of usable SMs.
+int max_cluster_pairs(ug_engine* h);
 
 int stem_prepare(ug_engine* h, const ug_stem_desc* d, StemLaunch* out);
 int stem_launch(ug_engine* h, const StemLaunch* l, cudaStream_t s);
