@@ -37,6 +37,10 @@ hdr = (f"# ncu --set full --clock-control none of ONE 128-image pipeline pass, e
        "# rows up to resize_u8_kernel: UNet micro-batch of 128 + bbox + crop-resize; from s2d_pack_kernel on: GoogLeNet over 128 crops\n"
        "# conv_multi_kernel<act, taps, epilogue mode, K-split, TMA residual, CTA pairs>; conv_pair_kernel<epilogue mode, TMA residual>\n"
        "# tensor pipe % = sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed (at the full 1.965 GHz clock)\n"
+       "# smem pipe % = l1tex__data_pipe_lsu_wavefronts_mem_shared (LDS / STS issued by threads: epilogue staging, im2col building); the operand\n"
+       "#   reads of tcgen05.mma and the TMA writes into shared memory do not pass through the LSU and are NOT in this counter — the operand-bandwidth\n"
+       "#   bound of the N = 64 layers is shown by the issue-rate microbenchmarks (profiles/r01_mma_multi_issuer.txt, r02_mma_pair.txt: 48 cycles per\n"
+       "#   M=128 N=64 K=16 MMA whatever the number of chains, against 32 cycles of math), not by an ncu counter\n"
        "# % of HBM peak divides by the COPY peak 6552.6 GB/s; write-dominated kernels are bounded by the write roof 3.86 TB/s (r02_bandwidth_probe.txt)\n\n")
 open(f"{P}/{rnd}_ncu_kernels.md", "w").write(hdr + table)
 # DRAM bytes per launch of the dominant kernel family (conv_multi_kernel + conv_pair_kernel)
