@@ -112,6 +112,30 @@ def test_fold_bn_matches_batchnorm_eval():
     assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
 
 
+def test_conv1_space_to_depth_algebra():
+    """GoogLeNet conv1 (7x7 stride 2 pad 3 over 3 channels) == the four-row-tap GEMM over overlapping 4-pixel windows of the
+    2x2 space-to-depth image that the engine runs (ug_s2d_desc + pack.pack_conv1_s2d: K index r2*64 + s2*16 + (dy*2+dx)*3 + c).
+    fp32 on the CPU; the bf16 rounding of the packed weight is the only difference allowed."""
+    torch.manual_seed(4)
+    S, cout = 20, 5
+    x = torch.randn(2, 3, S, S)
+    w = torch.randn(cout, 3, 7, 7) * 0.1
+    ref = torch.nn.functional.conv2d(x, w.to(torch.bfloat16).float(), stride=2, padding=3)        # [2, cout, 10, 10]
+    # packed image: pixel (Y, X) holds source pixels (2Y+dy-3, 2X+dx-3), channel (dy*2+dx)*3 + c, zero outside; Q = S/2 + 3
+    Q = S // 2 + 3
+    xp = torch.zeros(2, 3, 2 * Q, 2 * Q)
+    xp[:, :, 3:3 + S, 3:3 + S] = x
+    s2d = xp.reshape(2, 3, Q, 2, Q, 2).permute(0, 2, 4, 3, 5, 1).reshape(2, Q, Q, 12)              # [n, Y, X, (dy,dx,c)]
+    s2d = torch.cat([s2d, torch.zeros(2, Q, Q, 4)], -1)                                             # 16 channels per pixel
+    wp = pack.pack_conv1_s2d(w).float().reshape(cout, 4, 64)                                        # [co, r2, window of 4 px x 16 ch]
+    O = S // 2
+    out = torch.zeros(2, cout, O, O)
+    for r2 in range(4):                       # row tap r2: A row of output (y, x) = the 64-element window at packed (y + r2, x .. x+3)
+        win = torch.stack([s2d[:, r2:r2 + O, s2:s2 + O, :] for s2 in range(4)], 3).reshape(2, O, O, 64)
+        out += torch.einsum("nyxk,ok->noyx", win, wp[:, r2])
+    assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4)
+
+
 class _Loader(list):
     """A list of reference-style batches: {'image': float tensor, 'filename': [str]}."""
 
