@@ -46,14 +46,15 @@
 // instructions of the chunk loop of a plain-store layer.
 //
 // CTA pairs (kPair = 1, 128-column n-tiles with streamed weights): the issuers of these layers waited for weight tiles
-// 18 % of their time (profiles/r02_pair_kernel.txt) — every CTA streams the whole weight matrix from L2 once per two pixel
+// 18 % of their time (profiles/r02_pair128.txt) — every CTA streams the whole weight matrix from L2 once per two pixel
 // tiles, ~2 GB per layer and ~7.5 TB/s of L2 -> SM traffic at 128 images.  A cluster of two CTAs runs
 // tcgen05.mma.cta_group::2 (M = 256 over both SMs): each CTA loads only HALF of the rows of every weight tile (the
 // tensor cores exchange them), so the weight traffic per SM halves and the ring holds twice as many tiles.  Protocol as
 // in conv_pair.cu: only the leader CTA issues; its a_full / b_full barriers collect the TMA bytes of both CTAs;
 // tcgen05.commit multicasts to the a_empty / b_empty / acc_full barriers of both; the peer's epilogue warps return
 // accumulators with remote arrives on the leader's acc_empty; pixel tiles past the end are zero-filled / clipped by TMA
-// so that both CTAs run the same number of rounds.
+// so that both CTAs run the same number of rounds.  With kRT the CoordAtt3 combine of a pair kernel gets its residual
+// sub-tiles by TMA too: the weight warp is busy streaming, so ONE EXTRA WARP (warp 12, 416 threads) produces them.
 #include <cfloat>
 #include <cstring>
 #include <cstdlib>
